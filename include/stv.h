@@ -1,0 +1,140 @@
+/* stv.h — C ABI of libstv (slowtv_monodepth_b200/csrc), the B200 (sm_100a) kernels behind the SlowTV-monodepth
+ * training hot path.
+ *
+ * The reference (jspenmar/slowtv_monodepth) has no native layer: its "FFI" for this path is a set of Python
+ * nn.Module.forward / handler signatures resolved through src/registry.py. Each entry point below replaces the ATen op
+ * chain launched by one of those call sites (cited per function, paths under /root/reference); the host-side Python
+ * mirror in slowtv_monodepth_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 (unless typed otherwise), NCHW contiguous, owned by the caller;
+ *   - the library never allocates, frees or synchronises; all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - `const float* const* x` arguments are HOST arrays of device pointers (one per scale);
+ *   - return value 0 = success, otherwise an STV_E_* code; stv_last_error() returns a human-readable message
+ *     (thread-local) for the last failing call;
+ *   - scratch memory is passed in as `ws` with at least the number of bytes reported by the matching *_workspace_bytes().
+ */
+#ifndef STV_H_
+#define STV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STV_OK 0
+#define STV_E_ARG 1       /* invalid argument (shape, null pointer, unsupported configuration) */
+#define STV_E_WORKSPACE 2 /* workspace too small */
+#define STV_E_CUDA 3      /* CUDA runtime / launch error */
+
+#define STV_MAX_SCALES 8
+#define STV_MAX_SUPPORT 8
+#define STV_SEL_STATIC 255 /* `sel` value: pixel auto-masked (identity error won) */
+#define STV_SEL_MEAN 254   /* `sel` value: use_min=0, every support frame contributes 1/n */
+
+int stv_version(void);
+const char* stv_last_error(void);
+/* Number of kernels launched by this library since load (all threads); used by bench.py's `gpu_launches`. */
+unsigned long long stv_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Photometric view-synthesis loss: replaces handlers.image_recon (src/core/handlers.py:14-67) =
+ *   ViewSynth.forward (src/tools/geometry.py:366-391: BackprojectDepth :304-316, ProjectPoints :329-350, grid_sample :364)
+ *   + ReconstructionLoss.forward (src/losses/reconstruction.py:98-126: compute_photo :79-96, apply_automask :59-77)
+ *   + PhotoError / SSIMError / DenseL1Error (src/losses/photometric.py:11-88).
+ * Index order of every (S, b, ...) tensor is s*b + i, of (n, b, ...) k*b + i, as in handlers.py:48-60.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int b, n, S, H, W;
+    float w_ssim, w_l1;       /* 0.85/0.15 for loss_name='ssim', 0/1 for 'l1' (reconstruction.py:37-41) */
+    int use_min;              /* reconstruction.py:43-44 */
+    int use_automask;         /* reconstruction.py:59-77 */
+    uint64_t noise_seed;      /* automask tie-break noise when `noise == NULL`: 0 = none, else in-kernel Philox normal */
+    int64_t depth_stride_s;   /* unused when per-scale pointers are given; reserved */
+} stv_photo_cfg;
+
+size_t stv_photo_workspace_bytes(const stv_photo_cfg* cfg);
+
+/* loss (device scalar) = mean over (S,b,H,W) of the reduced, auto-masked photometric error.
+ * depth: S pointers to (b,1,H,W) upsampled depth maps; tgt (b,3,H,W); supp (n,b,3,H,W); T (n,b,4,4); K, Kinv (b,4,4);
+ * noise: NULL or (S,b,H,W) standard-normal samples replacing randn_like (reconstruction.py:72);
+ * sel (S,b,H,W) u8: per-pixel decision (support index | STV_SEL_STATIC | STV_SEL_MEAN), consumed by the backward;
+ * warp0: NULL or (n,b,3,H,W) warped support frames at scale 0 (handlers.py:66). */
+int stv_photo_fwd(const stv_photo_cfg* cfg, const float* const* depth, const float* tgt, const float* supp,
+                  const float* T, const float* K, const float* Kinv, const float* noise,
+                  float* loss, uint8_t* sel, float* warp0, void* ws, size_t ws_bytes, void* stream);
+
+/* Backward of stv_photo_fwd w.r.t. depth, T, K and Kinv. grad_loss: device scalar dL/dloss.
+ * g_depth: S pointers to (b,1,H,W) (overwritten); gT (n,b,4,4) (overwritten; row 3 = 0);
+ * gK, gKinv (b,4,4) nullable (overwritten; only the 3x3 block is non-zero). */
+int stv_photo_bwd(const stv_photo_cfg* cfg, const float* const* depth, const float* tgt, const float* supp,
+                  const float* T, const float* K, const float* Kinv, const uint8_t* sel, const float* grad_loss,
+                  float* const* g_depth, float* gT, float* gK, float* gKinv, void* ws, size_t ws_bytes, void* stream);
+
+/* compute_photo (reconstruction.py:79-96) on its own: pred (n,b,3,H,W) vs target (b,3,H,W) -> err (b,1,H,W).
+ * Forward only (used for the identity/static error and by `depth_regr`, src/core/trainer.py:430). */
+int stv_photo_error(const stv_photo_cfg* cfg /* b,n,H,W,w_ssim,w_l1,use_min */, const float* pred, const float* tgt,
+                    float* err, void* stream);
+
+/* ViewSynth.forward (src/tools/geometry.py:366-391) on its own: input (B,C,H,W), depth (B,1,H,W), T,K,Kinv (B,4,4) ->
+ * warp (B,C,H,W), depth_warp (B,1,H,W), mask_valid (B,1,H,W) u8. Any C; used by the stand-alone ViewSynth module. */
+int stv_view_synth_fwd(int B, int C, int H, int W, const float* input, const float* depth, const float* T,
+                       const float* K, const float* Kinv, float* warp, float* depth_warp, uint8_t* mask_valid,
+                       void* stream);
+/* Backward w.r.t. depth/T/K/Kinv (and input when g_input != NULL, accumulated with atomics into a zeroed buffer).
+ * g_warp (B,C,H,W), g_depth_warp (B,1,H,W) nullable. partial: workspace of stv_view_synth_workspace_bytes(). */
+size_t stv_view_synth_workspace_bytes(int B, int C, int H, int W);
+int stv_view_synth_bwd(int B, int C, int H, int W, const float* input, const float* depth, const float* T,
+                       const float* K, const float* Kinv, const float* g_warp, const float* g_depth_warp,
+                       float* g_depth, float* gT, float* gK, float* gKinv, float* g_input,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Disparity post-processing: replaces ops.interpolate_like (src/tools/ops.py:311-314, trainer.py:320) fused with
+ * to_scaled / to_inv (src/tools/geometry.py:62-76, 86-90, trainer.py:49,321).
+ * disp (b,1,h,w) -> disp_up (b,1,H,W) [nullable], depth_up (b,1,H,W). min_depth/max_depth <= 0 mean "unset".
+ * ------------------------------------------------------------------------------------------------------------------ */
+int stv_disp_to_depth_fwd(int b, int h, int w, int H, int W, float min_depth, float max_depth, const float* disp,
+                          float* disp_up, float* depth_up, void* stream);
+/* g_disp (b,1,h,w) = d(depth_up)/d(disp)^T g_depth_up [+ d(disp_up)/d(disp)^T g_disp_up when non-NULL]. Deterministic gather. */
+int stv_disp_to_depth_bwd(int b, int h, int w, int H, int W, float min_depth, float max_depth, const float* disp,
+                          const float* g_depth_up, const float* g_disp_up, float* g_disp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Edge-aware smoothness: replaces handlers.disp_smooth (src/core/handlers.py:262-281) = per scale
+ *   interpolate_like(imgs, disp) (:278) + SmoothReg.forward (src/regularizers/smooth.py:71-97, compute_grad :12-30,
+ *   ops.mean_normalize src/tools/ops.py:279-286); loss = mean_s(loss_s / scale_div[s]).
+ * disp: S pointers to (b,1,h_s,w_s); img (b,3,H,W).
+ * disp_grad / image_grad: NULL or (b,1,h_0,w_0) logging maps of the FIRST scale (handlers.py:280).
+ * stats: workspace-resident per (s,i) {mean, loss_sum} consumed by the backward (kept inside `ws`).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int b, S, H, W;
+    int h[STV_MAX_SCALES], w[STV_MAX_SCALES];
+    float scale_div[STV_MAX_SCALES]; /* 2**s of the reference's dict key (handlers.py:279) */
+    int use_edges;                   /* smooth.py:91-94 */
+} stv_smooth_cfg;
+
+size_t stv_smooth_workspace_bytes(const stv_smooth_cfg* cfg);
+int stv_smooth_fwd(const stv_smooth_cfg* cfg, const float* const* disp, const float* img, float* loss,
+                   float* disp_grad, float* image_grad, void* ws, size_t ws_bytes, void* stream);
+/* `ws` must be the workspace filled by the matching stv_smooth_fwd call. g_disp: S pointers (overwritten). */
+int stv_smooth_bwd(const stv_smooth_cfg* cfg, const float* const* disp, const float* img, const float* grad_loss,
+                   float* const* g_disp, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Optimiser: replaces torch.optim.AdamW(foreach) built by timm create_optimizer_v2 (src/tools/parsers.py:205-243)
+ * on one flat fp32 parameter/gradient buffer. `wd` is a per-element weight-decay mask value selector: elements in
+ * [0, n_decay) use `weight_decay`, elements in [n_decay, n) use 0 (timm excludes biases / 1-D params).
+ * grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). step is 1-based.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int stv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, size_t n_decay,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, int step,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STV_H_ */

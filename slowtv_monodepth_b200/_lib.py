@@ -1,0 +1,105 @@
+"""ctypes binding of libstv.so (the C ABI declared in include/stv.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+LIB_PATH = Path(__file__).resolve().parent/'libstv.so'
+MAX_SCALES = 8
+SEL_STATIC, SEL_MEAN = 255, 254
+
+_lib = None
+
+
+class StvError(RuntimeError):
+    pass
+
+
+class PhotoCfg(C.Structure):
+    _fields_ = [('b', C.c_int), ('n', C.c_int), ('S', C.c_int), ('H', C.c_int), ('W', C.c_int),
+                ('w_ssim', C.c_float), ('w_l1', C.c_float), ('use_min', C.c_int), ('use_automask', C.c_int),
+                ('noise_seed', C.c_uint64), ('depth_stride_s', C.c_int64)]
+
+
+class SmoothCfg(C.Structure):
+    _fields_ = [('b', C.c_int), ('S', C.c_int), ('H', C.c_int), ('W', C.c_int),
+                ('h', C.c_int*MAX_SCALES), ('w', C.c_int*MAX_SCALES), ('scale_div', C.c_float*MAX_SCALES),
+                ('use_edges', C.c_int)]
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    'stv_version': (C.c_int, []),
+    'stv_last_error': (C.c_char_p, []),
+    'stv_launch_count': (C.c_ulonglong, []),
+    'stv_photo_workspace_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
+    'stv_photo_fwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'stv_photo_bwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'stv_photo_error': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P]),
+    'stv_view_synth_fwd': (C.c_int, [C.c_int]*4 + [_P]*9),
+    'stv_view_synth_workspace_bytes': (C.c_size_t, [C.c_int]*4),
+    'stv_view_synth_bwd': (C.c_int, [C.c_int]*4 + [_P]*13 + [C.c_size_t, _P]),
+    'stv_disp_to_depth_fwd': (C.c_int, [C.c_int]*5 + [C.c_float]*2 + [_P]*4),
+    'stv_disp_to_depth_bwd': (C.c_int, [C.c_int]*5 + [C.c_float]*2 + [_P]*5),
+    'stv_smooth_workspace_bytes': (C.c_size_t, [C.POINTER(SmoothCfg)]),
+    'stv_smooth_fwd': (C.c_int, [C.POINTER(SmoothCfg), _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'stv_smooth_bwd': (C.c_int, [C.POINTER(SmoothCfg), _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'stv_adamw_step': (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_size_t] + [C.c_float]*6 + [C.c_int, _P]),
+}
+
+
+def exported_symbols() -> list[str]:
+    """Every entry point include/stv.h declares (checked by the CPU test-suite against the built library)."""
+    return list(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    """Load libstv.so once. Raises if it has not been built (`python -m slowtv_monodepth_b200._build`)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.is_file():
+            raise StvError(f'{LIB_PATH} is missing: build it with `python -m slowtv_monodepth_b200._build` '
+                           f'(there is no CPU/PyTorch fallback for the CUDA path).')
+        h = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(h, name)  # AttributeError if the symbol is not exported.
+            fn.restype, fn.argtypes = res, args
+        _lib = h
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().stv_last_error().decode()
+        if rc == 1: raise ValueError(f'{what}: {msg}')  # Reference convention: ValueError for bad shapes/args.
+        raise StvError(f'{what} failed (code {rc}): {msg}')
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def ptr_array(ts) -> C.Array:
+    return (C.c_void_p*len(ts))(*[t.data_ptr() for t in ts])
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*ts: torch.Tensor | None, what: str = 'stv') -> None:
+    for t in ts:
+        if t is None: continue
+        if not t.is_cuda:
+            raise StvError(f'{what}: expected CUDA tensors, got a {t.device} tensor (there is no CPU fallback).')
+        if t.dtype != torch.float32 and t.dtype != torch.uint8:
+            raise ValueError(f'{what}: expected float32 tensors, got {t.dtype}.')
+
+
+def launch_count() -> int:
+    return int(lib().stv_launch_count())

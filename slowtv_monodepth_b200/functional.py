@@ -1,0 +1,270 @@
+"""Autograd bindings of the libstv kernels (the host side of the C ABI in include/stv.h).
+
+Each `torch.autograd.Function` enqueues hand-written sm_100a kernels on the current CUDA stream through ctypes; torch is
+used only for device memory, streams and the autograd graph around the kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+__all__ = ['photo_loss', 'photo_error', 'smooth_loss', 'disp_to_depth', 'view_synth', 'adamw_step_']
+
+
+def _f32c(t: Tensor | None) -> Tensor | None:
+    if t is None: return None
+    if t.dtype != torch.float32: raise ValueError(f'Expected float32, got {t.dtype}.')
+    return t.contiguous()
+
+
+def _ws(nbytes: int, device) -> Tensor:
+    return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Fused view-synthesis photometric loss
+# ---------------------------------------------------------------------------------------------------------------------
+class _PhotoLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg: L.PhotoCfg, want_warp: bool, tgt, supp, T, K, Kinv, noise, *depths):
+        L.require_cuda(tgt, supp, T, K, Kinv, noise, *depths, what='photo_loss')
+        lib, dev = L.lib(), tgt.device
+        b, n, S, H, W = cfg.b, cfg.n, cfg.S, cfg.H, cfg.W
+        with torch.cuda.device(dev):
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            sel = torch.empty((S, b, H, W), dtype=torch.uint8, device=dev)
+            warp0 = torch.empty((n, b, 3, H, W), dtype=torch.float32, device=dev) if want_warp else None
+            nws = lib.stv_photo_workspace_bytes(C.byref(cfg))
+            ws = _ws(nws, dev)
+            L.check(lib.stv_photo_fwd(C.byref(cfg), L.ptr_array(depths), L.ptr(tgt), L.ptr(supp), L.ptr(T), L.ptr(K),
+                                      L.ptr(Kinv), L.ptr(noise), L.ptr(loss), L.ptr(sel), L.ptr(warp0), L.ptr(ws),
+                                      ws.numel(), L.stream()), 'stv_photo_fwd')
+        ctx.cfg, ctx.nws = cfg, nws
+        ctx.save_for_backward(tgt, supp, T, K, Kinv, sel, *depths)
+        ctx.mark_non_differentiable(sel)
+        if warp0 is None: warp0 = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(warp0)
+        return loss, sel, warp0
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_sel, _g_warp):
+        tgt, supp, T, K, Kinv, sel, *depths = ctx.saved_tensors
+        cfg, lib, dev = ctx.cfg, L.lib(), tgt.device
+        need_d = any(ctx.needs_input_grad[8:])
+        need_T, need_K, need_Ki = ctx.needs_input_grad[4], ctx.needs_input_grad[5], ctx.needs_input_grad[6]
+        if not (need_d or need_T or need_K or need_Ki): return (None,)*(8 + len(depths))
+        with torch.cuda.device(dev):
+            g_loss = g_loss.to(torch.float32).contiguous()
+            g_depths = [torch.empty_like(d) for d in depths]
+            gT = torch.empty_like(T)
+            want_k = need_K or need_Ki
+            gK = torch.empty_like(K) if want_k else None
+            gKi = torch.empty_like(Kinv) if want_k else None
+            ws = _ws(ctx.nws, dev)
+            L.check(lib.stv_photo_bwd(C.byref(cfg), L.ptr_array(depths), L.ptr(tgt), L.ptr(supp), L.ptr(T), L.ptr(K),
+                                      L.ptr(Kinv), L.ptr(sel), L.ptr(g_loss), L.ptr_array(g_depths), L.ptr(gT), L.ptr(gK),
+                                      L.ptr(gKi), L.ptr(ws), ws.numel(), L.stream()), 'stv_photo_bwd')
+        return (None, None, None, None, gT if need_T else None, gK if need_K else None, gKi if need_Ki else None, None,
+                *[g if ctx.needs_input_grad[8 + j] else None for j, g in enumerate(g_depths)])
+
+
+def _photo_cfg(b, n, S, H, W, loss_name, use_min, use_automask, noise_seed) -> L.PhotoCfg:
+    if loss_name == 'ssim': w_ssim, w_l1 = 0.85, 0.15  # PhotoError(weight_ssim=0.85), src/losses/reconstruction.py:38
+    elif loss_name == 'l1': w_ssim, w_l1 = 0.0, 1.0    # DenseL1Error, reconstruction.py:39
+    else: raise ValueError(f'The fused photometric loss supports loss_name in {{ssim, l1}}, got "{loss_name}".')
+    return L.PhotoCfg(b=b, n=n, S=S, H=H, W=W, w_ssim=w_ssim, w_l1=w_l1, use_min=int(use_min),
+                      use_automask=int(use_automask), noise_seed=int(noise_seed), depth_stride_s=0)
+
+
+def photo_loss(depths: list[Tensor], tgt: Tensor, supp: Tensor, T: Tensor, K: Tensor, K_inv: Tensor | None = None, *,
+               loss_name: str = 'ssim', use_min: bool = True, use_automask: bool = True, noise: Tensor | None = None,
+               noise_seed: int = 0, want_warp: bool = False):
+    """Fused warp + photometric loss over all scales and support frames.
+
+    depths: S x (b,1,H,W); tgt (b,3,H,W); supp (n,b,3,H,W); T (n,b,4,4); K (b,4,4); K_inv (b,4,4) or None (= K^-1,
+    differentiable, as `ViewSynth.forward` does with `K.inverse()`, src/tools/geometry.py:383).
+    noise: None or (S*b,1,H,W) explicit tie-break noise (parity tests); otherwise `noise_seed != 0` draws it in-kernel.
+    -> loss (), sel (S,b,H,W) uint8, warp0 (n,b,3,H,W) | None.
+    """
+    S = len(depths)
+    b, _, H, W = tgt.shape
+    n = supp.shape[0]
+    if supp.shape != (n, b, 3, H, W): raise ValueError(f'Invalid support frames shape. ({tuple(supp.shape)} vs. {(n, b, 3, H, W)})')
+    if T.shape != (n, b, 4, 4): raise ValueError(f'Invalid transforms shape. ({tuple(T.shape)} vs. {(n, b, 4, 4)})')
+    if K.shape != (b, 4, 4): raise ValueError(f'Invalid intrinsics shape. ({tuple(K.shape)} vs. {(b, 4, 4)})')
+    for d in depths:
+        if d.shape != (b, 1, H, W): raise ValueError(f'Invalid depth shape. ({tuple(d.shape)} vs. {(b, 1, H, W)})')
+    if noise is not None and noise.numel() != S*b*H*W:
+        raise ValueError(f'Invalid noise shape. ({tuple(noise.shape)} vs. {(S*b, 1, H, W)})')
+    if K_inv is None: K_inv = torch.linalg.inv_ex(K)[0]
+    cfg = _photo_cfg(b, n, S, H, W, loss_name, use_min, use_automask, noise_seed)
+    loss, sel, warp0 = _PhotoLoss.apply(cfg, want_warp, _f32c(tgt), _f32c(supp), _f32c(T), _f32c(K), _f32c(K_inv),
+                                        _f32c(noise), *[_f32c(d) for d in depths])
+    return loss, sel, (warp0 if want_warp else None)
+
+
+def photo_error(pred: Tensor, target: Tensor, *, loss_name: str = 'ssim', use_min: bool = True) -> Tensor:
+    """`ReconstructionLoss.compute_photo` without gradient: pred (n,b,3,H,W) | (b,3,H,W), target (b,3,H,W) -> (b,1,H,W)."""
+    if pred.ndim == 4: pred = pred[None]
+    n, b, _, H, W = pred.shape
+    L.require_cuda(pred, target, what='photo_error')
+    cfg = _photo_cfg(b, n, 1, H, W, loss_name, use_min, False, 0)
+    pred, target = _f32c(pred.detach()), _f32c(target.detach())
+    with torch.cuda.device(pred.device):
+        err = torch.empty((b, 1, H, W), dtype=torch.float32, device=pred.device)
+        L.check(L.lib().stv_photo_error(C.byref(cfg), L.ptr(pred), L.ptr(target), L.ptr(err), L.stream()), 'stv_photo_error')
+    return err
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Edge-aware smoothness
+# ---------------------------------------------------------------------------------------------------------------------
+class _SmoothLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg: L.SmoothCfg, want_maps: bool, img, *disps):
+        L.require_cuda(img, *disps, what='smooth_loss')
+        lib, dev = L.lib(), img.device
+        with torch.cuda.device(dev):
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            dg = torch.empty_like(disps[0]) if want_maps else None
+            ig = torch.empty_like(disps[0]) if want_maps else None
+            ws = _ws(lib.stv_smooth_workspace_bytes(C.byref(cfg)), dev)
+            L.check(lib.stv_smooth_fwd(C.byref(cfg), L.ptr_array(disps), L.ptr(img), L.ptr(loss), L.ptr(dg), L.ptr(ig),
+                                       L.ptr(ws), ws.numel(), L.stream()), 'stv_smooth_fwd')
+        ctx.cfg = cfg
+        ctx.save_for_backward(img, ws, *disps)
+        if dg is None: dg = ig = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(dg, ig)
+        return loss, dg, ig
+
+    @staticmethod
+    def backward(ctx, g_loss, _a, _b):
+        img, ws, *disps = ctx.saved_tensors
+        cfg, dev = ctx.cfg, img.device
+        with torch.cuda.device(dev):
+            g_loss = g_loss.to(torch.float32).contiguous()
+            gds = [torch.empty_like(d) for d in disps]
+            L.check(L.lib().stv_smooth_bwd(C.byref(cfg), L.ptr_array(disps), L.ptr(img), L.ptr(g_loss), L.ptr_array(gds),
+                                           L.ptr(ws), ws.numel(), L.stream()), 'stv_smooth_bwd')
+        return (None, None, None, *gds)
+
+
+def smooth_loss(disps: list[Tensor], img: Tensor, *, scales: list[int] | None = None, use_edges: bool = True,
+                want_maps: bool = False):
+    """All-scale edge-aware smoothness: mean_s(SmoothReg(disp_s, resize(img))/2**scale_s).
+    disps: list of (b,1,h_s,w_s); img (b,3,H,W) -> loss (), disp_grad|None, image_grad|None (first scale)."""
+    S = len(disps)
+    if S > L.MAX_SCALES: raise ValueError(f'At most {L.MAX_SCALES} scales are supported, got {S}.')
+    b, c, H, W = img.shape
+    if c != 3: raise ValueError(f'Expected a 3-channel image, got {c} channels.')
+    scales = list(range(S)) if scales is None else list(scales)
+    cfg = L.SmoothCfg(b=b, S=S, H=H, W=W, use_edges=int(use_edges))
+    for j, d in enumerate(disps):
+        if d.ndim != 4 or d.shape[0] != b or d.shape[1] != 1: raise ValueError(f'Invalid disparity shape {tuple(d.shape)}.')
+        cfg.h[j], cfg.w[j], cfg.scale_div[j] = d.shape[2], d.shape[3], float(2**scales[j])
+    loss, dg, ig = _SmoothLoss.apply(cfg, want_maps, _f32c(img), *[_f32c(d) for d in disps])
+    return loss, (dg if want_maps else None), (ig if want_maps else None)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Disparity -> upsampled depth
+# ---------------------------------------------------------------------------------------------------------------------
+class _DispToDepth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, H: int, W: int, min_depth: float, max_depth: float):
+        L.require_cuda(disp, what='disp_to_depth')
+        b, _, h, w = disp.shape
+        with torch.cuda.device(disp.device):
+            disp_up = torch.empty((b, 1, H, W), dtype=torch.float32, device=disp.device)
+            depth_up = torch.empty_like(disp_up)
+            L.check(L.lib().stv_disp_to_depth_fwd(b, h, w, H, W, min_depth, max_depth, L.ptr(disp), L.ptr(disp_up),
+                                                  L.ptr(depth_up), L.stream()), 'stv_disp_to_depth_fwd')
+        ctx.save_for_backward(disp)
+        ctx.args = (H, W, min_depth, max_depth)
+        ctx.set_materialize_grads(False)
+        return disp_up, depth_up
+
+    @staticmethod
+    def backward(ctx, g_disp_up, g_depth_up):
+        if g_disp_up is None and g_depth_up is None: return None, None, None, None, None
+        disp, = ctx.saved_tensors
+        H, W, mn, mx = ctx.args
+        b, _, h, w = disp.shape
+        with torch.cuda.device(disp.device):
+            g = torch.empty_like(disp)
+            L.check(L.lib().stv_disp_to_depth_bwd(b, h, w, H, W, mn, mx, L.ptr(disp), L.ptr(_f32c(g_depth_up)),
+                                                  L.ptr(_f32c(g_disp_up)), L.ptr(g), L.stream()), 'stv_disp_to_depth_bwd')
+        return g, None, None, None, None
+
+
+def disp_to_depth(disp: Tensor, size: tuple[int, int], min_depth: float | None, max_depth: float | None):
+    """Bilinear upsample (align_corners=False) fused with to_scaled/to_inv: (b,1,h,w) -> disp_up, depth_up (b,1,H,W)."""
+    if disp.ndim != 4 or disp.shape[1] != 1: raise ValueError(f'Invalid disparity shape {tuple(disp.shape)}.')
+    if (min_depth or max_depth):
+        if not min_depth or min_depth <= 0: raise ValueError(f'Min depth must be greater than 0. ({min_depth})')
+        if max_depth and max_depth < min_depth: raise ValueError(f'Max depth must be greater than min. ({max_depth} vs. {min_depth})')
+    return _DispToDepth.apply(_f32c(disp), int(size[0]), int(size[1]), float(min_depth or 0), float(max_depth or 0))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Stand-alone ViewSynth
+# ---------------------------------------------------------------------------------------------------------------------
+class _ViewSynth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, depth, T, K, Kinv):
+        L.require_cuda(inp, depth, T, K, Kinv, what='view_synth')
+        B, Cc, H, W = inp.shape
+        dev = inp.device
+        with torch.cuda.device(dev):
+            warp = torch.empty_like(inp)
+            dwarp = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+            valid = torch.empty((B, 1, H, W), dtype=torch.uint8, device=dev)
+            L.check(L.lib().stv_view_synth_fwd(B, Cc, H, W, L.ptr(inp), L.ptr(depth), L.ptr(T), L.ptr(K), L.ptr(Kinv),
+                                               L.ptr(warp), L.ptr(dwarp), L.ptr(valid), L.stream()), 'stv_view_synth_fwd')
+        ctx.save_for_backward(inp, depth, T, K, Kinv)
+        valid = valid.bool()
+        ctx.mark_non_differentiable(valid)
+        return warp, dwarp, valid
+
+    @staticmethod
+    def backward(ctx, g_warp, g_dwarp, _g_valid):
+        inp, depth, T, K, Kinv = ctx.saved_tensors
+        B, Cc, H, W = inp.shape
+        dev, lib = inp.device, L.lib()
+        with torch.cuda.device(dev):
+            g_depth, gT, gK, gKi = torch.empty_like(depth), torch.empty_like(T), torch.empty_like(K), torch.empty_like(Kinv)
+            g_inp = torch.zeros_like(inp) if ctx.needs_input_grad[0] else None
+            ws = _ws(lib.stv_view_synth_workspace_bytes(B, Cc, H, W), dev)
+            L.check(lib.stv_view_synth_bwd(B, Cc, H, W, L.ptr(inp), L.ptr(depth), L.ptr(T), L.ptr(K), L.ptr(Kinv),
+                                           L.ptr(_f32c(g_warp)), L.ptr(_f32c(g_dwarp)), L.ptr(g_depth), L.ptr(gT),
+                                           L.ptr(gK), L.ptr(gKi), L.ptr(g_inp), L.ptr(ws), ws.numel(), L.stream()),
+                    'stv_view_synth_bwd')
+        return g_inp, g_depth, gT, gK, gKi
+
+
+def view_synth(inp: Tensor, depth: Tensor, T: Tensor, K: Tensor, K_inv: Tensor | None = None):
+    """`ViewSynth.forward` (src/tools/geometry.py:366-391): -> (input_warp, depth_warp, mask_valid)."""
+    B, _, H, W = inp.shape
+    if depth.shape != (B, 1, H, W): raise ValueError(f'Invalid depth shape. ({tuple(depth.shape)} vs. {(B, 1, H, W)})')
+    if T.shape != (B, 4, 4) or K.shape != (B, 4, 4): raise ValueError(f'Invalid T/K shape. ({tuple(T.shape)}, {tuple(K.shape)})')
+    if K_inv is None: K_inv = torch.linalg.inv_ex(K)[0]
+    return _ViewSynth.apply(_f32c(inp), _f32c(depth), _f32c(T), _f32c(K), _f32c(K_inv))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Optimiser step
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def adamw_step_(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, *, n_decay: int, lr: float, beta1: float,
+                beta2: float, eps: float, weight_decay: float, step: int, grad_scale: float = 1.0) -> None:
+    """In-place fused AdamW on flat fp32 buffers; elements [0, n_decay) get weight decay."""
+    L.require_cuda(param, grad, exp_avg, exp_avg_sq, what='adamw_step_')
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if not t.is_contiguous() or t.numel() != param.numel(): raise ValueError('adamw_step_: buffers must be flat, contiguous, same size.')
+    with torch.cuda.device(param.device):
+        L.check(L.lib().stv_adamw_step(L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(), n_decay,
+                                       lr, beta1, beta2, eps, weight_decay, grad_scale, step, L.stream()), 'stv_adamw_step')

@@ -1,0 +1,56 @@
+"""Photometric reconstruction loss — host-side mirror of `src/losses/{photometric,reconstruction}.py` (reference).
+
+`ReconstructionLoss` keeps the reference's constructor and `forward` / `compute_photo` contracts. The training hot path
+never calls `forward` on already-warped images: `slowtv_monodepth_b200.handlers.image_recon` hands the un-warped support
+frames, depths and poses to the fused libstv kernel (`fused()` below), so the warped frames never exist in HBM.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import functional as F_
+
+__all__ = ['ReconstructionLoss']
+
+
+class ReconstructionLoss(nn.Module):
+    """Reference: src/losses/reconstruction.py:13-126.
+
+    :param loss_name: 'ssim' (0.85 SSIM + 0.15 L1) or 'l1'. ('l2' is only used by `feat_recon`, out of scope.)
+    :param use_min: minimum reprojection over the support frames instead of the mean.
+    :param use_automask: mask pixels whose un-warped support frame already explains the target better.
+    :param mask_name: explainability / uncertainty weighting (not part of the KBR configuration) — rejected loudly.
+    """
+    def __init__(self, loss_name: str = 'ssim', use_min: bool = False, use_automask: bool = False, mask_name: str | None = None):
+        super().__init__()
+        if mask_name not in {'explainability', 'uncertainty', None}: raise ValueError(f'Invalid mask type: {mask_name}')
+        if mask_name is not None:
+            raise NotImplementedError(f'mask_name="{mask_name}" is outside the B200 hot path (SURVEY 8a row 14); use the reference class.')
+        if loss_name not in {'ssim', 'l1'}:
+            raise KeyError(f'loss_name="{loss_name}" is not provided by the B200 photometric kernels (ssim | l1).')
+        self.loss_name, self.use_min, self.use_automask, self.mask_name = loss_name, use_min, use_automask, mask_name
+        self.noise_seed = 0x5107  # Base seed of the in-kernel tie-break noise; advanced every call.
+        self._calls = 0
+
+    def compute_photo(self, pred: Tensor, target: Tensor, mask: Tensor | None = None) -> Tensor:
+        """pred (*n,b,3,h,w), target (b,3,h,w) -> (b,1,h,w). Forward only (used for automasks and `depth_regr`)."""
+        if mask is not None: raise ValueError('Weighting masks are not supported by the B200 photometric kernels.')
+        return F_.photo_error(pred, target, loss_name=self.loss_name, use_min=self.use_min)
+
+    def fused(self, depths: list[Tensor], target: Tensor, source: Tensor, T: Tensor, K: Tensor, K_inv: Tensor | None = None,
+              noise: Tensor | None = None, want_warp: bool = False):
+        """Warp + loss in one kernel. -> (loss, {'automask': (S,b,1,H,W) bool}, sel, warp0)."""
+        self._calls += 1
+        loss, sel, warp0 = F_.photo_loss(depths, target, source, T, K, K_inv, loss_name=self.loss_name, use_min=self.use_min,
+                                         use_automask=self.use_automask, noise=noise,
+                                         noise_seed=(self.noise_seed + self._calls) if self.use_automask else 0,
+                                         want_warp=want_warp)
+        ld = {'automask': (sel != 255).unsqueeze(2)} if self.use_automask else {}
+        return loss, ld, sel, warp0
+
+    def forward(self, pred: Tensor, target: Tensor, source: Tensor | None = None, mask: Tensor | None = None):
+        raise NotImplementedError(
+            'ReconstructionLoss.forward on pre-warped images is not part of the B200 hot path: the warp is fused into the '
+            'loss kernel. Call slowtv_monodepth_b200.handlers.image_recon (installed over src.core.handlers.image_recon).')
