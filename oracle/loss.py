@@ -21,8 +21,11 @@ from torch import Tensor
 EPS32 = 1.1920928955078125e-07  # torch.finfo(torch.float32).eps; reference `ops.eps` (src/tools/ops.py:63-66)
 
 
+FORCE_EPS32 = False  # Tests set this so a float64 run models "the float32 reference with exact arithmetic".
+
+
 def _eps(x: Tensor) -> float:
-    return torch.finfo(x.dtype).eps
+    return EPS32 if FORCE_EPS32 else torch.finfo(x.dtype).eps
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -101,9 +101,11 @@ __global__ void __launch_bounds__(SM_NT) smooth_fwd_kernel(SmoothParams p) {
     if (q < hw) {
         const int y = q/w, x = q - y*w;
         const float* d = p.disp[s] + (size_t)i*hw;
-        const float d0 = __ldg(d + q)*inv_m;
-        const float dx = x + 1 < w ? fabsf(d0 - __ldg(d + q + 1)*inv_m) : 0.f;
-        const float dy = y + 1 < h ? fabsf(d0 - __ldg(d + q + w)*inv_m) : 0.f;
+        // __fmul_rn: every normalised value is rounded once, identically in every thread (an FMA-contracted a*m - b*m would
+        // turn exact ties into rounding noise of random sign).
+        const float d0 = __fmul_rn(__ldg(d + q), inv_m);
+        const float dx = x + 1 < w ? fabsf(d0 - __fmul_rn(__ldg(d + q + 1), inv_m)) : 0.f;
+        const float dy = y + 1 < h ? fabsf(d0 - __fmul_rn(__ldg(d + q + w), inv_m)) : 0.f;
         float ix, iy;
         edge_terms(p, p.img + (size_t)i*3*p.H*p.W, s, y, x, ix, iy);
         v = p.use_edges ? dx*expf(-ix) + dy*expf(-iy) : dx + dy;
@@ -149,22 +151,22 @@ __global__ void __launch_bounds__(SM_NT) smooth_bwd_kernel(SmoothParams p) {
     const int y = q/w, x = q - y*w;
     const float* d = p.disp[s] + (size_t)i*hw;
     const float* img = p.img + (size_t)i*3*p.H*p.W;
-    const float d0 = __ldg(d + q)*inv_m;
+    const float d0 = __fmul_rn(__ldg(d + q), inv_m);
     auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
     float g = 0.f;
     float ix, iy;
     edge_terms(p, img, s, y, x, ix, iy);
-    if (x + 1 < w) g += sgn(d0 - __ldg(d + q + 1)*inv_m)*(p.use_edges ? expf(-ix) : 1.f);
-    if (y + 1 < h) g += sgn(d0 - __ldg(d + q + w)*inv_m)*(p.use_edges ? expf(-iy) : 1.f);
+    if (x + 1 < w) g += sgn(d0 - __fmul_rn(__ldg(d + q + 1), inv_m))*(p.use_edges ? expf(-ix) : 1.f);
+    if (y + 1 < h) g += sgn(d0 - __fmul_rn(__ldg(d + q + w), inv_m))*(p.use_edges ? expf(-iy) : 1.f);
     if (x > 0) {
         float jx, jy;
         edge_terms(p, img, s, y, x - 1, jx, jy);
-        g -= sgn(__ldg(d + q - 1)*inv_m - d0)*(p.use_edges ? expf(-jx) : 1.f);
+        g -= sgn(__fmul_rn(__ldg(d + q - 1), inv_m) - d0)*(p.use_edges ? expf(-jx) : 1.f);
     }
     if (y > 0) {
         float jx, jy;
         edge_terms(p, img, s, y - 1, x, jx, jy);
-        g -= sgn(__ldg(d + q - w)*inv_m - d0)*(p.use_edges ? expf(-jy) : 1.f);
+        g -= sgn(__fmul_rn(__ldg(d + q - w), inv_m) - d0)*(p.use_edges ? expf(-jy) : 1.f);
     }
     float out = gs*g*inv_m;
     if (mean >= STV_EPS32) out -= gs*Li*inv_m/(float)hw;  // d/d mean through the normalisation (clamp passes at equality)

@@ -39,6 +39,13 @@ def cast(inp: dict, dtype, device='cpu') -> dict:
             for k, v in inp.items()}
 
 
+class eps32:
+    """Context: the oracle uses float32's eps whatever dtype it runs in (the kernels are float32, like the reference's
+    training configuration), so a float64 oracle run is the exact-arithmetic version of the float32 reference."""
+    def __enter__(self): self.old, OL.FORCE_EPS32 = OL.FORCE_EPS32, True
+    def __exit__(self, *a): OL.FORCE_EPS32 = self.old
+
+
 def run_oracle(inp: dict, cfg: dict, dtype=torch.float64, forced_sel=None, w_smooth: float = 1e-3) -> dict:
     d = cast(inp, dtype)
     disps = [x.clone().requires_grad_() for x in d['disps']]
@@ -50,13 +57,65 @@ def run_oracle(inp: dict, cfg: dict, dtype=torch.float64, forced_sel=None, w_smo
     l_rec, o = OL.image_recon(depths, d['imgs'], d['supp_imgs'], Ts, K, cfg.get('use_min', True), cfg.get('use_automask', True),
                               d['noise'], loss_name=cfg.get('loss_name', 'ssim'), forced_sel=forced_sel)
     l_sm, o2 = OL.disp_smooth(disps, d['imgs'], True)
+    for x in depths: x.retain_grad()
     (l_rec + w_smooth*l_sm).backward()
     out = dict(loss_recon=l_rec.detach(), loss_smooth=l_sm.detach(), g_aa=aa.grad, g_t=t.grad, g_K=K.grad,
                warp0=o['supp_imgs_warp'].detach(), sel=o['sel'], err=o['err'].detach(), depth_up0=depths[0].detach(),
                disp_grad=o2['disp_grad'].detach(), image_grad=o2['image_grad'].detach())
     for s, x in enumerate(disps): out[f'g_disp{s}'] = x.grad
+    for s, x in enumerate(depths): out[f'g_depth{s}'] = x.grad
     if 'automask' in o: out['automask0'] = o['automask']
     return out
+
+
+def unstable_pixels(inp: dict, cfg: dict, tol_val: float = 4e-6, tol_pos: float = 5e-4):
+    """Pixels whose float32 result may legitimately differ O(1) from the exact one because a *discrete* event sits within
+    float32 rounding of flipping (computed from the float64 oracle):
+      - |warp - target| < tol_val on some channel (sign of the L1 sub-gradient),
+      - sample position within tol_pos of a texel boundary or of the image border (bilinear gradient is discontinuous),
+      - projected depth within tol_val of the 0.1 clamp.
+    -> (bad (S*b,1,H,W) bool, candidate errors (S*b, n[+1], H, W) for decision margins)."""
+    d = cast(inp, torch.float64)
+    n, S = d['supp_imgs'].shape[0], cfg['S']
+    H, W = d['imgs'].shape[-2:]
+    Ts = OL.T_from_AAt(d['aa'], d['t'])
+    mn, mx = cfg.get('min_depth', 0.1), cfg.get('max_depth', 100.)
+    dep = torch.cat([OL.disp_to_depth(OL.resize_bilinear(x, (H, W)), mn, mx) for x in d['disps']], 0)
+    tgt = d['imgs'].repeat(S, 1, 1, 1)
+    name = cfg.get('loss_name', 'ssim')
+    fn = OL.photo_error if name == 'ssim' else (lambda p, t: (p - t).abs().mean(1, keepdim=True))
+    bad = torch.zeros(S*cfg['b'], 1, H, W, dtype=torch.bool)
+    errs = []
+    for k in range(n):
+        Tk, Kk = Ts[k].repeat(S, 1, 1), d['K'].repeat(S, 1, 1)
+        ix, iy, z, _ = OL.warp_coords(dep, Tk, Kk)
+        w = OL.sample_bilinear_border(d['supp_imgs'][k].repeat(S, 1, 1, 1), ix, iy)
+        errs.append(fn(w, tgt))
+        bad |= ((w - tgt).abs() < tol_val).any(1, keepdim=True)
+        for c, size in ((ix, W), (iy, H)):
+            cc = c.clamp(0, size - 1)
+            bad |= (((cc - cc.round()).abs() < tol_pos) & (c > -tol_pos) & (c < size - 1 + tol_pos)).unsqueeze(1)
+        bad |= ((z - 0.1).abs() < tol_val)
+    cands = torch.cat(errs, 1)
+    if not cfg.get('use_min', True): cands = cands.mean(1, keepdim=True)
+    if cfg.get('use_automask', True):
+        st = OL.compute_photo(d['supp_imgs'].repeat(1, S, 1, 1, 1), tgt, cfg.get('use_min', True), name)
+        cands = torch.cat([cands, st + OL.EPS32*d['noise']], 1)
+    return bad, cands
+
+
+def footprint(bad: torch.Tensor, f: int) -> torch.Tensor:
+    """Low-resolution pixels (factor f) whose bilinear-upsampling footprint touches a bad full-resolution pixel."""
+    import torch.nn.functional as F
+    x = bad.float()
+    if f == 1: return bad
+    x = F.max_pool2d(x, kernel_size=2*f + 1, stride=1, padding=f)
+    return F.max_pool2d(x, kernel_size=f, stride=f) > 0
+
+
+def rel_masked(a, b, good) -> float:
+    a, b = a.detach().double().cpu()*good, b.detach().double().cpu()*good
+    return ((a - b).norm()/b.norm().clamp(min=1e-30)).item()
 
 
 def run_cuda(inp: dict, cfg: dict, w_smooth: float = 1e-3, device='cuda') -> dict:
@@ -72,6 +131,7 @@ def run_cuda(inp: dict, cfg: dict, w_smooth: float = 1e-3, device='cuda') -> dic
     H, W = d['imgs'].shape[-2:]
     mn, mx = cfg.get('min_depth', 0.1), cfg.get('max_depth', 100.)
     depths = {s: G.upsample_to_depth(x, (H, W), mn, mx)[1] for s, x in enumerate(disps)}
+    for x in depths.values(): x.retain_grad()
     crit = ReconstructionLoss(cfg.get('loss_name', 'ssim'), cfg.get('use_min', True), cfg.get('use_automask', True))
     l_rec, ld, sel, warp0 = crit.fused(list(depths.values()), d['imgs'], d['supp_imgs'], Ts, K, noise=d['noise'], want_warp=True)
     o = {'supp_imgs_warp': warp0, **{k: v[0] for k, v in ld.items()}}
@@ -81,5 +141,6 @@ def run_cuda(inp: dict, cfg: dict, w_smooth: float = 1e-3, device='cuda') -> dic
                warp0=o['supp_imgs_warp'], depth_up0=depths[0].detach(), disp_grad=o2['disp_grad'], image_grad=o2['image_grad'],
                sel=sel.flatten(0, 1).unsqueeze(1))
     for s, x in enumerate(disps): out[f'g_disp{s}'] = x.grad
+    for s, x in depths.items(): out[f'g_depth{s}'] = x.grad
     if 'automask' in o: out['automask0'] = o['automask']
     return out
