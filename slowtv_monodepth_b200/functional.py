@@ -15,6 +15,39 @@ from . import _lib as L
 __all__ = ['photo_loss', 'photo_error', 'smooth_loss', 'disp_to_depth', 'view_synth', 'adamw_step_']
 
 
+# Optional per-call device timing of the fused loss kernels (bench.py's roofline figures): when enabled, a pair of CUDA
+# events brackets each library call on the launching stream; `kernel_timings()` resolves them after a synchronize.
+_TIMING: dict[str, list] | None = None
+
+
+def enable_kernel_timing(on: bool = True) -> None:
+    global _TIMING
+    _TIMING = {} if on else None
+
+
+class _timed:
+    def __init__(self, name: str): self.name = name
+
+    def __enter__(self):
+        if _TIMING is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+
+    def __exit__(self, *a):
+        if _TIMING is not None:
+            self.ev[1].record()
+            _TIMING.setdefault(self.name, []).append(self.ev)
+
+
+def kernel_timings() -> dict[str, list[float]]:
+    """Milliseconds per recorded call, keyed by entry point. Call after torch.cuda.synchronize()."""
+    return {k: [a.elapsed_time(b) for a, b in v] for k, v in (_TIMING or {}).items()}
+
+
+def reset_kernel_timings() -> None:
+    if _TIMING is not None: _TIMING.clear()
+
+
 def _f32c(t: Tensor | None) -> Tensor | None:
     if t is None: return None
     if t.dtype != torch.float32: raise ValueError(f'Expected float32, got {t.dtype}.')
@@ -40,9 +73,10 @@ class _PhotoLoss(torch.autograd.Function):
             warp0 = torch.empty((n, b, 3, H, W), dtype=torch.float32, device=dev) if want_warp else None
             nws = lib.stv_photo_workspace_bytes(C.byref(cfg))
             ws = _ws(nws, dev)
-            L.check(lib.stv_photo_fwd(C.byref(cfg), L.ptr_array(depths), L.ptr(tgt), L.ptr(supp), L.ptr(T), L.ptr(K),
-                                      L.ptr(Kinv), L.ptr(noise), L.ptr(loss), L.ptr(sel), L.ptr(warp0), L.ptr(ws),
-                                      ws.numel(), L.stream()), 'stv_photo_fwd')
+            with _timed('stv_photo_fwd'):
+                L.check(lib.stv_photo_fwd(C.byref(cfg), L.ptr_array(depths), L.ptr(tgt), L.ptr(supp), L.ptr(T), L.ptr(K),
+                                          L.ptr(Kinv), L.ptr(noise), L.ptr(loss), L.ptr(sel), L.ptr(warp0), L.ptr(ws),
+                                          ws.numel(), L.stream()), 'stv_photo_fwd')
         ctx.cfg, ctx.nws = cfg, nws
         ctx.save_for_backward(tgt, supp, T, K, Kinv, sel, *depths)
         ctx.mark_non_differentiable(sel)
@@ -65,9 +99,10 @@ class _PhotoLoss(torch.autograd.Function):
             gK = torch.empty_like(K) if want_k else None
             gKi = torch.empty_like(Kinv) if want_k else None
             ws = _ws(ctx.nws, dev)
-            L.check(lib.stv_photo_bwd(C.byref(cfg), L.ptr_array(depths), L.ptr(tgt), L.ptr(supp), L.ptr(T), L.ptr(K),
-                                      L.ptr(Kinv), L.ptr(sel), L.ptr(g_loss), L.ptr_array(g_depths), L.ptr(gT), L.ptr(gK),
-                                      L.ptr(gKi), L.ptr(ws), ws.numel(), L.stream()), 'stv_photo_bwd')
+            with _timed('stv_photo_bwd'):
+                L.check(lib.stv_photo_bwd(C.byref(cfg), L.ptr_array(depths), L.ptr(tgt), L.ptr(supp), L.ptr(T), L.ptr(K),
+                                          L.ptr(Kinv), L.ptr(sel), L.ptr(g_loss), L.ptr_array(g_depths), L.ptr(gT), L.ptr(gK),
+                                          L.ptr(gKi), L.ptr(ws), ws.numel(), L.stream()), 'stv_photo_bwd')
         return (None, None, None, None, gT if need_T else None, gK if need_K else None, gKi if need_Ki else None, None,
                 *[g if ctx.needs_input_grad[8 + j] else None for j, g in enumerate(g_depths)])
 
@@ -133,8 +168,9 @@ class _SmoothLoss(torch.autograd.Function):
             dg = torch.empty_like(disps[0]) if want_maps else None
             ig = torch.empty_like(disps[0]) if want_maps else None
             ws = _ws(lib.stv_smooth_workspace_bytes(C.byref(cfg)), dev)
-            L.check(lib.stv_smooth_fwd(C.byref(cfg), L.ptr_array(disps), L.ptr(img), L.ptr(loss), L.ptr(dg), L.ptr(ig),
-                                       L.ptr(ws), ws.numel(), L.stream()), 'stv_smooth_fwd')
+            with _timed('stv_smooth_fwd'):
+                L.check(lib.stv_smooth_fwd(C.byref(cfg), L.ptr_array(disps), L.ptr(img), L.ptr(loss), L.ptr(dg), L.ptr(ig),
+                                           L.ptr(ws), ws.numel(), L.stream()), 'stv_smooth_fwd')
         ctx.cfg = cfg
         ctx.save_for_backward(img, ws, *disps)
         if dg is None: dg = ig = torch.empty(0, device=dev)
@@ -148,8 +184,9 @@ class _SmoothLoss(torch.autograd.Function):
         with torch.cuda.device(dev):
             g_loss = g_loss.to(torch.float32).contiguous()
             gds = [torch.empty_like(d) for d in disps]
-            L.check(L.lib().stv_smooth_bwd(C.byref(cfg), L.ptr_array(disps), L.ptr(img), L.ptr(g_loss), L.ptr_array(gds),
-                                           L.ptr(ws), ws.numel(), L.stream()), 'stv_smooth_bwd')
+            with _timed('stv_smooth_bwd'):
+                L.check(L.lib().stv_smooth_bwd(C.byref(cfg), L.ptr_array(disps), L.ptr(img), L.ptr(g_loss), L.ptr_array(gds),
+                                               L.ptr(ws), ws.numel(), L.stream()), 'stv_smooth_bwd')
         return (None, None, None, *gds)
 
 

@@ -1,0 +1,179 @@
+"""Feature-pyramid encoders with timm's `features_only=True` contract (the reference builds them with
+`timm.create_model(enc_name, features_only=True, ...)`, src/networks/depth.py:97, src/networks/pose.py:40).
+
+timm (pinned 0.6.12, docker/environment.yml:287) is a third-party dependency that is not part of the reference tree, so
+the arithmetic is restated here from its published architectures, keeping timm's module / parameter names so that a
+reference checkpoint's `nets.*.encoder.*` keys line up:
+
+  resnet18        conv1, bn1, act1, maxpool, layer{1..4}.{0,1}.{conv1,bn1,conv2,bn2,downsample.{0,1}}
+                  features = outputs of act1, layer1..4; channels [64,64,128,256,512], reductions [2,4,8,16,32]
+  convnext_{tiny,small,base}
+                  stem_0 (4x4 s4 conv), stem_1 (LayerNorm2d), stages_{0..3}.{downsample.{0,1}, blocks.N.{conv_dw,norm,
+                  mlp.fc1,mlp.fc2,gamma}};  features = outputs of stages_0..3; reductions [4,8,16,32]
+
+ConvNeXt runs channels-last end to end (its LayerNorm / Linear layers are over the channel axis); the pointwise MLP is
+the GEMM-shaped part that goes to the tcgen05 kernels (see ops_gemm.py), the depthwise 7x7 + LayerNorm is HBM-bound.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+
+__all__ = ['create_encoder', 'ResNetEncoder', 'ConvNeXtEncoder', 'FeatureInfo']
+
+
+class FeatureInfo:
+    """Minimal stand-in for timm's `feature_info` (only what the reference reads: depth.py:98, pose.py:41)."""
+    def __init__(self, channels: list[int], reduction: list[int]):
+        self._c, self._r = list(channels), list(reduction)
+
+    def channels(self) -> list[int]: return list(self._c)
+    def reduction(self) -> list[int]: return list(self._r)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ResNet (BasicBlock)
+# ---------------------------------------------------------------------------------------------------------------------
+class BasicBlock(nn.Module):
+    def __init__(self, cin: int, cout: int, stride: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+    def forward(self, x: Tensor) -> Tensor:
+        y = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        y = self.bn2(self.conv2(y))
+        sc = x if self.downsample is None else self.downsample(x)
+        return F.relu(y + sc, inplace=True)
+
+
+class ResNetEncoder(nn.Module):
+    def __init__(self, layers=(2, 2, 2, 2), in_chans: int = 3):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_chans, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        chans = [64, 128, 256, 512]
+        cin = 64
+        for i, (c, nblk) in enumerate(zip(chans, layers)):
+            blocks = [BasicBlock(cin if j == 0 else c, c, (1 if i == 0 else 2) if j == 0 else 1) for j in range(nblk)]
+            setattr(self, f'layer{i + 1}', nn.Sequential(*blocks))
+            cin = c
+        self.feature_info = FeatureInfo([64, 64, 128, 256, 512], [2, 4, 8, 16, 32])
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        # timm resnet init: kaiming-normal (fan_out, relu) convs; BN weight 1 / bias 0; zero_init_last on bn2.
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d): nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+        for m in self.modules():
+            if isinstance(m, BasicBlock): nn.init.zeros_(m.bn2.weight)
+
+    def forward(self, x: Tensor) -> list[Tensor]:
+        x = x.contiguous(memory_format=torch.channels_last)
+        f0 = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        x = F.max_pool2d(f0, 3, 2, 1)
+        feats = [f0]
+        for i in range(1, 5):
+            x = getattr(self, f'layer{i}')(x)
+            feats.append(x)
+        return feats
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ConvNeXt
+# ---------------------------------------------------------------------------------------------------------------------
+class LayerNorm2d(nn.LayerNorm):
+    """LayerNorm over the channel axis of an NCHW tensor (timm `LayerNorm2d`, eps 1e-6)."""
+    def __init__(self, c: int): super().__init__(c, eps=1e-6)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return F.layer_norm(x.permute(0, 2, 3, 1), self.normalized_shape, self.weight, self.bias, self.eps).permute(0, 3, 1, 2)
+
+
+class Mlp(nn.Module):
+    def __init__(self, c: int):
+        super().__init__()
+        self.fc1 = nn.Linear(c, 4*c)
+        self.fc2 = nn.Linear(4*c, c)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.fc2(F.gelu(self.fc1(x)))
+
+
+class ConvNeXtBlock(nn.Module):
+    """x + gamma * fc2(GELU(fc1(LN(dwconv7x7(x)))))  (timm `ConvNeXtBlock`, ls_init_value=1e-6, no drop-path at train default)."""
+    def __init__(self, c: int):
+        super().__init__()
+        self.conv_dw = nn.Conv2d(c, c, 7, 1, 3, groups=c)
+        self.norm = nn.LayerNorm(c, eps=1e-6)
+        self.mlp = Mlp(c)
+        self.gamma = nn.Parameter(1e-6*torch.ones(c))
+
+    def forward(self, x: Tensor) -> Tensor:
+        y = self.conv_dw(x).permute(0, 2, 3, 1)  # NHWC view of a channels-last tensor: no copy
+        y = self.mlp(self.norm(y))*self.gamma
+        return x + y.permute(0, 3, 1, 2)
+
+
+class ConvNeXtStage(nn.Module):
+    def __init__(self, cin: int, cout: int, depth: int, stride: int):
+        super().__init__()
+        self.downsample = nn.Sequential(LayerNorm2d(cin), nn.Conv2d(cin, cout, 2, 2)) if stride > 1 else nn.Identity()
+        self.blocks = nn.Sequential(*[ConvNeXtBlock(cout) for _ in range(depth)])
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.blocks(self.downsample(x))
+
+
+class ConvNeXtEncoder(nn.Module):
+    def __init__(self, depths=(3, 3, 9, 3), dims=(96, 192, 384, 768), in_chans: int = 3):
+        super().__init__()
+        self.stem_0 = nn.Conv2d(in_chans, dims[0], 4, 4)
+        self.stem_1 = LayerNorm2d(dims[0])
+        cin = dims[0]
+        for i, (d, c) in enumerate(zip(depths, dims)):
+            setattr(self, f'stages_{i}', ConvNeXtStage(cin, c, d, 1 if i == 0 else 2))
+            cin = c
+        self.feature_info = FeatureInfo(list(dims), [4, 8, 16, 32])
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        for m in self.modules():  # timm convnext `_init_weights`: trunc_normal(std=.02) weights, zero biases
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.trunc_normal_(m.weight, std=.02)
+                if m.bias is not None: nn.init.zeros_(m.bias)
+
+    def forward(self, x: Tensor) -> list[Tensor]:
+        x = x.contiguous(memory_format=torch.channels_last)
+        x = self.stem_1(self.stem_0(x))
+        feats = []
+        for i in range(4):
+            x = getattr(self, f'stages_{i}')(x)
+            feats.append(x)
+        return feats
+
+
+_RESNETS = {'resnet18': (2, 2, 2, 2), 'resnet34': (3, 4, 6, 3)}
+_CONVNEXTS = {
+    'convnext_tiny': ((3, 3, 9, 3), (96, 192, 384, 768)),
+    'convnext_small': ((3, 3, 27, 3), (96, 192, 384, 768)),
+    'convnext_base': ((3, 3, 27, 3), (128, 256, 512, 1024)),
+}
+
+
+def create_encoder(name: str, in_chans: int = 3, pretrained: bool = False) -> nn.Module:
+    """`timm.create_model(name, features_only=True, in_chans=..., pretrained=...)` for the encoders the KBR configs use."""
+    if pretrained:
+        raise RuntimeError('ImageNet-pretrained weights are not available offline; load a checkpoint with load_state_dict instead.')
+    if name in _RESNETS: return ResNetEncoder(_RESNETS[name], in_chans)
+    if name in _CONVNEXTS: return ConvNeXtEncoder(*_CONVNEXTS[name], in_chans)
+    raise KeyError(f'Unknown encoder "{name}". Available: {sorted(_RESNETS) + sorted(_CONVNEXTS)}')

@@ -1,0 +1,76 @@
+"""Flat-buffer AdamW + gradient all-reduce for the data-parallel training step.
+
+Reference behaviour being replaced: `timm.optim.create_optimizer_v2(nets, opt='adamw', lr, weight_decay)`
+(src/tools/parsers.py:205-243) -> torch.optim.AdamW(foreach) with timm's rule that biases and 1-D parameters get no weight
+decay, and Lightning's DDP gradient averaging (api/train/train.py:105-106).
+
+Here every parameter of every network lives in ONE contiguous fp32 buffer (decayed parameters first), gradients in a
+second one, so that (a) the optimiser is a single libstv kernel launch and (b) the data-parallel exchange is a single NCCL
+all-reduce over NVLink on a side stream, with no per-tensor bookkeeping on the host.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import functional as F_
+
+__all__ = ['FlatAdamW']
+
+
+class FlatAdamW:
+    def __init__(self, module: nn.Module, lr: float = 1e-4, weight_decay: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        if not named: raise ValueError('No trainable parameters.')
+        no_decay = lambda n, p: p.ndim <= 1 or n.endswith('.bias')  # timm `param_groups_weight_decay`
+        self.params = [p for n, p in named if not no_decay(n, p)] + [p for n, p in named if no_decay(n, p)]
+        self.n_decay = sum(p.numel() for n, p in named if not no_decay(n, p))
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + n].view(p.shape)
+            p.grad = self.grad[off:off + n].view(p.shape)
+            off += n
+        self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.step_count = 0
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._work = None
+
+    def zero_grad(self) -> None:
+        """Gradients are accumulated in place into the flat buffer, so they are zeroed (one memset), not set to None."""
+        self.grad.zero_()
+
+    def all_reduce_async(self):
+        """Sum-all-reduce of the flat gradient buffer (the 1/world scale is folded into the optimiser kernel)."""
+        if self.world > 1: self._work = dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, async_op=True)
+
+    def step(self) -> None:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        self.step_count += 1
+        if self.flat.is_cuda:
+            F_.adamw_step_(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, n_decay=self.n_decay, lr=self.lr,
+                           beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
+                           step=self.step_count, grad_scale=1.0/self.world)
+        else:
+            self._step_host()
+
+    @torch.no_grad()
+    def _step_host(self) -> None:
+        """Host-tensor arithmetic used only by the CPU (gloo) tests of the multi-process logic; same update rule."""
+        b1, b2 = self.betas
+        g = self.grad/self.world
+        self.flat[:self.n_decay].mul_(1 - self.lr*self.weight_decay)
+        self.exp_avg.mul_(b1).add_(g, alpha=1 - b1)
+        self.exp_avg_sq.mul_(b2).addcmul_(g, g, value=1 - b2)
+        bc1, bc2 = 1 - b1**self.step_count, 1 - b2**self.step_count
+        self.flat.addcdiv_(self.exp_avg, self.exp_avg_sq.sqrt()/bc2**0.5 + self.eps, value=-self.lr/bc1)

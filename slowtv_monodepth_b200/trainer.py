@@ -1,0 +1,115 @@
+"""The per-step training loop — host-side mirror of `MonoDepthModule` (src/core/trainer.py, reference) without Lightning.
+
+`MonoDepthStep.step(batch)` follows the reference's `step` -> `forward` -> `forward_postprocess` -> `forward_loss`
+(trainer.py:115-190, 192-278, 280-348, 350-472) for the KBR loss set {img_recon, disp_smooth}, with the differences that
+matter on a B200:
+  * no device syncs inside the step (the reference's timers sync 18x per step, trainer.py:69, and its f-string / comparison
+    use of the device tensor `supp_idxs` adds ~5 more per support frame, trainer.py:242-253);
+  * upsample + disp->depth, the whole view-synthesis loss and the smoothness term are libstv kernels;
+  * the pose network sees all n*b image pairs in one batch (as the reference does, trainer.py:243-249).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import geometry as G
+from . import handlers as H
+from .losses import ReconstructionLoss
+from .networks import DepthNet, PoseNet
+from .regularizers import SmoothReg
+
+__all__ = ['MonoDepthStep', 'default_cfg']
+
+NET_REG = {'depth': DepthNet, 'pose': PoseNet}
+LOSS_REG = {'img_recon': ReconstructionLoss, 'disp_smooth': SmoothReg}
+
+
+def default_cfg(depth_enc: str = 'convnext_tiny', pose_enc: str = 'resnet18', learn_K: bool = False) -> dict:
+    """The KBR-style configuration of BASELINE.json config 3 (cfg/abl_learn_K/default.yaml + cfg/kbr/default.yaml:18-28,105-125)."""
+    return {
+        'net': {'depth': {'enc_name': depth_enc, 'pretrained': False, 'dec_name': 'monodepth', 'out_scales': [0, 1, 2, 3]},
+                'pose': {'enc_name': pose_enc, 'pretrained': False, 'learn_K': learn_K}},
+        'loss': {'img_recon': {'weight': 1, 'loss_name': 'ssim', 'use_min': True, 'use_automask': True},
+                 'disp_smooth': {'weight': 0.001, 'use_edges': True}},
+        'optimizer': {'type': 'adamw', 'lr': 1e-4, 'weight_decay': 1e-3},
+        'trainer': {'min_depth': 0.1, 'max_depth': 100, 'always_fwd_pose': False},
+    }
+
+
+class MonoDepthStep(nn.Module):
+    def __init__(self, cfg: dict):
+        super().__init__()
+        self.cfg = cfg
+        nets = {}
+        for k, kw in cfg['net'].items():
+            if kw is None: continue
+            if k not in NET_REG: raise KeyError(f'Unrecognized key: {k}.')
+            nets[k] = NET_REG[k](**kw)
+        self.nets = nn.ModuleDict(nets)
+        self.losses, self.weights = {}, {}
+        for k, kw in cfg['loss'].items():
+            if kw is None: continue
+            if k not in LOSS_REG: raise ValueError(f'Missing loss key: "{k}"')
+            kw = dict(kw)
+            self.weights[k] = float(kw.pop('weight', 1))
+            self.losses[k] = LOSS_REG[k](**kw)
+        tr = cfg.get('trainer', {})
+        self.min_depth, self.max_depth = tr.get('min_depth'), tr.get('max_depth')
+        self.always_fwd_pose = tr.get('always_fwd_pose', True)
+        self.scales = self.nets['depth'].out_scales
+
+    # -- trainer.py:192-278 ------------------------------------------------------------------------------------------
+    def forward(self, x: dict) -> dict:
+        fwd = {}
+        idxs = [int(i) for i in x['supp_idxs']]  # host ints: no device sync
+        fwd |= self.nets['depth'](x['imgs'])
+        if 'pose' in self.nets:
+            inv = lambda i: self.always_fwd_pose and i < 0
+            pairs = torch.stack([torch.cat([s, x['imgs']] if inv(i) else [x['imgs'], s], dim=1)
+                                 for i, s in zip(idxs, x['supp_imgs']) if i != 0])  # (n, b, 6, h, w)
+            sh = pairs.shape[:2]
+            out = self.nets['pose'](pairs.flatten(0, 1))
+            Ts = G.T_from_AAt(aa=out['R'][:, 0], t=out['t'][:, 0]).unflatten(0, sh)
+            for i, T in zip([i for i in idxs if i != 0], Ts):
+                fwd[f'T_{i}'] = torch.linalg.inv_ex(T)[0] if inv(i) else T
+            if 'fs' in out:
+                fwd['fs'], fwd['cs'] = out['fs'].unflatten(0, sh), out['cs'].unflatten(0, sh)
+                K = PoseNet.build_K(out['fs'], out['cs']).unflatten(0, sh)[0]  # first support frame only (trainer.py:259)
+                fwd['K'] = G.resize_K(K, x['imgs'].shape[-2:])
+        fwd['_idxs'] = idxs
+        return fwd
+
+    # -- trainer.py:280-348 ------------------------------------------------------------------------------------------
+    def forward_postprocess(self, fwd: dict, x: dict, y: dict) -> dict:
+        size = x['imgs'].shape[-2:]
+        up = {s: G.upsample_to_depth(d, size, self.min_depth, self.max_depth) for s, d in fwd['disp'].items()}
+        fwd['disp_up'] = {s: v[0] for s, v in up.items()}
+        fwd['depth_up'] = {s: v[1] for s, v in up.items()}
+        fwd['Ts'] = torch.stack([fwd[f'T_{i}'] for i in fwd['_idxs']])
+        return fwd
+
+    # -- trainer.py:350-472 ------------------------------------------------------------------------------------------
+    def forward_loss(self, fwd: dict, x: dict, y: dict, want_maps: bool = False):
+        loss, loss_dict = 0., {}
+        for k, crit in self.losses.items():
+            if k == 'img_recon':
+                l, ld = H.image_recon(crit, None, depths=fwd['depth_up'], masks=None, imgs=y['imgs'], supp_imgs=y['supp_imgs'],
+                                      Ts=fwd['Ts'], Ks=fwd.get('K', y['K']), want_warp=want_maps)
+            elif k == 'disp_smooth':
+                l, ld = H.disp_smooth(crit, fwd['disp'], y['imgs'], want_maps=want_maps)
+            else:
+                raise ValueError(f'Missing loss key: "{k}"')
+            loss = loss + self.weights[k]*l
+            loss_dict[f'loss_{k}'] = l
+            loss_dict.update(ld)
+        return loss, loss_dict
+
+    # -- trainer.py:115-190 ------------------------------------------------------------------------------------------
+    def step(self, batch, mode: str = 'train', want_maps: bool = False):
+        x, y, m = batch
+        fwd = self.forward(x)
+        fwd = self.forward_postprocess(fwd, x, y)
+        loss, loss_dict = self.forward_loss(fwd, x, y, want_maps=want_maps or mode != 'train')
+        return loss, loss_dict, fwd

@@ -1,0 +1,60 @@
+"""CPU: the C-ABI shared library loads and exports exactly what include/stv.h declares; argument validation that needs no
+GPU behaves like the reference (ValueError for bad shapes / arguments)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared():
+    txt = (ROOT/'include'/'stv.h').read_text()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(stv_[a-z0-9_]+)\s*\(', txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from slowtv_monodepth_b200 import _lib as L
+    lib = L.lib()
+    declared = _declared()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/stv.h but not exported by libstv.so'
+    assert sorted(L.exported_symbols()) == declared, 'ctypes signatures out of sync with include/stv.h'
+    assert lib.stv_version() >= 100
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu():
+    from slowtv_monodepth_b200 import _lib as L
+    lib = L.lib()
+    cfg = L.PhotoCfg(b=1, n=2, S=9, H=16, W=16, w_ssim=0.85, w_l1=0.15, use_min=1, use_automask=1, noise_seed=0, depth_stride_s=0)
+    assert lib.stv_photo_workspace_bytes(C.byref(cfg)) == 0  # S > STV_MAX_SCALES
+    assert b'STV_MAX_SCALES' in lib.stv_last_error()
+    cfg.S = 4
+    assert lib.stv_photo_workspace_bytes(C.byref(cfg)) > 0
+    rc = lib.stv_photo_fwd(C.byref(cfg), None, None, None, None, None, None, None, None, None, None, None, 0, None)
+    assert rc == 1 and b'NULL' in lib.stv_last_error()
+    with pytest.raises(ValueError): L.check(rc, 'stv_photo_fwd')
+    cfg.H = 2
+    assert lib.stv_photo_fwd(C.byref(cfg), None, None, None, None, None, None, None, None, None, None, None, 0, None) == 1
+    assert lib.stv_adamw_step(None, None, None, None, 8, 0, 1e-3, .9, .999, 1e-8, 0., 1., 1, None) == 1
+    assert lib.stv_disp_to_depth_fwd(1, 0, 4, 8, 8, 0.1, 100., None, None, None, None) == 1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from slowtv_monodepth_b200 import _lib as L
+    monkeypatch.setattr(L, '_lib', None)
+    monkeypatch.setattr(L, 'LIB_PATH', tmp_path/'libstv.so')
+    with pytest.raises(L.StvError): L.lib()
+
+
+def test_cpu_tensors_are_refused():
+    import torch
+    from slowtv_monodepth_b200 import _lib as L, functional as F_
+    t = torch.zeros(1, 3, 8, 8)
+    with pytest.raises(L.StvError):
+        F_.photo_loss([torch.zeros(1, 1, 8, 8)], t, t[None], torch.eye(4)[None, None], torch.eye(4)[None])
+    with pytest.raises(L.StvError):
+        F_.smooth_loss([torch.zeros(1, 1, 8, 8)], t)
