@@ -9,7 +9,10 @@ from pathlib import Path
 
 import torch
 
-LIB_PATH = Path(__file__).resolve().parent/'libstv.so'
+import os
+
+# STV_LIB: developer override used to A/B-test differently tuned builds of the same sources.
+LIB_PATH = Path(os.environ.get('STV_LIB') or Path(__file__).resolve().parent/'libstv.so')
 MAX_SCALES = 8
 SEL_STATIC, SEL_MEAN = 255, 254
 

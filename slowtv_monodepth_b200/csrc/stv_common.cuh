@@ -168,16 +168,14 @@ __device__ __forceinline__ void ssim_err_grad(float S1, float S2, float S3, floa
     c = -0.5f*k*dr_dS3;
 }
 
-// Counter-based standard normal (Philox-style mixing + Box-Muller); one value per (seed, index).
+// Counter-based tie-break noise for the auto-mask (the reference adds eps * randn, src/losses/reconstruction.py:72, only so
+// that exact ties between the warped and the static error do not always resolve one way). One 32-bit hash per pixel; the sum
+// of its four bytes, centred and scaled to unit variance, is a bell-shaped (Irwin-Hall, n=4) stand-in for N(0,1).
 __device__ __forceinline__ float hash_normal(uint64_t seed, uint64_t idx) {
-    uint64_t z = seed + idx*0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30))*0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27))*0x94D049BB133111EBull;
-    z ^= z >> 31;
-    const uint32_t a = (uint32_t)z, b = (uint32_t)(z >> 32);
-    const float u1 = ((float)(a >> 8) + 1.0f)*(1.0f/16777216.0f);  // (0, 1]
-    const float u2 = (float)(b >> 8)*(1.0f/16777216.0f);
-    return sqrtf(-2.0f*__logf(u1))*__cosf(6.283185307179586f*u2);
+    uint32_t h = (uint32_t)idx*0x9E3779B1u + (uint32_t)(idx >> 32)*0x85EBCA77u + (uint32_t)seed;
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    const int sum = (int)(h & 255u) + (int)((h >> 8) & 255u) + (int)((h >> 16) & 255u) + (int)(h >> 24);
+    return ((float)sum - 510.0f)*(1.0f/147.80f);  // var of one byte = (256^2 - 1)/12; four of them -> sigma = 147.80
 }
 
 }  // namespace stv

@@ -13,6 +13,7 @@
 // HBM traffic per target pixel (fp32): target 12 B + depth 4 B per scale + gathered support texels (L1/L2 resident
 // between neighbouring pixels) + 1 B decision byte per scale; see DESIGN.md for the roofline accounting.
 #include "stv_common.cuh"
+#include "stv_f2.cuh"
 
 namespace stv {
 
@@ -37,6 +38,7 @@ struct PhotoParams {
     float* partial;   // fwd: one float per block; bwd: n_acc floats per (block, k)
     uint8_t* sel;
     float* warp0;
+    cudaTextureObject_t supp_tex;  // supp viewed as one (n*b*3*H) x W single-channel texture (0 = not available)
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
@@ -97,61 +99,203 @@ __device__ __forceinline__ void pair_sums(const float (*sw)[COLS], const float (
     }
 }
 
-// Photometric error of RUN centres (rows top+1.., column col+1 of the halo-1 tiles) for one support frame.
-__device__ __forceinline__ void photo_run(const float (*sw)[PH1][PW1], const float (*st)[PH1][PW1], int top, int col,
-                                          const float (*T1)[RUN], const float (*T2)[RUN], float w_ssim, float w_l1,
-                                          float* ek) {
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward-side machinery (v2): transposed shared tiles + packed fp32x2 math + texture-gather sampling.
+//
+// Shared tiles are stored [channel][column][row] so that the RUN+2 = 6 vertically consecutive rows a thread needs from one
+// column are 3 aligned 8-byte words: LDS.64 loads whose two lanes are exactly the row pairs the packed FADD2/FFMA2 box-filter
+// arithmetic consumes. With a column stride of PH1 = 18 words, the 16 lanes of an LDS.64 phase hit all 32 banks once.
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward-side tiling: many small blocks per SM (each block alternates a memory phase and a compute phase separated by
+// barriers, so independent blocks are what overlaps the two).
+#ifndef STV_FWD_TH
+#define STV_FWD_TH 8
+#endif
+#ifndef STV_FWD_NT
+#define STV_FWD_NT 256
+#endif
+constexpr int FTW = 64, FTH = STV_FWD_TH;    // forward tile
+constexpr int FNT = STV_FWD_NT;              // threads per block of the forward-side kernels
+constexpr int FRUN = FTH*FTW/FNT;            // vertically consecutive centres per thread (2 or 4)
+constexpr int FNP = FRUN/2;                  // packed centre pairs per thread
+static_assert(FRUN == 2 || FRUN == 4, "forward kernels support 2 or 4 centres per thread");
+constexpr int FPW = FTW + 2, FPH = FTH + 2;  // tile + halo 1
+constexpr int NPOS = (FPH*FPW + FNT - 1)/FNT;  // halo-1 positions per thread in phase 1
+typedef float TileT[FPW][FPH];               // one channel, transposed
+
+// Window sums (3x3, as packed row pairs) of one channel for the FRUN centres of a thread:
+//   rows top..top+FRUN+1 of columns col..col+2 ; centres are rows top+1..top+FRUN of column col+1.
+struct WinSums { f2 S1[FNP], S2[FNP], S3[FNP]; f2 wc[FNP + 1], tc[FNP + 1]; };
+
+__device__ __forceinline__ f2 mid2(f2 a, f2 b) { return mk2(hi2(a), lo2(b)); }
+
+__device__ __forceinline__ void pair_sums_t(const TileT& sw, const TileT& st, int top, int col, WinSums& o) {
+    f2 h1[FNP + 1], h2[FNP + 1], h3[FNP + 1];
 #pragma unroll
-    for (int j = 0; j < RUN; ++j) ek[j] = 0.f;
+    for (int j = 0; j < FNP + 1; ++j) {
+        const f2 a = ld2(&sw[col][top + 2*j]), b = ld2(&sw[col + 1][top + 2*j]), c = ld2(&sw[col + 2][top + 2*j]);
+        const f2 ta = ld2(&st[col][top + 2*j]), tb = ld2(&st[col + 1][top + 2*j]), tc = ld2(&st[col + 2][top + 2*j]);
+        h1[j] = a + b + c;
+        h2[j] = fma2(a, a, fma2(b, b, c*c));
+        h3[j] = fma2(a, ta, fma2(b, tb, c*tc));
+        o.wc[j] = b; o.tc[j] = tb;
+    }
+#pragma unroll
+    for (int j = 0; j < FNP; ++j) {
+        o.S1[j] = h1[j] + h1[j + 1] + mid2(h1[j], h1[j + 1]);
+        o.S2[j] = h2[j] + h2[j + 1] + mid2(h2[j], h2[j + 1]);
+        o.S3[j] = h3[j] + h3[j + 1] + mid2(h3[j], h3[j + 1]);
+    }
+}
+
+__device__ __forceinline__ void target_sums_t(const TileT& st, int top, int col, f2* T1, f2* T2) {
+    f2 h1[FNP + 1], h2[FNP + 1];
+#pragma unroll
+    for (int j = 0; j < FNP + 1; ++j) {
+        const f2 a = ld2(&st[col][top + 2*j]), b = ld2(&st[col + 1][top + 2*j]), c = ld2(&st[col + 2][top + 2*j]);
+        h1[j] = a + b + c;
+        h2[j] = fma2(a, a, fma2(b, b, c*c));
+    }
+#pragma unroll
+    for (int j = 0; j < FNP; ++j) {
+        T1[j] = h1[j] + h1[j + 1] + mid2(h1[j], h1[j + 1]);
+        T2[j] = h2[j] + h2[j + 1] + mid2(h2[j], h2[j + 1]);
+    }
+}
+
+// SSIM error of a pixel pair (packed), clamp to [0,1] by the saturating FMA.  (src/losses/photometric.py:40-50)
+__device__ __forceinline__ void ssim_pair(f2 S1, f2 S2, f2 S3, f2 T1, f2 T2, float& e0, float& e1) {
+    const f2 k = splat2(1.f/9.f), two = splat2(2.f), nk = splat2(-1.f/9.f);
+    const f2 mx = S1*k, my = T1*k;
+    const f2 mxy = mx*my, mxx = mx*mx, myy = my*my;
+    // -(sigma) = mean^2 - E[.]  keeps everything in FFMA2 form (no packed negate exists)
+    const f2 nsxx = fma2(S2, nk, mxx), nsyy = fma2(T2, nk, myy), nsxy = fma2(S3, nk, mxy);
+    const f2 num = fma2(two, mxy, splat2(STV_C1))*fma2(splat2(-2.f), nsxy, splat2(STV_C2));
+    const f2 den = (mxx + myy + splat2(STV_C1))*fma2(splat2(-1.f), nsxx + nsyy, splat2(STV_C2));
+    e0 = __saturatef(fmaf(-0.5f*lo2(num), rcp_fast(lo2(den)), 0.5f));
+    e1 = __saturatef(fmaf(-0.5f*hi2(num), rcp_fast(hi2(den)), 0.5f));
+}
+
+// Photometric error of the thread's FRUN centres for one support frame.
+__device__ __forceinline__ void photo_run_t(const TileT* sw, const TileT* st, int top, int col, const f2 (*T1)[FNP],
+                                            const f2 (*T2)[FNP], float w_ssim, float w_l1, float* ek) {
+#pragma unroll
+    for (int j = 0; j < FRUN; ++j) ek[j] = 0.f;
+    const float ws = w_ssim*(1.f/3.f), wl = w_l1*(1.f/3.f);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+        WinSums w;
+        pair_sums_t(sw[c], st[c], top, col, w);
         if (w_ssim > 0.f) {
-            float S1[RUN], S2[RUN], S3[RUN];
-            pair_sums<PW1, RUN>(sw[c], st[c], top, col, S1, S2, S3);
 #pragma unroll
-            for (int j = 0; j < RUN; ++j) ek[j] = fmaf(w_ssim*(1.f/3.f), ssim_err(S1[j], S2[j], S3[j], T1[c][j], T2[c][j]), ek[j]);
+            for (int j = 0; j < FNP; ++j) {
+                float e0, e1;
+                ssim_pair(w.S1[j], w.S2[j], w.S3[j], T1[c][j], T2[c][j], e0, e1);
+                ek[2*j] = fmaf(ws, e0, ek[2*j]);
+                ek[2*j + 1] = fmaf(ws, e1, ek[2*j + 1]);
+            }
         }
         if (w_l1 > 0.f) {
 #pragma unroll
-            for (int j = 0; j < RUN; ++j)
-                ek[j] = fmaf(w_l1*(1.f/3.f), fabsf(sw[c][top + 1 + j][col + 1] - st[c][top + 1 + j][col + 1]), ek[j]);
+            for (int j = 0; j < FNP; ++j) {  // centre 2j is the high lane of pair j, centre 2j+1 the low lane of pair j+1
+                ek[2*j] = fmaf(wl, fabsf(hi2(w.wc[j]) - hi2(w.tc[j])), ek[2*j]);
+                ek[2*j + 1] = fmaf(wl, fabsf(lo2(w.wc[j + 1]) - lo2(w.tc[j + 1])), ek[2*j + 1]);
+            }
         }
     }
+}
+
+// Loads the halo-1 window of a 3-channel image into transposed tiles.
+__device__ __forceinline__ void load_tile3_t(TileT* dst, const float* __restrict__ img, int y0, int x0, int H, int W) {
+    const int HW = H*W;
+    for (int q = threadIdx.x; q < FPH*FPW; q += FNT) {
+        const int py = q/FPW, px = q - py*FPW;
+        const int ya = clampi(reflect_idx(y0 + py, H), 0, H - 1), xa = clampi(reflect_idx(x0 + px, W), 0, W - 1);
+        const float* p = img + ya*W + xa;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dst[c][px][py] = __ldg(p + c*HW);
+    }
+}
+
+// Bilinear border sample of the 3 channels of support frame `plane0/3` at pixel-unit position (ix, iy).
+//   TEX: one TLD4 (texture gather) per channel returns the 2x2 footprint with hardware address clamping; the footprint is
+//        addressed at its texel centre (x0+1, y0+1) so the fixed-point coordinate conversion cannot move it.
+//   !TEX: four read-only loads per channel (used when the frames do not meet the texture alignment rules).
+template <bool TEX>
+__device__ __forceinline__ void sample3(const PhotoParams& p, const float* __restrict__ sp, int plane0, float ix, float iy,
+                                        float* out) {
+    const int H = p.H, W = p.W;
+    ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float wx = ix - x0f, wy = iy - y0f;
+    if (TEX) {
+        const float xc = x0f + 1.f, yc = y0f + 1.f + (float)(plane0*H);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float4 g = tex2Dgather<float4>(p.supp_tex, xc, yc + (float)(c*H), 0);  // x=(0,1) y=(1,1) z=(1,0) w=(0,0)
+            const float top = fmaf(wx, g.z - g.w, g.w), bot = fmaf(wx, g.y - g.x, g.x);
+            out[c] = fmaf(wy, bot - top, top);
+        }
+    } else {
+        const int x0 = (int)x0f, y0 = (int)y0f, x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+        const int o00 = y0*W + x0, o01 = y0*W + x1, o10 = y1*W + x0, o11 = y1*W + x1, HW = H*W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* q = sp + c*HW;
+            const float a = __ldg(q + o00), b = __ldg(q + o01), cc = __ldg(q + o10), d = __ldg(q + o11);
+            const float top = fmaf(wx, b - a, a), bot = fmaf(wx, d - cc, cc);
+            out[c] = fmaf(wy, bot - top, top);
+        }
+    }
+}
+
+// Projection of pixel (u, v) with depth d to the sample position in the support frame (rows 9-11 of SURVEY 8a).
+__device__ __forceinline__ void project_fast(const Cam& c, float u, float v, float d, float sx, float sy, float& ix, float& iy) {
+    float P[3], Q[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) P[r] = fmaf(c.Ki[r*3], u, fmaf(c.Ki[r*3 + 1], v, c.Ki[r*3 + 2]))*d;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) Q[r] = fmaf(c.R[r*3], P[0], fmaf(c.R[r*3 + 1], P[1], fmaf(c.R[r*3 + 2], P[2], c.t[r])));
+    const float inv = rcp_fast(fmaxf(Q[2], STV_MIN_Z));  // max(max(z, eps), 0.1) == max(z, 0.1)
+    const float nx = Q[0]*inv, ny = Q[1]*inv, nz = Q[2]*inv;
+    ix = fmaf(fmaf(c.K0[0], nx, fmaf(c.K0[1], ny, c.K0[2]*nz)), sx, -0.5f);
+    iy = fmaf(fmaf(c.K1[0], nx, fmaf(c.K1[1], ny, c.K1[2]*nz)), sy, -0.5f);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // compute_photo on un-warped frames: identity (static) error for the auto-mask, and the stand-alone entry point.
 // grid = (tiles, b)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) photo_error_kernel(PhotoParams p, const float* __restrict__ pred,
-                                                         float* __restrict__ err) {
-    __shared__ float st[3][PH1][PW1];
-    __shared__ float sw[3][PH1][PW1];
+__global__ void __launch_bounds__(FNT) photo_error_kernel(PhotoParams p, const float* __restrict__ pred,
+                                                            float* __restrict__ err) {
+    __shared__ __align__(16) float st[3][FPW][FPH];
+    __shared__ __align__(16) float sw[3][FPW][FPH];
     const int tile = blockIdx.x, i = blockIdx.y;
-    const int tx0 = (tile % p.tiles_x)*TW, ty0 = (tile/p.tiles_x)*TH;
+    const int tx0 = (tile % p.tiles_x)*FTW, ty0 = (tile/p.tiles_x)*FTH;
     const int H = p.H, W = p.W, HW = H*W;
-    load_tile3<PH1, PW1>(st, p.tgt + (size_t)i*3*HW, ty0 - 1, tx0 - 1, H, W);
+    load_tile3_t(st, p.tgt + (size_t)i*3*HW, ty0 - 1, tx0 - 1, H, W);
     __syncthreads();
-    const int lx = threadIdx.x & (TW - 1), top = (threadIdx.x/TW)*RUN;
-    float T1[3][RUN], T2[3][RUN];
+    const int lx = threadIdx.x & (FTW - 1), top = (threadIdx.x/FTW)*FRUN;
+    f2 T1[3][FNP], T2[3][FNP];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) target_sums<PH1, PW1, RUN>(st[c], top, lx, T1[c], T2[c]);
+    for (int c = 0; c < 3; ++c) target_sums_t(st[c], top, lx, T1[c], T2[c]);
 
-    float ered[RUN];
+    float ered[FRUN];
 #pragma unroll
-    for (int j = 0; j < RUN; ++j) ered[j] = p.use_min ? INFINITY : 0.f;
+    for (int j = 0; j < FRUN; ++j) ered[j] = p.use_min ? INFINITY : 0.f;
     for (int k = 0; k < p.n; ++k) {
-        load_tile3<PH1, PW1>(sw, pred + ((size_t)k*p.b + i)*3*HW, ty0 - 1, tx0 - 1, H, W);
+        load_tile3_t(sw, pred + ((size_t)k*p.b + i)*3*HW, ty0 - 1, tx0 - 1, H, W);
         __syncthreads();
-        float ek[RUN];
-        photo_run(sw, st, top, lx, T1, T2, p.w_ssim, p.w_l1, ek);
+        float ek[FRUN];
+        photo_run_t(sw, st, top, lx, T1, T2, p.w_ssim, p.w_l1, ek);
 #pragma unroll
-        for (int j = 0; j < RUN; ++j) ered[j] = p.use_min ? fminf(ered[j], ek[j]) : ered[j] + ek[j];
+        for (int j = 0; j < FRUN; ++j) ered[j] = p.use_min ? fminf(ered[j], ek[j]) : ered[j] + ek[j];
         __syncthreads();
     }
     const int x = tx0 + lx;
 #pragma unroll
-    for (int j = 0; j < RUN; ++j) {
+    for (int j = 0; j < FRUN; ++j) {
         const int y = ty0 + top + j;
         if (y < H && x < W) err[(size_t)i*HW + y*W + x] = p.use_min ? ered[j] : ered[j]/(float)p.n;
     }
@@ -160,59 +304,102 @@ __global__ void __launch_bounds__(NT) photo_error_kernel(PhotoParams p, const fl
 // ---------------------------------------------------------------------------------------------------------------------
 // Forward. grid = (tiles, b, S)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) photo_fwd_kernel(PhotoParams p) {
-    __shared__ float st[3][PH1][PW1];
-    __shared__ float sw[3][PH1][PW1];
+#ifndef STV_FWD_MINB
+#define STV_FWD_MINB 4  // measured on B200 at 8x384x640, n=2, S=4: (TH, NT, MINB) = (8, 256, 4) is the fastest of six variants
+#endif
+template <bool TEX>
+__global__ void __launch_bounds__(FNT, STV_FWD_MINB) photo_fwd_kernel(PhotoParams p) {
+    __shared__ __align__(16) float st[3][FPW][FPH];
+    __shared__ __align__(16) float sw[3][FPW][FPH];
     __shared__ float red[32];
     const int tile = blockIdx.x, i = blockIdx.y, s = blockIdx.z;
-    const int tx0 = (tile % p.tiles_x)*TW, ty0 = (tile/p.tiles_x)*TH;
+    const int tx0 = (tile % p.tiles_x)*FTW, ty0 = (tile/p.tiles_x)*FTH;
     const int H = p.H, W = p.W, HW = H*W;
     const float sx = (float)W/(float)(W - 1), sy = (float)H/(float)(H - 1);
 
-    load_tile3<PH1, PW1>(st, p.tgt + (size_t)i*3*HW, ty0 - 1, tx0 - 1, H, W);
+    // Per-thread halo positions (branch-free: surplus threads of the last round redo the final position). The mirrored
+    // pixel and its depth do not depend on the support frame, so they are resolved once.
+    const float* __restrict__ dp = p.depth[s] + (size_t)i*HW;
+    const float* __restrict__ tg = p.tgt + (size_t)i*3*HW;
+    float pu[NPOS], pv[NPOS], pd[NPOS];
+    int so[NPOS];  // offset of the position inside one transposed tile
+#pragma unroll
+    for (int it = 0; it < NPOS; ++it) {
+        const int q = min((int)threadIdx.x + it*FNT, FPH*FPW - 1);
+        const int py = q/FPW, px = q - py*FPW;
+        const int ya = clampi(reflect_idx(ty0 - 1 + py, H), 0, H - 1), xa = clampi(reflect_idx(tx0 - 1 + px, W), 0, W - 1);
+        const int o = ya*W + xa;
+        so[it] = px*FPH + py;
+        pu[it] = (float)xa; pv[it] = (float)ya;
+        pd[it] = __ldg(dp + o);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) (&st[c][0][0])[so[it]] = __ldg(tg + c*HW + o);
+    }
     __syncthreads();
-    const int lx = threadIdx.x & (TW - 1), top = (threadIdx.x/TW)*RUN;
-    float T1[3][RUN], T2[3][RUN];
+    const int lx = threadIdx.x & (FTW - 1), top = (threadIdx.x/FTW)*FRUN;
+    f2 T1[3][FNP], T2[3][FNP];
     if (p.w_ssim > 0.f) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) target_sums<PH1, PW1, RUN>(st[c], top, lx, T1[c], T2[c]);
+        for (int c = 0; c < 3; ++c) target_sums_t(st[c], top, lx, T1[c], T2[c]);
     }
 
-    float ered[RUN];
-    int ksel[RUN];
+    float ered[FRUN];
+    int ksel[FRUN];
 #pragma unroll
-    for (int j = 0; j < RUN; ++j) { ered[j] = p.use_min ? INFINITY : 0.f; ksel[j] = p.use_min ? 0 : STV_SEL_MEAN; }
+    for (int j = 0; j < FRUN; ++j) { ered[j] = p.use_min ? INFINITY : 0.f; ksel[j] = p.use_min ? 0 : STV_SEL_MEAN; }
 
-    const float* __restrict__ dp = p.depth[s] + (size_t)i*HW;
+    // Identity error (+ tie-break noise) of the thread's centres: requested now, consumed after the support-frame loop.
+    float e0v[FRUN];
+    {
+        const int x = min(tx0 + lx, W - 1);
+#pragma unroll
+        for (int j = 0; j < FRUN; ++j) {
+            const int y = min(ty0 + top + j, H - 1);
+            const size_t pix = (size_t)i*HW + y*W + x, nidx = (size_t)s*p.b*HW + pix;
+            e0v[j] = 0.f;
+            if (p.use_automask) {
+                e0v[j] = __ldg(p.e0 + pix);
+                if (p.noise) e0v[j] = fmaf(STV_EPS32, __ldg(p.noise + nidx), e0v[j]);
+                else if (p.seed) e0v[j] = fmaf(STV_EPS32, hash_normal(p.seed, nidx), e0v[j]);
+            }
+        }
+    }
+
     const bool want_warp = p.warp0 != nullptr && s == 0;
     for (int k = 0; k < p.n; ++k) {
         Cam cam;
         load_cam(cam, p.T + ((size_t)k*p.b + i)*16, p.K + (size_t)i*16, p.Kinv + (size_t)i*16);
-        const float* __restrict__ sp = p.supp + ((size_t)k*p.b + i)*3*HW;
-        // phase 1: warp the tile + halo into shared memory
-        for (int q = threadIdx.x; q < PH1*PW1; q += NT) {
-            const int py = q/PW1, px = q - py*PW1;
-            const int yy = ty0 - 1 + py, xx = tx0 - 1 + px;
-            const int ya = clampi(reflect_idx(yy, H), 0, H - 1), xa = clampi(reflect_idx(xx, W), 0, W - 1);
-            const float d = __ldg(dp + ya*W + xa);
-            Proj pr;
-            project(cam, (float)xa, (float)ya, d, sx, sy, pr);
-            Taps t;
-            make_taps(pr.ix, pr.iy, H, W, t);
-            const bool own = want_warp && py >= 1 && py <= TH && px >= 1 && px <= TW && yy < H && xx < W;
+        const int plane0 = (k*p.b + i)*3;
+        const float* __restrict__ sp = p.supp + (size_t)plane0*HW;
+        // phase 1: warp the tile + halo into shared memory. Sample positions first, then all gathers, then the lerps, so
+        // that every thread keeps several texture requests in flight.
+        float ix[NPOS], iy[NPOS];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float v = sample_plane(sp + c*HW, t);
-                sw[c][py][px] = v;
-                if (own) p.warp0[(((size_t)k*p.b + i)*3 + c)*HW + yy*W + xx] = v;
-            }
+        for (int it = 0; it < NPOS; ++it) project_fast(cam, pu[it], pv[it], pd[it], sx, sy, ix[it], iy[it]);
+#pragma unroll
+        for (int it = 0; it < NPOS; ++it) {
+            float v[3];
+            sample3<TEX>(p, sp, plane0, ix[it], iy[it], v);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) (&sw[c][0][0])[so[it]] = v[c];
         }
         __syncthreads();
-        // phase 2: photometric error, reduce over support frames (first index wins ties, as torch.min)
-        float ek[RUN];
-        photo_run(sw, st, top, lx, T1, T2, p.w_ssim, p.w_l1, ek);
+        if (want_warp) {  // logging path (scale 0 only): the block's interior of the warped frame goes to HBM
+            const int x = tx0 + lx;
 #pragma unroll
-        for (int j = 0; j < RUN; ++j) {
+            for (int j = 0; j < FRUN; ++j) {
+                const int y = ty0 + top + j;
+                if (y < H && x < W) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) p.warp0[((size_t)plane0 + c)*HW + y*W + x] = sw[c][lx + 1][top + 1 + j];
+                }
+            }
+        }
+        // phase 2: photometric error, reduce over support frames (first index wins ties, as torch.min)
+        float ek[FRUN];
+        photo_run_t(sw, st, top, lx, T1, T2, p.w_ssim, p.w_l1, ek);
+#pragma unroll
+        for (int j = 0; j < FRUN; ++j) {
             if (p.use_min) { if (ek[j] < ered[j]) { ered[j] = ek[j]; ksel[j] = k; } }
             else ered[j] += ek[j];
         }
@@ -222,19 +409,13 @@ __global__ void __launch_bounds__(NT) photo_fwd_kernel(PhotoParams p) {
     float acc = 0.f;
     const int x = tx0 + lx;
 #pragma unroll
-    for (int j = 0; j < RUN; ++j) {
+    for (int j = 0; j < FRUN; ++j) {
         const int y = ty0 + top + j;
         if (y < H && x < W) {
             float e = p.use_min ? ered[j] : ered[j]/(float)p.n;
             int sel = ksel[j];
             const size_t pix = (size_t)i*HW + y*W + x;
-            if (p.use_automask) {
-                float e0 = __ldg(p.e0 + pix);
-                const size_t nidx = (size_t)s*p.b*HW + pix;
-                if (p.noise) e0 = fmaf(STV_EPS32, __ldg(p.noise + nidx), e0);
-                else if (p.seed) e0 = fmaf(STV_EPS32, hash_normal(p.seed, nidx), e0);
-                if (!(e <= e0)) { e = e0; sel = STV_SEL_STATIC; }  // torch.min(cat(err, static)): index 0 wins ties
-            }
+            if (p.use_automask && !(e <= e0v[j])) { e = e0v[j]; sel = STV_SEL_STATIC; }  // torch.min(cat(err, static)): index 0 wins ties
             p.sel[(size_t)s*p.b*HW + pix] = (uint8_t)sel;
             acc += e;
         }
@@ -476,35 +657,42 @@ __global__ void __launch_bounds__(NT) photo_bwd_kernel(PhotoParams p) {
 //   gT[k,i,r,c]   (r<3)   = sum_{s,tile} partial[((s*b+i)*tiles+tile)*n + k][r*4+c]
 //   gK[i,r,c]     (r<2)   = sum_{s,tile,k} partial[...][12 + r*3 + c]
 //   gKinv[i,r,c]  (r<3)   = sum_{s,tile,k} partial[...][18 + r*3 + c]
-__global__ void photo_bwd_finalize_kernel(const float* __restrict__ partial, int b, int n, int S, int tiles,
-                                          float* __restrict__ gT, float* __restrict__ gK, float* __restrict__ gKinv) {
+__global__ void __launch_bounds__(128) photo_bwd_finalize_kernel(const float* __restrict__ partial, int b, int n, int S, int tiles,
+                                                                 float* __restrict__ gT, float* __restrict__ gK,
+                                                                 float* __restrict__ gKinv) {
+    // One warp per output element; lanes stride over the partial rows, then a fixed-shape shuffle tree (deterministic).
     constexpr int NA = N_ACC_T + N_ACC_K;
     const int nT = n*b*16, nK = b*16;
-    const int idx = blockIdx.x*blockDim.x + threadIdx.x;
+    const int idx = (blockIdx.x*blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (idx >= nT + 2*nK) return;
+    float* out;
+    int off, i, k0, k1, e;
+    bool live;
     if (idx < nT) {
-        const int c = idx & 3, r = (idx >> 2) & 3, ki = idx >> 4, k = ki/b, i = ki - k*b;
-        double a = 0.0;
-        if (r < 3)
-            for (int s = 0; s < S; ++s)
-                for (int t = 0; t < tiles; ++t)
-                    a += (double)partial[((((size_t)s*b + i)*tiles + t)*n + k)*NA + r*4 + c];
-        gT[idx] = (float)a;
-    } else if (idx < nT + 2*nK) {
-        const int which = (idx - nT)/nK, e = (idx - nT) - which*nK;
-        float* out = which == 0 ? gK : gKinv;
-        if (out == nullptr) return;
-        const int c = e & 3, r = (e >> 2) & 3, i = e >> 4;
-        double a = 0.0;
-        const bool live = c < 3 && (which == 0 ? r < 2 : r < 3);
-        if (live) {
-            const int off = which == 0 ? 12 + r*3 + c : 18 + r*3 + c;
-            for (int s = 0; s < S; ++s)
-                for (int t = 0; t < tiles; ++t)
-                    for (int k = 0; k < n; ++k)
-                        a += (double)partial[((((size_t)s*b + i)*tiles + t)*n + k)*NA + off];
-        }
-        out[e] = (float)a;
+        const int c = idx & 3, r = (idx >> 2) & 3, ki = idx >> 4;
+        k0 = ki/b; k1 = k0 + 1; i = ki - k0*b;
+        out = gT; e = idx; off = r*4 + c; live = r < 3;
+    } else {
+        const int which = (idx - nT)/nK;
+        e = (idx - nT) - which*nK;
+        out = which == 0 ? gK : gKinv;
+        const int c = e & 3, r = (e >> 2) & 3;
+        i = e >> 4; k0 = 0; k1 = n;
+        live = c < 3 && (which == 0 ? r < 2 : r < 3);
+        off = which == 0 ? 12 + r*3 + c : 18 + r*3 + c;
     }
+    if (out == nullptr) return;
+    double a = 0.0;
+    if (live) {
+        const int rows = S*tiles;
+        for (int q = lane; q < rows; q += 32) {
+            const int s = q/tiles, t = q - s*tiles;
+            for (int k = k0; k < k1; ++k) a += (double)partial[((((size_t)s*b + i)*tiles + t)*n + k)*NA + off];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) out[e] = (float)a;
 }
 
 }  // namespace stv
@@ -533,15 +721,83 @@ static void fill_params(PhotoParams& p, const stv_photo_cfg* c) {
     p.tiles_x = (c->W + TW - 1)/TW; p.tiles_y = (c->H + TH - 1)/TH;
 }
 
+static void use_fwd_tiles(PhotoParams& p) { p.tiles_x = (p.W + FTW - 1)/FTW; p.tiles_y = (p.H + FTH - 1)/FTH; }
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// ---- texture view of the support frames -------------------------------------------------------------------------------
+// The (n,b,3,H,W) support tensor is bound as ONE single-channel float texture of n*b*3*H rows x W columns (pitch W*4), so the
+// sampler's 2x2 footprint is one TLD4 per channel with hardware address clamping in x. Texture objects are cached per
+// (device, pointer, shape): PyTorch's caching allocator hands the same buffers back every step, so steady state creates none.
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
+namespace {
+struct TexKey {
+    int dev; const void* ptr; int rows, W;
+    bool operator==(const TexKey& o) const { return dev == o.dev && ptr == o.ptr && rows == o.rows && W == o.W; }
+};
+struct TexKeyHash {
+    size_t operator()(const TexKey& k) const {
+        return std::hash<const void*>()(k.ptr) ^ (std::hash<long long>()(((long long)k.rows << 32) | (unsigned)k.W)*31 + k.dev);
+    }
+};
+struct TexEntry { cudaTextureObject_t tex; unsigned long long stamp; };
+std::mutex g_tex_mu;
+std::unordered_map<TexKey, TexEntry, TexKeyHash> g_tex;
+unsigned long long g_tex_clock = 0;
+constexpr size_t TEX_CACHE_MAX = 64;
+}  // namespace
+
+// Returns 0 when the buffer cannot be bound (alignment / size limits): callers then use the plain-load kernels.
+static cudaTextureObject_t supp_texture(const float* supp, int rows, int W) {
+    static const bool disabled = getenv("STV_NO_TEX") != nullptr;  // developer switch: force the plain-load kernels
+    if (disabled) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    static thread_local int prop_dev = -1;
+    static thread_local size_t tex_align = 512, pitch_align = 32;
+    static thread_local int max_w = 0, max_h = 0;
+    if (prop_dev != dev) {
+        cudaDeviceProp pr;
+        if (cudaGetDeviceProperties(&pr, dev) != cudaSuccess) return 0;
+        tex_align = pr.textureAlignment; pitch_align = pr.texturePitchAlignment;
+        max_w = pr.maxTexture2DLinear[0]; max_h = pr.maxTexture2DLinear[1];
+        prop_dev = dev;
+    }
+    const size_t pitch = (size_t)W*sizeof(float);
+    if (((uintptr_t)supp % tex_align) != 0 || (pitch % pitch_align) != 0 || W > max_w || rows > max_h || rows >= (1 << 23)) return 0;
+    std::lock_guard<std::mutex> lock(g_tex_mu);
+    const TexKey key{dev, supp, rows, W};
+    auto it = g_tex.find(key);
+    if (it != g_tex.end()) { it->second.stamp = ++g_tex_clock; return it->second.tex; }
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypePitch2D;
+    rd.res.pitch2D.devPtr = const_cast<float*>(supp);
+    rd.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+    rd.res.pitch2D.width = W; rd.res.pitch2D.height = rows; rd.res.pitch2D.pitchInBytes = pitch;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+    cudaTextureObject_t tex = 0;
+    if (cudaCreateTextureObject(&tex, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (g_tex.size() >= TEX_CACHE_MAX) {  // evict the least recently used view (long idle by construction)
+        auto old = g_tex.begin();
+        for (auto j = g_tex.begin(); j != g_tex.end(); ++j) if (j->second.stamp < old->second.stamp) old = j;
+        cudaDestroyTextureObject(old->second.tex);
+        g_tex.erase(old);
+    }
+    g_tex[key] = TexEntry{tex, ++g_tex_clock};
+    return tex;
+}
 
 extern "C" size_t stv_photo_workspace_bytes(const stv_photo_cfg* c) {
     if (check_cfg(c) != STV_OK) return 0;
-    const size_t tiles = (size_t)((c->W + TW - 1)/TW)*((c->H + TH - 1)/TH);
-    const size_t nblk = tiles*c->b*c->S;
+    const size_t tiles_b = (size_t)((c->W + TW - 1)/TW)*((c->H + TH - 1)/TH);
+    const size_t tiles_f = (size_t)((c->W + FTW - 1)/FTW)*((c->H + FTH - 1)/FTH);
     const size_t e0 = align256((size_t)c->b*c->H*c->W*sizeof(float));
-    const size_t part_fwd = align256(nblk*sizeof(float));
-    const size_t part_bwd = align256(nblk*c->n*(N_ACC_T + N_ACC_K)*sizeof(float));
+    const size_t part_fwd = align256(tiles_f*c->b*c->S*sizeof(float));
+    const size_t part_bwd = align256(tiles_b*c->b*c->S*c->n*(N_ACC_T + N_ACC_K)*sizeof(float));
     return e0 + (part_fwd > part_bwd ? part_fwd : part_bwd);
 }
 
@@ -550,9 +806,10 @@ extern "C" int stv_photo_error(const stv_photo_cfg* c, const float* pred, const 
     STV_REQUIRE(pred && tgt && err, "stv_photo_error: NULL pointer");
     PhotoParams p{};
     fill_params(p, c);
+    use_fwd_tiles(p);
     p.tgt = tgt;
     dim3 grid(p.tiles_x*p.tiles_y, c->b);
-    photo_error_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(p, pred, err);
+    photo_error_kernel<<<grid, FNT, 0, (cudaStream_t)stream>>>(p, pred, err);
     count_launch();
     return check_launch("photo_error_kernel");
 }
@@ -571,6 +828,7 @@ extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, 
     cudaStream_t st = (cudaStream_t)stream;
     PhotoParams p{};
     fill_params(p, c);
+    use_fwd_tiles(p);
     for (int s = 0; s < c->S; ++s) p.depth[s] = depth[s];
     p.tgt = tgt; p.supp = supp; p.T = T; p.K = K; p.Kinv = Kinv; p.noise = noise;
     float* e0 = (float*)ws;
@@ -579,11 +837,13 @@ extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, 
     p.sel = sel; p.warp0 = warp0;
     const int tiles = p.tiles_x*p.tiles_y;
     if (c->use_automask) {
-        photo_error_kernel<<<dim3(tiles, c->b), NT, 0, st>>>(p, supp, e0);
+        photo_error_kernel<<<dim3(tiles, c->b), FNT, 0, st>>>(p, supp, e0);
         count_launch();
         if (int rc = check_launch("photo_error_kernel")) return rc;
     }
-    photo_fwd_kernel<<<dim3(tiles, c->b, c->S), NT, 0, st>>>(p);
+    p.supp_tex = supp_texture(supp, c->n*c->b*3*c->H, c->W);
+    if (p.supp_tex) photo_fwd_kernel<true><<<dim3(tiles, c->b, c->S), FNT, 0, st>>>(p);
+    else photo_fwd_kernel<false><<<dim3(tiles, c->b, c->S), FNT, 0, st>>>(p);
     count_launch();
     if (int rc = check_launch("photo_fwd_kernel")) return rc;
     const int nblk = tiles*c->b*c->S;
@@ -629,7 +889,7 @@ extern "C" int stv_photo_bwd(const stv_photo_cfg* c, const float* const* depth, 
         // (photo_bwd_kernel<false> writes only the first N_ACC_T entries.)
     }
     const int total = c->n*c->b*16 + 2*c->b*16;
-    photo_bwd_finalize_kernel<<<(total + 127)/128, 128, 0, st>>>(p.partial, c->b, c->n, c->S, tiles, gT, need_k ? gK : nullptr,
+    photo_bwd_finalize_kernel<<<(total*32 + 127)/128, 128, 0, st>>>(p.partial, c->b, c->n, c->S, tiles, gT, need_k ? gK : nullptr,
                                                                  need_k ? gKinv : nullptr);
     count_launch();
     return check_launch("photo_bwd_finalize_kernel");

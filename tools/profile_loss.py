@@ -1,0 +1,35 @@
+"""Developer aid: run the fused loss stack alone at a benchmark shape (for ncu captures and quick timing).
+  python tools/profile_loss.py [--b 8 --H 384 --W 640 --n 2 --S 4 --iters 5]"""
+import argparse
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch
+from slowtv_monodepth_b200 import geometry as G, handlers as Hd, synthetic as syn, functional as F_
+from slowtv_monodepth_b200.losses import ReconstructionLoss
+from slowtv_monodepth_b200.regularizers import SmoothReg
+
+ap = argparse.ArgumentParser()
+for k, v in dict(b=8, H=384, W=640, n=2, S=4, iters=5).items(): ap.add_argument(f'--{k}', type=int, default=v)
+a = ap.parse_args()
+dev = 'cuda'
+d = syn.make_loss_inputs(a.b, a.n, a.S, (a.H, a.W), seed=0)
+d = {k: ([x.to(dev) for x in v] if isinstance(v, list) else v.to(dev)) for k, v in d.items()}
+disps = [x.requires_grad_() for x in d['disps']]
+aa, t = d['aa'].requires_grad_(), d['t'].requires_grad_()
+crit, sm = ReconstructionLoss('ssim', True, True), SmoothReg(use_edges=True)
+F_.enable_kernel_timing(True)
+for it in range(a.iters):
+    Ts = G.T_from_AAt(aa, t)
+    depths = {s: G.upsample_to_depth(x, (a.H, a.W), 0.1, 100.)[1] for s, x in enumerate(disps)}
+    l1, _ = Hd.image_recon(crit, None, depths, None, d['imgs'], d['supp_imgs'], Ts, d['K'], want_warp=False)
+    l2, _ = Hd.disp_smooth(sm, dict(enumerate(disps)), d['imgs'], want_maps=False)
+    (l1 + 1e-3*l2).backward()
+torch.cuda.synchronize()
+px = a.b*a.H*a.W
+for k, v in F_.kernel_timings().items():
+    v = v[1:]
+    ms = sum(v)/len(v)
+    by = {'stv_photo_fwd': (12 + 12*a.n + 12*a.n*a.S + 4*a.S)*px, 'stv_photo_bwd': (12 + 12*a.n + 12*a.n*a.S + 8*a.S)*px}.get(k)
+    print(f'{k:16s} {ms*1e3:9.1f} us' + (f'  {by/1e9/(ms/1e3):8.1f} GB/s algorithmic' if by else ''))
+print('loss', l1.item(), l2.item())
