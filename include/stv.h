@@ -125,6 +125,26 @@ int stv_smooth_bwd(const stv_smooth_cfg* cfg, const float* const* disp, const fl
                    float* const* g_disp, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * ConvNeXt block, memory-bound half (channels-last (N,H,W,C) fp32): replaces the ATen/cuDNN ops launched by the timm
+ * ConvNeXt encoder the reference builds at src/networks/depth.py:97 (timm==0.6.12, third-party): `conv_dw` (depthwise 7x7,
+ * padding 3) and `norm` (LayerNorm over C, eps 1e-6) of every ConvNeXtBlock, plus their backward.
+ * w is the depthwise filter (C,1,7,7) contiguous = (C,49).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* y = dwconv7x7(x; w) [+ bias] [+ res]. flip != 0 applies the 180-degree rotated filter (= data gradient of the conv). */
+int stv_dwconv7_fwd(int N, int H, int W, int C, const float* x, const float* w, const float* bias, const float* res,
+                    float* y, int flip, void* stream);
+size_t stv_dwconv7_wgrad_workspace_bytes(int N, int H, int W, int C);
+/* gw (C,49) = d/dw, gb (C) = d/dbias (nullable), from the layer input x and the output gradient gy. */
+int stv_dwconv7_wgrad(int N, int H, int W, int C, const float* x, const float* gy, float* gw, float* gb, void* ws,
+                      size_t ws_bytes, void* stream);
+/* Row-wise LayerNorm of a (P, C) matrix; mean / rstd (P) are saved for the backward. */
+int stv_layernorm_fwd(long long P, int C, const float* x, const float* gamma, const float* beta, float eps, float* y,
+                      float* mean, float* rstd, void* stream);
+size_t stv_layernorm_bwd_workspace_bytes(long long P, int C);
+int stv_layernorm_bwd(long long P, int C, const float* dy, const float* x, const float* mean, const float* rstd,
+                      const float* gamma, float* dx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Optimiser: replaces torch.optim.AdamW(foreach) built by timm create_optimizer_v2 (src/tools/parsers.py:205-243)
  * on one flat fp32 parameter/gradient buffer. `wd` is a per-element weight-decay mask value selector: elements in
  * [0, n_decay) use `weight_decay`, elements in [n_decay, n) use 0 (timm excludes biases / 1-D params).

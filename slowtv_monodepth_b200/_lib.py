@@ -52,6 +52,12 @@ _SIGNATURES = {
     'stv_smooth_workspace_bytes': (C.c_size_t, [C.POINTER(SmoothCfg)]),
     'stv_smooth_fwd': (C.c_int, [C.POINTER(SmoothCfg), _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     'stv_smooth_bwd': (C.c_int, [C.POINTER(SmoothCfg), _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'stv_dwconv7_fwd': (C.c_int, [C.c_int]*4 + [_P]*5 + [C.c_int, _P]),
+    'stv_dwconv7_wgrad_workspace_bytes': (C.c_size_t, [C.c_int]*4),
+    'stv_dwconv7_wgrad': (C.c_int, [C.c_int]*4 + [_P]*5 + [C.c_size_t, _P]),
+    'stv_layernorm_fwd': (C.c_int, [C.c_longlong, C.c_int, _P, _P, _P, C.c_float, _P, _P, _P, _P]),
+    'stv_layernorm_bwd_workspace_bytes': (C.c_size_t, [C.c_longlong, C.c_int]),
+    'stv_layernorm_bwd': (C.c_int, [C.c_longlong, C.c_int] + [_P]*9 + [C.c_size_t, _P]),
     'stv_adamw_step': (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_size_t] + [C.c_float]*6 + [C.c_int, _P]),
 }
 

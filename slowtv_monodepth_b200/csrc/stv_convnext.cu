@@ -1,0 +1,288 @@
+// ConvNeXt block, memory-bound half: depthwise 7x7 convolution (forward / data-gradient / weight-gradient) and LayerNorm
+// over channels (forward / backward), all on channels-last (N, H, W, C) fp32 tensors.
+//
+// Why hand-written: the library path for the depthwise weight gradient in channels-last launches one scalar wgrad engine
+// plus two layout transposes PER CHANNEL GROUP (289 + 581 launches, ~30 ms of a 59 ms training step at 8x384x640 on B200;
+// profiles/round1_step_breakdown.md). These kernels are HBM/L2-bound by construction: every thread owns one channel, a warp
+// reads 128 contiguous bytes of a pixel, and the 7x7 window slides through registers.
+//
+// Reference call sites: the timm ConvNeXt encoder built at src/networks/depth.py:97 (third-party, see encoders.py).
+#include "stv_common.cuh"
+
+namespace stv {
+
+constexpr int DW_L = 8;    // output pixels along x per thread (forward / dgrad)
+constexpr int DW_RY = 4;   // output rows per block (weights stay in registers across them)
+
+// y[n,yy,xx,c] = (bias[c]) + sum_{ky,kx} w[c][ky][kx] * x[n, yy+ky-3, xx+kx-3, c]   (zero padding)  [+ res[n,yy,xx,c]]
+// FLIP = true uses w[c][6-ky][6-kx]: the data gradient of the same convolution.
+constexpr int DW_CB = 128;  // channels (= threads) per block; blockIdx.x = x_tile * n_channel_blocks + channel_block
+
+template <bool FLIP>
+__global__ void __launch_bounds__(DW_CB) dwconv7_kernel(int H, int W, int C, int ncb, const float* __restrict__ x,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        const float* __restrict__ res, float* __restrict__ y) {
+    const int c = (blockIdx.x % ncb)*DW_CB + threadIdx.x;
+    if (c >= C) return;
+    const int x0 = (blockIdx.x/ncb)*DW_L, y0 = blockIdx.y*DW_RY, n = blockIdx.z;
+    float wr[49];
+#pragma unroll
+    for (int t = 0; t < 49; ++t) wr[t] = __ldg(w + (size_t)c*49 + (FLIP ? 48 - t : t));
+    const float b = bias ? __ldg(bias + c) : 0.f;
+    const size_t img = (size_t)n*H*W*C;
+    for (int r = 0; r < DW_RY; ++r) {
+        const int yo = y0 + r;
+        if (yo >= H) break;
+        float acc[DW_L];
+#pragma unroll
+        for (int j = 0; j < DW_L; ++j) acc[j] = b;
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+            const int yy = yo + ky - 3;
+            if (yy < 0 || yy >= H) continue;
+            const float* row = x + img + (size_t)yy*W*C + c;
+#pragma unroll
+            for (int q = 0; q < DW_L + 6; ++q) {
+                const int xx = x0 + q - 3;
+                const float v = (xx >= 0 && xx < W) ? __ldg(row + (size_t)xx*C) : 0.f;
+#pragma unroll
+                for (int j = 0; j < DW_L; ++j) {
+                    const int kx = q - j;
+                    if (kx >= 0 && kx < 7) acc[j] = fmaf(wr[ky*7 + kx], v, acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DW_L; ++j) {
+            const int xx = x0 + j;
+            if (xx < W) {
+                const size_t o = img + ((size_t)yo*W + xx)*C + c;
+                y[o] = res ? acc[j] + __ldg(res + o) : acc[j];
+            }
+        }
+    }
+}
+
+// Weight gradient: gw[c][ky][kx] = sum_{n,y,x} gy[n,y,x,c] * x[n,y+ky-3,x+kx-3,c];  gb[c] = sum gy.
+// Each block owns a (WG_RY rows x WG_XW columns) patch of one image; a thread owns one channel and slides a 7x7 register
+// window of x along the row. Per-block partials go to the workspace; a second kernel adds them in a fixed order.
+constexpr int WG_RY = 4, WG_XW = 32;
+
+__global__ void __launch_bounds__(DW_CB) dwconv7_wgrad_kernel(int H, int W, int C, int ncb, const float* __restrict__ x,
+                                                              const float* __restrict__ gy, float* __restrict__ partial) {
+    const int c = (blockIdx.x % ncb)*DW_CB + threadIdx.x;
+    if (c >= C) return;
+    const int xb = (blockIdx.x/ncb)*WG_XW, yb = blockIdx.y*WG_RY, n = blockIdx.z;
+    const size_t img = (size_t)n*H*W*C;
+    float acc[49], gsum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 49; ++t) acc[t] = 0.f;
+    for (int r = 0; r < WG_RY; ++r) {
+        const int yo = yb + r;
+        if (yo >= H) break;
+        float win[7][7];  // win[ky][kx] = x[yo+ky-3][xo+kx-3]
+        auto ld = [&](int yy, int xx) -> float {
+            return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + img + ((size_t)yy*W + xx)*C + c) : 0.f;
+        };
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+            for (int kx = 1; kx < 7; ++kx) win[ky][kx] = ld(yo + ky - 3, xb + kx - 4);  // columns for xo = xb - 1
+        const int xe = min(xb + WG_XW, W);
+        for (int xo = xb; xo < xe; ++xo) {
+#pragma unroll
+            for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+                for (int kx = 0; kx < 6; ++kx) win[ky][kx] = win[ky][kx + 1];
+                win[ky][6] = ld(yo + ky - 3, xo + 3);
+            }
+            const float g = __ldg(gy + img + ((size_t)yo*W + xo)*C + c);
+            gsum += g;
+#pragma unroll
+            for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 7; ++kx) acc[ky*7 + kx] = fmaf(g, win[ky][kx], acc[ky*7 + kx]);
+        }
+    }
+    const size_t blk = ((size_t)blockIdx.z*gridDim.y + blockIdx.y)*(gridDim.x/ncb) + blockIdx.x/ncb;  // spatial patch index
+    float* out = partial + blk*50*C;
+#pragma unroll
+    for (int t = 0; t < 49; ++t) out[(size_t)t*C + c] = acc[t];
+    out[(size_t)49*C + c] = gsum;
+}
+
+// out[c*49 + t] = sum_blk partial[blk][t][c];  gb[c] = sum_blk partial[blk][49][c]. One warp per (t, 32-channel group).
+__global__ void __launch_bounds__(256) dwconv7_wgrad_reduce_kernel(int C, int nblk, const float* __restrict__ partial,
+                                                                   float* __restrict__ gw, float* __restrict__ gb) {
+    // thread -> (t, c); blocks of 256 threads over 50*C entries; fixed-order loop over nblk (coalesced across c).
+    const int e = blockIdx.x*blockDim.x + threadIdx.x;
+    if (e >= 50*C) return;
+    const int t = e/C, c = e - t*C;
+    double a = 0.0;
+    for (int b = 0; b < nblk; ++b) a += (double)partial[(size_t)b*50*C + e];
+    if (t < 49) gw[(size_t)c*49 + t] = (float)a;
+    else if (gb) gb[c] = (float)a;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LayerNorm over the last (channel) axis of a (P, C) matrix. One warp per row; rows are re-read from L1 between passes.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(long long P, int C, float eps, const float* __restrict__ x,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* __restrict__ y, float* __restrict__ mean,
+                                                            float* __restrict__ rstd) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= P) return;
+    const float* xr = x + row*C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    const float mu = warp_sum(s)/(float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = xr[c] - mu; v = fmaf(d, d, v); }
+    const float rs = rsqrtf(warp_sum(v)/(float)C + eps);
+    float* yr = y + row*C;
+    for (int c = lane; c < C; c += 32) yr[c] = fmaf((xr[c] - mu)*rs, __ldg(gamma + c), __ldg(beta + c));
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+}
+
+// dx = rstd * (dy*gamma - mean_c(dy*gamma) - xhat * mean_c(dy*gamma*xhat));  dgamma = sum_rows dy*xhat;  dbeta = sum_rows dy.
+// Each warp walks LN_ROWS consecutive rows and keeps its lanes' dgamma/dbeta slices in registers (C <= 32*LN_MAXPL).
+constexpr int LN_ROWS = 16, LN_MAXPL = 32;
+
+template <int PL>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(long long P, int C, const float* __restrict__ dy,
+                                                            const float* __restrict__ x, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                            float* __restrict__ dx, float* __restrict__ partial) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long row0 = ((long long)blockIdx.x*nw + wid)*LN_ROWS;
+    float dg[PL], db[PL], g[PL];
+#pragma unroll
+    for (int i = 0; i < PL; ++i) { dg[i] = db[i] = 0.f; const int c = lane + 32*i; g[i] = c < C ? __ldg(gamma + c) : 0.f; }
+    for (int r = 0; r < LN_ROWS; ++r) {
+        const long long row = row0 + r;
+        if (row >= P) break;
+        const float mu = mean[row], rs = rstd[row];
+        const float* xr = x + row*C;
+        const float* dr = dy + row*C;
+        float xh[PL], dyv[PL], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < PL; ++i) {
+            const int c = lane + 32*i;
+            const bool ok = c < C;
+            xh[i] = ok ? (xr[c] - mu)*rs : 0.f;
+            dyv[i] = ok ? dr[c] : 0.f;
+            const float t = dyv[i]*g[i];
+            s1 += t; s2 = fmaf(t, xh[i], s2);
+            dg[i] = fmaf(dyv[i], xh[i], dg[i]); db[i] += dyv[i];
+        }
+        s1 = warp_sum(s1)/(float)C; s2 = warp_sum(s2)/(float)C;
+        float* dxr = dx + row*C;
+#pragma unroll
+        for (int i = 0; i < PL; ++i) {
+            const int c = lane + 32*i;
+            if (c < C) dxr[c] = rs*(dyv[i]*g[i] - s1 - xh[i]*s2);
+        }
+    }
+    // Per-warp partials: partial[(blk*nw + wid)][2][C]
+    float* out = partial + ((size_t)blockIdx.x*nw + wid)*2*C;
+#pragma unroll
+    for (int i = 0; i < PL; ++i) {
+        const int c = lane + 32*i;
+        if (c < C) { out[c] = dg[i]; out[C + c] = db[i]; }
+    }
+}
+
+__global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(int C, int nrows, const float* __restrict__ partial,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int e = blockIdx.x*blockDim.x + threadIdx.x;
+    if (e >= 2*C) return;
+    double a = 0.0;
+    for (int r = 0; r < nrows; ++r) a += (double)partial[(size_t)r*2*C + e];
+    if (e < C) dgamma[e] = (float)a; else dbeta[e - C] = (float)a;
+}
+
+}  // namespace stv
+
+using namespace stv;
+
+static int round32(int c) { return (c + 31)/32*32; }
+
+extern "C" int stv_dwconv7_fwd(int N, int H, int W, int C, const float* x, const float* w, const float* bias, const float* res,
+                               float* y, int flip, void* stream) {
+    STV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 1024, "stv_dwconv7_fwd: bad shape (N=%d H=%d W=%d C=%d; C <= 1024)", N, H, W, C);
+    STV_REQUIRE(N <= 65535 && (H + DW_RY - 1)/DW_RY <= 65535, "stv_dwconv7_fwd: grid too large");
+    STV_REQUIRE(x && w && y, "stv_dwconv7_fwd: NULL pointer");
+    const int ncb = (C + DW_CB - 1)/DW_CB, nt = C < DW_CB ? round32(C) : DW_CB;
+    dim3 grid(((W + DW_L - 1)/DW_L)*ncb, (H + DW_RY - 1)/DW_RY, N);
+    if (flip) dwconv7_kernel<true><<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, x, w, bias, res, y);
+    else dwconv7_kernel<false><<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, x, w, bias, res, y);
+    count_launch();
+    return check_launch("dwconv7_kernel");
+}
+
+extern "C" size_t stv_dwconv7_wgrad_workspace_bytes(int N, int H, int W, int C) {
+    if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
+    return (size_t)N*((H + WG_RY - 1)/WG_RY)*((W + WG_XW - 1)/WG_XW)*50*C*sizeof(float);
+}
+
+extern "C" int stv_dwconv7_wgrad(int N, int H, int W, int C, const float* x, const float* gy, float* gw, float* gb, void* ws,
+                                 size_t ws_bytes, void* stream) {
+    STV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 1024, "stv_dwconv7_wgrad: bad shape");
+    STV_REQUIRE(N <= 65535 && (H + WG_RY - 1)/WG_RY <= 65535, "stv_dwconv7_wgrad: grid too large");
+    STV_REQUIRE(x && gy && gw, "stv_dwconv7_wgrad: NULL pointer");
+    const size_t need = stv_dwconv7_wgrad_workspace_bytes(N, H, W, C);
+    if (!ws || ws_bytes < need) { set_error("stv_dwconv7_wgrad: workspace too small (%zu < %zu bytes)", ws_bytes, need); return STV_E_WORKSPACE; }
+    const int ncb = (C + DW_CB - 1)/DW_CB, nt = C < DW_CB ? round32(C) : DW_CB;
+    dim3 grid(((W + WG_XW - 1)/WG_XW)*ncb, (H + WG_RY - 1)/WG_RY, N);
+    dwconv7_wgrad_kernel<<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, x, gy, (float*)ws);
+    count_launch();
+    if (int rc = check_launch("dwconv7_wgrad_kernel")) return rc;
+    const int nblk = (grid.x/ncb)*grid.y*grid.z;
+    dwconv7_wgrad_reduce_kernel<<<(50*C + 255)/256, 256, 0, (cudaStream_t)stream>>>(C, nblk, (const float*)ws, gw, gb);
+    count_launch();
+    return check_launch("dwconv7_wgrad_reduce_kernel");
+}
+
+extern "C" int stv_layernorm_fwd(long long P, int C, const float* x, const float* gamma, const float* beta, float eps, float* y,
+                                 float* mean, float* rstd, void* stream) {
+    STV_REQUIRE(P > 0 && C > 0, "stv_layernorm_fwd: bad shape");
+    STV_REQUIRE(x && gamma && beta && y && mean && rstd, "stv_layernorm_fwd: NULL pointer");
+    const long long blocks = (P + 7)/8;
+    STV_REQUIRE(blocks < (1ll << 31), "stv_layernorm_fwd: too many rows");
+    layernorm_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P, C, eps, x, gamma, beta, y, mean, rstd);
+    count_launch();
+    return check_launch("layernorm_fwd_kernel");
+}
+
+static long long ln_bwd_warps(long long P) { return (P + LN_ROWS - 1)/LN_ROWS; }
+
+extern "C" size_t stv_layernorm_bwd_workspace_bytes(long long P, int C) {
+    if (P <= 0 || C <= 0) return 0;
+    const long long blocks = (ln_bwd_warps(P) + 7)/8;
+    return (size_t)blocks*8*2*C*sizeof(float);
+}
+
+extern "C" int stv_layernorm_bwd(long long P, int C, const float* dy, const float* x, const float* mean, const float* rstd,
+                                 const float* gamma, float* dx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+                                 void* stream) {
+    STV_REQUIRE(P > 0 && C > 0 && C <= 32*LN_MAXPL, "stv_layernorm_bwd: bad shape (C <= %d)", 32*LN_MAXPL);
+    STV_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "stv_layernorm_bwd: NULL pointer");
+    const size_t need = stv_layernorm_bwd_workspace_bytes(P, C);
+    if (!ws || ws_bytes < need) { set_error("stv_layernorm_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, need); return STV_E_WORKSPACE; }
+    const long long blocks = (ln_bwd_warps(P) + 7)/8;
+    STV_REQUIRE(blocks < (1ll << 31), "stv_layernorm_bwd: too many rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    // Rows beyond P inside the last block write zero partials (their accumulators stay 0), so every slot is defined.
+    const int pl = (C + 31)/32;
+#define STV_LN_BWD(PL) layernorm_bwd_kernel<PL><<<(unsigned)blocks, 256, 0, st>>>(P, C, dy, x, mean, rstd, gamma, dx, (float*)ws)
+    if (pl <= 3) STV_LN_BWD(3); else if (pl <= 4) STV_LN_BWD(4); else if (pl <= 6) STV_LN_BWD(6); else if (pl <= 8) STV_LN_BWD(8);
+    else if (pl <= 12) STV_LN_BWD(12); else if (pl <= 16) STV_LN_BWD(16); else if (pl <= 24) STV_LN_BWD(24); else STV_LN_BWD(32);
+#undef STV_LN_BWD
+    count_launch();
+    if (int rc = check_launch("layernorm_bwd_kernel")) return rc;
+    layernorm_bwd_reduce_kernel<<<(2*C + 255)/256, 256, 0, st>>>(C, (int)(blocks*8), (const float*)ws, dgamma, dbeta);
+    count_launch();
+    return check_launch("layernorm_bwd_reduce_kernel");
+}

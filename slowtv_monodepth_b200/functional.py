@@ -12,7 +12,7 @@ from torch import Tensor
 
 from . import _lib as L
 
-__all__ = ['photo_loss', 'photo_error', 'smooth_loss', 'disp_to_depth', 'view_synth', 'adamw_step_']
+__all__ = ['photo_loss', 'photo_error', 'smooth_loss', 'disp_to_depth', 'view_synth', 'adamw_step_', 'dwconv7', 'layer_norm']
 
 
 # Optional per-call device timing of the fused loss kernels (bench.py's roofline figures): when enabled, a pair of CUDA
@@ -290,6 +290,83 @@ def view_synth(inp: Tensor, depth: Tensor, T: Tensor, K: Tensor, K_inv: Tensor |
     if T.shape != (B, 4, 4) or K.shape != (B, 4, 4): raise ValueError(f'Invalid T/K shape. ({tuple(T.shape)}, {tuple(K.shape)})')
     if K_inv is None: K_inv = torch.linalg.inv_ex(K)[0]
     return _ViewSynth.apply(_f32c(inp), _f32c(depth), _f32c(T), _f32c(K), _f32c(K_inv))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ConvNeXt block pieces (channels-last)
+# ---------------------------------------------------------------------------------------------------------------------
+class _DwConv7(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        L.require_cuda(x, w, b, what='dwconv7')
+        N, H, W, Cc = x.shape
+        with torch.cuda.device(x.device):
+            y = torch.empty_like(x)
+            L.check(L.lib().stv_dwconv7_fwd(N, H, W, Cc, L.ptr(x), L.ptr(w), L.ptr(b), None, L.ptr(y), 0, L.stream()), 'stv_dwconv7_fwd')
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        N, H, W, Cc = x.shape
+        gy = _f32c(gy)
+        lib, dev = L.lib(), x.device
+        gx = gw = gb = None
+        with torch.cuda.device(dev):
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                L.check(lib.stv_dwconv7_fwd(N, H, W, Cc, L.ptr(gy), L.ptr(w), None, None, L.ptr(gx), 1, L.stream()), 'stv_dwconv7_fwd(flip)')
+            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+                gw = torch.empty_like(w)
+                gb = torch.empty(Cc, dtype=torch.float32, device=dev) if ctx.has_bias else None
+                ws = _ws(lib.stv_dwconv7_wgrad_workspace_bytes(N, H, W, Cc), dev)
+                L.check(lib.stv_dwconv7_wgrad(N, H, W, Cc, L.ptr(x), L.ptr(gy), L.ptr(gw), L.ptr(gb), L.ptr(ws), ws.numel(), L.stream()),
+                        'stv_dwconv7_wgrad')
+        return gx, gw, gb
+
+
+def dwconv7(x: Tensor, weight: Tensor, bias: Tensor | None) -> Tensor:
+    """Depthwise 7x7 convolution, padding 3, on a channels-last (N,H,W,C) tensor; weight (C,1,7,7)."""
+    if x.ndim != 4 or weight.shape != (x.shape[-1], 1, 7, 7): raise ValueError(f'dwconv7: bad shapes {tuple(x.shape)}, {tuple(weight.shape)}')
+    return _DwConv7.apply(_f32c(x), _f32c(weight), _f32c(bias))
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps: float):
+        L.require_cuda(x, gamma, beta, what='layer_norm')
+        Cc = x.shape[-1]
+        P = x.numel()//Cc
+        with torch.cuda.device(x.device):
+            y = torch.empty_like(x)
+            mean = torch.empty(P, dtype=torch.float32, device=x.device)
+            rstd = torch.empty_like(mean)
+            L.check(L.lib().stv_layernorm_fwd(P, Cc, L.ptr(x), L.ptr(gamma), L.ptr(beta), eps, L.ptr(y), L.ptr(mean), L.ptr(rstd),
+                                              L.stream()), 'stv_layernorm_fwd')
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        Cc = x.shape[-1]
+        P = x.numel()//Cc
+        gy = _f32c(gy)
+        lib, dev = L.lib(), x.device
+        with torch.cuda.device(dev):
+            gx, gg, gb = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(gamma)
+            ws = _ws(lib.stv_layernorm_bwd_workspace_bytes(P, Cc), dev)
+            L.check(lib.stv_layernorm_bwd(P, Cc, L.ptr(gy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(gx), L.ptr(gg),
+                                          L.ptr(gb), L.ptr(ws), ws.numel(), L.stream()), 'stv_layernorm_bwd')
+        return gx, gg, gb, None
+
+
+def layer_norm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-6) -> Tensor:
+    """LayerNorm over the last axis of a contiguous tensor."""
+    if gamma.shape != (x.shape[-1],): raise ValueError(f'layer_norm: bad shapes {tuple(x.shape)}, {tuple(gamma.shape)}')
+    return _LayerNorm.apply(_f32c(x), _f32c(gamma), _f32c(beta), float(eps))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

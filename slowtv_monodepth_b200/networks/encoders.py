@@ -23,7 +23,24 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
+from .. import functional as F_
+
 __all__ = ['create_encoder', 'ResNetEncoder', 'ConvNeXtEncoder', 'FeatureInfo']
+
+
+def _stem_conv(x: Tensor, conv: nn.Conv2d) -> Tensor:
+    """First convolution of an encoder. Its 3 (depth) or 6 (pose) input channels disqualify every tensor-core implicit-GEMM
+    path (NHWC kernels need C % 4 == 0): the library falls back to a scalar fp32 engine whose weight-gradient alone costs
+    ~20 ms per step at 16x6x384x640. Zero-padding the input and weight channels to a multiple of 4 is arithmetically a no-op
+    (zeros contribute nothing forward; the padded weight slice is a temporary, so its gradient is dropped) and keeps the
+    parameter's shape/name as in the reference checkpoint."""
+    c = x.shape[1]
+    pad = (-c) % 4
+    if pad == 0: return conv(x)
+    x = F.pad(x, (0, 0, 0, 0, 0, pad))
+    w = F.pad(conv.weight, (0, 0, 0, 0, 0, pad))
+    return F.conv2d(x.contiguous(memory_format=torch.channels_last), w.contiguous(memory_format=torch.channels_last),
+                    conv.bias, conv.stride, conv.padding)
 
 
 class FeatureInfo:
@@ -79,7 +96,7 @@ class ResNetEncoder(nn.Module):
 
     def forward(self, x: Tensor) -> list[Tensor]:
         x = x.contiguous(memory_format=torch.channels_last)
-        f0 = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        f0 = F.relu(self.bn1(_stem_conv(x, self.conv1)), inplace=True)
         x = F.max_pool2d(f0, 3, 2, 1)
         feats = [f0]
         for i in range(1, 5):
@@ -119,7 +136,15 @@ class ConvNeXtBlock(nn.Module):
         self.gamma = nn.Parameter(1e-6*torch.ones(c))
 
     def forward(self, x: Tensor) -> Tensor:
-        y = self.conv_dw(x).permute(0, 2, 3, 1)  # NHWC view of a channels-last tensor: no copy
+        if x.is_cuda:
+            # libstv kernels on the channels-last buffer: depthwise 7x7 (fwd / dgrad / wgrad) and LayerNorm (fwd / bwd).
+            xl = x.permute(0, 2, 3, 1)  # NHWC view of a channels-last tensor: no copy
+            y = F_.dwconv7(xl, self.conv_dw.weight, self.conv_dw.bias)
+            y = F_.layer_norm(y, self.norm.weight, self.norm.bias, self.norm.eps)
+            y = self.mlp(y)*self.gamma
+            return x + y.permute(0, 3, 1, 2)
+        # Host tensors (CPU-side naming / shape tests only): stock ATen ops, same arithmetic.
+        y = self.conv_dw(x).permute(0, 2, 3, 1)
         y = self.mlp(self.norm(y))*self.gamma
         return x + y.permute(0, 3, 1, 2)
 
@@ -154,7 +179,7 @@ class ConvNeXtEncoder(nn.Module):
 
     def forward(self, x: Tensor) -> list[Tensor]:
         x = x.contiguous(memory_format=torch.channels_last)
-        x = self.stem_1(self.stem_0(x))
+        x = self.stem_1(_stem_conv(x, self.stem_0))
         feats = []
         for i in range(4):
             x = getattr(self, f'stages_{i}')(x)

@@ -1,0 +1,81 @@
+"""GPU: network kernels (through the C ABI) and the networks built on them vs the oracle restatements (float64 on CPU).
+Convolutions / GEMMs run in TF32 on the tensor cores, like the reference (`matmul: high`, cfg/default.yaml:171), so whole-
+network comparisons use TF32-appropriate bounds; the fp32 kernels (depthwise conv, LayerNorm) are held to 1e-5."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('shape', [(2, 24, 40, 96), (1, 7, 9, 33), (2, 12, 20, 192), (1, 6, 10, 160)])
+def test_dwconv7_matches_oracle(shape):
+    from slowtv_monodepth_b200 import functional as F_
+    N, H, W, C = shape
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, H, W, C, generator=g, dtype=torch.float64)
+    w = torch.randn(C, 1, 7, 7, generator=g, dtype=torch.float64)*0.2
+    b = torch.randn(C, generator=g, dtype=torch.float64)
+    gy = torch.randn(N, H, W, C, generator=g, dtype=torch.float64)
+
+    xr, wr, br = (t.clone().requires_grad_() for t in (x, w, b))
+    yr = F.conv2d(xr.permute(0, 3, 1, 2), wr, br, padding=3, groups=C).permute(0, 2, 3, 1)
+    yr.backward(gy)
+    xc, wc, bc = (t.float().cuda().requires_grad_() for t in (x, w, b))
+    yc = F_.dwconv7(xc, wc, bc)
+    yc.backward(gy.float().cuda())
+    assert U.rel(yc, yr) < 1e-5
+    assert U.rel(xc.grad, xr.grad) < 1e-5 and U.rel(wc.grad, wr.grad) < 1e-5 and U.rel(bc.grad, br.grad) < 1e-5
+
+
+@pytest.mark.parametrize('P,C', [(100, 96), (37, 33), (64, 768), (50, 1024), (9, 160)])
+def test_layernorm_matches_oracle(P, C):
+    from slowtv_monodepth_b200 import functional as F_
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(P, C, generator=g, dtype=torch.float64)*2 + 0.5
+    ga, be = torch.randn(C, generator=g, dtype=torch.float64), torch.randn(C, generator=g, dtype=torch.float64)
+    gy = torch.randn(P, C, generator=g, dtype=torch.float64)
+    xr, gr, br = (t.clone().requires_grad_() for t in (x, ga, be))
+    F.layer_norm(xr, (C,), gr, br, 1e-6).backward(gy)
+    xc, gc, bc = (t.float().cuda().requires_grad_() for t in (x, ga, be))
+    yc = F_.layer_norm(xc, gc, bc, 1e-6)
+    yc.backward(gy.float().cuda())
+    assert U.rel(yc, F.layer_norm(x, (C,), ga, be, 1e-6)) < 1e-5
+    assert U.rel(xc.grad, xr.grad) < 2e-5 and U.rel(gc.grad, gr.grad) < 1e-5 and U.rel(bc.grad, br.grad) < 1e-5
+
+
+@pytest.mark.parametrize('enc', ['resnet18', 'convnext_tiny'])
+def test_networks_match_oracle_networks(enc):
+    """Product DepthNet / PoseNet on the GPU vs the oracle's restatement in float64 on the CPU, shared weights.
+    fp32-exact matmuls here (TF32 off) isolate kernel/logic errors from TF32 rounding."""
+    from oracle import nets as ON
+    from slowtv_monodepth_b200.networks import DepthNet, PoseNet
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(2)
+        od, op = ON.DepthNet(enc).double(), ON.PoseNet('resnet18', learn_K=True).double()
+        with torch.no_grad():  # make the residual branches matter (layer-scale 1e-6 / zero-init BN would hide errors)
+            for n, p in od.named_parameters():
+                if n.endswith('gamma'): p.fill_(0.5)
+                if n.endswith('bn2.weight'): p.fill_(1.0)
+        pd, pp = DepthNet(enc, pretrained=False), PoseNet('resnet18', learn_K=True)
+        pd.load_state_dict({k: v.float() for k, v in od.state_dict().items()})
+        pp.load_state_dict({k: v.float() for k, v in op.state_dict().items()})
+        pd, pp = pd.cuda().train(), pp.cuda().train()
+        x = torch.randn(2, 3, 64, 96, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+        a, b = od(x), pd(x.float().cuda())
+        for s in range(4): assert U.rel(b['disp'][s], a['disp'][s]) < 2e-4, (s, U.rel(b['disp'][s], a['disp'][s]))
+        la = sum((v*v).sum() for v in a['disp'].values()); lb = sum((v*v).sum() for v in b['disp'].values())
+        ga = dict(zip([n for n, _ in od.named_parameters()], torch.autograd.grad(la, list(od.parameters()))))
+        gb = dict(zip([n for n, _ in pd.named_parameters()], torch.autograd.grad(lb, list(pd.parameters()))))
+        worst = max((U.rel(gb[n], ga[n]), n) for n in ga if ga[n].abs().max() > 1e-12)
+        assert worst[0] < 5e-3, worst
+        x6 = torch.randn(2, 6, 64, 96, generator=torch.Generator().manual_seed(4), dtype=torch.float64)
+        a, b = op(x6), pp(x6.float().cuda())
+        for k in ('R', 't', 'fs', 'cs'): assert U.rel(b[k], a[k]) < 1e-4, k
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
