@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(long long P, int C, 
 
 // dx = rstd * (dy*gamma - mean_c(dy*gamma) - xhat * mean_c(dy*gamma*xhat));  dgamma = sum_rows dy*xhat;  dbeta = sum_rows dy.
 // Each warp walks LN_ROWS consecutive rows and keeps its lanes' dgamma/dbeta slices in registers (C <= 32*LN_MAXPL).
-constexpr int LN_ROWS = 16, LN_MAXPL = 32;
+constexpr int LN_ROWS = 32, LN_MAXPL = 32;
 
 template <int PL>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(long long P, int C, const float* __restrict__ dy,
@@ -185,21 +185,34 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(long long P, int C, 
             if (c < C) dxr[c] = rs*(dyv[i]*g[i] - s1 - xh[i]*s2);
         }
     }
-    // Per-warp partials: partial[(blk*nw + wid)][2][C]
-    float* out = partial + ((size_t)blockIdx.x*nw + wid)*2*C;
+    // Block partial: the 8 warps are added in a fixed order through shared memory, one row [2][C] per block.
+    extern __shared__ float sred[];  // [nw][2*C]
 #pragma unroll
     for (int i = 0; i < PL; ++i) {
         const int c = lane + 32*i;
-        if (c < C) { out[c] = dg[i]; out[C + c] = db[i]; }
+        if (c < C) { sred[(size_t)wid*2*C + c] = dg[i]; sred[(size_t)wid*2*C + C + c] = db[i]; }
+    }
+    __syncthreads();
+    float* out = partial + (size_t)blockIdx.x*2*C;
+    for (int e = threadIdx.x; e < 2*C; e += blockDim.x) {
+        float a = 0.f;
+        for (int w2 = 0; w2 < nw; ++w2) a += sred[(size_t)w2*2*C + e];
+        out[e] = a;
     }
 }
 
-__global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(int C, int nrows, const float* __restrict__ partial,
-                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+__global__ void __launch_bounds__(64) layernorm_bwd_reduce_kernel(int C, int nrows, const float* __restrict__ partial,
+                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int e = blockIdx.x*blockDim.x + threadIdx.x;
     if (e >= 2*C) return;
-    double a = 0.0;
-    for (int r = 0; r < nrows; ++r) a += (double)partial[(size_t)r*2*C + e];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four independent chains (fixed association -> deterministic)
+    int r = 0;
+    for (; r + 3 < nrows; r += 4) {
+        a0 += (double)partial[(size_t)r*2*C + e]; a1 += (double)partial[(size_t)(r + 1)*2*C + e];
+        a2 += (double)partial[(size_t)(r + 2)*2*C + e]; a3 += (double)partial[(size_t)(r + 3)*2*C + e];
+    }
+    for (; r < nrows; ++r) a0 += (double)partial[(size_t)r*2*C + e];
+    const double a = (a0 + a1) + (a2 + a3);
     if (e < C) dgamma[e] = (float)a; else dbeta[e - C] = (float)a;
 }
 
@@ -261,7 +274,7 @@ static long long ln_bwd_warps(long long P) { return (P + LN_ROWS - 1)/LN_ROWS; }
 extern "C" size_t stv_layernorm_bwd_workspace_bytes(long long P, int C) {
     if (P <= 0 || C <= 0) return 0;
     const long long blocks = (ln_bwd_warps(P) + 7)/8;
-    return (size_t)blocks*8*2*C*sizeof(float);
+    return (size_t)blocks*2*C*sizeof(float);
 }
 
 extern "C" int stv_layernorm_bwd(long long P, int C, const float* dy, const float* x, const float* mean, const float* rstd,
@@ -276,13 +289,20 @@ extern "C" int stv_layernorm_bwd(long long P, int C, const float* dy, const floa
     cudaStream_t st = (cudaStream_t)stream;
     // Rows beyond P inside the last block write zero partials (their accumulators stay 0), so every slot is defined.
     const int pl = (C + 31)/32;
-#define STV_LN_BWD(PL) layernorm_bwd_kernel<PL><<<(unsigned)blocks, 256, 0, st>>>(P, C, dy, x, mean, rstd, gamma, dx, (float*)ws)
+    static bool attr_done = false;
+    if (!attr_done) {  // C > 768 needs more than the default 48 KB of dynamic shared memory for the block reduction
+        const int mx = 8*2*32*LN_MAXPL*(int)sizeof(float);
+        cudaFuncSetAttribute(layernorm_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(layernorm_bwd_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        attr_done = true;
+    }
+#define STV_LN_BWD(PL) layernorm_bwd_kernel<PL><<<(unsigned)blocks, 256, (size_t)8*2*C*sizeof(float), st>>>(P, C, dy, x, mean, rstd, gamma, dx, (float*)ws)
     if (pl <= 3) STV_LN_BWD(3); else if (pl <= 4) STV_LN_BWD(4); else if (pl <= 6) STV_LN_BWD(6); else if (pl <= 8) STV_LN_BWD(8);
     else if (pl <= 12) STV_LN_BWD(12); else if (pl <= 16) STV_LN_BWD(16); else if (pl <= 24) STV_LN_BWD(24); else STV_LN_BWD(32);
 #undef STV_LN_BWD
     count_launch();
     if (int rc = check_launch("layernorm_bwd_kernel")) return rc;
-    layernorm_bwd_reduce_kernel<<<(2*C + 255)/256, 256, 0, st>>>(C, (int)(blocks*8), (const float*)ws, dgamma, dbeta);
+    layernorm_bwd_reduce_kernel<<<(2*C + 63)/64, 64, 0, st>>>(C, (int)blocks, (const float*)ws, dgamma, dbeta);
     count_launch();
     return check_launch("layernorm_bwd_reduce_kernel");
 }
