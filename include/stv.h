@@ -145,6 +145,41 @@ int stv_layernorm_bwd(long long P, int C, const float* dy, const float* x, const
                       const float* gamma, float* dx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Tensor-core products of the network layers (tcgen05.mma kind::tf32 + TMA + TMEM; fp32 storage, TF32 multiply, fp32
+ * accumulate = the reference's `torch.set_float32_matmul_precision('high')`, src/core/trainer.py:30).
+ * Replaces the cuBLAS / cuDNN calls behind nn.Linear and 1x1 nn.Conv2d (forward, data gradient, weight gradient) of the
+ * timm encoders (src/networks/depth.py:97, pose.py:40) and the pose heads (src/networks/pose.py:46,75-106).
+ *
+ *   C[M,N] (+)= epilogue( sum_k A[m,k] * B[n,k] )
+ * a_mn = 0: A is stored row-major [M][lda] (k contiguous);  a_mn = 1: A is stored [K][lda] (m contiguous).
+ * b_mn = 0: B is stored row-major [N][ldb] (k contiguous);  b_mn = 1: B is stored [K][ldb] (n contiguous).
+ * Epilogue, in this order:  v = acc + bias[n];  aux[m,n] = v;  v = act(v);  v *= gamma[n];  v += res[m,n];
+ *                           v *= act'(dact_src[m,n]);  C[m,n] = v  (accumulate = 0)  or  C[m,n] += v  (atomic).
+ * `dact_src` holds the pre-activation for GELU and the activation OUTPUT for ReLU / ELU / sigmoid.
+ * aux / res / dact_src share C's leading dimension ldc. Alignment: every pointer 16 bytes; N, lda, ldb, ldc multiples of 4.
+ * split_k > 1 partitions the reduction over gridDim.z and requires accumulate = 1 into a pre-initialised C.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define STV_ACT_NONE 0
+#define STV_ACT_RELU 1
+#define STV_ACT_GELU 2    /* exact (erf) GELU, torch.nn.functional.gelu default */
+#define STV_ACT_ELU 3     /* alpha = 1 */
+#define STV_ACT_SIGMOID 4
+
+typedef struct {
+    const float* bias;     /* [N] or NULL */
+    float* aux;            /* [M][ldc] or NULL */
+    const float* gamma;    /* [N] or NULL */
+    const float* res;      /* [M][ldc] or NULL */
+    const float* dact_src; /* [M][ldc] or NULL */
+    int act;               /* STV_ACT_* applied forward */
+    int dact;              /* STV_ACT_* whose derivative multiplies the result when dact_src != NULL */
+    int accumulate;
+} stv_gemm_epi;
+
+int stv_gemm_tf32(int M, int N, int K, const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn,
+                  float* C, long long ldc, const stv_gemm_epi* epi, int split_k, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Optimiser: replaces torch.optim.AdamW(foreach) built by timm create_optimizer_v2 (src/tools/parsers.py:205-243)
  * on one flat fp32 parameter/gradient buffer. `wd` is a per-element weight-decay mask value selector: elements in
  * [0, n_decay) use `weight_decay`, elements in [n_decay, n) use 0 (timm excludes biases / 1-D params).

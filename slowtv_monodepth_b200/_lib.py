@@ -29,6 +29,14 @@ class PhotoCfg(C.Structure):
                 ('noise_seed', C.c_uint64), ('depth_stride_s', C.c_int64)]
 
 
+class GemmEpi(C.Structure):
+    _fields_ = [('bias', C.c_void_p), ('aux', C.c_void_p), ('gamma', C.c_void_p), ('res', C.c_void_p), ('dact_src', C.c_void_p),
+                ('act', C.c_int), ('dact', C.c_int), ('accumulate', C.c_int)]
+
+
+ACT = {None: 0, 'none': 0, 'relu': 1, 'gelu': 2, 'elu': 3, 'sigmoid': 4}
+
+
 class SmoothCfg(C.Structure):
     _fields_ = [('b', C.c_int), ('S', C.c_int), ('H', C.c_int), ('W', C.c_int),
                 ('h', C.c_int*MAX_SCALES), ('w', C.c_int*MAX_SCALES), ('scale_div', C.c_float*MAX_SCALES),
@@ -58,6 +66,8 @@ _SIGNATURES = {
     'stv_layernorm_fwd': (C.c_int, [C.c_longlong, C.c_int, _P, _P, _P, C.c_float, _P, _P, _P, _P]),
     'stv_layernorm_bwd_workspace_bytes': (C.c_size_t, [C.c_longlong, C.c_int]),
     'stv_layernorm_bwd': (C.c_int, [C.c_longlong, C.c_int] + [_P]*9 + [C.c_size_t, _P]),
+    'stv_gemm_tf32': (C.c_int, [C.c_int]*3 + [_P, C.c_longlong, C.c_int, _P, C.c_longlong, C.c_int, _P, C.c_longlong,
+                                C.POINTER(GemmEpi), C.c_int, _P]),
     'stv_adamw_step': (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_size_t] + [C.c_float]*6 + [C.c_int, _P]),
 }
 

@@ -1,0 +1,281 @@
+// TF32 tensor-core GEMM for the network layers (tcgen05.mma kind::tf32, fp32 operands straight from HBM via TMA, fp32
+// accumulators in TMEM) with fused epilogues. One kernel covers the forward, data-gradient and weight-gradient products of
+// every Linear / 1x1-convolution layer by choosing, per operand, whether the reduction index is the contiguous one in memory
+// ("K-major") or the strided one ("MN-major"):
+//
+//   C[M,N] (+)= epilogue( sum_k A[m,k] * B[n,k] )
+//     forward   Y  = X  W^T      A = X  (M x in, K-major)      B = W (out x in, K-major)
+//     dgrad     dX = dY W        A = dY (M x out, K-major)     B = W (out x in) read as MN-major (reduction over `out`)
+//     wgrad     dW = dY^T X      A = dY read MN-major          B = X read MN-major (reduction over the M pixels), split-K
+//
+// Reference numerics being matched: fp32 storage with TF32 matmuls (`torch.set_float32_matmul_precision('high')`,
+// src/core/trainer.py:30; cfg/default.yaml:171). Call sites replaced: the `nn.Linear` / 1x1 `nn.Conv2d` layers of the timm
+// encoders built at src/networks/depth.py:97 / pose.py:40 and of the pose heads (src/networks/pose.py:46,75-106).
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0    TMA producer: per 32-wide k-block, box loads of A and B slabs into a ring of smem stages (mbarrier expect_tx)
+//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases stages / signals the epilogue
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias / activation / layer-scale / residual /
+//             activation-backward -> 128-bit global stores, or red.global.add.v4 when accumulating (split-K, grad buffers)
+#include <mutex>
+
+#include "stv_common.cuh"
+#include "stv_tc.cuh"
+
+namespace stv {
+
+constexpr int GEMM_BM = 128, GEMM_BK = 32, GEMM_THREADS = 192, GEMM_MAX_STAGES = 8;
+constexpr int GEMM_A_BYTES = GEMM_BM*GEMM_BK*4;  // 16 KB per stage
+constexpr int SLAB_MN_BYTES = 32*128;            // MN-major slab: 32 k-rows x 128 B
+
+struct GemmParams {
+    int M, N, K;
+    int bn, stages, a_mn, b_mn;
+    int kb_total, kb_per_split;
+    float* C;
+    long long ldc;
+    stv_gemm_epi e;
+};
+
+__device__ __forceinline__ float act_fwd(int act, float x) {
+    switch (act) {
+        case STV_ACT_RELU: return fmaxf(x, 0.f);
+        case STV_ACT_GELU: return 0.5f*x*(1.f + erff(x*0.70710678118654752f));
+        case STV_ACT_ELU: return x > 0.f ? x : expm1f(x);
+        case STV_ACT_SIGMOID: return 1.f/(1.f + __expf(-x));
+        default: return x;
+    }
+}
+// Derivative of the activation. `s` is the saved tensor: the pre-activation for GELU, the OUTPUT for the others.
+__device__ __forceinline__ float act_bwd(int act, float s) {
+    switch (act) {
+        case STV_ACT_RELU: return s > 0.f ? 1.f : 0.f;
+        case STV_ACT_GELU: return 0.5f*(1.f + erff(s*0.70710678118654752f)) + s*0.3989422804014327f*__expf(-0.5f*s*s);
+        case STV_ACT_ELU: return s > 0.f ? 1.f : s + 1.f;
+        case STV_ACT_SIGMOID: return s*(1.f - s);
+        default: return 1.f;
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = tc::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);  // slabs need 1024-byte alignment (128 B swizzle atom)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b_bytes = p.bn*GEMM_BK*4;
+    const int stage_bytes = GEMM_A_BYTES + b_bytes;
+    uint64_t* full = (uint64_t*)(smem + (size_t)p.stages*stage_bytes);
+    uint64_t* empty = full + GEMM_MAX_STAGES;
+    uint64_t* tmem_full = empty + GEMM_MAX_STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+    const int m0 = blockIdx.x*GEMM_BM, n0 = blockIdx.y*p.bn;
+    const int kb0 = blockIdx.z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+    const uint32_t tmem_cols = p.bn <= 32 ? 32u : p.bn <= 64 ? 64u : p.bn <= 128 ? 128u : 256u;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        tc::mbar_init(tmem_full, 1);
+        tc::fence_barrier_init();
+    } else if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, tmem_cols);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it/p.stages) & 1u;
+                tc::mbar_wait(&empty[s], ph ^ 1u);
+                tc::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+                uint8_t* a = smem + (size_t)s*stage_bytes;
+                uint8_t* b = a + GEMM_A_BYTES;
+                const int k = kb*GEMM_BK;
+                if (!p.a_mn) tc::tma_load_2d(a, &tmA, &full[s], k, m0);
+                else
+                    for (int j = 0; j < GEMM_BM/32; ++j) tc::tma_load_2d(a + j*SLAB_MN_BYTES, &tmA, &full[s], m0 + 32*j, k);
+                if (!p.b_mn) tc::tma_load_2d(b, &tmB, &full[s], k, n0);
+                else
+                    for (int j = 0; j < p.bn/32; ++j) tc::tma_load_2d(b + j*SLAB_MN_BYTES, &tmB, &full[s], n0 + 32*j, k);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::umma_idesc_tf32(GEMM_BM, p.bn, p.a_mn != 0, p.b_mn != 0);
+            int it = 0;
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it/p.stages) & 1u;
+                tc::mbar_wait(&full[s], ph);
+                tc::tcgen05_fence_after();
+                const uint32_t a = tc::smem_u32(smem + (size_t)s*stage_bytes), b = a + GEMM_A_BYTES;
+#pragma unroll
+                for (int k8 = 0; k8 < GEMM_BK/8; ++k8) {
+                    const uint64_t da = p.a_mn ? tc::umma_desc_mnmajor(a, k8, SLAB_MN_BYTES) : tc::umma_desc_kmajor(a, k8);
+                    const uint64_t db = p.b_mn ? tc::umma_desc_mnmajor(b, k8, SLAB_MN_BYTES) : tc::umma_desc_kmajor(b, k8);
+                    tc::umma_tf32(tmem_base, da, db, idesc, (it > 0 || k8 > 0) ? 1u : 0u);
+                }
+                tc::umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+            }
+            tc::umma_commit(tmem_full);      // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;              // TMEM lane quarter this warp may read: lanes 32q .. 32q+31
+        const int row = m0 + q*32 + lane;
+        tc::mbar_wait(tmem_full, 0);
+        tc::tcgen05_fence_after();
+        const stv_gemm_epi& e = p.e;
+        const bool row_ok = row < p.M;
+        const size_t roff = (size_t)row*p.ldc;
+        for (int c = 0; c < p.bn; c += 32) {
+            uint32_t v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(q*32) << 16) + (uint32_t)c, v);
+            tc::tmem_ld_wait();
+            if (!row_ok) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = n0 + c + 4*j;
+                if (n >= p.N) break;
+                float4 r = make_float4(__uint_as_float(v[4*j]), __uint_as_float(v[4*j + 1]), __uint_as_float(v[4*j + 2]),
+                                       __uint_as_float(v[4*j + 3]));
+                if (e.bias) {
+                    const float4 bb = __ldg((const float4*)(e.bias + n));
+                    r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+                }
+                if (e.aux) *(float4*)(e.aux + roff + n) = r;
+                if (e.act) { r.x = act_fwd(e.act, r.x); r.y = act_fwd(e.act, r.y); r.z = act_fwd(e.act, r.z); r.w = act_fwd(e.act, r.w); }
+                if (e.gamma) {
+                    const float4 g = __ldg((const float4*)(e.gamma + n));
+                    r.x *= g.x; r.y *= g.y; r.z *= g.z; r.w *= g.w;
+                }
+                if (e.res) {
+                    const float4 s = __ldg((const float4*)(e.res + roff + n));
+                    r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
+                }
+                if (e.dact_src) {
+                    const float4 s = __ldg((const float4*)(e.dact_src + roff + n));
+                    r.x *= act_bwd(e.dact, s.x); r.y *= act_bwd(e.dact, s.y); r.z *= act_bwd(e.dact, s.z); r.w *= act_bwd(e.dact, s.w);
+                }
+                if (e.accumulate) tc::red_add_v4(p.C + roff + n, r.x, r.y, r.z, r.w);
+                else *(float4*)(p.C + roff + n) = r;
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    });
+    return fn;
+}
+
+// fp32 row-major matrix [rows][ld] with `cols` valid columns; box = {32 floats, box_rows}, zero OOB fill.
+// mn_major = 0: 128-byte swizzle (K-major slabs); 1: 128-byte swizzle with 32-byte atoms (MN-major tf32 slabs).
+int make_tmap_2d(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows, int mn_major) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the CUDA driver"); return STV_E_CUDA; }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld*4};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for a %lld x %lld matrix, ld %lld, box rows %d, base %p", (int)r, rows, cols, ld,
+                  box_rows, (const void*)base);
+        return STV_E_CUDA;
+    }
+    return STV_OK;
+}
+
+static int pick_bn(int N) {
+    // Largest tile width (multiple of 32, <= 256) that wastes the fewest columns; ties -> the wider tile.
+    int best = 32, best_cost = 1 << 30;
+    for (int bn = 256; bn >= 32; bn -= 32) {
+        const int tiles = (N + bn - 1)/bn, cost = tiles*bn;
+        if (cost < best_cost) { best = bn; best_cost = cost; }
+    }
+    return best;
+}
+
+}  // namespace stv
+
+using namespace stv;
+
+extern "C" int stv_gemm_tf32(int M, int N, int K, const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn,
+                             float* C, long long ldc, const stv_gemm_epi* epi, int split_k, void* stream) {
+    STV_REQUIRE(M > 0 && N > 0 && K > 0, "stv_gemm_tf32: empty problem (M=%d N=%d K=%d)", M, N, K);
+    STV_REQUIRE(A && B && C, "stv_gemm_tf32: null operand");
+    STV_REQUIRE(N % 4 == 0 && ldc % 4 == 0 && ((uintptr_t)C & 15) == 0, "stv_gemm_tf32: N and ldc must be multiples of 4, C 16-byte aligned");
+    STV_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0,
+                "stv_gemm_tf32: lda/ldb must be multiples of 4 and A/B 16-byte aligned (TMA)");
+    STV_REQUIRE(lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K), "stv_gemm_tf32: leading dimension smaller than the row length");
+    stv_gemm_epi e = {};
+    if (epi) e = *epi;
+    STV_REQUIRE(split_k >= 1, "stv_gemm_tf32: split_k must be >= 1");
+    STV_REQUIRE(split_k == 1 || e.accumulate, "stv_gemm_tf32: split_k > 1 needs an accumulating epilogue");
+    STV_REQUIRE(!(e.accumulate && (e.aux || e.act || e.res)), "stv_gemm_tf32: accumulate cannot be combined with aux/act/res");
+    if (e.bias) STV_REQUIRE(((uintptr_t)e.bias & 15) == 0, "stv_gemm_tf32: bias must be 16-byte aligned");
+    if (e.gamma) STV_REQUIRE(((uintptr_t)e.gamma & 15) == 0, "stv_gemm_tf32: gamma must be 16-byte aligned");
+
+    GemmParams p = {};
+    p.M = M; p.N = N; p.K = K;
+    p.bn = pick_bn(N);
+    p.a_mn = a_mn != 0; p.b_mn = b_mn != 0;
+    p.kb_total = (K + GEMM_BK - 1)/GEMM_BK;
+    split_k = split_k < p.kb_total ? split_k : p.kb_total;
+    p.kb_per_split = (p.kb_total + split_k - 1)/split_k;
+    split_k = (p.kb_total + p.kb_per_split - 1)/p.kb_per_split;  // every split non-empty
+    p.C = C; p.ldc = ldc; p.e = e;
+    const int stage_bytes = GEMM_A_BYTES + p.bn*GEMM_BK*4;
+    const int budget = p.bn <= 128 ? 100*1024 : 200*1024;        // two resident CTAs per SM for the narrower tiles
+    int stages = budget/stage_bytes;
+    stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
+    stages = stages > p.kb_per_split ? (p.kb_per_split < 2 ? 2 : p.kb_per_split) : stages;
+    p.stages = stages;
+    const size_t smem = (size_t)stages*stage_bytes + 1024 /*alignment slack*/ + (2*GEMM_MAX_STAGES + 1)*8 + 16;
+
+    CUtensorMap tmA, tmB;
+    int rc = a_mn ? make_tmap_2d(&tmA, A, K, M, lda, 32, 1) : make_tmap_2d(&tmA, A, M, K, lda, GEMM_BM, 0);
+    if (rc) return rc;
+    rc = b_mn ? make_tmap_2d(&tmB, B, K, N, ldb, 32, 1) : make_tmap_2d(&tmB, B, N, K, ldb, p.bn, 0);
+    if (rc) return rc;
+
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024); });
+    if (attr_err != cudaSuccess) { set_error("stv_gemm_tf32: cudaFuncSetAttribute failed (%s)", cudaGetErrorString(attr_err)); return STV_E_CUDA; }
+
+    const dim3 grid((M + GEMM_BM - 1)/GEMM_BM, (N + p.bn - 1)/p.bn, split_k);
+    gemm_tf32_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+    count_launch();
+    return check_launch("stv_gemm_tf32");
+}

@@ -1,0 +1,166 @@
+// Blackwell (sm_100a) tensor-core plumbing for libstv: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (TMEM allocation,
+// UMMA shared-memory / instruction descriptors, tcgen05.mma kind::tf32, tcgen05.ld) as thin inline-PTX wrappers.
+//
+// Operand staging convention used by every GEMM-shaped kernel in this library ("slabs"):
+//   a slab is R rows x 128 bytes (32 fp32) of shared memory, 1024-byte aligned, swizzled as a TMA box {32 floats, R rows} is.
+//   * K-major operand  (reduction index contiguous in memory): rows = M/N index, the 128 bytes = 32 consecutive k.
+//       128-byte swizzle (16-byte chunk index XOR (row & 7); CU_TENSOR_MAP_SWIZZLE_128B; UMMA layout type SWIZZLE_128B).
+//       descriptor: SBO = 1024 B (next 8-row group), one MMA (K = 8 tf32 = 32 B) advances the start address by 32 B.
+//   * MN-major operand (M/N index contiguous in memory): rows = k index, the 128 bytes = 32 consecutive m (or n).
+//       For 32-bit (tf32) data the tensor core accepts ONE MN-major layout: "128B swizzle with a 32-byte atom"
+//       (32-byte chunk index XOR (row & 3); TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; UMMA layout type SWIZZLE_128B_BASE32B),
+//       whose swizzle atom is 4 k-rows deep. descriptor: LBO = slab size (next 32 m), SBO = 512 B (next 4 k);
+//       one MMA (K = 8) consumes 8 rows = advances the start address by 1024 B.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace stv { namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t globaltimer() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ---- mbarrier -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Blocking wait with a watchdog: a pipeline bug must surface as a trapped kernel (CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3FFu) == 0 && globaltimer() - t0 > 4000000000ull) __trap();
+    }
+}
+
+// ---- proxies / fences -----------------------------------------------------------------------------------------------
+// Makes generic-proxy shared-memory writes (st.shared / cp.async) visible to the async proxy (TMA, tcgen05.mma).
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMA ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+// 2-D tiled load: box origin (x = inner/contiguous coordinate, y = row) -> smem, completes `bar` by byte count.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+
+// ---- cp.async (generic-proxy gather path of the implicit-GEMM loaders) ----------------------------------------------
+// 16-byte copy; src_bytes = 0 writes zeros (padding) without touching `src`.
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- TMEM -----------------------------------------------------------------------------------------------------------
+// Whole-warp calls. ncols: power of two in [32, 512].
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread t of the warp receives lane (addr.lane + t), columns addr.col .. +31.
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(addr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(addr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- UMMA descriptors -----------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 | [46,48) version = 1
+//   [49,52) base offset = 0 (slabs are 1024 B aligned) | [61,64) layout type: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+// K-major slab (rows = m/n, 128-byte swizzle): the MMA at k-offset `k8` (units of 8 tf32 = 32 B) within the 32-wide k-block.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t slab, int k8) { return umma_desc(slab + k8*32, 16, 1024, 2); }
+// MN-major slabs (rows = k, 32-byte-atom swizzle), `slab_bytes` apart for consecutive groups of 32 m/n.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t slab, int k8, uint32_t slab_bytes) {
+    return umma_desc(slab + k8*1024, slab_bytes, 512, 1);
+}
+// Instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor bit layout):
+//   [4,6) D format = 1 (F32) | [7,10) A format = 2 (TF32) | [10,13) B format = 2 | [15] A MN-major | [16] B MN-major
+//   [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread on behalf of the CTA.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrives on `bar` once every previously issued tcgen05.mma of this thread has completed (implies fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- epilogue stores ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+}}  // namespace stv::tc

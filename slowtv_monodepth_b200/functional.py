@@ -12,7 +12,7 @@ from torch import Tensor
 
 from . import _lib as L
 
-__all__ = ['photo_loss', 'photo_error', 'smooth_loss', 'disp_to_depth', 'view_synth', 'adamw_step_', 'dwconv7', 'layer_norm']
+__all__ = ['photo_loss', 'photo_error', 'smooth_loss', 'disp_to_depth', 'view_synth', 'adamw_step_', 'dwconv7', 'layer_norm', 'gemm_tf32']
 
 
 # Optional per-call device timing of the fused loss kernels (bench.py's roofline figures): when enabled, a pair of CUDA
@@ -367,6 +367,88 @@ def layer_norm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-6) -> Ten
     """LayerNorm over the last axis of a contiguous tensor."""
     if gamma.shape != (x.shape[-1],): raise ValueError(f'layer_norm: bad shapes {tuple(x.shape)}, {tuple(gamma.shape)}')
     return _LayerNorm.apply(_f32c(x), _f32c(gamma), _f32c(beta), float(eps))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Tensor-core GEMM (tcgen05 kind::tf32) with fused epilogue
+# ---------------------------------------------------------------------------------------------------------------------
+def gemm_tf32(A: Tensor, B: Tensor, *, a_mn: bool = False, b_mn: bool = False, out: Tensor | None = None, bias: Tensor | None = None,
+              act: str | None = None, aux: Tensor | None = None, gamma: Tensor | None = None, res: Tensor | None = None,
+              dact: str | None = None, dact_src: Tensor | None = None, accumulate: bool = False, split_k: int = 1) -> Tensor:
+    """C[M,N] (+)= epilogue(sum_k A[m,k] B[n,k]) on the tcgen05 tensor cores (include/stv.h: stv_gemm_tf32). No autograd.
+
+    A: (M,K) if not a_mn else (K,M);  B: (N,K) if not b_mn else (K,N); both 2-D with unit inner stride (row stride free).
+    out / aux / res / dact_src: (M,N), same row stride. Returns `out` (allocated when None)."""
+    L.require_cuda(A, B, out, bias, aux, gamma, res, dact_src, what='gemm_tf32')
+    for t in (A, B):
+        if t.ndim != 2 or t.stride(1) != 1:
+            raise ValueError(f'gemm_tf32: operands must be 2-D with unit inner stride, got {tuple(t.shape)} / {t.stride()}')
+    K, M = A.shape if a_mn else A.shape[::-1]
+    Kb, N = B.shape if b_mn else B.shape[::-1]
+    if K != Kb: raise ValueError(f'gemm_tf32: reduction sizes differ ({K} vs. {Kb})')
+    dev = A.device
+    with torch.cuda.device(dev):
+        if out is None:
+            if accumulate: raise ValueError('gemm_tf32: accumulate needs an existing `out`.')
+            out = torch.empty((M, N), dtype=torch.float32, device=dev)
+        if out.shape != (M, N) or out.stride(1) != 1: raise ValueError(f'gemm_tf32: bad output {tuple(out.shape)} / {out.stride()}')
+        for t in (aux, res, dact_src):
+            if t is not None and (t.shape != (M, N) or t.stride() != out.stride()):
+                raise ValueError('gemm_tf32: aux / res / dact_src must match the output shape and strides.')
+        for t in (bias, gamma):
+            if t is not None and (t.shape != (N,) or not t.is_contiguous()): raise ValueError('gemm_tf32: bias / gamma must be contiguous (N,).')
+        epi = L.GemmEpi(bias=L.ptr(bias), aux=L.ptr(aux), gamma=L.ptr(gamma), res=L.ptr(res), dact_src=L.ptr(dact_src),
+                        act=L.ACT[act], dact=L.ACT[dact], accumulate=int(accumulate))
+        with _timed('stv_gemm_tf32'):
+            L.check(L.lib().stv_gemm_tf32(M, N, K, L.ptr(A), A.stride(0), int(a_mn), L.ptr(B), B.stride(0), int(b_mn), L.ptr(out),
+                                          out.stride(0), C.byref(epi), int(split_k), L.stream()), 'stv_gemm_tf32')
+    return out
+
+
+def _split_k(out_rows: int, out_cols: int, k: int) -> int:
+    """Reduction splits for a weight-gradient product: enough CTAs for ~2 waves of 148 SMs, >= 4 k-blocks of 32 per split."""
+    tiles = ((out_rows + 127)//128)*((out_cols + 255)//256)
+    return max(1, min((2*148 + tiles - 1)//tiles, k//128))
+
+
+class _ConvNeXtMlp(torch.autograd.Function):
+    """out = res + gamma * (GELU(x W1^T + b1) W2^T + b2) on (M, C) rows — the pointwise half of a timm ConvNeXtBlock
+    (`mlp.fc1`, GELU, `mlp.fc2`, `gamma`, residual; the reference builds it at src/networks/depth.py:97).
+
+    Two tcgen05 GEMMs forward (bias+GELU and bias+layer-scale+residual fused into their epilogues) and four backward
+    (GELU' fused into the fc2 data gradient; both weight gradients as split-K products accumulated with red.global.add)."""
+    @staticmethod
+    def forward(ctx, x, res, w1, b1, w2, b2, gamma):
+        M, Cc = x.shape
+        z = torch.empty((M, w1.shape[0]), dtype=torch.float32, device=x.device)
+        h = torch.empty_like(z)
+        gemm_tf32(x, w1, bias=b1, act='gelu', aux=z, out=h)
+        out = gemm_tf32(h, w2, bias=b2, gamma=gamma, res=res)
+        ctx.save_for_backward(x, z, h, w1, w2, b2, gamma)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, z, h, w1, w2, b2, gamma = ctx.saved_tensors
+        g = _f32c(g)
+        M, Cc = x.shape
+        Hd = w1.shape[0]
+        w2g = w2*gamma[:, None]                                              # (C, 4C): layer-scale folded into fc2
+        dz = gemm_tf32(g, w2g, b_mn=True, dact='gelu', dact_src=z)           # (M, 4C) = (g W2g) * GELU'(z)
+        dx = gemm_tf32(dz, w1, b_mn=True) if ctx.needs_input_grad[0] else None
+        dw1 = torch.zeros_like(w1)
+        gemm_tf32(dz, x, a_mn=True, b_mn=True, out=dw1, accumulate=True, split_k=_split_k(Hd, Cc, M))
+        G = torch.zeros_like(w2)                                             # g^T h, before the layer-scale
+        gemm_tf32(g, h, a_mn=True, b_mn=True, out=G, accumulate=True, split_k=_split_k(Cc, Hd, M))
+        gs = g.sum(0)
+        return (dx, g if ctx.needs_input_grad[1] else None, dw1, dz.sum(0), G*gamma[:, None], gamma*gs, (w2*G).sum(1) + b2*gs)
+
+
+def convnext_mlp(x: Tensor, res: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, gamma: Tensor) -> Tensor:
+    """x, res: (M, C) contiguous rows (channels-last pixels); w1 (4C, C), w2 (C, 4C). -> (M, C)."""
+    if x.ndim != 2 or res.shape != x.shape or w1.shape[1] != x.shape[1] or w2.shape != w1.shape[::-1]:
+        raise ValueError(f'convnext_mlp: bad shapes {tuple(x.shape)}, {tuple(res.shape)}, {tuple(w1.shape)}, {tuple(w2.shape)}')
+    return _ConvNeXtMlp.apply(_f32c(x), _f32c(res), _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2), _f32c(gamma))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

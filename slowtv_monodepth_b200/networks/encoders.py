@@ -137,12 +137,16 @@ class ConvNeXtBlock(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         if x.is_cuda:
-            # libstv kernels on the channels-last buffer: depthwise 7x7 (fwd / dgrad / wgrad) and LayerNorm (fwd / bwd).
+            # libstv kernels on the channels-last buffer: depthwise 7x7 (fwd / dgrad / wgrad), LayerNorm (fwd / bwd) and the
+            # pointwise MLP as tcgen05 TF32 GEMMs with bias+GELU / bias+layer-scale+residual epilogues.
             xl = x.permute(0, 2, 3, 1)  # NHWC view of a channels-last tensor: no copy
+            if not xl.is_contiguous(): xl = xl.contiguous()
             y = F_.dwconv7(xl, self.conv_dw.weight, self.conv_dw.bias)
             y = F_.layer_norm(y, self.norm.weight, self.norm.bias, self.norm.eps)
-            y = self.mlp(y)*self.gamma
-            return x + y.permute(0, 3, 1, 2)
+            c = xl.shape[-1]
+            out = F_.convnext_mlp(y.view(-1, c), xl.view(-1, c), self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight,
+                                  self.mlp.fc2.bias, self.gamma)
+            return out.view(xl.shape).permute(0, 3, 1, 2)
         # Host tensors (CPU-side naming / shape tests only): stock ATen ops, same arithmetic.
         y = self.conv_dw(x).permute(0, 2, 3, 1)
         y = self.mlp(self.norm(y))*self.gamma

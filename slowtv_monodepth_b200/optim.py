@@ -26,10 +26,13 @@ class FlatAdamW:
         if not named: raise ValueError('No trainable parameters.')
         no_decay = lambda n, p: p.ndim <= 1 or n.endswith('.bias')  # timm `param_groups_weight_decay`
         self.params = [p for n, p in named if not no_decay(n, p)] + [p for n, p in named if no_decay(n, p)]
-        self.n_decay = sum(p.numel() for n, p in named if not no_decay(n, p))
         dev = self.params[0].device
-        total = sum(p.numel() for p in self.params)
-        self.flat = torch.empty(total, dtype=torch.float32, device=dev)
+        # Every parameter starts on a 16-byte boundary (TMA / 128-bit loads read weights and biases in place); the decayed
+        # block is padded as a whole so that [0, n_decay) stays one contiguous range. Padding elements stay zero.
+        al = lambda n: (n + 3)//4*4
+        self.n_decay = sum(al(p.numel()) for n, p in named if not no_decay(n, p))
+        total = sum(al(p.numel()) for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
@@ -47,7 +50,7 @@ class FlatAdamW:
             view(self.flat).copy_(p.data)
             p.data = view(self.flat)
             p.grad = view(self.grad)
-            off += n
+            off += al(n)
         self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
         self.step_count = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
