@@ -180,6 +180,44 @@ int stv_gemm_tf32(int M, int N, int K, const float* A, long long lda, int a_mn, 
                   float* C, long long ldc, const stv_gemm_epi* epi, int split_k, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Spatial convolutions as implicit GEMMs on the tcgen05 tensor cores (TF32 multiply, fp32 accumulate; activations fp32
+ * channels-last (N,H,W,C); filters (Cout,R,S,Cin) contiguous, i.e. a PyTorch channels-last (Cout,Cin,R,S) weight).
+ * Replaces the cuDNN calls behind every nn.Conv2d of the Monodepth decoder (src/networks/decoders/monodepth.py:51-89,
+ * utils.py:44-54: reflect-padded 3x3 + ELU / sigmoid, with the `F.interpolate(scale_factor=2, 'nearest')` and skip
+ * `torch.cat` of :76-79 fused into the operand gather), of the pose network (src/networks/pose.py:40,46,75-106) and of the
+ * timm encoder stems / down-sampling layers (src/networks/depth.py:97).
+ *
+ * The convolution input is the VIRTUAL tensor V = cat(src1', src2) along channels (C = C1 + C2), where src1' is src1 itself
+ * (up1 = 0) or its nearest x2 upsampling (up1 = 1: src1 is stored as (N, H/2, W/2, C1)); V is padded by `pad` with zeros or by
+ * reflection. It is never materialised. Output size P = (H + 2 pad - R)/stride + 1 (same for Q).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int N, H, W;   /* batch, height, width of the virtual input V */
+    int C1, C2;    /* channels of src1 / src2 (C2 = 0: single source); multiples of 4 */
+    int up1;       /* 1: src1 is stored at half resolution and nearest-upsampled x2 on the fly */
+    int Cout, R, S, stride, pad;
+    int reflect;   /* 0: zero padding; 1: reflection padding (nn.Conv2d(padding_mode='reflect')) */
+} stv_conv_geom;
+
+/* y (N,P,Q,Cout) = epilogue(conv(V, w)); the epilogue is the one of stv_gemm_tf32 (bias, activation, aux, ...; no accumulate). */
+int stv_conv_fprop(const stv_conv_geom* g, const float* src1, const float* src2, const float* w, float* y,
+                   const stv_gemm_epi* epi, void* stream);
+/* dv = d loss / d V given dy (N,P,Q,Cout); Cout % 4 == 0. With zero padding dv is (N,H,W,C); with reflection padding dv is
+ * produced on the PADDED grid (N, H+2pad, W+2pad, C) and stv_grad_pull folds the border back. */
+int stv_conv_dgrad(const stv_conv_geom* g, const float* dy, const float* w, float* dv, const stv_gemm_epi* epi, void* stream);
+/* dw (Cout,R,S,C) += dy^T im2col(V) (atomic accumulation: dw must be initialised); Cout % 4 == 0. split_k <= 0: automatic. */
+int stv_conv_wgrad(const stv_conv_geom* g, const float* src1, const float* src2, const float* dy, float* dw, int split_k,
+                   void* stream);
+/* dst (N,H,W,C) (+)= slice/fold/pool of src (N, H*pool + 2 pad, W*pool + 2 pad, Cs): channels [c_off, c_off + C), the
+ * reflection-padding border folded back onto the interior, and pool x pool (1 or 2) sum-pooling (adjoint of nearest x2). */
+int stv_grad_pull(int N, int H, int W, int C, const float* src, int Cs, int c_off, int pad, int pool, float* dst, int accumulate,
+                  void* stream);
+/* dz[m,c] = da[m,c] * act'(y[m,c]) (y = activation OUTPUT; pre-activation for GELU); dbias[c] += sum_m dz[m,c] (nullable). */
+int stv_act_bwd(long long M, int C, const float* da, const float* y, int act, float* dz, float* dbias, void* stream);
+/* out[c] += sum_m x[m*ld + c] */
+int stv_colsum(long long M, int C, long long ld, const float* x, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Optimiser: replaces torch.optim.AdamW(foreach) built by timm create_optimizer_v2 (src/tools/parsers.py:205-243)
  * on one flat fp32 parameter/gradient buffer. `wd` is a per-element weight-decay mask value selector: elements in
  * [0, n_decay) use `weight_decay`, elements in [n_decay, n) use 0 (timm excludes biases / 1-D params).

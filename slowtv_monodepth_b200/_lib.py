@@ -37,6 +37,10 @@ class GemmEpi(C.Structure):
 ACT = {None: 0, 'none': 0, 'relu': 1, 'gelu': 2, 'elu': 3, 'sigmoid': 4}
 
 
+class ConvGeom(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ('N', 'H', 'W', 'C1', 'C2', 'up1', 'Cout', 'R', 'S', 'stride', 'pad', 'reflect')]
+
+
 class SmoothCfg(C.Structure):
     _fields_ = [('b', C.c_int), ('S', C.c_int), ('H', C.c_int), ('W', C.c_int),
                 ('h', C.c_int*MAX_SCALES), ('w', C.c_int*MAX_SCALES), ('scale_div', C.c_float*MAX_SCALES),
@@ -68,6 +72,12 @@ _SIGNATURES = {
     'stv_layernorm_bwd': (C.c_int, [C.c_longlong, C.c_int] + [_P]*9 + [C.c_size_t, _P]),
     'stv_gemm_tf32': (C.c_int, [C.c_int]*3 + [_P, C.c_longlong, C.c_int, _P, C.c_longlong, C.c_int, _P, C.c_longlong,
                                 C.POINTER(GemmEpi), C.c_int, _P]),
+    'stv_conv_fprop': (C.c_int, [C.POINTER(ConvGeom), _P, _P, _P, _P, C.POINTER(GemmEpi), _P]),
+    'stv_conv_dgrad': (C.c_int, [C.POINTER(ConvGeom), _P, _P, _P, C.POINTER(GemmEpi), _P]),
+    'stv_conv_wgrad': (C.c_int, [C.POINTER(ConvGeom), _P, _P, _P, _P, C.c_int, _P]),
+    'stv_grad_pull': (C.c_int, [C.c_int]*4 + [_P] + [C.c_int]*4 + [_P, C.c_int, _P]),
+    'stv_act_bwd': (C.c_int, [C.c_longlong, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
+    'stv_colsum': (C.c_int, [C.c_longlong, C.c_int, C.c_longlong, _P, _P, _P]),
     'stv_adamw_step': (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_size_t] + [C.c_float]*6 + [C.c_int, _P]),
 }
 

@@ -21,6 +21,7 @@
 
 #include "stv_common.cuh"
 #include "stv_tc.cuh"
+#include "stv_epi.cuh"
 
 namespace stv {
 
@@ -36,26 +37,6 @@ struct GemmParams {
     long long ldc;
     stv_gemm_epi e;
 };
-
-__device__ __forceinline__ float act_fwd(int act, float x) {
-    switch (act) {
-        case STV_ACT_RELU: return fmaxf(x, 0.f);
-        case STV_ACT_GELU: return 0.5f*x*(1.f + erff(x*0.70710678118654752f));
-        case STV_ACT_ELU: return x > 0.f ? x : expm1f(x);
-        case STV_ACT_SIGMOID: return 1.f/(1.f + __expf(-x));
-        default: return x;
-    }
-}
-// Derivative of the activation. `s` is the saved tensor: the pre-activation for GELU, the OUTPUT for the others.
-__device__ __forceinline__ float act_bwd(int act, float s) {
-    switch (act) {
-        case STV_ACT_RELU: return s > 0.f ? 1.f : 0.f;
-        case STV_ACT_GELU: return 0.5f*(1.f + erff(s*0.70710678118654752f)) + s*0.3989422804014327f*__expf(-0.5f*s*s);
-        case STV_ACT_ELU: return s > 0.f ? 1.f : s + 1.f;
-        case STV_ACT_SIGMOID: return s*(1.f - s);
-        default: return 1.f;
-    }
-}
 
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -134,46 +115,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
     } else {
-        const int q = warp & 3;              // TMEM lane quarter this warp may read: lanes 32q .. 32q+31
-        const int row = m0 + q*32 + lane;
         tc::mbar_wait(tmem_full, 0);
         tc::tcgen05_fence_after();
-        const stv_gemm_epi& e = p.e;
-        const bool row_ok = row < p.M;
-        const size_t roff = (size_t)row*p.ldc;
-        for (int c = 0; c < p.bn; c += 32) {
-            uint32_t v[32];
-            tc::tmem_ld32(tmem_base + ((uint32_t)(q*32) << 16) + (uint32_t)c, v);
-            tc::tmem_ld_wait();
-            if (!row_ok) continue;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int n = n0 + c + 4*j;
-                if (n >= p.N) break;
-                float4 r = make_float4(__uint_as_float(v[4*j]), __uint_as_float(v[4*j + 1]), __uint_as_float(v[4*j + 2]),
-                                       __uint_as_float(v[4*j + 3]));
-                if (e.bias) {
-                    const float4 bb = __ldg((const float4*)(e.bias + n));
-                    r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
-                }
-                if (e.aux) *(float4*)(e.aux + roff + n) = r;
-                if (e.act) { r.x = act_fwd(e.act, r.x); r.y = act_fwd(e.act, r.y); r.z = act_fwd(e.act, r.z); r.w = act_fwd(e.act, r.w); }
-                if (e.gamma) {
-                    const float4 g = __ldg((const float4*)(e.gamma + n));
-                    r.x *= g.x; r.y *= g.y; r.z *= g.z; r.w *= g.w;
-                }
-                if (e.res) {
-                    const float4 s = __ldg((const float4*)(e.res + roff + n));
-                    r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
-                }
-                if (e.dact_src) {
-                    const float4 s = __ldg((const float4*)(e.dact_src + roff + n));
-                    r.x *= act_bwd(e.dact, s.x); r.y *= act_bwd(e.dact, s.y); r.z *= act_bwd(e.dact, s.z); r.w *= act_bwd(e.dact, s.w);
-                }
-                if (e.accumulate) tc::red_add_v4(p.C + roff + n, r.x, r.y, r.z, r.w);
-                else *(float4*)(p.C + roff + n) = r;
-            }
-        }
+        epilogue_tile(tmem_base, warp & 3, lane, m0, n0, p.bn, p.M, p.N, p.C, p.ldc, p.e);
     }
     tc::tcgen05_fence_before();
     __syncthreads();

@@ -405,6 +405,110 @@ def gemm_tf32(A: Tensor, B: Tensor, *, a_mn: bool = False, b_mn: bool = False, o
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Implicit-GEMM convolution (tcgen05) with fused upsample / concat / padding / bias / activation
+# ---------------------------------------------------------------------------------------------------------------------
+def _geom(src1: Tensor, src2: Tensor | None, w_phys: Tensor, up1: bool, stride: int, pad: int, reflect: bool) -> tuple[L.ConvGeom, int, int]:
+    N, h1, w1, C1 = src1.shape
+    H, W = (2*h1, 2*w1) if up1 else (h1, w1)
+    C2 = 0 if src2 is None else src2.shape[3]
+    if src2 is not None and src2.shape[:3] != (N, H, W): raise ValueError(f'conv2d_nhwc: skip tensor {tuple(src2.shape)} does not match {(N, H, W)}')
+    Cout, R, S, Cin = w_phys.shape
+    if Cin != C1 + C2: raise ValueError(f'conv2d_nhwc: filter expects {Cin} input channels, got {C1} + {C2}')
+    g = L.ConvGeom(N=N, H=H, W=W, C1=C1, C2=C2, up1=int(up1), Cout=Cout, R=R, S=S, stride=stride, pad=pad, reflect=int(reflect))
+    return g, (H + 2*pad - R)//stride + 1, (W + 2*pad - S)//stride + 1
+
+
+def act_bwd(dA: Tensor, y: Tensor, act: str | None, dbias: Tensor | None = None) -> Tensor:
+    """dZ = dA * act'(y) on (..., C) channels-last tensors; dbias (C) += column sums of dZ."""
+    Cc = y.shape[-1]
+    M = y.numel()//Cc
+    dA = _f32c(dA)
+    with torch.cuda.device(y.device):
+        dZ = torch.empty_like(y)
+        L.check(L.lib().stv_act_bwd(M, Cc, L.ptr(dA), L.ptr(y), L.ACT[act], L.ptr(dZ), L.ptr(dbias), L.stream()), 'stv_act_bwd')
+    return dZ
+
+
+def colsum(x: Tensor) -> Tensor:
+    """Column sums of a (..., C) contiguous tensor -> (C)."""
+    Cc = x.shape[-1]
+    with torch.cuda.device(x.device):
+        out = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+        L.check(L.lib().stv_colsum(x.numel()//Cc, Cc, Cc, L.ptr(x), L.ptr(out), L.stream()), 'stv_colsum')
+    return out
+
+
+def grad_pull(dv: Tensor, shape: tuple[int, int, int, int], c_off: int, pad: int, pool: int) -> Tensor:
+    """Gradient of one real source tensor (N,H,W,C) from the virtual-input gradient dv (N, H*pool+2pad, W*pool+2pad, Cs)."""
+    N, H, W, Cc = shape
+    with torch.cuda.device(dv.device):
+        dst = torch.empty(shape, dtype=torch.float32, device=dv.device)
+        L.check(L.lib().stv_grad_pull(N, H, W, Cc, L.ptr(dv), dv.shape[3], c_off, pad, pool, L.ptr(dst), 0, L.stream()), 'stv_grad_pull')
+    return dst
+
+
+class _Conv2dNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src1, src2, w, b, up1: bool, stride: int, pad: int, reflect: bool, act):
+        L.require_cuda(src1, src2, w, b, what='conv2d_nhwc')
+        w_phys = w.permute(0, 2, 3, 1).contiguous()  # (Cout,R,S,Cin): free for channels-last filters (the flat parameter buffer)
+        g, P, Q = _geom(src1, src2, w_phys, up1, stride, pad, reflect)
+        dev = src1.device
+        with torch.cuda.device(dev):
+            y = torch.empty((g.N, P, Q, g.Cout), dtype=torch.float32, device=dev)
+            epi = L.GemmEpi(bias=L.ptr(b), act=L.ACT[act])
+            with _timed('stv_conv_fprop'):
+                L.check(L.lib().stv_conv_fprop(C.byref(g), L.ptr(src1), L.ptr(src2), L.ptr(w_phys), L.ptr(y), C.byref(epi), L.stream()),
+                        'stv_conv_fprop')
+        ctx.save_for_backward(src1, src2, w_phys, y)
+        ctx.g, ctx.act, ctx.has_bias = g, act, b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dA):
+        src1, src2, w_phys, y = ctx.saved_tensors
+        g, act, lib, dev = ctx.g, ctx.act, L.lib(), y.device
+        Cout, Cin = g.Cout, g.C1 + g.C2
+        with torch.cuda.device(dev):
+            db = torch.zeros(Cout, dtype=torch.float32, device=dev) if ctx.has_bias else None
+            dZ = act_bwd(dA, y, act, db)
+            wq = w_phys
+            if Cout % 4:  # narrow heads (1-channel disparity): pad the output-channel axis to 4 for the TMA-fed operands
+                cp = (-Cout) % 4
+                dZ = torch.nn.functional.pad(dZ, (0, cp))
+                wq = torch.nn.functional.pad(w_phys, (0, 0, 0, 0, 0, 0, 0, cp))
+                g = L.ConvGeom.from_buffer_copy(g); g.Cout = Cout + cp
+            dw = None
+            if ctx.needs_input_grad[2]:
+                dw = torch.zeros_like(wq)
+                with _timed('stv_conv_wgrad'):
+                    L.check(lib.stv_conv_wgrad(C.byref(g), L.ptr(src1), L.ptr(src2), L.ptr(dZ), L.ptr(dw), 0, L.stream()), 'stv_conv_wgrad')
+                dw = dw[:Cout].permute(0, 3, 1, 2)
+            d1 = d2 = None
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+                pd = g.pad if g.reflect else 0
+                dv = torch.empty((g.N, g.H + 2*pd, g.W + 2*pd, Cin), dtype=torch.float32, device=dev)
+                with _timed('stv_conv_dgrad'):
+                    L.check(lib.stv_conv_dgrad(C.byref(g), L.ptr(dZ), L.ptr(wq), L.ptr(dv), None, L.stream()), 'stv_conv_dgrad')
+                if not g.reflect and not g.up1 and g.C2 == 0: d1 = dv
+                else:
+                    if ctx.needs_input_grad[0]: d1 = grad_pull(dv, tuple(src1.shape), 0, pd, 2 if g.up1 else 1)
+                    if src2 is not None and ctx.needs_input_grad[1]: d2 = grad_pull(dv, tuple(src2.shape), g.C1, pd, 1)
+        return d1, d2, dw, db, None, None, None, None, None
+
+
+def conv2d_nhwc(src1: Tensor, w: Tensor, b: Tensor | None = None, *, src2: Tensor | None = None, up1: bool = False, stride: int = 1,
+                pad: int = 0, reflect: bool = False, act: str | None = None) -> Tensor:
+    """act(conv2d(cat(up2(src1) if up1 else src1, src2), w) + b) on channels-last tensors.
+
+    src1 (N,h,w,C1), src2 (N,H,W,C2) | None: contiguous NHWC, C1 and C2 multiples of 4; w: the nn.Conv2d weight (Cout,Cin,R,S)
+    (free when stored channels-last); -> (N,P,Q,Cout) contiguous NHWC. Differentiable in src1, src2, w, b."""
+    if src1.ndim != 4 or w.ndim != 4: raise ValueError(f'conv2d_nhwc: expected 4-D tensors, got {tuple(src1.shape)}, {tuple(w.shape)}')
+    if act not in (None, 'none', 'relu', 'elu', 'sigmoid'): raise ValueError(f'conv2d_nhwc: unsupported activation {act!r}')
+    return _Conv2dNHWC.apply(_f32c(src1), _f32c(src2), w, _f32c(b), bool(up1), int(stride), int(pad), bool(reflect), act)
+
+
 def _split_k(out_rows: int, out_cols: int, k: int) -> int:
     """Reduction splits for a weight-gradient product: enough CTAs for ~2 waves of 148 SMs, >= 4 k-blocks of 32 per split."""
     tiles = ((out_rows + 127)//128)*((out_cols + 255)//256)

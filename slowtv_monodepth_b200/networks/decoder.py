@@ -11,6 +11,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
+from .. import functional as F_
+
 __all__ = ['MonodepthDecoder']
 
 _ACT = {'sigmoid': torch.sigmoid, 'relu': F.relu, 'none': lambda x: x, None: lambda x: x}
@@ -52,6 +54,7 @@ class MonodepthDecoder(nn.Module):
         return self.decoder[self._idx[name]]
 
     def forward(self, feat: list[Tensor]) -> dict[int, Tensor]:
+        if feat[-1].is_cuda and self.upsample_mode == 'nearest': return self.forward_nhwc(feat)
         out, act = {}, _ACT[self.out_act]
         x = feat[-1]
         for i in range(4, -1, -1):
@@ -60,4 +63,21 @@ class MonodepthDecoder(nn.Module):
             if self.use_skip and 2**i in self.enc_sc: x = torch.cat([x, feat[self.enc_sc.index(2**i)]], dim=1)
             x = self.layer(f'upconv_{i}_1')(x)
             if i in self.out_sc: out[i] = act(self.layer(f'outconv_{i}')(x)).contiguous()
+        return out
+
+    def forward_nhwc(self, feat: list[Tensor]) -> dict[int, Tensor]:
+        """The same network on channels-last tensors with libstv tcgen05 implicit-GEMM convolutions: reflection padding,
+        nearest x2 upsampling and the skip concatenation are resolved inside the operand gather (no padded / upsampled /
+        concatenated tensor is ever written), bias + ELU / sigmoid in the epilogue."""
+        f = [t.permute(0, 2, 3, 1) for t in feat]
+        out, act = {}, (None if self.out_act in ('none', None) else self.out_act)
+        x = f[-1]
+        for i in range(4, -1, -1):
+            c0, c1 = self.layer(f'upconv_{i}_0').conv, self.layer(f'upconv_{i}_1').conv
+            x = F_.conv2d_nhwc(x, c0.weight, c0.bias, pad=1, reflect=True, act='elu')
+            skip = f[self.enc_sc.index(2**i)] if self.use_skip and 2**i in self.enc_sc else None
+            x = F_.conv2d_nhwc(x, c1.weight, c1.bias, src2=skip, up1=True, pad=1, reflect=True, act='elu')
+            if i in self.out_sc:
+                h = self.layer(f'outconv_{i}')
+                out[i] = F_.conv2d_nhwc(x, h.weight, h.bias, pad=1, reflect=True, act=act).permute(0, 3, 1, 2)
         return out

@@ -29,18 +29,32 @@ __all__ = ['create_encoder', 'ResNetEncoder', 'ConvNeXtEncoder', 'FeatureInfo']
 
 
 def _stem_conv(x: Tensor, conv: nn.Conv2d) -> Tensor:
-    """First convolution of an encoder. Its 3 (depth) or 6 (pose) input channels disqualify every tensor-core implicit-GEMM
-    path (NHWC kernels need C % 4 == 0): the library falls back to a scalar fp32 engine whose weight-gradient alone costs
-    ~20 ms per step at 16x6x384x640. Zero-padding the input and weight channels to a multiple of 4 is arithmetically a no-op
-    (zeros contribute nothing forward; the padded weight slice is a temporary, so its gradient is dropped) and keeps the
-    parameter's shape/name as in the reference checkpoint."""
-    c = x.shape[1]
-    pad = (-c) % 4
-    if pad == 0: return conv(x)
-    x = F.pad(x, (0, 0, 0, 0, 0, pad))
-    w = F.pad(conv.weight, (0, 0, 0, 0, 0, pad))
-    return F.conv2d(x.contiguous(memory_format=torch.channels_last), w.contiguous(memory_format=torch.channels_last),
-                    conv.bias, conv.stride, conv.padding)
+    """First convolution of an encoder on a HOST tensor (CPU-side naming / shape tests only): stock ATen convolution."""
+    return conv(x)
+
+
+def _to_nhwc4(x: Tensor) -> Tensor:
+    """(N,C,H,W) image batch -> contiguous channels-last (N,H,W,C') with C' = C rounded up to a multiple of 4 (zero channels):
+    the 16-byte gather granularity of the implicit-GEMM loader. One small copy per step (the only layout conversion)."""
+    x = x.permute(0, 2, 3, 1)
+    pad = (-x.shape[-1]) % 4
+    return F.pad(x, (0, pad)) if pad else x.contiguous()
+
+
+def _stem_conv_nhwc(x4: Tensor, conv: nn.Conv2d) -> Tensor:
+    """Stem convolution on the zero-padded channels-last input. The filter's input-channel axis is zero-padded to match
+    (arithmetically a no-op; the padded slice is a temporary, so the parameter keeps the reference checkpoint's shape and its
+    gradient is the un-padded slice)."""
+    pad = x4.shape[-1] - conv.weight.shape[1]
+    w = F.pad(conv.weight, (0, 0, 0, 0, 0, pad)) if pad else conv.weight
+    return F_.conv2d_nhwc(x4, w, conv.bias, stride=conv.stride[0], pad=conv.padding[0])
+
+
+def _bn_nhwc(x: Tensor, bn: nn.BatchNorm2d, relu: bool = False) -> Tensor:
+    """Train-mode BatchNorm (per-GPU batch statistics, as the reference) on a channels-last tensor."""
+    y = F.batch_norm(x.permute(0, 3, 1, 2), bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps)
+    if relu: y = F.relu(y, inplace=True)
+    return y.permute(0, 2, 3, 1)
 
 
 class FeatureInfo:
@@ -67,9 +81,18 @@ class BasicBlock(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
 
     def forward(self, x: Tensor) -> Tensor:
+        if x.is_cuda: return self.forward_nhwc(x)
         y = F.relu(self.bn1(self.conv1(x)), inplace=True)
         y = self.bn2(self.conv2(y))
         sc = x if self.downsample is None else self.downsample(x)
+        return F.relu(y + sc, inplace=True)
+
+    def forward_nhwc(self, x: Tensor) -> Tensor:
+        """x (N,H,W,C) channels-last; convolutions are libstv tcgen05 implicit GEMMs."""
+        s = self.conv1.stride[0]
+        y = _bn_nhwc(F_.conv2d_nhwc(x, self.conv1.weight, None, stride=s, pad=1), self.bn1, relu=True)
+        y = _bn_nhwc(F_.conv2d_nhwc(y, self.conv2.weight, None, pad=1), self.bn2)
+        sc = x if self.downsample is None else _bn_nhwc(F_.conv2d_nhwc(x, self.downsample[0].weight, None, stride=s), self.downsample[1])
         return F.relu(y + sc, inplace=True)
 
 
@@ -95,7 +118,14 @@ class ResNetEncoder(nn.Module):
             if isinstance(m, BasicBlock): nn.init.zeros_(m.bn2.weight)
 
     def forward(self, x: Tensor) -> list[Tensor]:
-        x = x.contiguous(memory_format=torch.channels_last)
+        if x.is_cuda:
+            f0 = _bn_nhwc(_stem_conv_nhwc(_to_nhwc4(x), self.conv1), self.bn1, relu=True)
+            x = F.max_pool2d(f0.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+            feats = [f0]
+            for i in range(1, 5):
+                for blk in getattr(self, f'layer{i}'): x = blk.forward_nhwc(x)
+                feats.append(x)
+            return [f.permute(0, 3, 1, 2) for f in feats]  # (N,C,H,W) views of the channels-last buffers
         f0 = F.relu(self.bn1(_stem_conv(x, self.conv1)), inplace=True)
         x = F.max_pool2d(f0, 3, 2, 1)
         feats = [f0]
@@ -136,21 +166,20 @@ class ConvNeXtBlock(nn.Module):
         self.gamma = nn.Parameter(1e-6*torch.ones(c))
 
     def forward(self, x: Tensor) -> Tensor:
-        if x.is_cuda:
-            # libstv kernels on the channels-last buffer: depthwise 7x7 (fwd / dgrad / wgrad), LayerNorm (fwd / bwd) and the
-            # pointwise MLP as tcgen05 TF32 GEMMs with bias+GELU / bias+layer-scale+residual epilogues.
-            xl = x.permute(0, 2, 3, 1)  # NHWC view of a channels-last tensor: no copy
-            if not xl.is_contiguous(): xl = xl.contiguous()
-            y = F_.dwconv7(xl, self.conv_dw.weight, self.conv_dw.bias)
-            y = F_.layer_norm(y, self.norm.weight, self.norm.bias, self.norm.eps)
-            c = xl.shape[-1]
-            out = F_.convnext_mlp(y.view(-1, c), xl.view(-1, c), self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight,
-                                  self.mlp.fc2.bias, self.gamma)
-            return out.view(xl.shape).permute(0, 3, 1, 2)
         # Host tensors (CPU-side naming / shape tests only): stock ATen ops, same arithmetic.
         y = self.conv_dw(x).permute(0, 2, 3, 1)
         y = self.mlp(self.norm(y))*self.gamma
         return x + y.permute(0, 3, 1, 2)
+
+    def forward_nhwc(self, xl: Tensor) -> Tensor:
+        """xl (N,H,W,C) channels-last. libstv kernels: depthwise 7x7 (fwd / dgrad / wgrad), LayerNorm (fwd / bwd) and the
+        pointwise MLP as tcgen05 TF32 GEMMs with bias+GELU / bias+layer-scale+residual epilogues."""
+        y = F_.dwconv7(xl, self.conv_dw.weight, self.conv_dw.bias)
+        y = F_.layer_norm(y, self.norm.weight, self.norm.bias, self.norm.eps)
+        c = xl.shape[-1]
+        out = F_.convnext_mlp(y.view(-1, c), xl.reshape(-1, c), self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight,
+                              self.mlp.fc2.bias, self.gamma)
+        return out.view(xl.shape)
 
 
 class ConvNeXtStage(nn.Module):
@@ -161,6 +190,14 @@ class ConvNeXtStage(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         return self.blocks(self.downsample(x))
+
+    def forward_nhwc(self, x: Tensor) -> Tensor:
+        if not isinstance(self.downsample, nn.Identity):
+            ln, conv = self.downsample[0], self.downsample[1]
+            x = F_.layer_norm(x, ln.weight, ln.bias, ln.eps)
+            x = F_.conv2d_nhwc(x, conv.weight, conv.bias, stride=2)
+        for blk in self.blocks: x = blk.forward_nhwc(x)
+        return x
 
 
 class ConvNeXtEncoder(nn.Module):
@@ -182,7 +219,14 @@ class ConvNeXtEncoder(nn.Module):
                 if m.bias is not None: nn.init.zeros_(m.bias)
 
     def forward(self, x: Tensor) -> list[Tensor]:
-        x = x.contiguous(memory_format=torch.channels_last)
+        if x.is_cuda:
+            x = _stem_conv_nhwc(_to_nhwc4(x), self.stem_0)
+            x = F_.layer_norm(x, self.stem_1.weight, self.stem_1.bias, self.stem_1.eps)
+            feats = []
+            for i in range(4):
+                x = getattr(self, f'stages_{i}').forward_nhwc(x)
+                feats.append(x.permute(0, 3, 1, 2))  # (N,C,H,W) view of the channels-last buffer
+            return feats
         x = self.stem_1(_stem_conv(x, self.stem_0))
         feats = []
         for i in range(4):

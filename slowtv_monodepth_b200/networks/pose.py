@@ -6,6 +6,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
+from .. import functional as F_
 from .encoders import create_encoder
 
 __all__ = ['PoseNet']
@@ -44,11 +45,30 @@ class PoseNet(nn.Module):
                             z, z, o, z,
                             z, z, z, o], dim=-1).unflatten(-1, (4, 4))
 
+    @staticmethod
+    def _head_nhwc(head: nn.Sequential, feat: Tensor) -> Tensor:
+        """conv3x3+ReLU, conv3x3+ReLU, conv1x1 on a channels-last tensor, then the spatial mean -> (B, cout)."""
+        y = F_.conv2d_nhwc(feat, head[0][0].weight, head[0][0].bias, pad=1, act='relu')
+        y = F_.conv2d_nhwc(y, head[1][0].weight, head[1][0].bias, pad=1, act='relu')
+        return F_.conv2d_nhwc(y, head[2].weight, head[2].bias).mean(dim=(1, 2))
+
     def forward(self, x: Tensor) -> dict:
+        if x.is_cuda: return self.forward_nhwc(x)
         feat = self.squeeze(self.encoder(x)[-1])
         out = self.pose_eps*self.decoders['pose'](feat).mean(dim=(2, 3)).unflatten(-1, (self.n_imgs, 6))
         res = {'R': out[..., :3], 't': out[..., 3:]}
         if self.learn_K:
             res['fs'] = F.softplus(self.decoders['focal'](feat).mean(dim=(2, 3)))
             res['cs'] = torch.sigmoid(self.decoders['offset'](feat).mean(dim=(2, 3)))
+        return res
+
+    def forward_nhwc(self, x: Tensor) -> dict:
+        """Same network; every convolution is a libstv tcgen05 implicit GEMM on channels-last tensors."""
+        feat = self.encoder(x)[-1].permute(0, 2, 3, 1)
+        feat = F_.conv2d_nhwc(feat, self.squeeze[0].weight, self.squeeze[0].bias, act='relu')
+        out = self.pose_eps*self._head_nhwc(self.decoders['pose'], feat).unflatten(-1, (self.n_imgs, 6))
+        res = {'R': out[..., :3], 't': out[..., 3:]}
+        if self.learn_K:
+            res['fs'] = F.softplus(self._head_nhwc(self.decoders['focal'], feat))
+            res['cs'] = torch.sigmoid(self._head_nhwc(self.decoders['offset'], feat))
         return res

@@ -1,0 +1,102 @@
+"""GPU: tcgen05 implicit-GEMM convolutions (stv_conv_fprop / dgrad / wgrad + stv_grad_pull / stv_act_bwd, through the C ABI) vs
+torch's float64 conv2d on the explicitly materialised virtual input (nearest x2 upsample -> concat -> reflect / zero pad).
+
+Operands are small integers (or quarter-integers), exactly representable in TF32 with exact fp32 sums, so the linear cases
+must match BIT-EXACTLY: any error in the gather indexing, swizzles, descriptors, padding / fold / pool logic is visible.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from slowtv_monodepth_b200 import functional as F_
+
+pytestmark = pytest.mark.gpu
+
+#        N  H   W   C1  C2  up1    Cout R  st pad reflect
+CASES = {
+    'zero3x3':        (2, 12, 20, 32, 0, False, 64, 3, 1, 1, False),
+    'reflect3x3_c16': (2, 10, 14, 16, 0, False, 16, 3, 1, 1, True),
+    'up_cat_reflect': (2, 12, 16, 32, 64, True, 32, 3, 1, 1, True),
+    'up_reflect':     (1, 8, 12, 32, 0, True, 16, 3, 1, 1, True),
+    'stride2_3x3':    (2, 12, 16, 64, 0, False, 128, 3, 2, 1, False),
+    'stride2_1x1':    (2, 12, 16, 64, 0, False, 128, 1, 2, 0, False),
+    'stem7x7_s2':     (2, 20, 28, 8, 0, False, 64, 7, 2, 3, False),
+    'patch4x4_s4':    (2, 16, 24, 4, 0, False, 96, 4, 4, 0, False),
+    'down2x2_s2':     (2, 12, 16, 96, 0, False, 192, 2, 2, 0, False),
+    'odd_sizes':      (3, 9, 11, 48, 0, False, 40, 3, 1, 1, True),
+    'wide_multi_tile': (2, 40, 56, 64, 0, False, 288, 3, 1, 1, False),
+    'head_cout1':     (2, 10, 14, 16, 0, False, 1, 3, 1, 1, True),
+}
+
+
+def _ints(shape, gen, lo=-2, hi=3):
+    return torch.randint(lo, hi, shape, generator=gen, device='cuda').float()
+
+
+def _make(case, gen, scale=1.0):
+    N, H, W, C1, C2, up1, Cout, R, st, pad, refl = CASES[case]
+    s1 = _ints((N, H//2, W//2, C1) if up1 else (N, H, W, C1), gen)*scale
+    s2 = _ints((N, H, W, C2), gen)*scale if C2 else None
+    w = (_ints((Cout, C1 + C2, R, R), gen)*scale).contiguous(memory_format=torch.channels_last)
+    b = _ints((Cout,), gen)*scale
+    return s1, s2, w, b, dict(up1=up1, stride=st, pad=pad, reflect=refl)
+
+
+def _ref(s1, s2, w, b, up1, stride, pad, reflect, act=None):
+    x = s1.permute(0, 3, 1, 2).double()
+    if up1: x = F.interpolate(x, scale_factor=2, mode='nearest')
+    if s2 is not None: x = torch.cat([x, s2.permute(0, 3, 1, 2).double()], 1)
+    if reflect and pad: x, pad = F.pad(x, (pad,)*4, mode='reflect'), 0
+    y = F.conv2d(x, w.double(), b.double() if b is not None else None, stride, pad)
+    y = {None: lambda v: v, 'relu': torch.relu, 'elu': F.elu, 'sigmoid': torch.sigmoid}[act](y)
+    return y.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize('case', list(CASES))
+def test_fprop_exact(case):
+    gen = torch.Generator(device='cuda').manual_seed(sum(map(ord, case)))
+    s1, s2, w, b, kw = _make(case, gen)
+    got = F_.conv2d_nhwc(s1, w, b, src2=s2, **kw)
+    want = _ref(s1, s2, w, b, **kw).float()
+    assert got.shape == want.shape
+    assert torch.equal(got, want), f'max |diff| = {(got - want).abs().max().item()}'
+
+
+@pytest.mark.parametrize('case', list(CASES))
+def test_backward_exact(case):
+    gen = torch.Generator(device='cuda').manual_seed(sum(map(ord, case)) + 1)
+    s1, s2, w, b, kw = _make(case, gen)
+    leaves = [t.clone().requires_grad_() for t in (s1, s2, w, b) if t is not None]
+    a1, a2, aw, ab = (leaves[0], leaves[1], leaves[2], leaves[3]) if s2 is not None else (leaves[0], None, leaves[1], leaves[2])
+    y = F_.conv2d_nhwc(a1, aw, ab, src2=a2, **kw)
+    dA = _ints(tuple(y.shape), gen, -1, 2)
+    y.backward(dA)
+    refs = [t.detach().double().requires_grad_() for t in (s1, s2, w, b) if t is not None]
+    r1, r2, rw, rb = (refs[0], refs[1], refs[2], refs[3]) if s2 is not None else (refs[0], None, refs[1], refs[2])
+    _ref(r1, r2, rw, rb, **kw).backward(dA.double())
+    for name, g, r in (('d_src1', a1, r1), ('d_src2', a2, r2), ('d_w', aw, rw), ('d_b', ab, rb)):
+        if g is None: continue
+        assert g.grad is not None, name
+        assert torch.equal(g.grad, r.grad.float()), f'{name}: max |diff| = {(g.grad - r.grad.float()).abs().max().item()}'
+
+
+@pytest.mark.parametrize('act', ['relu', 'elu', 'sigmoid'])
+def test_activation_forward_backward(act):
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    case = 'head_cout1' if act == 'sigmoid' else 'up_cat_reflect'
+    s1, s2, w, b, kw = _make(case, gen, scale=0.125)
+    leaves = [t.clone().requires_grad_() for t in (s1, s2, w, b) if t is not None]
+    a1, a2, aw, ab = (leaves[0], leaves[1], leaves[2], leaves[3]) if s2 is not None else (leaves[0], None, leaves[1], leaves[2])
+    y = F_.conv2d_nhwc(a1, aw, ab, src2=a2, act=act, **kw)
+    dA = _ints(tuple(y.shape), gen, -1, 2)
+    y.backward(dA)
+    refs = [t.detach().double().requires_grad_() for t in (s1, s2, w, b) if t is not None]
+    r1, r2, rw, rb = (refs[0], refs[1], refs[2], refs[3]) if s2 is not None else (refs[0], None, refs[1], refs[2])
+    yr = _ref(r1, r2, rw, rb, act=act, **kw)
+    yr.backward(dA.double())
+    assert (y.double() - yr).abs().max() < 1e-5
+    # The backward products run in TF32: dZ = dA*act'(y) is no longer TF32-exact, so compare norm-wise at TF32 accuracy.
+    for name, g, r in (('d_src1', a1, r1), ('d_src2', a2, r2), ('d_w', aw, rw), ('d_b', ab, rb)):
+        if g is None: continue
+        err = (g.grad.double() - r.grad).norm()/r.grad.norm().clamp(min=1e-12)
+        assert err < 2e-3, f'{name}: rel err {err.item():.3e}'
