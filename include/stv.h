@@ -208,6 +208,9 @@ int stv_conv_dgrad(const stv_conv_geom* g, const float* dy, const float* w, floa
 /* dw (Cout,R,S,C) += dy^T im2col(V) (atomic accumulation: dw must be initialised); Cout % 4 == 0. split_k <= 0: automatic. */
 int stv_conv_wgrad(const stv_conv_geom* g, const float* src1, const float* src2, const float* dy, float* dw, int split_k,
                    void* stream);
+/* out (N, H+2p, W+2p, C1+C2) = the virtual input V materialised: cat(up2(src1) | src1, src2), reflection-padded by p = g.pad when
+ * g.reflect (p = 0 otherwise). Lets a reflect / upsample / concat convolution run through the TMA im2col path (pad 0 on `out`). */
+int stv_vpad(const stv_conv_geom* g, const float* src1, const float* src2, float* out, void* stream);
 /* dst (N,H,W,C) (+)= slice/fold/pool of src (N, H*pool + 2 pad, W*pool + 2 pad, Cs): channels [c_off, c_off + C), the
  * reflection-padding border folded back onto the interior, and pool x pool (1 or 2) sum-pooling (adjoint of nearest x2). */
 int stv_grad_pull(int N, int H, int W, int C, const float* src, int Cs, int c_off, int pad, int pool, float* dst, int accumulate,
@@ -216,6 +219,20 @@ int stv_grad_pull(int N, int H, int W, int C, const float* src, int Cs, int c_of
 int stv_act_bwd(long long M, int C, const float* da, const float* y, int act, float* dz, float* dbias, void* stream);
 /* out[c] += sum_m x[m*ld + c] */
 int stv_colsum(long long M, int C, long long ld, const float* x, float* out, void* stream);
+
+/* Train-mode BatchNorm over the M = N*H*W rows of a channels-last (M, C) matrix, fused with the residual add and ReLU that
+ * follow it in a ResNet BasicBlock: y = [relu]((x - mean_c) * rstd_c * gamma_c + beta_c [+ res]). Replaces the cuDNN batch-norm
+ * + ATen add / relu kernels behind nn.BatchNorm2d / F.relu of the timm ResNet encoder (src/networks/pose.py:40, depth.py:97).
+ * Batch statistics per GPU (biased variance for normalisation); run_mean / run_var (nullable) get nn.BatchNorm2d's momentum
+ * update with the unbiased variance. mean / rstd (C) are saved for the backward. C % 4 == 0. */
+size_t stv_bn_workspace_bytes(int C);
+int stv_bn_fwd(long long M, int C, const float* x, const float* gamma, const float* beta, const float* res, int relu, float eps,
+               float momentum, float* y, float* mean, float* rstd, float* run_mean, float* run_var, void* ws, size_t ws_bytes,
+               void* stream);
+/* dz = dy * (y > 0) when relu; dres = dz (nullable); dx = gamma rstd (dz - mean_m(dz) - xhat mean_m(dz xhat)); dgamma, dbeta (C). */
+int stv_bn_bwd(long long M, int C, const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
+               const float* gamma, int relu, float* dx, float* dres, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+               void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Optimiser: replaces torch.optim.AdamW(foreach) built by timm create_optimizer_v2 (src/tools/parsers.py:205-243)

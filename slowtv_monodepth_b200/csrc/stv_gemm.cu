@@ -22,21 +22,9 @@
 #include "stv_common.cuh"
 #include "stv_tc.cuh"
 #include "stv_epi.cuh"
+#include "stv_gemm.cuh"
 
 namespace stv {
-
-constexpr int GEMM_BM = 128, GEMM_BK = 32, GEMM_THREADS = 192, GEMM_MAX_STAGES = 8;
-constexpr int GEMM_A_BYTES = GEMM_BM*GEMM_BK*4;  // 16 KB per stage
-constexpr int SLAB_MN_BYTES = 32*128;            // MN-major slab: 32 k-rows x 128 B
-
-struct GemmParams {
-    int M, N, K;
-    int bn, stages, a_mn, b_mn;
-    int kb_total, kb_per_split;
-    float* C;
-    long long ldc;
-    stv_gemm_epi e;
-};
 
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -75,6 +63,27 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0) {
         if (lane == 0) {
+            const ConvOperand& cv = p.cv;
+            // im2col state of the single producer thread (all integer divisions happen here, once per CTA / k-block)
+            int bn_ = 0, bw = 0, bh = 0;              // mode 1: image index and TMA base coordinate of the tile's first row
+            int tap = 0, cb = 0;                      // mode 1: current filter tap and channel block
+            int slab_c[8], slab_rs[8];                // mode 2: channel origin and (r << 8 | s) of every 32-column slab
+            if (cv.mode == 1) {
+                const int hw = cv.gridH*cv.gridW;
+                bn_ = m0/hw;
+                const int rem = m0 - bn_*hw, py = rem/cv.gridW, px = rem - py*cv.gridW;
+                bw = cv.lw + px*cv.stride; bh = cv.lh + py*cv.stride;
+                tap = kb0/cv.cblocks; cb = kb0 - tap*cv.cblocks;
+            } else if (cv.mode == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = n0 + 32*j, t = col/cv.C;
+                    const bool ok = j < p.bn/32 && t < cv.R*cv.S;
+                    slab_c[j] = ok ? col - t*cv.C : cv.C;  // channel coordinate C = fully out of bounds = zeros
+                    const int r = ok ? t/cv.S : 0, sx = ok ? t - r*cv.S : 0;
+                    slab_rs[j] = (r << 8) | sx;
+                }
+            }
             int it = 0;
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % p.stages;
@@ -84,10 +93,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint8_t* a = smem + (size_t)s*stage_bytes;
                 uint8_t* b = a + GEMM_A_BYTES;
                 const int k = kb*GEMM_BK;
+                if (cv.mode == 1) {
+                    const int r = tap/cv.S, sx = tap - r*cv.S;
+                    tc::tma_load_im2col_4d(a, &tmA, &full[s], cb*GEMM_BK, bw, bh, bn_, (uint16_t)(cv.flip ? cv.S - 1 - sx : sx),
+                                           (uint16_t)(cv.flip ? cv.R - 1 - r : r));
+                    if (!p.b_mn) tc::tma_load_2d(b, &tmB, &full[s], k, n0);
+                    else
+                        for (int j = 0; j < p.bn/32; ++j)
+                            tc::tma_load_2d(b + j*SLAB_MN_BYTES, &tmB, &full[s], tap*cv.b_tap_cols + n0 + 32*j, cb*GEMM_BK);
+                    if (++cb == cv.cblocks) { cb = 0; ++tap; }
+                    continue;
+                }
                 if (!p.a_mn) tc::tma_load_2d(a, &tmA, &full[s], k, m0);
                 else
                     for (int j = 0; j < GEMM_BM/32; ++j) tc::tma_load_2d(a + j*SLAB_MN_BYTES, &tmA, &full[s], m0 + 32*j, k);
-                if (!p.b_mn) tc::tma_load_2d(b, &tmB, &full[s], k, n0);
+                if (cv.mode == 2) {
+                    const int hw = cv.gridH*cv.gridW, n = k/hw, rem = k - n*hw, py = rem/cv.gridW, px = rem - py*cv.gridW;
+                    const int w = cv.lw + px*cv.stride, h = cv.lh + py*cv.stride;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < p.bn/32)
+                            tc::tma_load_im2col_4d(b + j*SLAB_MN_BYTES, &tmB, &full[s], slab_c[j], w, h, n, (uint16_t)(slab_rs[j] & 255),
+                                                   (uint16_t)(slab_rs[j] >> 8));
+                } else if (!p.b_mn) tc::tma_load_2d(b, &tmB, &full[s], k, n0);
                 else
                     for (int j = 0; j < p.bn/32; ++j) tc::tma_load_2d(b + j*SLAB_MN_BYTES, &tmB, &full[s], n0 + 32*j, k);
             }
@@ -117,7 +145,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else {
         tc::mbar_wait(tmem_full, 0);
         tc::tcgen05_fence_after();
-        epilogue_tile(tmem_base, warp & 3, lane, m0, n0, p.bn, p.M, p.N, p.C, p.ldc, p.e);
+        // Every MMA has retired (tmem_full), so the operand ring is free: its first bytes stage the transposed output chunks.
+        epilogue_tile(tmem_base, warp & 3, lane, m0, n0, p.bn, p.M, p.N, p.C, p.ldc, p.e, (float*)smem + (warp & 3)*EPI_WARP_FLOATS);
     }
     tc::tcgen05_fence_before();
     __syncthreads();
@@ -160,14 +189,64 @@ int make_tmap_2d(CUtensorMap* tm, const float* base, long long rows, long long c
     return STV_OK;
 }
 
-static int pick_bn(int N) {
-    // Largest tile width (multiple of 32, <= 256) that wastes the fewest columns; ties -> the wider tile.
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap_im2col(CUtensorMap* tm, const float* base, int N, int H, int W, int C, int lw, int lh, int uw, int uh, int stride,
+                     int pixels, int mn_major) {
+    static EncodeIm2colFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeIm2colFn)ptr;
+    });
+    if (!fn) { set_error("cuTensorMapEncodeIm2col is not available from the CUDA driver"); return STV_E_CUDA; }
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)C*4, (cuuint64_t)W*C*4, (cuuint64_t)H*W*C*4};
+    const int lower[2] = {lw, lh}, upper[2] = {uw, uh};
+    const cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, lower, upper, 32u, (cuuint32_t)pixels, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeIm2col failed (%d): tensor (%d,%d,%d,%d), corners (%d,%d)/(%d,%d), stride %d, %d pixels", (int)r, N, H, W, C,
+                  lw, lh, uw, uh, stride, pixels);
+        return STV_E_CUDA;
+    }
+    return STV_OK;
+}
+
+// Tile width: the multiple of 32 (<= 256) that wastes the fewest columns (ties -> wider); when the resulting grid would leave
+// SMs idle (few row tiles: the deep, low-resolution layers) it is narrowed, down to 64, until the grid covers the 148 SMs.
+int pick_bn(int N, long long row_tiles) {
     int best = 32, best_cost = 1 << 30;
     for (int bn = 256; bn >= 32; bn -= 32) {
         const int tiles = (N + bn - 1)/bn, cost = tiles*bn;
         if (cost < best_cost) { best = bn; best_cost = cost; }
     }
+    while (best > 64 && best % 64 == 0 && row_tiles*((N + best - 1)/best) < 148) best /= 2;
     return best;
+}
+
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int splits, cudaStream_t stream, const char* what) {
+    const int stage_bytes = GEMM_A_BYTES + p.bn*GEMM_BK*4;
+    int stages = (110*1024)/stage_bytes;                         // two resident CTAs per SM when that leaves >= 3 stages,
+    if (stages < 3) stages = (200*1024)/stage_bytes;             // else one CTA with a deep ring
+    stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
+    stages = stages > p.kb_per_split ? (p.kb_per_split < 2 ? 2 : p.kb_per_split) : stages;
+    p.stages = stages;
+    const size_t smem = (size_t)stages*stage_bytes + 1024 /*alignment slack*/ + (2*GEMM_MAX_STAGES + 1)*8 + 16;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024); });
+    if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute failed (%s)", what, cudaGetErrorString(attr_err)); return STV_E_CUDA; }
+    const dim3 grid((p.M + GEMM_BM - 1)/GEMM_BM, (p.N + p.bn - 1)/p.bn, splits);
+    gemm_tf32_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
+    count_launch();
+    return check_launch(what);
 }
 
 }  // namespace stv
@@ -192,34 +271,17 @@ extern "C" int stv_gemm_tf32(int M, int N, int K, const float* A, long long lda,
 
     GemmParams p = {};
     p.M = M; p.N = N; p.K = K;
-    p.bn = pick_bn(N);
+    p.bn = pick_bn(N, (M + GEMM_BM - 1)/GEMM_BM);
     p.a_mn = a_mn != 0; p.b_mn = b_mn != 0;
     p.kb_total = (K + GEMM_BK - 1)/GEMM_BK;
     split_k = split_k < p.kb_total ? split_k : p.kb_total;
     p.kb_per_split = (p.kb_total + split_k - 1)/split_k;
     split_k = (p.kb_total + p.kb_per_split - 1)/p.kb_per_split;  // every split non-empty
     p.C = C; p.ldc = ldc; p.e = e;
-    const int stage_bytes = GEMM_A_BYTES + p.bn*GEMM_BK*4;
-    const int budget = p.bn <= 128 ? 100*1024 : 200*1024;        // two resident CTAs per SM for the narrower tiles
-    int stages = budget/stage_bytes;
-    stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
-    stages = stages > p.kb_per_split ? (p.kb_per_split < 2 ? 2 : p.kb_per_split) : stages;
-    p.stages = stages;
-    const size_t smem = (size_t)stages*stage_bytes + 1024 /*alignment slack*/ + (2*GEMM_MAX_STAGES + 1)*8 + 16;
-
     CUtensorMap tmA, tmB;
     int rc = a_mn ? make_tmap_2d(&tmA, A, K, M, lda, 32, 1) : make_tmap_2d(&tmA, A, M, K, lda, GEMM_BM, 0);
     if (rc) return rc;
     rc = b_mn ? make_tmap_2d(&tmB, B, K, N, ldb, 32, 1) : make_tmap_2d(&tmB, B, N, K, ldb, p.bn, 0);
     if (rc) return rc;
-
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024); });
-    if (attr_err != cudaSuccess) { set_error("stv_gemm_tf32: cudaFuncSetAttribute failed (%s)", cudaGetErrorString(attr_err)); return STV_E_CUDA; }
-
-    const dim3 grid((M + GEMM_BM - 1)/GEMM_BM, (N + p.bn - 1)/p.bn, split_k);
-    gemm_tf32_kernel<<<grid, GEMM_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
-    count_launch();
-    return check_launch("stv_gemm_tf32");
+    return launch_gemm(tmA, tmB, p, split_k, (cudaStream_t)stream, "stv_gemm_tf32");
 }

@@ -1,0 +1,44 @@
+// Shared declarations of the tcgen05 GEMM kernel (stv_gemm.cu) for the convolution front-ends (stv_conv.cu).
+#pragma once
+#include "stv_common.cuh"
+#include "stv_tc.cuh"
+
+namespace stv {
+
+constexpr int GEMM_BM = 128, GEMM_BK = 32, GEMM_THREADS = 192, GEMM_MAX_STAGES = 8;
+constexpr int GEMM_A_BYTES = GEMM_BM*GEMM_BK*4;  // 16 KB per stage
+constexpr int SLAB_MN_BYTES = 32*128;            // MN-major slab: 32 k-rows x 128 B
+
+// im2col addressing of one operand through a TMA im2col tensor map over a channels-last (N,H,W,C) tensor.
+//   mode 1  A = im2col rows (fprop / stride-1 dgrad): GEMM row m = grid pixel (n, py, px); k-block = (filter tap, 32 channels)
+//   mode 2  B = im2col rows (wgrad): reduction index = grid pixel; every 32-column slab of the tile = (filter tap, 32 channels)
+struct ConvOperand {
+    int mode;
+    int gridH, gridW;   // pixel grid enumerated by the GEMM rows (mode 1) / the reduction index (mode 2)
+    int stride, lw, lh; // TMA base coordinate of grid pixel (py, px): (lh + py*stride, lw + px*stride)
+    int R, S, C;        // filter taps; channels of the im2col tensor
+    int cblocks;        // mode 1: k-blocks per tap = ceil(C/32)
+    int flip;           // dgrad: tap (r, s) reads offsets (R-1-r, S-1-s)
+    int b_tap_cols;     // dgrad: B (filters, MN-major boxes) column coordinate = tap*b_tap_cols + n0 + 32*slab, row = channel block
+};
+
+struct GemmParams {
+    int M, N, K;
+    int bn, stages, a_mn, b_mn;
+    int kb_total, kb_per_split;
+    float* C;
+    long long ldc;
+    stv_gemm_epi e;
+    ConvOperand cv;
+};
+
+int make_tmap_2d(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows, int mn_major);
+// Channels-last (N,H,W,C) fp32 tensor read in im2col mode: boxes of `pixels` base pixels x 32 channels, base pixels restricted
+// to [lw, W + uw) x [lh, H + uh) and stepped by `stride`; out-of-image pixels / channels read as zeros.
+int make_tmap_im2col(CUtensorMap* tm, const float* base, int N, int H, int W, int C, int lw, int lh, int uw, int uh, int stride,
+                     int pixels, int mn_major);
+int pick_bn(int N, long long row_tiles);
+// Fills p.stages, launches grid (ceil(M/128), ceil(N/bn), splits). p.bn, p.kb_total, p.kb_per_split must be set.
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int splits, cudaStream_t stream, const char* what);
+
+}  // namespace stv

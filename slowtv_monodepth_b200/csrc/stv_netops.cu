@@ -99,6 +99,133 @@ __global__ void __launch_bounds__(256) colsum_kernel(long long M, int C, long lo
     }
 }
 
+// ---- train-mode BatchNorm over the rows of a channels-last (M, C) matrix (M = N*H*W) ------------------------------------------
+// Reference: the nn.BatchNorm2d layers of the timm ResNet encoder (src/networks/pose.py:40, depth.py:97), batch statistics
+// per GPU (no SyncBN, api/train/train.py:105-119). Statistics are accumulated in double (block partials -> atomicAdd(double)).
+__global__ void __launch_bounds__(256) bn_stats_kernel(long long M, int C, const float* __restrict__ X, double* __restrict__ sums,
+                                                       int rows_per_block) {
+    __shared__ float red[2][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x*32 + tx;
+    const long long r0 = (long long)blockIdx.y*rows_per_block, r1 = min(r0 + rows_per_block, M);
+    float s = 0.f, q = 0.f;
+    if (c < C)
+        for (long long r = r0 + ty; r < r1; r += 8) {
+            const float v = __ldg(X + (size_t)r*C + c);
+            s += v;
+            q = fmaf(v, v, q);
+        }
+    red[0][ty][tx] = s;
+    red[1][ty][tx] = q;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        double ds = 0., dq = 0.;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ds += red[0][k][tx]; dq += red[1][k][tx]; }
+        atomicAdd(sums + c, ds);
+        atomicAdd(sums + C + c, dq);
+    }
+}
+
+// mean / rstd from the sums; running statistics updated like nn.BatchNorm2d (momentum, unbiased variance).
+__global__ void bn_finalize_kernel(long long M, int C, const double* __restrict__ sums, float eps, float momentum, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ run_mean, float* __restrict__ run_var) {
+    const int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = sums[c]/(double)M;
+    double var = sums[C + c]/(double)M - m*m;
+    var = var > 0. ? var : 0.;
+    mean[c] = (float)m;
+    rstd[c] = (float)(1.0/sqrt(var + (double)eps));
+    if (run_mean) {
+        run_mean[c] = (1.f - momentum)*run_mean[c] + momentum*(float)m;
+        run_var[c] = (1.f - momentum)*run_var[c] + momentum*(float)(var*(double)M/(double)(M > 1 ? M - 1 : 1));
+    }
+}
+
+// y = [relu]( (x - mean)*rstd*gamma + beta [+ res] ), 4 channels per thread.
+__global__ void __launch_bounds__(256) bn_apply_kernel(long long total4, int C, const float* __restrict__ X, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float* __restrict__ res, int relu,
+                                                       float* __restrict__ Y) {
+    const int c4 = C >> 2;
+    for (long long i = blockIdx.x*(long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x*blockDim.x) {
+        const int c = (int)(i % c4)*4;
+        const float4 x = __ldg((const float4*)X + i), m = __ldg((const float4*)(mean + c)), r = __ldg((const float4*)(rstd + c));
+        const float4 g = __ldg((const float4*)(gamma + c)), b = __ldg((const float4*)(beta + c));
+        float4 y = make_float4(fmaf((x.x - m.x)*r.x, g.x, b.x), fmaf((x.y - m.y)*r.y, g.y, b.y), fmaf((x.z - m.z)*r.z, g.z, b.z),
+                               fmaf((x.w - m.w)*r.w, g.w, b.w));
+        if (res) { const float4 s = __ldg((const float4*)res + i); y.x += s.x; y.y += s.y; y.z += s.z; y.w += s.w; }
+        if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+        ((float4*)Y)[i] = y;
+    }
+}
+
+// sums[c] += sum_m dz, sums[C + c] += sum_m dz*xhat, with dz = dy*(y > 0) when relu.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(long long M, int C, const float* __restrict__ dY, const float* __restrict__ Y,
+                                                            const float* __restrict__ X, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, int relu, double* __restrict__ sums,
+                                                            int rows_per_block) {
+    __shared__ float red[2][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x*32 + tx;
+    const long long r0 = (long long)blockIdx.y*rows_per_block, r1 = min(r0 + rows_per_block, M);
+    float s = 0.f, q = 0.f;
+    if (c < C) {
+        const float m = __ldg(mean + c), rs = __ldg(rstd + c);
+        for (long long r = r0 + ty; r < r1; r += 8) {
+            const size_t o = (size_t)r*C + c;
+            float g = __ldg(dY + o);
+            if (relu && !(__ldg(Y + o) > 0.f)) g = 0.f;
+            s += g;
+            q = fmaf(g, (__ldg(X + o) - m)*rs, q);
+        }
+    }
+    red[0][ty][tx] = s;
+    red[1][ty][tx] = q;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        double ds = 0., dq = 0.;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ds += red[0][k][tx]; dq += red[1][k][tx]; }
+        atomicAdd(sums + c, ds);
+        atomicAdd(sums + C + c, dq);
+    }
+}
+
+// dx = gamma*rstd*(dz - dbeta/M - xhat*dgamma/M); dres = dz (nullable); also emits dgamma / dbeta as floats (block 0).
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(long long total4, long long M, int C, const float* __restrict__ dY,
+                                                           const float* __restrict__ Y, const float* __restrict__ X,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ gamma, const double* __restrict__ sums, int relu,
+                                                           float* __restrict__ dX, float* __restrict__ dRes, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta) {
+    const int c4 = C >> 2;
+    const float invM = 1.f/(float)M;
+    if (blockIdx.x == 0)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta[c] = (float)sums[c]; dgamma[c] = (float)sums[C + c]; }
+    for (long long i = blockIdx.x*(long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x*blockDim.x) {
+        const int c = (int)(i % c4)*4;
+        float4 g = __ldg((const float4*)dY + i);
+        if (relu) {
+            const float4 y = __ldg((const float4*)Y + i);
+            g.x = y.x > 0.f ? g.x : 0.f; g.y = y.y > 0.f ? g.y : 0.f; g.z = y.z > 0.f ? g.z : 0.f; g.w = y.w > 0.f ? g.w : 0.f;
+        }
+        if (dRes) ((float4*)dRes)[i] = g;
+        const float4 x = __ldg((const float4*)X + i), m = __ldg((const float4*)(mean + c)), r = __ldg((const float4*)(rstd + c));
+        const float4 ga = __ldg((const float4*)(gamma + c));
+        const float gv[4] = {g.x, g.y, g.z, g.w}, xv[4] = {x.x, x.y, x.z, x.w}, mv[4] = {m.x, m.y, m.z, m.w}, rv[4] = {r.x, r.y, r.z, r.w},
+                    gav[4] = {ga.x, ga.y, ga.z, ga.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float xh = (xv[k] - mv[k])*rv[k];
+            o[k] = gav[k]*rv[k]*(gv[k] - (float)sums[c + k]*invM - xh*(float)sums[C + c + k]*invM);
+        }
+        ((float4*)dX)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 static int rows_per_block(long long M, int C) {
     // ~4 waves of 148 SMs x 8 resident blocks, at least 64 rows per block.
     const long long col_blocks = (C + 31)/32;
@@ -148,4 +275,45 @@ extern "C" int stv_colsum(long long M, int C, long long ld, const float* X, floa
     colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, ld, X, out, rpb);
     count_launch();
     return check_launch("stv_colsum");
+}
+
+/* ---- BatchNorm (train mode) ---- */
+extern "C" size_t stv_bn_workspace_bytes(int C) { return (size_t)2*C*sizeof(double); }
+
+extern "C" int stv_bn_fwd(long long M, int C, const float* x, const float* gamma, const float* beta, const float* res, int relu, float eps,
+                          float momentum, float* y, float* mean, float* rstd, float* run_mean, float* run_var, void* ws, size_t ws_bytes,
+                          void* stream) {
+    STV_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && x && gamma && beta && y && mean && rstd, "stv_bn_fwd: bad arguments (C must be a multiple of 4)");
+    STV_REQUIRE(ws && ws_bytes >= stv_bn_workspace_bytes(C), "stv_bn_fwd: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sums = (double*)ws;
+    if (cudaMemsetAsync(sums, 0, stv_bn_workspace_bytes(C), st) != cudaSuccess) return check_launch("stv_bn_fwd(memset)");
+    const int rpb = rows_per_block(M, C);
+    const dim3 grid((C + 31)/32, (unsigned)((M + rpb - 1)/rpb));
+    bn_stats_kernel<<<grid, 256, 0, st>>>(M, C, x, sums, rpb);
+    bn_finalize_kernel<<<(C + 127)/128, 128, 0, st>>>(M, C, sums, eps, momentum, mean, rstd, run_mean, run_var);
+    const long long total4 = M*(C/4);
+    const int blocks = (int)((total4 + 255)/256 < 148ll*16 ? (total4 + 255)/256 : 148ll*16);
+    bn_apply_kernel<<<blocks, 256, 0, st>>>(total4, C, x, mean, rstd, gamma, beta, res, relu, y);
+    count_launch(3);
+    return check_launch("stv_bn_fwd");
+}
+
+extern "C" int stv_bn_bwd(long long M, int C, const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
+                          const float* gamma, int relu, float* dx, float* dres, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+                          void* stream) {
+    STV_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && dy && x && mean && rstd && gamma && dx && dgamma && dbeta && (!relu || y),
+                "stv_bn_bwd: bad arguments (C must be a multiple of 4)");
+    STV_REQUIRE(ws && ws_bytes >= stv_bn_workspace_bytes(C), "stv_bn_bwd: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sums = (double*)ws;
+    if (cudaMemsetAsync(sums, 0, stv_bn_workspace_bytes(C), st) != cudaSuccess) return check_launch("stv_bn_bwd(memset)");
+    const int rpb = rows_per_block(M, C);
+    const dim3 grid((C + 31)/32, (unsigned)((M + rpb - 1)/rpb));
+    bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(M, C, dy, y, x, mean, rstd, relu, sums, rpb);
+    const long long total4 = M*(C/4);
+    const int blocks = (int)((total4 + 255)/256 < 148ll*16 ? (total4 + 255)/256 : 148ll*16);
+    bn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(total4, M, C, dy, y, x, mean, rstd, gamma, sums, relu, dx, dres, dgamma, dbeta);
+    count_launch(2);
+    return check_launch("stv_bn_bwd");
 }

@@ -51,10 +51,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Blocking wait with a watchdog: a pipeline bug must surface as a trapped kernel (CUDA error), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = globaltimer();
+    uint64_t t0 = 0;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3FFu) == 0 && globaltimer() - t0 > 4000000000ull) __trap();
+        __nanosleep(32);  // back off: polling warps must not take issue slots from the warps they are waiting for
+        if ((++spins & 0xFFFu) == 0) {
+            const uint64_t now = globaltimer();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
     }
 }
 
@@ -76,6 +81,17 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// im2col-mode load from a channels-last (N,H,W,C) tensor map: `pixelsPerColumn` base pixels starting at (n, h, w) — walking W,
+// then H, then N inside the map's bounding box with its traversal strides — each read at the filter-tap offset (off_h, off_w),
+// channels c .. c+31; pixels / channels outside the tensor are zero-filled. Rows land as a TMA box does (128 B, swizzled).
+__device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+
 // ---- cp.async (generic-proxy gather path of the implicit-GEMM loaders) ----------------------------------------------
 // 16-byte copy; src_bytes = 0 writes zeros (padding) without touching `src`.
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
@@ -84,6 +100,19 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// Waits until at most `n` (0..7, warp-uniform) of this thread's most recent cp.async groups are still pending.
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+    switch (n) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        case 4: cp_async_wait<4>(); break;
+        case 5: cp_async_wait<5>(); break;
+        case 6: cp_async_wait<6>(); break;
+        default: cp_async_wait<7>(); break;
+    }
+}
 
 // ---- TMEM -----------------------------------------------------------------------------------------------------------
 // Whole-warp calls. ncols: power of two in [32, 512].

@@ -454,12 +454,26 @@ class _Conv2dNHWC(torch.autograd.Function):
         L.require_cuda(src1, src2, w, b, what='conv2d_nhwc')
         w_phys = w.permute(0, 2, 3, 1).contiguous()  # (Cout,R,S,Cin): free for channels-last filters (the flat parameter buffer)
         g, P, Q = _geom(src1, src2, w_phys, up1, stride, pad, reflect)
-        dev = src1.device
+        lib, dev = L.lib(), src1.device
+        Cin = g.C1 + g.C2
+        # The TMA im2col path needs one real, zero-padded tensor with channels % 32 == 0. A virtual input (reflection padding,
+        # nearest x2 upsampling, skip concatenation) with such a channel count is materialised ONCE by stv_vpad (the reference
+        # does it in three passes: interpolate, cat, pad) and convolved with pad 0; otherwise (3/6/16-channel layers) the
+        # cp.async gather kernel resolves the virtual input on the fly.
+        ctx.virt = None
         with torch.cuda.device(dev):
+            if (reflect or up1 or src2 is not None) and Cin % 32 == 0:
+                pv = pad if reflect else 0
+                V = torch.empty((g.N, g.H + 2*pv, g.W + 2*pv, Cin), dtype=torch.float32, device=dev)
+                L.check(lib.stv_vpad(C.byref(g), L.ptr(src1), L.ptr(src2), L.ptr(V), L.stream()), 'stv_vpad')
+                ctx.virt = (tuple(src1.shape), None if src2 is None else tuple(src2.shape), g.C1, pv, 2 if up1 else 1)
+                g = L.ConvGeom(N=g.N, H=g.H + 2*pv, W=g.W + 2*pv, C1=Cin, C2=0, up1=0, Cout=g.Cout, R=g.R, S=g.S, stride=stride,
+                               pad=0 if reflect else pad, reflect=0)
+                src1, src2 = V, None
             y = torch.empty((g.N, P, Q, g.Cout), dtype=torch.float32, device=dev)
             epi = L.GemmEpi(bias=L.ptr(b), act=L.ACT[act])
             with _timed('stv_conv_fprop'):
-                L.check(L.lib().stv_conv_fprop(C.byref(g), L.ptr(src1), L.ptr(src2), L.ptr(w_phys), L.ptr(y), C.byref(epi), L.stream()),
+                L.check(lib.stv_conv_fprop(C.byref(g), L.ptr(src1), L.ptr(src2), L.ptr(w_phys), L.ptr(y), C.byref(epi), L.stream()),
                         'stv_conv_fprop')
         ctx.save_for_backward(src1, src2, w_phys, y)
         ctx.g, ctx.act, ctx.has_bias = g, act, b is not None
@@ -491,7 +505,11 @@ class _Conv2dNHWC(torch.autograd.Function):
                 dv = torch.empty((g.N, g.H + 2*pd, g.W + 2*pd, Cin), dtype=torch.float32, device=dev)
                 with _timed('stv_conv_dgrad'):
                     L.check(lib.stv_conv_dgrad(C.byref(g), L.ptr(dZ), L.ptr(wq), L.ptr(dv), None, L.stream()), 'stv_conv_dgrad')
-                if not g.reflect and not g.up1 and g.C2 == 0: d1 = dv
+                if ctx.virt is not None:  # dv is the gradient of the materialised (padded) virtual input
+                    shape1, shape2, c1, pv, pool = ctx.virt
+                    if ctx.needs_input_grad[0]: d1 = grad_pull(dv, shape1, 0, pv, pool)
+                    if shape2 is not None and ctx.needs_input_grad[1]: d2 = grad_pull(dv, shape2, c1, pv, 1)
+                elif not g.reflect and not g.up1 and g.C2 == 0: d1 = dv
                 else:
                     if ctx.needs_input_grad[0]: d1 = grad_pull(dv, tuple(src1.shape), 0, pd, 2 if g.up1 else 1)
                     if src2 is not None and ctx.needs_input_grad[1]: d2 = grad_pull(dv, tuple(src2.shape), g.C1, pd, 1)
@@ -509,10 +527,56 @@ def conv2d_nhwc(src1: Tensor, w: Tensor, b: Tensor | None = None, *, src2: Tenso
     return _Conv2dNHWC.apply(_f32c(src1), _f32c(src2), w, _f32c(b), bool(up1), int(stride), int(pad), bool(reflect), act)
 
 
+class _BatchNormNHWC(torch.autograd.Function):
+    """Train-mode BatchNorm over the rows of a channels-last tensor, fused with the residual add and ReLU that follow."""
+    @staticmethod
+    def forward(ctx, x, gamma, beta, res, run_mean, run_var, relu: bool, eps: float, momentum: float):
+        L.require_cuda(x, gamma, beta, res, what='batch_norm_nhwc')
+        Cc = x.shape[-1]
+        M = x.numel()//Cc
+        lib, dev = L.lib(), x.device
+        with torch.cuda.device(dev):
+            y = torch.empty_like(x)
+            mean = torch.empty(Cc, dtype=torch.float32, device=dev)
+            rstd = torch.empty_like(mean)
+            ws = _ws(lib.stv_bn_workspace_bytes(Cc), dev)
+            L.check(lib.stv_bn_fwd(M, Cc, L.ptr(x), L.ptr(gamma), L.ptr(beta), L.ptr(res), int(relu), eps, momentum, L.ptr(y), L.ptr(mean),
+                                   L.ptr(rstd), L.ptr(run_mean), L.ptr(run_var), L.ptr(ws), ws.numel(), L.stream()), 'stv_bn_fwd')
+        ctx.save_for_backward(x, y, mean, rstd, gamma)
+        ctx.relu, ctx.has_res = relu, res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, rstd, gamma = ctx.saved_tensors
+        Cc = x.shape[-1]
+        M = x.numel()//Cc
+        lib, dev = L.lib(), x.device
+        dy = _f32c(dy)
+        with torch.cuda.device(dev):
+            dx = torch.empty_like(x)
+            dres = torch.empty_like(x) if ctx.has_res and ctx.relu else None
+            dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+            ws = _ws(lib.stv_bn_workspace_bytes(Cc), dev)
+            L.check(lib.stv_bn_bwd(M, Cc, L.ptr(dy), L.ptr(y), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), int(ctx.relu), L.ptr(dx),
+                                   L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), ws.numel(), L.stream()), 'stv_bn_bwd')
+        if ctx.has_res and not ctx.relu: dres = dy
+        return dx, dgamma, dbeta, dres, None, None, None, None, None
+
+
+def batch_norm_nhwc(x: Tensor, gamma: Tensor, beta: Tensor, *, res: Tensor | None = None, relu: bool = False, run_mean: Tensor | None = None,
+                    run_var: Tensor | None = None, eps: float = 1e-5, momentum: float = 0.1) -> Tensor:
+    """[relu](batch_norm(x) [+ res]) with per-call batch statistics over all but the last axis of a contiguous tensor; the
+    running statistics (if given) are updated in place like nn.BatchNorm2d in training mode."""
+    if x.shape[-1] % 4: raise ValueError(f'batch_norm_nhwc: channels must be a multiple of 4, got {x.shape[-1]}')
+    if res is not None and res.shape != x.shape: raise ValueError('batch_norm_nhwc: residual shape mismatch')
+    return _BatchNormNHWC.apply(_f32c(x), _f32c(gamma), _f32c(beta), _f32c(res), run_mean, run_var, bool(relu), float(eps), float(momentum))
+
+
 def _split_k(out_rows: int, out_cols: int, k: int) -> int:
     """Reduction splits for a weight-gradient product: enough CTAs for ~2 waves of 148 SMs, >= 4 k-blocks of 32 per split."""
     tiles = ((out_rows + 127)//128)*((out_cols + 255)//256)
-    return max(1, min((2*148 + tiles - 1)//tiles, k//128))
+    return max(1, min((2*148)//tiles, k//128))  # floor: tiles*splits <= 296 CTAs = two full waves, no 1-CTA tail wave
 
 
 class _ConvNeXtMlp(torch.autograd.Function):

@@ -50,11 +50,16 @@ def _stem_conv_nhwc(x4: Tensor, conv: nn.Conv2d) -> Tensor:
     return F_.conv2d_nhwc(x4, w, conv.bias, stride=conv.stride[0], pad=conv.padding[0])
 
 
-def _bn_nhwc(x: Tensor, bn: nn.BatchNorm2d, relu: bool = False) -> Tensor:
-    """Train-mode BatchNorm (per-GPU batch statistics, as the reference) on a channels-last tensor."""
-    y = F.batch_norm(x.permute(0, 3, 1, 2), bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps)
-    if relu: y = F.relu(y, inplace=True)
-    return y.permute(0, 2, 3, 1)
+def _bn_nhwc(x: Tensor, bn: nn.BatchNorm2d, relu: bool = False, res: Tensor | None = None) -> Tensor:
+    """[relu](BatchNorm(x) [+ res]) on a channels-last tensor. Training mode (per-GPU batch statistics, as the reference): one
+    libstv launch set with the residual add and ReLU fused; evaluation mode (running statistics) is a plain affine map."""
+    if bn.training:
+        return F_.batch_norm_nhwc(x, bn.weight, bn.bias, res=res, relu=relu, run_mean=bn.running_mean, run_var=bn.running_var,
+                                  eps=bn.eps, momentum=bn.momentum)
+    scale = bn.weight*torch.rsqrt(bn.running_var + bn.eps)
+    y = x*scale + (bn.bias - bn.running_mean*scale)
+    if res is not None: y = y + res
+    return F.relu(y) if relu else y
 
 
 class FeatureInfo:
@@ -91,9 +96,8 @@ class BasicBlock(nn.Module):
         """x (N,H,W,C) channels-last; convolutions are libstv tcgen05 implicit GEMMs."""
         s = self.conv1.stride[0]
         y = _bn_nhwc(F_.conv2d_nhwc(x, self.conv1.weight, None, stride=s, pad=1), self.bn1, relu=True)
-        y = _bn_nhwc(F_.conv2d_nhwc(y, self.conv2.weight, None, pad=1), self.bn2)
         sc = x if self.downsample is None else _bn_nhwc(F_.conv2d_nhwc(x, self.downsample[0].weight, None, stride=s), self.downsample[1])
-        return F.relu(y + sc, inplace=True)
+        return _bn_nhwc(F_.conv2d_nhwc(y, self.conv2.weight, None, pad=1), self.bn2, relu=True, res=sc)
 
 
 class ResNetEncoder(nn.Module):

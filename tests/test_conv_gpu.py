@@ -26,6 +26,12 @@ CASES = {
     'odd_sizes':      (3, 9, 11, 48, 0, False, 40, 3, 1, 1, True),
     'wide_multi_tile': (2, 40, 56, 64, 0, False, 288, 3, 1, 1, False),
     'head_cout1':     (2, 10, 14, 16, 0, False, 1, 3, 1, 1, True),
+    'head_cout1_c32': (2, 10, 14, 32, 0, False, 1, 3, 1, 1, True),
+    'cat16_16_up':    (2, 12, 16, 16, 16, True, 32, 3, 1, 1, True),
+    'zero3x3_c16':    (2, 12, 20, 16, 0, False, 32, 3, 1, 1, False),
+    'pose_head_1x1':  (3, 6, 10, 256, 0, False, 12, 1, 1, 0, False),
+    'tall_batch':     (5, 7, 33, 64, 0, False, 64, 3, 1, 1, False),
+    'reflect_cout16': (2, 16, 24, 32, 0, False, 16, 3, 1, 1, True),
 }
 
 

@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 from slowtv_monodepth_b200 import functional as F_
 
-ap = argparse.ArgumentParser(); ap.add_argument('--b', type=int, default=8); a = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument('--b', type=int, default=8); ap.add_argument('--only', default=''); a = ap.parse_args()
 torch.backends.cudnn.benchmark = True; torch.backends.cudnn.allow_tf32 = True
 dev = 'cuda'
 #         name            H    W    C1   C2  up1   Cout R st pad reflect
@@ -40,6 +40,7 @@ def timeit(fn, n=5):
 
 print(f'{"layer":12s} {"GF(fwd)":>8s} | ours fwd  bwd (ms) TF/s(fwd) | cudnn fwd  bwd (ms)')
 for name, H, W, C1, C2, up1, Cout, R, st, pad, refl in SHAPES:
+    if a.only and name not in a.only.split(','): continue
     N = a.b*(2 if name.startswith('res') else 1)
     s1 = torch.randn((N, H//2, W//2, C1) if up1 else (N, H, W, C1), device=dev).requires_grad_()
     s2 = torch.randn(N, H, W, C2, device=dev).requires_grad_() if C2 else None
