@@ -154,7 +154,7 @@ int stv_layernorm_bwd(long long P, int C, const float* dy, const float* x, const
  * a_mn = 0: A is stored row-major [M][lda] (k contiguous);  a_mn = 1: A is stored [K][lda] (m contiguous).
  * b_mn = 0: B is stored row-major [N][ldb] (k contiguous);  b_mn = 1: B is stored [K][ldb] (n contiguous).
  * Epilogue, in this order:  v = acc + bias[n];  aux[m,n] = v;  v = act(v);  v *= gamma[n];  v += res[m,n];
- *                           v *= act'(dact_src[m,n]);  C[m,n] = v  (accumulate = 0)  or  C[m,n] += v  (atomic).
+ *                           v *= act'(dact_src[m,n]);  C[m,n] = v  (accumulate = 0)  or  C[m,n] += v  (atomic);  colsum[n] += v.
  * `dact_src` holds the pre-activation for GELU and the activation OUTPUT for ReLU / ELU / sigmoid.
  * aux / res / dact_src share C's leading dimension ldc. Alignment: every pointer 16 bytes; N, lda, ldb, ldc multiples of 4.
  * split_k > 1 partitions the reduction over gridDim.z and requires accumulate = 1 into a pre-initialised C.
@@ -171,6 +171,7 @@ typedef struct {
     const float* gamma;    /* [N] or NULL */
     const float* res;      /* [M][ldc] or NULL */
     const float* dact_src; /* [M][ldc] or NULL */
+    float* colsum;         /* [N] or NULL: colsum[n] += sum_m (final value written for C[m,n]) — bias gradients, atomically accumulated */
     int act;               /* STV_ACT_* applied forward */
     int dact;              /* STV_ACT_* whose derivative multiplies the result when dact_src != NULL */
     int accumulate;
@@ -208,9 +209,10 @@ int stv_conv_dgrad(const stv_conv_geom* g, const float* dy, const float* w, floa
 /* dw (Cout,R,S,C) += dy^T im2col(V) (atomic accumulation: dw must be initialised); Cout % 4 == 0. split_k <= 0: automatic. */
 int stv_conv_wgrad(const stv_conv_geom* g, const float* src1, const float* src2, const float* dy, float* dw, int split_k,
                    void* stream);
-/* out (N, H+2p, W+2p, C1+C2) = the virtual input V materialised: cat(up2(src1) | src1, src2), reflection-padded by p = g.pad when
- * g.reflect (p = 0 otherwise). Lets a reflect / upsample / concat convolution run through the TMA im2col path (pad 0 on `out`). */
-int stv_vpad(const stv_conv_geom* g, const float* src1, const float* src2, float* out, void* stream);
+/* out (N, H+2p, W+2p, Cp) = the virtual input V materialised: cat(up2(src1) | src1, src2), reflection-padded by p = g.pad when
+ * g.reflect (p = 0 otherwise), channels [C1+C2, Cp) zero. Lets a reflect / upsample / concat / narrow-channel convolution run
+ * through the TMA im2col path (pad 0 on `out`, filters zero-padded to Cp input channels). */
+int stv_vpad(const stv_conv_geom* g, const float* src1, const float* src2, int Cp, float* out, void* stream);
 /* dst (N,H,W,C) (+)= slice/fold/pool of src (N, H*pool + 2 pad, W*pool + 2 pad, Cs): channels [c_off, c_off + C), the
  * reflection-padding border folded back onto the interior, and pool x pool (1 or 2) sum-pooling (adjoint of nearest x2). */
 int stv_grad_pull(int N, int H, int W, int C, const float* src, int Cs, int c_off, int pad, int pool, float* dst, int accumulate,

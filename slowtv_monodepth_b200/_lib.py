@@ -31,7 +31,7 @@ class PhotoCfg(C.Structure):
 
 class GemmEpi(C.Structure):
     _fields_ = [('bias', C.c_void_p), ('aux', C.c_void_p), ('gamma', C.c_void_p), ('res', C.c_void_p), ('dact_src', C.c_void_p),
-                ('act', C.c_int), ('dact', C.c_int), ('accumulate', C.c_int)]
+                ('colsum', C.c_void_p), ('act', C.c_int), ('dact', C.c_int), ('accumulate', C.c_int)]
 
 
 ACT = {None: 0, 'none': 0, 'relu': 1, 'gelu': 2, 'elu': 3, 'sigmoid': 4}
@@ -75,7 +75,7 @@ _SIGNATURES = {
     'stv_conv_fprop': (C.c_int, [C.POINTER(ConvGeom), _P, _P, _P, _P, C.POINTER(GemmEpi), _P]),
     'stv_conv_dgrad': (C.c_int, [C.POINTER(ConvGeom), _P, _P, _P, C.POINTER(GemmEpi), _P]),
     'stv_conv_wgrad': (C.c_int, [C.POINTER(ConvGeom), _P, _P, _P, _P, C.c_int, _P]),
-    'stv_vpad': (C.c_int, [C.POINTER(ConvGeom), _P, _P, _P, _P]),
+    'stv_vpad': (C.c_int, [C.POINTER(ConvGeom), _P, _P, C.c_int, _P, _P]),
     'stv_grad_pull': (C.c_int, [C.c_int]*4 + [_P] + [C.c_int]*4 + [_P, C.c_int, _P]),
     'stv_act_bwd': (C.c_int, [C.c_longlong, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     'stv_colsum': (C.c_int, [C.c_longlong, C.c_int, C.c_longlong, _P, _P, _P]),

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(CV_THREADS) conv_igemm_kernel(const __grid_con
         // ---- epilogue ------------------------------------------------------------------------------------------------
         tc::mbar_wait(sm.tmem_full, 0);
         tc::tcgen05_fence_after();
-        epilogue_tile(tmem_base, warp, lane, m0, n0, p.bn, p.M, p.N, p.C, p.ldc, p.e, (float*)sm.tiles + warp*EPI_WARP_FLOATS);
+        epilogue_tile(tmem_base, warp, lane, m0, n0, p.bn, p.M, p.N, p.C, RowMap{p.ldc, 0, 0, 0, 0, 0, 0, 0, 0}, p.e, (float*)sm.tiles + warp*EPI_WARP_FLOATS);
     } else if (warp == 4) {
         if (lane == 0) {
             for (int it = 0; it < nk; ++it) {
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(CV_THREADS) conv_wgrad_kernel(const __grid_con
         for (int it = max(nk - lag, 0); it < nk; ++it) CV_PRODUCER_PUBLISH(it);
         tc::mbar_wait(sm.tmem_full, 0);
         tc::tcgen05_fence_after();
-        epilogue_tile(tmem_base, warp, lane, m0, n0, p.bn, p.M, p.N, p.C, p.ldc, p.e, (float*)sm.tiles + warp*EPI_WARP_FLOATS);
+        epilogue_tile(tmem_base, warp, lane, m0, n0, p.bn, p.M, p.N, p.C, RowMap{p.ldc, 0, 0, 0, 0, 0, 0, 0, 0}, p.e, (float*)sm.tiles + warp*EPI_WARP_FLOATS);
     } else if (warp == 4) {
         if (lane == 0) {
             for (int it = 0; it < nk; ++it) {
@@ -449,6 +449,7 @@ static int dgrad_tma(const stv_conv_geom* g, int P, int Q, const float* dy, cons
     ConvOperand& cv = p.cv;
     cv.mode = 1; cv.gridH = g->H; cv.gridW = g->W; cv.stride = 1; cv.lw = g->pad - (g->S - 1); cv.lh = g->pad - (g->R - 1);
     cv.R = g->R; cv.S = g->S; cv.C = g->Cout; cv.cblocks = (g->Cout + GEMM_BK - 1)/GEMM_BK; cv.flip = 1; cv.b_tap_cols = Cin;
+    cv.r0 = cv.s0 = 0; cv.tstep = 1; cv.Sfull = g->S;
     p.kb_total = g->R*g->S*cv.cblocks; p.kb_per_split = p.kb_total;
     p.C = dx; p.ldc = Cin;
     if (epi) p.e = *epi;
@@ -456,6 +457,40 @@ static int dgrad_tma(const stv_conv_geom* g, int P, int Q, const float* dy, cons
     if (int rc = make_tmap_im2col(&tmA, dy, g->N, P, Q, g->Cout, cv.lw, cv.lh, cv.lw + (g->W - Q), cv.lh + (g->H - P), 1, GEMM_BM, 0)) return rc;
     if (int rc = make_tmap_2d(&tmB, w, g->Cout, (long long)g->R*g->S*Cin, (long long)g->R*g->S*Cin, 32, 1)) return rc;
     return launch_gemm(tmA, tmB, p, 1, st, "stv_conv_dgrad(tma)");
+}
+
+// Data gradient of a stride-s convolution as s*s stride-1 problems: output pixels of parity (a, b) only see the filter taps
+// r = (a + pad) mod s + s*i, s = (b + pad) mod s + s*j, read from dY at (y' + q_a - i, x' + q_b - j), q_a = (a + pad - r_a)/s.
+static int dgrad_tma_strided(const stv_conv_geom* g, int P, int Q, const float* dy, const float* w, float* dx, const stv_gemm_epi* epi,
+                             cudaStream_t st) {
+    const int Cin = g->C1 + g->C2, s = g->stride, Hs = g->H/s, Ws = g->W/s;
+    bool all = true;
+    for (int a = 0; a < s; ++a) all = all && ((a + g->pad) % s < g->R) && ((a + g->pad) % s < g->S);
+    if (!all && cudaMemsetAsync(dx, 0, (size_t)g->N*g->H*g->W*Cin*sizeof(float), st) != cudaSuccess) return check_launch("stv_conv_dgrad(memset)");
+    CUtensorMap tmB;
+    if (int rc = make_tmap_2d(&tmB, w, g->Cout, (long long)g->R*g->S*Cin, (long long)g->R*g->S*Cin, 32, 1)) return rc;
+    for (int a = 0; a < s; ++a)
+        for (int b = 0; b < s; ++b) {
+            const int ra = (a + g->pad) % s, sb = (b + g->pad) % s;
+            if (ra >= g->R || sb >= g->S) continue;
+            const int na = (g->R - ra + s - 1)/s, nb = (g->S - sb + s - 1)/s, qa = (a + g->pad - ra)/s, qb = (b + g->pad - sb)/s;
+            GemmParams p = {};
+            p.M = g->N*Hs*Ws; p.N = Cin; p.K = na*nb*g->Cout;
+            p.bn = pick_bn(p.N, (p.M + GEMM_BM - 1)/GEMM_BM);
+            p.b_mn = 1;
+            ConvOperand& cv = p.cv;
+            cv.mode = 1; cv.gridH = Hs; cv.gridW = Ws; cv.stride = 1; cv.lw = qb - (nb - 1); cv.lh = qa - (na - 1);
+            cv.R = na; cv.S = nb; cv.C = g->Cout; cv.cblocks = (g->Cout + GEMM_BK - 1)/GEMM_BK; cv.flip = 1; cv.b_tap_cols = Cin;
+            cv.r0 = ra; cv.s0 = sb; cv.tstep = s; cv.Sfull = g->S;
+            p.kb_total = na*nb*cv.cblocks; p.kb_per_split = p.kb_total;
+            p.C = dx; p.ldc = Cin;
+            p.remap = 1; p.oH = g->H; p.oW = g->W; p.ost = s; p.oa = a; p.ob = b;
+            if (epi) p.e = *epi;
+            CUtensorMap tmA;
+            if (int rc = make_tmap_im2col(&tmA, dy, g->N, P, Q, g->Cout, cv.lw, cv.lh, cv.lw + (Ws - Q), cv.lh + (Hs - P), 1, GEMM_BM, 0)) return rc;
+            if (int rc = launch_gemm(tmA, tmB, p, 1, st, "stv_conv_dgrad(tma, strided)")) return rc;
+        }
+    return STV_OK;
 }
 
 static int wgrad_tma(const stv_conv_geom* g, int P, int Q, const float* x, const float* dy, float* dw, int split_k, cudaStream_t st) {
@@ -485,10 +520,10 @@ static int wgrad_tma(const stv_conv_geom* g, int P, int Q, const float* x, const
     return launch_gemm(tmA, tmB, p, split_k, st, "stv_conv_wgrad(tma)");
 }
 
-// out (N, H+2p, W+2p, C1+C2) = reflection-pad_p(cat(up2(src1) | src1, src2)); p = g.pad when g.reflect else 0.
-__global__ void vpad_kernel(int N, int H, int W, int C1, int C2, int up1, int pad, const float* __restrict__ s1, const float* __restrict__ s2,
-                            float* __restrict__ out) {
-    const int Cc = C1 + C2, c4n = Cc >> 2, Hp = H + 2*pad, Wp = W + 2*pad;
+// out (N, H+2p, W+2p, Cp) = reflection-pad_p(cat(up2(src1) | src1, src2)), channels [C1+C2, Cp) zero; p = g.pad when g.reflect else 0.
+__global__ void vpad_kernel(int N, int H, int W, int C1, int C2, int Cp, int up1, int pad, const float* __restrict__ s1,
+                            const float* __restrict__ s2, float* __restrict__ out) {
+    const int Cc = C1 + C2, c4n = Cp >> 2, Hp = H + 2*pad, Wp = W + 2*pad;
     const long long total = (long long)N*Hp*Wp*c4n;
     for (long long idx = blockIdx.x*(long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x*blockDim.x) {
         const int c = (int)(idx % c4n)*4;
@@ -496,10 +531,14 @@ __global__ void vpad_kernel(int N, int H, int W, int C1, int C2, int up1, int pa
         const int xp = (int)(r % Wp); r /= Wp;
         const int yp = (int)(r % Hp);
         const int n = (int)(r/Hp);
-        const int y = reflect_any(yp - pad, H), x = reflect_any(xp - pad, W);
-        const float* src = c < C1 ? (up1 ? s1 + ((size_t)(n*(H >> 1) + (y >> 1))*(W >> 1) + (x >> 1))*C1 + c : s1 + ((size_t)(n*H + y)*W + x)*C1 + c)
-                                  : s2 + ((size_t)(n*H + y)*W + x)*C2 + (c - C1);
-        ((float4*)out)[idx] = __ldg((const float4*)src);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < Cc) {
+            const int y = reflect_any(yp - pad, H), x = reflect_any(xp - pad, W);
+            const float* src = c < C1 ? (up1 ? s1 + ((size_t)(n*(H >> 1) + (y >> 1))*(W >> 1) + (x >> 1))*C1 + c : s1 + ((size_t)(n*H + y)*W + x)*C1 + c)
+                                      : s2 + ((size_t)(n*H + y)*W + x)*C2 + (c - C1);
+            v = __ldg((const float4*)src);
+        }
+        ((float4*)out)[idx] = v;
     }
 }
 
@@ -507,14 +546,15 @@ __global__ void vpad_kernel(int N, int H, int W, int C1, int C2, int up1, int pa
 
 using namespace stv;
 
-extern "C" int stv_vpad(const stv_conv_geom* g, const float* src1, const float* src2, float* out, void* stream) {
+extern "C" int stv_vpad(const stv_conv_geom* g, const float* src1, const float* src2, int Cp, float* out, void* stream) {
     int P, Q;
     if (int rc = check_geom(g, "stv_vpad", P, Q)) return rc;
     STV_REQUIRE(src1 && out && (g->C2 == 0 || src2), "stv_vpad: null pointer");
+    STV_REQUIRE(Cp >= g->C1 + g->C2 && Cp % 4 == 0, "stv_vpad: padded channel count %d must be a multiple of 4 and >= %d", Cp, g->C1 + g->C2);
     const int pad = g->reflect ? g->pad : 0;
-    const long long total = (long long)g->N*(g->H + 2*pad)*(g->W + 2*pad)*((g->C1 + g->C2)/4);
+    const long long total = (long long)g->N*(g->H + 2*pad)*(g->W + 2*pad)*(Cp/4);
     const int blocks = (int)((total + 255)/256 < 148ll*32 ? (total + 255)/256 : 148ll*32);
-    vpad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g->N, g->H, g->W, g->C1, g->C2, g->up1, pad, src1, src2 ? src2 : src1, out);
+    vpad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g->N, g->H, g->W, g->C1, g->C2, Cp, g->up1, pad, src1, src2 ? src2 : src1, out);
     count_launch();
     return check_launch("stv_vpad");
 }
@@ -557,6 +597,9 @@ extern "C" int stv_conv_dgrad(const stv_conv_geom* g, const float* dy, const flo
     const int Cin = g->C1 + g->C2;
     if (g->stride == 1 && !g->reflect && Cin % 4 == 0 && g->pad <= 120 && g->R <= 120 && g->S <= 120 && (long long)g->N*g->H*g->W < (1ll << 31))
         return dgrad_tma(g, P, Q, dy, w, dv, epi, (cudaStream_t)stream);
+    if (g->stride > 1 && !g->reflect && g->H % g->stride == 0 && g->W % g->stride == 0 && g->pad <= 120 && g->R <= 120 && g->S <= 120 &&
+        !(epi && (epi->aux || epi->res || epi->dact_src)) && (long long)g->N*g->H*g->W < (1ll << 31))
+        return dgrad_tma_strided(g, P, Q, dy, w, dv, epi, (cudaStream_t)stream);
     // Gathered tensor = dY (N, P, Q, Cout); grid pixels = (padded, when reflecting) input pixels.
     ConvParams p = {};
     Gather& G = p.g;

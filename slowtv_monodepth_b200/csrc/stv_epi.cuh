@@ -5,10 +5,24 @@
 
 namespace stv {
 
+// Branch-free erf (Abramowitz & Stegun 7.1.26, |abs err| <= 1.5e-7) given e = exp(-u*u): one MUFU.RCP + 5 FMA. erff() costs ~3x
+// the instructions and branches on |u|, which serialises the four elements of a float4 in the epilogue warps.
+__device__ __forceinline__ float erf_fast(float u, float e) {
+    const float t = __frcp_rn(fmaf(0.3275911f, fabsf(u), 1.f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    return copysignf(fmaf(-p*t, e, 1.f), u);
+}
+
 __device__ __forceinline__ float act_fwd(int act, float x) {
     switch (act) {
         case STV_ACT_RELU: return fmaxf(x, 0.f);
-        case STV_ACT_GELU: return 0.5f*x*(1.f + erff(x*0.70710678118654752f));
+        case STV_ACT_GELU: {  // exact (erf) GELU, torch.nn.functional.gelu default
+            const float u = x*0.70710678118654752f;
+            return 0.5f*x*(1.f + erf_fast(u, __expf(-u*u)));
+        }
         case STV_ACT_ELU: return x > 0.f ? x : __expf(x) - 1.f;  // |abs err| < 2e-7; expm1f costs ~4x the instructions
         case STV_ACT_SIGMOID: return 1.f/(1.f + __expf(-x));
         default: return x;
@@ -18,28 +32,37 @@ __device__ __forceinline__ float act_fwd(int act, float x) {
 __device__ __forceinline__ float act_bwd(int act, float s) {
     switch (act) {
         case STV_ACT_RELU: return s > 0.f ? 1.f : 0.f;
-        case STV_ACT_GELU: return 0.5f*(1.f + erff(s*0.70710678118654752f)) + s*0.3989422804014327f*__expf(-0.5f*s*s);
+        case STV_ACT_GELU: {  // Phi(s) + s*phi(s); exp(-s^2/2) is shared by the erf and the density term
+            const float u = s*0.70710678118654752f, e = __expf(-u*u);
+            return fmaf(s*0.3989422804014327f, e, 0.5f*(1.f + erf_fast(u, e)));
+        }
         case STV_ACT_ELU: return s > 0.f ? 1.f : s + 1.f;
         case STV_ACT_SIGMOID: return s*(1.f - s);
         default: return 1.f;
     }
 }
 
-// One warp drains its 32 TMEM lanes (= 32 output rows) of a 128 x bn fp32 accumulator tile, 32 columns at a time:
-//   v = acc + bias[n];  aux = v;  v = act(v);  v *= gamma[n];  v += res;  v *= act'(dact_src);  C = v  or  C += v (red.add).
-// q = TMEM lane quarter of the calling warp (warp index & 3). Row r of the tile is output row m0 + r at C + (m0 + r)*ldc.
-// tcgen05.ld hands every thread ONE ROW (32 consecutive columns); written out like that, each store instruction would touch
-// 32 different 128-byte lines. The chunk is therefore transposed through `xs` (this warp's 32 x EPI_LD float staging tile in
-// shared memory) so that 8 lanes cover the 128 contiguous bytes of a row and every global access (C, aux, res, dact_src) is
-// a full-line, coalesced 128-bit access.
+// Output row -> element offset. Plain GEMM / convolution outputs are row-major (row*ldc). A stride-s data gradient is computed
+// as s*s stride-1 sub-problems, one per output parity (a, b): row (n, y', x') of a sub-problem lands at pixel (n, s*y'+a, s*x'+b).
+struct RowMap {
+    long long ldc;
+    int remap, gH, gW, oH, oW, ost, oa, ob;
+    __device__ __forceinline__ size_t off(int row) const {
+        if (!remap) return (size_t)row*ldc;
+        const int hw = gH*gW, n = row/hw, rem = row - n*hw, y = rem/gW, x = rem - y*gW;
+        return ((size_t)(n*oH + y*ost + oa)*oW + (x*ost + ob))*ldc;
+    }
+};
+
 constexpr int EPI_LD = 36;                       // floats per staged row: 16-byte aligned, conflict-free for 128-bit accesses
 constexpr int EPI_WARP_FLOATS = 32*EPI_LD;       // staging floats per epilogue warp
 
+// Chunks c_first, c_first + c_step, ... of the tile are handled by this warp (two warps per lane quarter split the columns).
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int q, int lane, int m0, int n0, int bn, int M, int N, float* C,
-                                              long long ldc, const stv_gemm_epi& e, float* xs) {
+                                              const RowMap& rm, const stv_gemm_epi& e, float* xs, int c_first = 0, int c_step = 32) {
     const bool vec = (N & 3) == 0;
     const int rsub = lane >> 3, cq = (lane & 7)*4;
-    for (int c = 0; c < bn; c += 32) {
+    for (int c = c_first; c < bn; c += c_step) {
         if (n0 + c >= N) break;  // warp-uniform
         uint32_t v[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(q*32) << 16) + (uint32_t)c, v);
@@ -55,6 +78,9 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int q, int lan
                 const float4 bb = e.bias ? __ldg((const float4*)(e.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 gg = e.gamma ? __ldg((const float4*)(e.gamma + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
                 const int row0 = m0 + q*32 + rsub;
+                size_t roffs[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) roffs[i] = row0 + 4*i < M ? rm.off(row0 + 4*i) : 0;
                 // The epilogue's own global reads (residual OR activation-derivative source) are issued for the whole chunk
                 // up front: with one resident warp per scheduler a load placed next to its use costs a full memory latency.
                 const float* __restrict__ pre_src = e.res ? e.res : e.dact_src;
@@ -62,13 +88,14 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int q, int lan
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int row = row0 + 4*i;
-                    pre[i] = (pre_src && row < M) ? __ldg((const float4*)(pre_src + (size_t)row*ldc + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    pre[i] = (pre_src && row < M) ? __ldg((const float4*)(pre_src + roffs[i] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int row = row0 + 4*i;
                     if (row >= M) break;
-                    const size_t o = (size_t)row*ldc + n;
+                    const size_t o = roffs[i] + n;
                     float4 x = *(const float4*)(xs + (4*i + rsub)*EPI_LD + cq);
                     x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
                     if (e.aux) *(float4*)(e.aux + o) = x;
@@ -81,13 +108,24 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int q, int lan
                     }
                     if (e.accumulate) tc::red_add_v4(C + o, x.x, x.y, x.z, x.w);
                     else *(float4*)(C + o) = x;
+                    cs.x += x.x; cs.y += x.y; cs.z += x.z; cs.w += x.w;
+                }
+                if (e.colsum) {  // lanes l, l^8, l^16, l^24 hold the same 4 columns (different rows): combine, then one red per column group
+                    // (all 32 lanes of the warp reach this point together when n < N for the whole warp; guard with the active mask)
+                    const unsigned am = __activemask();
+#pragma unroll
+                    for (int o = 8; o <= 16; o <<= 1) {
+                        cs.x += __shfl_xor_sync(am, cs.x, o); cs.y += __shfl_xor_sync(am, cs.y, o);
+                        cs.z += __shfl_xor_sync(am, cs.z, o); cs.w += __shfl_xor_sync(am, cs.w, o);
+                    }
+                    if (rsub == 0) tc::red_add_v4(e.colsum + n, cs.x, cs.y, cs.z, cs.w);
                 }
             }
             __syncwarp();
         } else {  // narrow outputs (e.g. the 1-channel disparity heads): one row per thread, scalar columns
             const int row = m0 + q*32 + lane;
             if (row >= M) continue;
-            const size_t roff = (size_t)row*ldc;
+            const size_t roff = rm.off(row);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int n = n0 + c + j;

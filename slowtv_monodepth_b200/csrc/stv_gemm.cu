@@ -12,11 +12,12 @@
 // src/core/trainer.py:30; cfg/default.yaml:171). Call sites replaced: the `nn.Linear` / 1x1 `nn.Conv2d` layers of the timm
 // encoders built at src/networks/depth.py:97 / pose.py:40 and of the pose heads (src/networks/pose.py:46,75-106).
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Structure (one 128 x BN output tile per CTA, 320 threads):
 //   warp 0    TMA producer: per 32-wide k-block, box loads of A and B slabs into a ring of smem stages (mbarrier expect_tx)
 //   warp 1    TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit releases stages / signals the epilogue
-//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias / activation / layer-scale / residual /
-//             activation-backward -> 128-bit global stores, or red.global.add.v4 when accumulating (split-K, grad buffers)
+//   warps 2-9 epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> shared-memory transpose -> bias / activation /
+//             layer-scale / residual / activation-backward / column sums -> coalesced 128-bit global stores, or
+//             red.global.add.v4 when accumulating (split-K, grad buffers)
 #include <mutex>
 
 #include "stv_common.cuh"
@@ -100,7 +101,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (!p.b_mn) tc::tma_load_2d(b, &tmB, &full[s], k, n0);
                     else
                         for (int j = 0; j < p.bn/32; ++j)
-                            tc::tma_load_2d(b + j*SLAB_MN_BYTES, &tmB, &full[s], tap*cv.b_tap_cols + n0 + 32*j, cb*GEMM_BK);
+                            tc::tma_load_2d(b + j*SLAB_MN_BYTES, &tmB, &full[s], ((cv.r0 + cv.tstep*r)*cv.Sfull + cv.s0 + cv.tstep*sx)*cv.b_tap_cols + n0 + 32*j,
+                                            cb*GEMM_BK);
                     if (++cb == cv.cblocks) { cb = 0; ++tap; }
                     continue;
                 }
@@ -146,7 +148,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc::mbar_wait(tmem_full, 0);
         tc::tcgen05_fence_after();
         // Every MMA has retired (tmem_full), so the operand ring is free: its first bytes stage the transposed output chunks.
-        epilogue_tile(tmem_base, warp & 3, lane, m0, n0, p.bn, p.M, p.N, p.C, p.ldc, p.e, (float*)smem + (warp & 3)*EPI_WARP_FLOATS);
+        const RowMap rm = {p.ldc, p.remap, p.cv.gridH, p.cv.gridW, p.oH, p.oW, p.ost, p.oa, p.ob};
+        // Warps 2..9: lane quarter = warp & 3 (the TMEM lanes a warp may read), column chunks interleaved between the two warps
+        // of a quarter — the epilogue math (GELU, GELU') is what bounds the narrow-K layers, so it gets 8 of the 10 warps.
+        const int ew = warp - 2;
+        epilogue_tile(tmem_base, warp & 3, lane, m0, n0, p.bn, p.M, p.N, p.C, rm, p.e, (float*)smem + ew*EPI_WARP_FLOATS, (ew >> 2)*32, 64);
     }
     tc::tcgen05_fence_before();
     __syncthreads();

@@ -5,7 +5,7 @@
 
 namespace stv {
 
-constexpr int GEMM_BM = 128, GEMM_BK = 32, GEMM_THREADS = 192, GEMM_MAX_STAGES = 8;
+constexpr int GEMM_BM = 128, GEMM_BK = 32, GEMM_THREADS = 320, GEMM_MAX_STAGES = 8;  // warps: TMA, MMA, 8 x epilogue
 constexpr int GEMM_A_BYTES = GEMM_BM*GEMM_BK*4;  // 16 KB per stage
 constexpr int SLAB_MN_BYTES = 32*128;            // MN-major slab: 32 k-rows x 128 B
 
@@ -19,7 +19,8 @@ struct ConvOperand {
     int R, S, C;        // filter taps; channels of the im2col tensor
     int cblocks;        // mode 1: k-blocks per tap = ceil(C/32)
     int flip;           // dgrad: tap (r, s) reads offsets (R-1-r, S-1-s)
-    int b_tap_cols;     // dgrad: B (filters, MN-major boxes) column coordinate = tap*b_tap_cols + n0 + 32*slab, row = channel block
+    int b_tap_cols;     // dgrad: B (filters, MN-major boxes) column = full_tap*b_tap_cols + n0 + 32*slab, row = channel block, where
+    int r0, s0, tstep, Sfull;  //   full_tap = (r0 + tstep*r)*Sfull + (s0 + tstep*s): the sub-filter of one output parity (strided dgrad)
 };
 
 struct GemmParams {
@@ -30,6 +31,7 @@ struct GemmParams {
     long long ldc;
     stv_gemm_epi e;
     ConvOperand cv;
+    int remap, oH, oW, ost, oa, ob;  // RowMap of the output (stv_epi.cuh); rows enumerate (n, cv.gridH, cv.gridW) when remap != 0
 };
 
 int make_tmap_2d(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows, int mn_major);

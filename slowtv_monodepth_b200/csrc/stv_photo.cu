@@ -452,7 +452,7 @@ struct BwdSmem {
 };
 
 template <bool NEED_K>
-__global__ void __launch_bounds__(NT) photo_bwd_kernel(PhotoParams p) {
+__global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(PhotoParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
     constexpr int NACC = N_ACC_T + (NEED_K ? N_ACC_K : 0);

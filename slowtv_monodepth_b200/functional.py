@@ -374,12 +374,13 @@ def layer_norm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-6) -> Ten
 # ---------------------------------------------------------------------------------------------------------------------
 def gemm_tf32(A: Tensor, B: Tensor, *, a_mn: bool = False, b_mn: bool = False, out: Tensor | None = None, bias: Tensor | None = None,
               act: str | None = None, aux: Tensor | None = None, gamma: Tensor | None = None, res: Tensor | None = None,
-              dact: str | None = None, dact_src: Tensor | None = None, accumulate: bool = False, split_k: int = 1) -> Tensor:
+              dact: str | None = None, dact_src: Tensor | None = None, colsum: Tensor | None = None, accumulate: bool = False,
+              split_k: int = 1) -> Tensor:
     """C[M,N] (+)= epilogue(sum_k A[m,k] B[n,k]) on the tcgen05 tensor cores (include/stv.h: stv_gemm_tf32). No autograd.
 
     A: (M,K) if not a_mn else (K,M);  B: (N,K) if not b_mn else (K,N); both 2-D with unit inner stride (row stride free).
     out / aux / res / dact_src: (M,N), same row stride. Returns `out` (allocated when None)."""
-    L.require_cuda(A, B, out, bias, aux, gamma, res, dact_src, what='gemm_tf32')
+    L.require_cuda(A, B, out, bias, aux, gamma, res, dact_src, colsum, what='gemm_tf32')
     for t in (A, B):
         if t.ndim != 2 or t.stride(1) != 1:
             raise ValueError(f'gemm_tf32: operands must be 2-D with unit inner stride, got {tuple(t.shape)} / {t.stride()}')
@@ -395,9 +396,9 @@ def gemm_tf32(A: Tensor, B: Tensor, *, a_mn: bool = False, b_mn: bool = False, o
         for t in (aux, res, dact_src):
             if t is not None and (t.shape != (M, N) or t.stride() != out.stride()):
                 raise ValueError('gemm_tf32: aux / res / dact_src must match the output shape and strides.')
-        for t in (bias, gamma):
-            if t is not None and (t.shape != (N,) or not t.is_contiguous()): raise ValueError('gemm_tf32: bias / gamma must be contiguous (N,).')
-        epi = L.GemmEpi(bias=L.ptr(bias), aux=L.ptr(aux), gamma=L.ptr(gamma), res=L.ptr(res), dact_src=L.ptr(dact_src),
+        for t in (bias, gamma, colsum):
+            if t is not None and (t.shape != (N,) or not t.is_contiguous()): raise ValueError('gemm_tf32: bias / gamma / colsum must be contiguous (N,).')
+        epi = L.GemmEpi(bias=L.ptr(bias), aux=L.ptr(aux), gamma=L.ptr(gamma), res=L.ptr(res), dact_src=L.ptr(dact_src), colsum=L.ptr(colsum),
                         act=L.ACT[act], dact=L.ACT[dact], accumulate=int(accumulate))
         with _timed('stv_gemm_tf32'):
             L.check(L.lib().stv_gemm_tf32(M, N, K, L.ptr(A), A.stride(0), int(a_mn), L.ptr(B), B.stride(0), int(b_mn), L.ptr(out),
@@ -461,15 +462,21 @@ class _Conv2dNHWC(torch.autograd.Function):
         # does it in three passes: interpolate, cat, pad) and convolved with pad 0; otherwise (3/6/16-channel layers) the
         # cp.async gather kernel resolves the virtual input on the fly.
         ctx.virt = None
+        ctx.cin = Cin
         with torch.cuda.device(dev):
-            if (reflect or up1 or src2 is not None) and Cin % 32 == 0:
+            virt = reflect or up1 or src2 is not None
+            Cp = (Cin + 31)//32*32
+            if (virt or Cp != Cin) and Cin >= 16:
+                # Narrow layers (the 16-channel decoder level 0) are zero-padded to 32 channels on the way: the extra k-columns
+                # multiply zero filter taps, and the TMA path is several times faster than the 16-byte gather.
                 pv = pad if reflect else 0
-                V = torch.empty((g.N, g.H + 2*pv, g.W + 2*pv, Cin), dtype=torch.float32, device=dev)
-                L.check(lib.stv_vpad(C.byref(g), L.ptr(src1), L.ptr(src2), L.ptr(V), L.stream()), 'stv_vpad')
+                V = torch.empty((g.N, g.H + 2*pv, g.W + 2*pv, Cp), dtype=torch.float32, device=dev)
+                L.check(lib.stv_vpad(C.byref(g), L.ptr(src1), L.ptr(src2), Cp, L.ptr(V), L.stream()), 'stv_vpad')
                 ctx.virt = (tuple(src1.shape), None if src2 is None else tuple(src2.shape), g.C1, pv, 2 if up1 else 1)
-                g = L.ConvGeom(N=g.N, H=g.H + 2*pv, W=g.W + 2*pv, C1=Cin, C2=0, up1=0, Cout=g.Cout, R=g.R, S=g.S, stride=stride,
+                g = L.ConvGeom(N=g.N, H=g.H + 2*pv, W=g.W + 2*pv, C1=Cp, C2=0, up1=0, Cout=g.Cout, R=g.R, S=g.S, stride=stride,
                                pad=0 if reflect else pad, reflect=0)
                 src1, src2 = V, None
+                if Cp != Cin: w_phys = torch.nn.functional.pad(w_phys, (0, Cp - Cin))
             y = torch.empty((g.N, P, Q, g.Cout), dtype=torch.float32, device=dev)
             epi = L.GemmEpi(bias=L.ptr(b), act=L.ACT[act])
             with _timed('stv_conv_fprop'):
@@ -498,7 +505,7 @@ class _Conv2dNHWC(torch.autograd.Function):
                 dw = torch.zeros_like(wq)
                 with _timed('stv_conv_wgrad'):
                     L.check(lib.stv_conv_wgrad(C.byref(g), L.ptr(src1), L.ptr(src2), L.ptr(dZ), L.ptr(dw), 0, L.stream()), 'stv_conv_wgrad')
-                dw = dw[:Cout].permute(0, 3, 1, 2)
+                dw = dw[:Cout, :, :, :ctx.cin].permute(0, 3, 1, 2)
             d1 = d2 = None
             if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
                 pd = g.pad if g.reflect else 0
@@ -573,6 +580,35 @@ def batch_norm_nhwc(x: Tensor, gamma: Tensor, beta: Tensor, *, res: Tensor | Non
     return _BatchNormNHWC.apply(_f32c(x), _f32c(gamma), _f32c(beta), _f32c(res), run_mean, run_var, bool(relu), float(eps), float(momentum))
 
 
+class _Linear(torch.autograd.Function):
+    """y = act(x W^T + b) on (M, K) rows: one tcgen05 GEMM forward (bias + activation in the epilogue), up to two backward."""
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        y = gemm_tf32(x, w, bias=b, act=act)
+        ctx.save_for_backward(x, w, y)
+        ctx.act, ctx.has_bias = act, b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        db = torch.zeros(w.shape[0], dtype=torch.float32, device=y.device) if ctx.has_bias else None
+        dz = act_bwd(dy, y, ctx.act, db)
+        dx = gemm_tf32(dz, w, b_mn=True) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(w)
+            gemm_tf32(dz, x, a_mn=True, b_mn=True, out=dw, accumulate=True, split_k=_split_k(w.shape[0], w.shape[1], x.shape[0]))
+        return dx, dw, db, None
+
+
+def linear(x: Tensor, w: Tensor, b: Tensor | None = None, act: str | None = None) -> Tensor:
+    """act(x @ w.T + b): x (M,K), w (N,K), K and N multiples of 4; act in {None, relu, elu, sigmoid} (derivative from the output)."""
+    if x.ndim != 2 or w.ndim != 2 or x.shape[1] != w.shape[1]: raise ValueError(f'linear: bad shapes {tuple(x.shape)}, {tuple(w.shape)}')
+    if act == 'gelu': raise ValueError('linear: GELU needs the pre-activation; use convnext_mlp.')
+    return _Linear.apply(_f32c(x), _f32c(w), _f32c(b), act)
+
+
 def _split_k(out_rows: int, out_cols: int, k: int) -> int:
     """Reduction splits for a weight-gradient product: enough CTAs for ~2 waves of 148 SMs, >= 4 k-blocks of 32 per split."""
     tiles = ((out_rows + 127)//128)*((out_cols + 255)//256)
@@ -602,14 +638,15 @@ class _ConvNeXtMlp(torch.autograd.Function):
         M, Cc = x.shape
         Hd = w1.shape[0]
         w2g = w2*gamma[:, None]                                              # (C, 4C): layer-scale folded into fc2
-        dz = gemm_tf32(g, w2g, b_mn=True, dact='gelu', dact_src=z)           # (M, 4C) = (g W2g) * GELU'(z)
+        db1 = torch.zeros(Hd, dtype=torch.float32, device=g.device)
+        dz = gemm_tf32(g, w2g, b_mn=True, dact='gelu', dact_src=z, colsum=db1)  # (M, 4C) = (g W2g) * GELU'(z); db1 = its column sums
         dx = gemm_tf32(dz, w1, b_mn=True) if ctx.needs_input_grad[0] else None
         dw1 = torch.zeros_like(w1)
         gemm_tf32(dz, x, a_mn=True, b_mn=True, out=dw1, accumulate=True, split_k=_split_k(Hd, Cc, M))
         G = torch.zeros_like(w2)                                             # g^T h, before the layer-scale
         gemm_tf32(g, h, a_mn=True, b_mn=True, out=G, accumulate=True, split_k=_split_k(Cc, Hd, M))
-        gs = g.sum(0)
-        return (dx, g if ctx.needs_input_grad[1] else None, dw1, dz.sum(0), G*gamma[:, None], gamma*gs, (w2*G).sum(1) + b2*gs)
+        gs = colsum(g)
+        return (dx, g if ctx.needs_input_grad[1] else None, dw1, db1, G*gamma[:, None], gamma*gs, (w2*G).sum(1) + b2*gs)
 
 
 def convnext_mlp(x: Tensor, res: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, gamma: Tensor) -> Tensor:

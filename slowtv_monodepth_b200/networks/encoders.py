@@ -33,21 +33,32 @@ def _stem_conv(x: Tensor, conv: nn.Conv2d) -> Tensor:
     return conv(x)
 
 
-def _to_nhwc4(x: Tensor) -> Tensor:
-    """(N,C,H,W) image batch -> contiguous channels-last (N,H,W,C') with C' = C rounded up to a multiple of 4 (zero channels):
-    the 16-byte gather granularity of the implicit-GEMM loader. One small copy per step (the only layout conversion)."""
-    x = x.permute(0, 2, 3, 1)
-    pad = (-x.shape[-1]) % 4
-    return F.pad(x, (0, pad)) if pad else x.contiguous()
+def _stem_conv_nhwc(x: Tensor, conv: nn.Conv2d) -> Tensor:
+    """Stem convolution of an encoder on the (N,C,H,W) image batch -> channels-last (N,P,Q,Cout).
 
-
-def _stem_conv_nhwc(x4: Tensor, conv: nn.Conv2d) -> Tensor:
-    """Stem convolution on the zero-padded channels-last input. The filter's input-channel axis is zero-padded to match
-    (arithmetically a no-op; the padded slice is a temporary, so the parameter keeps the reference checkpoint's shape and its
-    gradient is the un-padded slice)."""
-    pad = x4.shape[-1] - conv.weight.shape[1]
+    The 3 / 6 input channels are too narrow for the tensor-core loaders (a TMA im2col box is 32 channels), so both stems are
+    rewritten, arithmetically exactly, as stride-1 problems over a space-to-depth view of the input:
+      * ConvNeXt `stem_0` (k x k, stride k, no padding — a patchify): one GEMM over (k*k*C)-long pixel-patch rows;
+      * ResNet `conv1` (7x7, stride 2, padding 3): the filter is zero-extended to 8x8 (one leading zero row / column), the
+        input zero-padded (4 before, 2 after) and 2x2 space-to-depth'ed with C zero-padded to 8, which turns it into a 4x4,
+        stride-1, unpadded convolution over 32 channels.
+    The filter rearrangements are tiny autograd ops on the parameter, so its shape / name / gradient stay the checkpoint's."""
+    N, Cc, H, W = x.shape
+    k, st, pd, Cout = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.out_channels
+    if k == st and pd == 0 and H % k == 0 and W % k == 0 and (k*k*Cc) % 4 == 0:
+        rows = x.view(N, Cc, H//k, k, W//k, k).permute(0, 2, 4, 3, 5, 1).reshape(-1, k*k*Cc)      # (r, s, c) within a patch
+        wmat = conv.weight.permute(0, 2, 3, 1).reshape(Cout, k*k*Cc)
+        return F_.linear(rows, wmat, conv.bias).view(N, H//k, W//k, Cout)
+    if k == 7 and st == 2 and pd == 3 and H % 2 == 0 and W % 2 == 0 and Cc <= 8:
+        xp = F.pad(x.permute(0, 2, 3, 1), (0, 8 - Cc, 4, 2, 4, 2))                               # (N, H+6, W+6, 8)
+        x2 = xp.view(N, (H + 6)//2, 2, (W + 6)//2, 2, 8).permute(0, 1, 3, 2, 4, 5).reshape(N, (H + 6)//2, (W + 6)//2, 32)
+        w8 = F.pad(conv.weight, (1, 0, 1, 0, 0, 8 - Cc))                                         # (Cout, 8, 8, 8): c, r', s'
+        w2 = w8.view(Cout, 8, 4, 2, 4, 2).permute(0, 3, 5, 1, 2, 4).reshape(Cout, 32, 4, 4)      # channel = (uy, ux, c); taps (ty, tx)
+        return F_.conv2d_nhwc(x2, w2, conv.bias)
+    pad = (-Cc) % 4
+    x4 = F.pad(x.permute(0, 2, 3, 1), (0, pad)) if pad else x.permute(0, 2, 3, 1).contiguous()
     w = F.pad(conv.weight, (0, 0, 0, 0, 0, pad)) if pad else conv.weight
-    return F_.conv2d_nhwc(x4, w, conv.bias, stride=conv.stride[0], pad=conv.padding[0])
+    return F_.conv2d_nhwc(x4, w, conv.bias, stride=st, pad=pd)
 
 
 def _bn_nhwc(x: Tensor, bn: nn.BatchNorm2d, relu: bool = False, res: Tensor | None = None) -> Tensor:
@@ -123,7 +134,7 @@ class ResNetEncoder(nn.Module):
 
     def forward(self, x: Tensor) -> list[Tensor]:
         if x.is_cuda:
-            f0 = _bn_nhwc(_stem_conv_nhwc(_to_nhwc4(x), self.conv1), self.bn1, relu=True)
+            f0 = _bn_nhwc(_stem_conv_nhwc(x, self.conv1), self.bn1, relu=True)
             x = F.max_pool2d(f0.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
             feats = [f0]
             for i in range(1, 5):
@@ -224,7 +235,7 @@ class ConvNeXtEncoder(nn.Module):
 
     def forward(self, x: Tensor) -> list[Tensor]:
         if x.is_cuda:
-            x = _stem_conv_nhwc(_to_nhwc4(x), self.stem_0)
+            x = _stem_conv_nhwc(x, self.stem_0)
             x = F_.layer_norm(x, self.stem_1.weight, self.stem_1.bias, self.stem_1.eps)
             feats = []
             for i in range(4):

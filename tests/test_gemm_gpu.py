@@ -107,7 +107,33 @@ def test_split_k_accumulate(split_k):
     assert torch.equal(out, want)
 
 
+def test_colsum_epilogue():
+    gen = torch.Generator(device='cuda').manual_seed(29)
+    M, N, K = 333, 200, 64
+    A, B = _ints((M, K), gen), _ints((N, K), gen)
+    cs = torch.ones(N, device='cuda')
+    got = F_.gemm_tf32(A, B, colsum=cs)
+    want = (A.double() @ B.double().t())
+    assert torch.equal(got, want.float()) and torch.equal(cs, (want.sum(0) + 1).float())
+
+
 def test_bad_arguments_raise():
     A, B = torch.zeros(8, 6, device='cuda'), torch.zeros(8, 6, device='cuda')
     with pytest.raises(ValueError): F_.gemm_tf32(A, B)  # K = 6 -> lda not a multiple of 4
     with pytest.raises(ValueError): F_.gemm_tf32(torch.zeros(8, 8, device='cuda'), torch.zeros(8, 12, device='cuda'))
+
+
+@pytest.mark.parametrize('act', [None, 'relu'])
+def test_linear_autograd(act):
+    gen = torch.Generator(device='cuda').manual_seed(23)
+    M, K, N = 520, 48, 96
+    x, w, b = _ints((M, K), gen).requires_grad_(), _ints((N, K), gen).requires_grad_(), _ints((N,), gen).requires_grad_()
+    y = F_.linear(x, w, b, act)
+    dy = _ints((M, N), gen)
+    y.backward(dy)
+    xr, wr, br = (t.detach().double().requires_grad_() for t in (x, w, b))
+    yr = xr @ wr.t() + br
+    if act == 'relu': yr = torch.relu(yr)
+    yr.backward(dy.double())
+    assert torch.equal(y, yr.float())
+    for a, r in ((x, xr), (w, wr), (b, br)): assert torch.equal(a.grad, r.grad.float())
