@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='enqueue every step eagerly instead of replaying the captured CUDA graph')
     return ap.parse_args()
 
 
@@ -151,7 +152,7 @@ def main() -> None:
     import torch.distributed as dist
     from slowtv_monodepth_b200 import _lib as L, functional as F_, synthetic as syn
     from slowtv_monodepth_b200.optim import FlatAdamW
-    from slowtv_monodepth_b200.trainer import MonoDepthStep, default_cfg
+    from slowtv_monodepth_b200.trainer import GraphedTrainStep, MonoDepthStep, default_cfg
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank, local = int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
@@ -181,13 +182,29 @@ def main() -> None:
     resident = [to_dev(bt) for bt in host]
     h2d_bytes = sum(v.numel()*v.element_size() for d in host[0][:2] for k, v in d.items() if k != 'supp_idxs')
 
-    def train_step(batch):
+    def eager_step(batch):
         opt.zero_grad()
         loss, _, _ = model.step(batch)
         loss.backward()
         opt.all_reduce_async()
         opt.step()
         return loss
+
+    for i in range(3): eager_step(resident[i % 2])   # first-use initialisation; also the photometric kernels' live timing below
+    F_.enable_kernel_timing(True)
+    for i in range(4): eager_step(resident[i % 2])
+    torch.cuda.synchronize()
+    kt = {k: v[1:] for k, v in F_.kernel_timings().items()}  # CUDA events around each libstv call on the launching stream
+    F_.enable_kernel_timing(False)
+    graphed, graph_note = None, 'eager (--no-graph)'
+    if not args.no_graph:
+        try:
+            graphed = GraphedTrainStep(model, opt, resident[0])
+            graph_note = 'CUDA graph replay of zero_grad+fwd+loss+bwd, then all-reduce + AdamW'
+        except Exception as e:  # keep the benchmark alive: report the eager number and say why
+            torch.cuda.synchronize()
+            graph_note = f'eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})'
+    train_step = eager_step if graphed is None else graphed.run
 
     def sync_all():
         torch.cuda.synchronize()
@@ -213,22 +230,21 @@ def main() -> None:
     # ---- value: device-resident inputs ------------------------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0: sampler.start()
-    F_.enable_kernel_timing(True)
     launches0 = L.launch_count()
+    eager_step(resident[0])
+    launches_per_step = L.launch_count() - launches0  # libstv kernels in one step (a graph replay launches the same kernels)
     ms = timed(lambda i: train_step(resident[i % 2]), args.steps)
     host_ms = timed.host_ms
-    launches = L.launch_count() - launches0
-    torch.cuda.synchronize()
-    kt = F_.kernel_timings()
-    F_.enable_kernel_timing(False)
+    launches = launches_per_step*args.steps
     clocks = sampler.stop() if rank == 0 else {}
 
     # ---- e2e: host batches through the public API -------------------------------------------------------------------
     last = {}
 
     def e2e_step(i):
-        batch = to_dev(host[i % 2])
-        last['loss'] = train_step(batch).item()  # D2H read of the step's result
+        # H2D of this step's batch (pinned host memory -> the step's input buffers) and a D2H read of its loss, every step.
+        batch = host[i % 2] if graphed is not None else to_dev(host[i % 2])
+        last['loss'] = train_step(batch).item()
     for i in range(2): e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
 
@@ -249,7 +265,7 @@ def main() -> None:
             'metric': 'training images/sec', 'value': round(b*world*args.steps/(ms/1e3), 3), 'unit': 'images/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(ms/args.steps, 3),
             'host_enqueue_ms_per_step': round(host_ms, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'global_batch': b*world, 'per_gpu_batch': b, 'parallelism': f'dp{world}',
+            'config': {'workload': WORKLOAD, 'global_batch': b*world, 'per_gpu_batch': b, 'parallelism': f'dp{world}', 'launch': graph_note,
                        'params': n_params, 'optimizer': 'adamw(lr=1e-4, wd=1e-3), fused flat-buffer kernel',
                        'l2_policy': 'inputs larger than L2: two rotating 141 MB batches + multi-GB activations per step',
                        'numerics': 'fp32 storage, TF32 tensor-core matmul/conv (reference: precision 32, matmul high), fp32 loss kernels'},

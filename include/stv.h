@@ -236,6 +236,12 @@ int stv_bn_bwd(long long M, int C, const float* dy, const float* y, const float*
                const float* gamma, int relu, float* dx, float* dres, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
                void* stream);
 
+/* Batched 4x4 inverse B = A^-1 (n matrices, row-major) and its backward gA = -B^T gB B^T: `K.inverse()` of ViewSynth.forward
+ * (src/tools/geometry.py:383) and `T.inverse()` of the backward poses (src/core/trainer.py:253). Stream-ordered, no host sync
+ * (ATen's batched LU synchronises the host and cannot be captured in a CUDA graph). */
+int stv_inv4x4(int n, const float* A, float* B, void* stream);
+int stv_inv4x4_bwd(int n, const float* B, const float* gB, float* gA, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Optimiser: replaces torch.optim.AdamW(foreach) built by timm create_optimizer_v2 (src/tools/parsers.py:205-243)
  * on one flat fp32 parameter/gradient buffer. `wd` is a per-element weight-decay mask value selector: elements in

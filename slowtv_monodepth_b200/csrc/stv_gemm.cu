@@ -41,7 +41,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tmem_full = empty + GEMM_MAX_STAGES;
     uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
-    const int m0 = blockIdx.x*GEMM_BM, n0 = blockIdx.y*p.bn;
+    // Column tiles are the fastest grid index: the CTAs that share one 128-row A tile are co-scheduled, so A is fetched from HBM
+    // once and re-read from L2; B (the filters) is small and always L2-resident.
+    const int m0 = blockIdx.y*GEMM_BM, n0 = blockIdx.x*p.bn;
     const int kb0 = blockIdx.z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
     const uint32_t tmem_cols = p.bn <= 32 ? 32u : p.bn <= 64 ? 64u : p.bn <= 128 ? 128u : 256u;
 
@@ -225,11 +227,14 @@ int make_tmap_im2col(CUtensorMap* tm, const float* base, int N, int H, int W, in
     return STV_OK;
 }
 
-// Tile width: the multiple of 32 (<= 256) that wastes the fewest columns (ties -> wider); when the resulting grid would leave
+// Tile width: the multiple of 32 (<= 128) that wastes the fewest columns (ties -> wider); when the resulting grid would leave
 // SMs idle (few row tiles: the deep, low-resolution layers) it is narrowed, down to 64, until the grid covers the 148 SMs.
 int pick_bn(int N, long long row_tiles) {
+    // <= 128 columns: a 128 x 128 tile keeps the operand ring at 32 KB per stage, so two CTAs (20 warps) stay resident per SM and
+    // one CTA's epilogue overlaps the other's main loop; wider tiles halve the residency and left the epilogue-heavy layers
+    // (GELU / GELU' over 4C columns with only 3-12 k-blocks) latency-bound.
     int best = 32, best_cost = 1 << 30;
-    for (int bn = 256; bn >= 32; bn -= 32) {
+    for (int bn = 128; bn >= 32; bn -= 32) {
         const int tiles = (N + bn - 1)/bn, cost = tiles*bn;
         if (cost < best_cost) { best = bn; best_cost = cost; }
     }
@@ -239,8 +244,7 @@ int pick_bn(int N, long long row_tiles) {
 
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int splits, cudaStream_t stream, const char* what) {
     const int stage_bytes = GEMM_A_BYTES + p.bn*GEMM_BK*4;
-    int stages = (110*1024)/stage_bytes;                         // two resident CTAs per SM when that leaves >= 3 stages,
-    if (stages < 3) stages = (200*1024)/stage_bytes;             // else one CTA with a deep ring
+    int stages = (110*1024)/stage_bytes;                         // two resident CTAs per SM (bn <= 128 -> at least 3 stages)
     stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
     stages = stages > p.kb_per_split ? (p.kb_per_split < 2 ? 2 : p.kb_per_split) : stages;
     p.stages = stages;
@@ -249,7 +253,8 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] { attr_err = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024); });
     if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute failed (%s)", what, cudaGetErrorString(attr_err)); return STV_E_CUDA; }
-    const dim3 grid((p.M + GEMM_BM - 1)/GEMM_BM, (p.N + p.bn - 1)/p.bn, splits);
+    const dim3 grid((p.N + p.bn - 1)/p.bn, (p.M + GEMM_BM - 1)/GEMM_BM, splits);
+    if (grid.y > 65535u) { set_error("%s: too many row tiles (%u)", what, grid.y); return STV_E_ARG; }
     gemm_tf32_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
     count_launch();
     return check_launch(what);

@@ -226,6 +226,73 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(long long total4, lon
     }
 }
 
+// ---- batched 4x4 inverse (intrinsics K -> K^-1, backward poses T -> T^-1) ------------------------------------------------------
+// Reference: `K.inverse()` in ViewSynth.forward (src/tools/geometry.py:383) and `T.inverse()` (src/core/trainer.py:253), which
+// ATen sends to a batched LU in cuSOLVER/MAGMA — host-synchronising and not CUDA-graph capturable. One thread per matrix:
+// Gauss-Jordan with partial pivoting in double, rounded once to fp32.
+__global__ void inv4x4_kernel(int n, const float* __restrict__ A, float* __restrict__ B) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a[4][8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { a[r][c] = (double)A[i*16 + r*4 + c]; a[r][4 + c] = r == c ? 1. : 0.; }
+#pragma unroll
+    for (int col = 0; col < 4; ++col) {
+        int piv = col;
+#pragma unroll
+        for (int r = col + 1; r < 4; ++r) if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (r == piv && piv != col) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { const double t = a[col][c]; a[col][c] = a[r][c]; a[r][c] = t; }
+            }
+        const double inv = 1.0/a[col][col];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[col][c] *= inv;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (r != col) {
+                const double f = a[r][col];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a[r][c] -= f*a[col][c];
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) B[i*16 + r*4 + c] = (float)a[r][4 + c];
+}
+
+// gA = -B^T gB B^T  with B = A^-1.
+__global__ void inv4x4_bwd_kernel(int n, const float* __restrict__ B, const float* __restrict__ gB, float* __restrict__ gA) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float b[16], g[16], t[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { b[k] = B[i*16 + k]; g[k] = gB[i*16 + k]; }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)      // t = B^T g
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v = fmaf(b[k*4 + r], g[k*4 + c], v);
+            t[r*4 + c] = v;
+        }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)      // gA = -t B^T
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v = fmaf(t[r*4 + k], b[c*4 + k], v);
+            gA[i*16 + r*4 + c] = -v;
+        }
+}
+
 static int rows_per_block(long long M, int C) {
     // ~4 waves of 148 SMs x 8 resident blocks, at least 64 rows per block.
     const long long col_blocks = (C + 31)/32;
@@ -316,4 +383,18 @@ extern "C" int stv_bn_bwd(long long M, int C, const float* dy, const float* y, c
     bn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(total4, M, C, dy, y, x, mean, rstd, gamma, sums, relu, dx, dres, dgamma, dbeta);
     count_launch(2);
     return check_launch("stv_bn_bwd");
+}
+
+extern "C" int stv_inv4x4(int n, const float* A, float* B, void* stream) {
+    STV_REQUIRE(n > 0 && A && B, "stv_inv4x4: empty batch / null pointer");
+    inv4x4_kernel<<<(n + 63)/64, 64, 0, (cudaStream_t)stream>>>(n, A, B);
+    count_launch();
+    return check_launch("stv_inv4x4");
+}
+
+extern "C" int stv_inv4x4_bwd(int n, const float* B, const float* gB, float* gA, void* stream) {
+    STV_REQUIRE(n > 0 && B && gB && gA, "stv_inv4x4_bwd: empty batch / null pointer");
+    inv4x4_bwd_kernel<<<(n + 63)/64, 64, 0, (cudaStream_t)stream>>>(n, B, gB, gA);
+    count_launch();
+    return check_launch("stv_inv4x4_bwd");
 }

@@ -135,7 +135,7 @@ def photo_loss(depths: list[Tensor], tgt: Tensor, supp: Tensor, T: Tensor, K: Te
         if d.shape != (b, 1, H, W): raise ValueError(f'Invalid depth shape. ({tuple(d.shape)} vs. {(b, 1, H, W)})')
     if noise is not None and noise.numel() != S*b*H*W:
         raise ValueError(f'Invalid noise shape. ({tuple(noise.shape)} vs. {(S*b, 1, H, W)})')
-    if K_inv is None: K_inv = torch.linalg.inv_ex(K)[0]
+    if K_inv is None: K_inv = inv4x4(K)
     cfg = _photo_cfg(b, n, S, H, W, loss_name, use_min, use_automask, noise_seed)
     loss, sel, warp0 = _PhotoLoss.apply(cfg, want_warp, _f32c(tgt), _f32c(supp), _f32c(T), _f32c(K), _f32c(K_inv),
                                         _f32c(noise), *[_f32c(d) for d in depths])
@@ -153,6 +153,32 @@ def photo_error(pred: Tensor, target: Tensor, *, loss_name: str = 'ssim', use_mi
         err = torch.empty((b, 1, H, W), dtype=torch.float32, device=pred.device)
         L.check(L.lib().stv_photo_error(C.byref(cfg), L.ptr(pred), L.ptr(target), L.ptr(err), L.stream()), 'stv_photo_error')
     return err
+
+
+class _Inv4x4(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A):
+        L.require_cuda(A, what='inv4x4')
+        with torch.cuda.device(A.device):
+            B = torch.empty_like(A)
+            L.check(L.lib().stv_inv4x4(A.numel()//16, L.ptr(A), L.ptr(B), L.stream()), 'stv_inv4x4')
+        ctx.save_for_backward(B)
+        return B
+
+    @staticmethod
+    def backward(ctx, gB):
+        B, = ctx.saved_tensors
+        gB = _f32c(gB)
+        with torch.cuda.device(B.device):
+            gA = torch.empty_like(B)
+            L.check(L.lib().stv_inv4x4_bwd(B.numel()//16, L.ptr(B), L.ptr(gB), L.ptr(gA), L.stream()), 'stv_inv4x4_bwd')
+        return gA
+
+
+def inv4x4(A: Tensor) -> Tensor:
+    """Differentiable inverse of (*, 4, 4) matrices — `K.inverse()` / `T.inverse()` without ATen's host-synchronising batched LU."""
+    if A.shape[-2:] != (4, 4): raise ValueError(f'inv4x4: expected (*, 4, 4), got {tuple(A.shape)}')
+    return _Inv4x4.apply(_f32c(A))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -288,7 +314,7 @@ def view_synth(inp: Tensor, depth: Tensor, T: Tensor, K: Tensor, K_inv: Tensor |
     B, _, H, W = inp.shape
     if depth.shape != (B, 1, H, W): raise ValueError(f'Invalid depth shape. ({tuple(depth.shape)} vs. {(B, 1, H, W)})')
     if T.shape != (B, 4, 4) or K.shape != (B, 4, 4): raise ValueError(f'Invalid T/K shape. ({tuple(T.shape)}, {tuple(K.shape)})')
-    if K_inv is None: K_inv = torch.linalg.inv_ex(K)[0]
+    if K_inv is None: K_inv = inv4x4(K)
     return _ViewSynth.apply(_f32c(inp), _f32c(depth), _f32c(T), _f32c(K), _f32c(K_inv))
 
 
@@ -611,7 +637,7 @@ def linear(x: Tensor, w: Tensor, b: Tensor | None = None, act: str | None = None
 
 def _split_k(out_rows: int, out_cols: int, k: int) -> int:
     """Reduction splits for a weight-gradient product: enough CTAs for ~2 waves of 148 SMs, >= 4 k-blocks of 32 per split."""
-    tiles = ((out_rows + 127)//128)*((out_cols + 255)//256)
+    tiles = ((out_rows + 127)//128)*((out_cols + 127)//128)
     return max(1, min((2*148)//tiles, k//128))  # floor: tiles*splits <= 296 CTAs = two full waves, no 1-CTA tail wave
 
 

@@ -14,13 +14,14 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
+from . import functional as F_
 from . import geometry as G
 from . import handlers as H
 from .losses import ReconstructionLoss
 from .networks import DepthNet, PoseNet
 from .regularizers import SmoothReg
 
-__all__ = ['MonoDepthStep', 'default_cfg']
+__all__ = ['MonoDepthStep', 'GraphedTrainStep', 'default_cfg']
 
 NET_REG = {'depth': DepthNet, 'pose': PoseNet}
 LOSS_REG = {'img_recon': ReconstructionLoss, 'disp_smooth': SmoothReg}
@@ -73,7 +74,7 @@ class MonoDepthStep(nn.Module):
             out = self.nets['pose'](pairs.flatten(0, 1))
             Ts = G.T_from_AAt(aa=out['R'][:, 0], t=out['t'][:, 0]).unflatten(0, sh)
             for i, T in zip([i for i in idxs if i != 0], Ts):
-                fwd[f'T_{i}'] = torch.linalg.inv_ex(T)[0] if inv(i) else T
+                fwd[f'T_{i}'] = F_.inv4x4(T) if inv(i) else T
             if 'fs' in out:
                 fwd['fs'], fwd['cs'] = out['fs'].unflatten(0, sh), out['cs'].unflatten(0, sh)
                 K = PoseNet.build_K(out['fs'], out['cs']).unflatten(0, sh)[0]  # first support frame only (trainer.py:259)
@@ -113,3 +114,48 @@ class MonoDepthStep(nn.Module):
         fwd = self.forward_postprocess(fwd, x, y)
         loss, loss_dict = self.forward_loss(fwd, x, y, want_maps=want_maps or mode != 'train')
         return loss, loss_dict, fwd
+
+
+class GraphedTrainStep:
+    """One training step (zero_grad -> networks -> losses -> backward) captured ONCE as a CUDA graph and replayed every step.
+
+    The step is ~1 800 kernel launches from ~1 000 Python-level operations; enqueueing them from the host takes longer than the
+    GPU needs to execute them, so the eager loop is launch-bound. Capturing is possible because nothing on the path synchronises
+    or allocates outside torch's graph-private pool: libstv entry points only enqueue kernels / memsets on the stream they are
+    given (tensor maps are host-encoded kernel arguments), and the matrix inverses are libstv kernels, not ATen's batched LU.
+    The gradient all-reduce (world > 1) and the AdamW kernel (its bias correction is a host scalar) stay outside the graph.
+
+    The auto-mask tie-break noise seed (a host integer, advanced per call in eager mode) is frozen at capture time: the noise
+    PATTERN then repeats every step — it only decides exact ties between the warped and the static error."""
+    def __init__(self, model: MonoDepthStep, opt, example_batch, warmup: int = 3):
+        self.model, self.opt = model, opt
+        x, y, _ = example_batch
+        clone = lambda d: {k: (v.clone() if torch.is_tensor(v) and v.is_cuda else v) for k, v in d.items()}
+        self.static = (clone(x), clone(y), {})
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)): self._fwd_bwd()   # lazy one-time initialisation must not happen under capture
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+
+    def _fwd_bwd(self) -> Tensor:
+        self.opt.zero_grad()
+        loss, _, _ = self.model.step(self.static)
+        loss.backward()
+        return loss.detach()
+
+    def load(self, batch) -> None:
+        """Copy a batch (host-pinned or device tensors) into the graph's static input buffers, stream-ordered."""
+        for dst, src in zip(self.static[:2], batch[:2]):
+            for k, v in dst.items():
+                if torch.is_tensor(v) and v.is_cuda: v.copy_(src[k], non_blocking=True)
+
+    def run(self, batch=None) -> Tensor:
+        if batch is not None: self.load(batch)
+        self.graph.replay()
+        self.opt.all_reduce_async()
+        self.opt.step()
+        return self.loss
