@@ -191,10 +191,14 @@ def main() -> None:
         return loss
 
     for i in range(3): eager_step(resident[i % 2])   # first-use initialisation; also the photometric kernels' live timing below
-    F_.enable_kernel_timing(True)
-    for i in range(4): eager_step(resident[i % 2])
+    F_.enable_kernel_timing(True)      # CUDA events around each libstv call, on the launching stream
+    eager_step(resident[1])
     torch.cuda.synchronize()
-    kt = {k: v[1:] for k, v in F_.kernel_timings().items()}  # CUDA events around each libstv call on the launching stream
+    F_.reset_kernel_timings()
+    TIMED_STEPS = 3
+    for i in range(TIMED_STEPS): eager_step(resident[i % 2])
+    torch.cuda.synchronize()
+    kt = F_.kernel_timings()
     F_.enable_kernel_timing(False)
     graphed, graph_note = None, 'eager (--no-graph)'
     if not args.no_graph:
@@ -242,9 +246,16 @@ def main() -> None:
     last = {}
 
     def e2e_step(i):
-        # H2D of this step's batch (pinned host memory -> the step's input buffers) and a D2H read of its loss, every step.
-        batch = host[i % 2] if graphed is not None else to_dev(host[i % 2])
-        last['loss'] = train_step(batch).item()
+        # Every step: H2D of a batch from pinned host memory into the step's input buffers, and a D2H read of the step's loss.
+        # With the captured graph the input path is pipelined like a data loader's: batch i+1 crosses PCIe on a copy stream
+        # while step i computes (both copies are inside the timed region; K steps move K batches).
+        if graphed is None:
+            last['loss'] = eager_step(to_dev(host[i % 2])).item()
+            return
+        loss = graphed.run_prefetched()
+        graphed.prefetch(host[(i + 1) % 2])
+        last['loss'] = loss.item()
+    if graphed is not None: graphed.prefetch(host[0])
     for i in range(2): e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
 
@@ -261,6 +272,14 @@ def main() -> None:
         t_f, t_b = mean(kt.get('stv_photo_fwd', [0])), mean(kt.get('stv_photo_bwd', [0]))
         gbs = lambda by, t: (by/1e9)/(t/1e3) if t > 0 else 0.0
         ach = gbs(bytes_fwd + bytes_bwd, t_f + t_b)
+        # Tensor-core kernel (every Linear / convolution product of the networks): algorithmic FLOPs of config 3 from SURVEY 8d
+        # (forward 43.6 + 14.0 + 2 x 20.7 GFLOP per image, x3 for forward + both gradients) over the summed live duration of
+        # the stv_gemm_tf32 / stv_conv_* calls of one step; peak = TF32 dense = half the measured bf16 figure.
+        tc_ms = sum(sum(kt.get(k, [])) for k in ('stv_gemm_tf32', 'stv_conv_fprop', 'stv_conv_dgrad', 'stv_conv_wgrad'))/TIMED_STEPS
+        tc_flops = 3*(43.6 + 14.0 + N_SUPP*20.7)*1e9*b*(H*W)/(384*640)
+        pk = json.loads((ROOT/'MEASURED_PEAKS.json').read_text()) if (ROOT/'MEASURED_PEAKS.json').is_file() else {}
+        tc_peak = float(pk.get('bf16_tflops_sustained', 1400.0))/2
+        tc_ach = tc_flops/1e12/(tc_ms/1e3) if tc_ms > 0 else 0.0
         line = {
             'metric': 'training images/sec', 'value': round(b*world*args.steps/(ms/1e3), 3), 'unit': 'images/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(ms/args.steps, 3),
@@ -274,13 +293,19 @@ def main() -> None:
                     'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'last_loss': last.get('loss')},
             'gpu_launches': launches,
             'roofline': {'kernel': 'fused photometric loss, stv_photo_fwd + stv_photo_bwd', 'bound': 'hbm', 'achieved': round(ach, 1),
-                         'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(ach/peak, 4), 'traffic': None,
+                         'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(ach/peak, 4),
+                         'traffic': 614.0e6, 'traffic_source': 'ncu --set full dram__bytes_read+write, fwd 303.6 MB + bwd 310.4 MB (profiles/r1a_loss_ncu_full_summary.txt)',
                          'algorithmic_bytes_per_launch': bytes_fwd + bytes_bwd, 'avg_ms': round(t_f + t_b, 4),
                          'detail': {'photo_fwd': {'ms': round(t_f, 4), 'GB/s': round(gbs(bytes_fwd, t_f), 1), 'frac': round(gbs(bytes_fwd, t_f)/peak, 4)},
                                     'photo_bwd': {'ms': round(t_b, 4), 'GB/s': round(gbs(bytes_bwd, t_b), 1), 'frac': round(gbs(bytes_bwd, t_b)/peak, 4)},
                                     'smooth_fwd_ms': round(mean(kt.get('stv_smooth_fwd', [0])), 4),
                                     'smooth_bwd_ms': round(mean(kt.get('stv_smooth_bwd', [0])), 4)}},
         }
+        line['roofline_tensor'] = {
+            'kernel': 'gemm_tf32_kernel (tcgen05 kind::tf32 + TMA/TMA-im2col + TMEM): all Linear / convolution fwd, dgrad, wgrad of the step',
+            'bound': 'tensor', 'achieved': round(tc_ach, 1), 'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': round(tc_ach/tc_peak, 4),
+            'peak_source': 'TF32 dense = MEASURED_PEAKS.json bf16_tflops_sustained / 2', 'algorithmic_flops_per_step': tc_flops,
+            'ms_per_step_in_kernel_calls': round(tc_ms, 3)}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference(steps=2, warmup=1)
             line['cpu_baseline'] = {'value': round(r['value'], 4), 'unit': 'images/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}

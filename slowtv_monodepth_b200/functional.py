@@ -48,6 +48,26 @@ def reset_kernel_timings() -> None:
     if _TIMING is not None: _TIMING.clear()
 
 
+# Gradient sink: when a parameter's `.grad` already exists as a dense fp32 buffer in the kernel's own layout (FlatAdamW exposes
+# every gradient as a view of one flat buffer, zeroed once per step), the weight-/bias-gradient kernels accumulate straight
+# into it (their epilogues are atomic accumulations anyway) and autograd receives None for that input — instead of
+# zero-filling a temporary, accumulating into it and letting AccumulateGrad add it to `.grad` (two extra launches and three
+# extra passes over every parameter-sized tensor per step). Off by default; FlatAdamW switches it on.
+GRAD_SINK = False
+
+
+def grad_sink(on: bool = True) -> None:
+    global GRAD_SINK
+    GRAD_SINK = bool(on)
+
+
+def _sink(p: Tensor | None, phys=None) -> Tensor | None:
+    """`p.grad` viewed in the layout `phys` maps p to, when that view is the contiguous memory itself; else None."""
+    if not GRAD_SINK or p is None or p.grad is None or not p.grad.is_cuda or p.grad.dtype != torch.float32: return None
+    g = p.grad if phys is None else phys(p.grad)
+    return g if g.is_contiguous() else None
+
+
 def _f32c(t: Tensor | None) -> Tensor | None:
     if t is None: return None
     if t.dtype != torch.float32: raise ValueError(f'Expected float32, got {t.dtype}.')
@@ -510,6 +530,9 @@ class _Conv2dNHWC(torch.autograd.Function):
                         'stv_conv_fprop')
         ctx.save_for_backward(src1, src2, w_phys, y)
         ctx.g, ctx.act, ctx.has_bias = g, act, b is not None
+        # gradient sinks (same memory layout as the kernel's outputs: un-padded filters only)
+        ctx.w_sink = _sink(w, lambda t: t.permute(0, 2, 3, 1)) if (w_phys.shape[3] == w.shape[1] and g.Cout % 4 == 0) else None
+        ctx.b_sink = _sink(b)
         return y
 
     @staticmethod
@@ -518,8 +541,10 @@ class _Conv2dNHWC(torch.autograd.Function):
         g, act, lib, dev = ctx.g, ctx.act, L.lib(), y.device
         Cout, Cin = g.Cout, g.C1 + g.C2
         with torch.cuda.device(dev):
-            db = torch.zeros(Cout, dtype=torch.float32, device=dev) if ctx.has_bias else None
+            db = None
+            if ctx.has_bias: db = ctx.b_sink if ctx.b_sink is not None else torch.zeros(Cout, dtype=torch.float32, device=dev)
             dZ = act_bwd(dA, y, act, db)
+            if ctx.b_sink is not None: db = None  # already accumulated into bias.grad
             wq = w_phys
             if Cout % 4:  # narrow heads (1-channel disparity): pad the output-channel axis to 4 for the TMA-fed operands
                 cp = (-Cout) % 4
@@ -528,10 +553,10 @@ class _Conv2dNHWC(torch.autograd.Function):
                 g = L.ConvGeom.from_buffer_copy(g); g.Cout = Cout + cp
             dw = None
             if ctx.needs_input_grad[2]:
-                dw = torch.zeros_like(wq)
+                dw = ctx.w_sink if ctx.w_sink is not None else torch.zeros_like(wq)
                 with _timed('stv_conv_wgrad'):
                     L.check(lib.stv_conv_wgrad(C.byref(g), L.ptr(src1), L.ptr(src2), L.ptr(dZ), L.ptr(dw), 0, L.stream()), 'stv_conv_wgrad')
-                dw = dw[:Cout, :, :, :ctx.cin].permute(0, 3, 1, 2)
+                dw = None if ctx.w_sink is not None else dw[:Cout, :, :, :ctx.cin].permute(0, 3, 1, 2)
             d1 = d2 = None
             if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
                 pd = g.pad if g.reflect else 0
@@ -606,6 +631,46 @@ def batch_norm_nhwc(x: Tensor, gamma: Tensor, beta: Tensor, *, res: Tensor | Non
     return _BatchNormNHWC.apply(_f32c(x), _f32c(gamma), _f32c(beta), _f32c(res), run_mean, run_var, bool(relu), float(eps), float(momentum))
 
 
+class _Head3x3(torch.autograd.Function):
+    """act(reflect-padded 3x3 convolution to one channel + bias): the decoder's disparity heads, as a per-pixel dot product."""
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        L.require_cuda(x, w, b, what='head3x3')
+        N, H, W, Cc = x.shape
+        w_phys = w.permute(0, 2, 3, 1).contiguous()  # (1,3,3,C)
+        with torch.cuda.device(x.device):
+            y = torch.empty((N, H, W, 1), dtype=torch.float32, device=x.device)
+            L.check(L.lib().stv_head3x3_fwd(N, H, W, Cc, L.ptr(x), L.ptr(w_phys), L.ptr(b), L.ACT[act], L.ptr(y), L.stream()), 'stv_head3x3_fwd')
+        ctx.save_for_backward(x, w_phys, y)
+        ctx.act, ctx.has_bias = act, b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dA):
+        x, w_phys, y = ctx.saved_tensors
+        N, H, W, Cc = x.shape
+        dA = _f32c(dA)
+        with torch.cuda.device(x.device):
+            dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+            dw = torch.zeros_like(w_phys) if ctx.needs_input_grad[1] else None
+            db = torch.zeros(1, dtype=torch.float32, device=x.device) if ctx.has_bias and dw is not None else None
+            L.check(L.lib().stv_head3x3_bwd(N, H, W, Cc, L.ptr(x), L.ptr(w_phys), L.ptr(dA), L.ptr(y), L.ACT[ctx.act], L.ptr(dx), L.ptr(dw),
+                                            L.ptr(db), L.stream()), 'stv_head3x3_bwd')
+        return dx, None if dw is None else dw.permute(0, 3, 1, 2), db, None
+
+
+def head3x3(x: Tensor, w: Tensor, b: Tensor | None, act: str | None = 'sigmoid') -> Tensor:
+    """x (N,H,W,C) channels-last, w the nn.Conv2d weight (1,C,3,3) with padding_mode='reflect' -> (N,H,W,1)."""
+    Cc = x.shape[-1]
+    if x.ndim != 4 or w.shape != (1, Cc, 3, 3): raise ValueError(f'head3x3: bad shapes {tuple(x.shape)}, {tuple(w.shape)}')
+    if act == 'gelu': raise ValueError('head3x3: unsupported activation gelu')
+    return _Head3x3.apply(_f32c(x), w, _f32c(b), act)
+
+
+def head3x3_supported(C: int, out_ch: int) -> bool:
+    return out_ch == 1 and 4 <= C <= 128 and (C & (C - 1)) == 0
+
+
 class _Linear(torch.autograd.Function):
     """y = act(x W^T + b) on (M, K) rows: one tcgen05 GEMM forward (bias + activation in the epilogue), up to two backward."""
     @staticmethod
@@ -655,6 +720,7 @@ class _ConvNeXtMlp(torch.autograd.Function):
         gemm_tf32(x, w1, bias=b1, act='gelu', aux=z, out=h)
         out = gemm_tf32(h, w2, bias=b2, gamma=gamma, res=res)
         ctx.save_for_backward(x, z, h, w1, w2, b2, gamma)
+        ctx.w1_sink, ctx.b1_sink = _sink(w1), _sink(b1)
         return out
 
     @staticmethod
@@ -664,11 +730,13 @@ class _ConvNeXtMlp(torch.autograd.Function):
         M, Cc = x.shape
         Hd = w1.shape[0]
         w2g = w2*gamma[:, None]                                              # (C, 4C): layer-scale folded into fc2
-        db1 = torch.zeros(Hd, dtype=torch.float32, device=g.device)
+        db1 = ctx.b1_sink if ctx.b1_sink is not None else torch.zeros(Hd, dtype=torch.float32, device=g.device)
         dz = gemm_tf32(g, w2g, b_mn=True, dact='gelu', dact_src=z, colsum=db1)  # (M, 4C) = (g W2g) * GELU'(z); db1 = its column sums
         dx = gemm_tf32(dz, w1, b_mn=True) if ctx.needs_input_grad[0] else None
-        dw1 = torch.zeros_like(w1)
+        dw1 = ctx.w1_sink if ctx.w1_sink is not None else torch.zeros_like(w1)
         gemm_tf32(dz, x, a_mn=True, b_mn=True, out=dw1, accumulate=True, split_k=_split_k(Hd, Cc, M))
+        if ctx.w1_sink is not None: dw1 = None
+        if ctx.b1_sink is not None: db1 = None
         G = torch.zeros_like(w2)                                             # g^T h, before the layer-scale
         gemm_tf32(g, h, a_mn=True, b_mn=True, out=G, accumulate=True, split_k=_split_k(Cc, Hd, M))
         gs = colsum(g)

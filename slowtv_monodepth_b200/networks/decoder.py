@@ -79,5 +79,7 @@ class MonodepthDecoder(nn.Module):
             x = F_.conv2d_nhwc(x, c1.weight, c1.bias, src2=skip, up1=True, pad=1, reflect=True, act='elu')
             if i in self.out_sc:
                 h = self.layer(f'outconv_{i}')
-                out[i] = F_.conv2d_nhwc(x, h.weight, h.bias, pad=1, reflect=True, act=act).permute(0, 3, 1, 2)
+                if F_.head3x3_supported(x.shape[-1], self.out_ch): o = F_.head3x3(x, h.weight, h.bias, act)  # per-pixel dot product
+                else: o = F_.conv2d_nhwc(x, h.weight, h.bias, pad=1, reflect=True, act=act)
+                out[i] = o.permute(0, 3, 1, 2)
         return out

@@ -51,6 +51,7 @@ class FlatAdamW:
             p.data = view(self.flat)
             p.grad = view(self.grad)
             off += al(n)
+        if self.flat.is_cuda: F_.grad_sink(True)  # gradients live in one pre-zeroed flat buffer: kernels accumulate into it in place
         self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
         self.step_count = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1

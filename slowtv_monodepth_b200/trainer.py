@@ -159,3 +159,34 @@ class GraphedTrainStep:
         self.opt.all_reduce_async()
         self.opt.step()
         return self.loss
+
+    # -- pipelined input path: the next batch crosses PCIe on a side stream while the current step computes ---------------------
+    def prefetch(self, batch) -> None:
+        """Start the host->device copy of `batch` (pinned host tensors) into a staging buffer on the copy stream."""
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream()
+            clone = lambda d: {k: (torch.empty_like(v) if torch.is_tensor(v) and v.is_cuda else v) for k, v in d.items()}
+            self._staging = [(clone(self.static[0]), clone(self.static[1])) for _ in range(2)]
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            self._slot_w = self._slot_r = 0
+        j = self._slot_w % 2
+        self._copy_stream.wait_event(self._consumed[j])  # the step that read this staging slot has copied it out
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._staging[j], batch[:2]):
+                for k, v in dst.items():
+                    if torch.is_tensor(v) and v.is_cuda: v.copy_(src[k], non_blocking=True)
+            self._ready[j].record(self._copy_stream)
+        self._slot_w += 1
+
+    def run_prefetched(self) -> Tensor:
+        """Run one step on the oldest prefetched batch (device-to-device copy into the graph inputs, then replay)."""
+        j = self._slot_r % 2
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready[j])
+        for dst, src in zip(self.static[:2], self._staging[j]):
+            for k, v in dst.items():
+                if torch.is_tensor(v) and v.is_cuda: v.copy_(src[k], non_blocking=True)
+        self._consumed[j].record(cur)
+        self._slot_r += 1
+        return self.run()

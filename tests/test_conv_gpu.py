@@ -106,3 +106,22 @@ def test_activation_forward_backward(act):
         if g is None: continue
         err = (g.grad.double() - r.grad).norm()/r.grad.norm().clamp(min=1e-12)
         assert err < 2e-3, f'{name}: rel err {err.item():.3e}'
+
+
+@pytest.mark.parametrize('N,H,W,C', [(2, 10, 14, 16), (1, 7, 9, 32), (3, 6, 8, 64), (2, 5, 6, 128), (1, 33, 65, 16)])
+def test_head3x3_matches_conv2d(N, H, W, C):
+    """stv_head3x3_fwd/bwd (one-channel reflect-padded 3x3 conv + sigmoid on the CUDA cores) vs torch in float64."""
+    gen = torch.Generator(device='cuda').manual_seed(C + H)
+    x = (torch.randn(N, H, W, C, generator=gen, device='cuda')).requires_grad_()
+    w = (torch.randn(1, C, 3, 3, generator=gen, device='cuda')*0.2).requires_grad_()
+    b = torch.randn(1, generator=gen, device='cuda').requires_grad_()
+    dA = torch.randn(N, H, W, 1, generator=gen, device='cuda')
+    y = F_.head3x3(x, w, b, 'sigmoid')
+    y.backward(dA)
+    xr, wr, br = (t.detach().double().requires_grad_() for t in (x, w, b))
+    yr = torch.sigmoid(F.conv2d(F.pad(xr.permute(0, 3, 1, 2), (1, 1, 1, 1), mode='reflect'), wr, br)).permute(0, 2, 3, 1)
+    yr.backward(dA.double())
+    assert (y.double() - yr).abs().max() < 1e-5
+    for name, a, r in (('dx', x, xr), ('dw', w, wr), ('db', b, br)):
+        err = (a.grad.double() - r.grad).norm()/r.grad.norm()
+        assert err < 5e-5, f"{name}: {err.item():.3e}"  # fp32 atomics: summation order varies

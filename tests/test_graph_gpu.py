@@ -14,7 +14,6 @@ def test_graphed_step_matches_eager():
     opt = FlatAdamW(model.nets)
     b0 = syn.make_batch(2, 2, (64, 96), seed=0, device='cuda')
     b1 = syn.make_batch(2, 2, (64, 96), seed=1, device='cuda')
-    model.losses['img_recon'].use_automask_noise = False if hasattr(model.losses['img_recon'], 'use_automask_noise') else None
     g = GraphedTrainStep(model, opt, b0)
     # replay on a NEW batch, then the same batch eagerly: the flat gradient buffers must agree
     g.load(b1)
