@@ -83,7 +83,7 @@ def cpu_reference(steps: int, warmup: int, batch: int = CPU_BATCH) -> dict:
                       f'(fwd + loss + bwd + AdamW, PyTorch {torch.__version__} CPU fp32, {cores} threads)'}
 
 
-def run_reference_arm(args) -> None:
+def run_reference_arm(args, out) -> None:
     if int(os.environ.get('RANK', '0')) != 0: return
     steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
     r = cpu_reference(steps, warmup)
@@ -97,7 +97,7 @@ def run_reference_arm(args) -> None:
         'e2e': {'value': round(r['value'], 4), 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -145,9 +145,19 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # Our arm
 # ---------------------------------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write banners there from C (e.g. "NCCL version ..." on the first
+    collective), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, 'w')
+
+
 def main() -> None:
     args = parse()
-    if args.impl == 'reference': return run_reference_arm(args)
+    out = _claim_stdout()
+    if args.impl == 'reference': return run_reference_arm(args, out)
 
     import torch.distributed as dist
     from slowtv_monodepth_b200 import _lib as L, functional as F_, synthetic as syn
@@ -309,7 +319,7 @@ def main() -> None:
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference(steps=2, warmup=1)
             line['cpu_baseline'] = {'value': round(r['value'], 4), 'unit': 'images/s', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1: dist.destroy_process_group()
 
 

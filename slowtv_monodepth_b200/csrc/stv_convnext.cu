@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_kernel(int H, int W, int C, int
 // Weight gradient: gw[c][ky][kx] = sum_{n,y,x} gy[n,y,x,c] * x[n,y+ky-3,x+kx-3,c];  gb[c] = sum gy.
 // Each block owns a (WG_RY rows x WG_XW columns) patch of one image; a thread owns one channel and slides a 7x7 register
 // window of x along the row. Per-block partials go to the workspace; a second kernel adds them in a fixed order.
-constexpr int WG_RY = 4, WG_XW = 32;
+constexpr int WG_RY = 4, WG_XW = 32, WG_U = 4;
 
 __global__ void __launch_bounds__(DW_CB) dwconv7_wgrad_kernel(int H, int W, int C, int ncb, const float* __restrict__ x,
                                                               const float* __restrict__ gy, float* __restrict__ partial) {
@@ -101,28 +101,37 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_wgrad_kernel(int H, int W, int 
     for (int r = 0; r < WG_RY; ++r) {
         const int yo = yb + r;
         if (yo >= H) break;
-        float win[7][7];  // win[ky][kx] = x[yo+ky-3][xo+kx-3]
+        // WG_U output pixels per iteration: their 7 x WG_U new window columns and WG_U gradients are loaded first (independent
+        // loads in flight), then 49 x WG_U FMAs run on the (7 + WG_U - 1)-wide register window; the window shifts once per iteration.
+        float win[7][6 + WG_U];  // win[ky][q] = x[yo+ky-3][xo+q-3] for the iteration starting at column xo
         auto ld = [&](int yy, int xx) -> float {
             return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + img + ((size_t)yy*W + xx)*C + c) : 0.f;
         };
 #pragma unroll
         for (int ky = 0; ky < 7; ++ky)
 #pragma unroll
-            for (int kx = 1; kx < 7; ++kx) win[ky][kx] = ld(yo + ky - 3, xb + kx - 4);  // columns for xo = xb - 1
+            for (int q = 0; q < 6; ++q) win[ky][q] = ld(yo + ky - 3, xb + q - 3);
         const int xe = min(xb + WG_XW, W);
-        for (int xo = xb; xo < xe; ++xo) {
-#pragma unroll
-            for (int ky = 0; ky < 7; ++ky) {
-#pragma unroll
-                for (int kx = 0; kx < 6; ++kx) win[ky][kx] = win[ky][kx + 1];
-                win[ky][6] = ld(yo + ky - 3, xo + 3);
-            }
-            const float g = __ldg(gy + img + ((size_t)yo*W + xo)*C + c);
-            gsum += g;
+        for (int xo = xb; xo < xe; xo += WG_U) {
 #pragma unroll
             for (int ky = 0; ky < 7; ++ky)
 #pragma unroll
-                for (int kx = 0; kx < 7; ++kx) acc[ky*7 + kx] = fmaf(g, win[ky][kx], acc[ky*7 + kx]);
+                for (int u = 0; u < WG_U; ++u) win[ky][6 + u] = ld(yo + ky - 3, xo + 3 + u);
+            float g[WG_U];
+#pragma unroll
+            for (int u = 0; u < WG_U; ++u) g[u] = xo + u < xe ? __ldg(gy + img + ((size_t)yo*W + xo + u)*C + c) : 0.f;
+#pragma unroll
+            for (int u = 0; u < WG_U; ++u) {
+                gsum += g[u];
+#pragma unroll
+                for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 7; ++kx) acc[ky*7 + kx] = fmaf(g[u], win[ky][u + kx], acc[ky*7 + kx]);
+            }
+#pragma unroll
+            for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) win[ky][q] = win[ky][q + WG_U];
         }
     }
     const size_t blk = ((size_t)blockIdx.z*gridDim.y + blockIdx.y)*(gridDim.x/ncb) + blockIdx.x/ncb;  // spatial patch index
@@ -168,20 +177,21 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(long long P, int C, 
 }
 
 // dx = rstd * (dy*gamma - mean_c(dy*gamma) - xhat * mean_c(dy*gamma*xhat));  dgamma = sum_rows dy*xhat;  dbeta = sum_rows dy.
-// Each warp walks LN_ROWS consecutive rows and keeps its lanes' dgamma/dbeta slices in registers (C <= 32*LN_MAXPL).
+// Each warp walks `rows` (<= LN_ROWS) consecutive rows and keeps its lanes' dgamma/dbeta slices in registers (C <= 32*LN_MAXPL).
+// `rows` shrinks for short matrices (the deep ConvNeXt stages have only 2-8 k rows) so that the grid still covers the SMs.
 constexpr int LN_ROWS = 32, LN_MAXPL = 32;
 
 template <int PL>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(long long P, int C, const float* __restrict__ dy,
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(long long P, int C, int rows, const float* __restrict__ dy,
                                                             const float* __restrict__ x, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                             float* __restrict__ dx, float* __restrict__ partial) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const long long row0 = ((long long)blockIdx.x*nw + wid)*LN_ROWS;
+    const long long row0 = ((long long)blockIdx.x*nw + wid)*rows;
     float dg[PL], db[PL], g[PL];
 #pragma unroll
     for (int i = 0; i < PL; ++i) { dg[i] = db[i] = 0.f; const int c = lane + 32*i; g[i] = c < C ? __ldg(gamma + c) : 0.f; }
-    for (int r = 0; r < LN_ROWS; ++r) {
+    for (int r = 0; r < rows; ++r) {
         const long long row = row0 + r;
         if (row >= P) break;
         const float mu = mean[row], rs = rstd[row];
@@ -294,7 +304,13 @@ extern "C" int stv_layernorm_fwd(long long P, int C, const float* x, const float
     return check_launch("layernorm_fwd_kernel");
 }
 
-static long long ln_bwd_warps(long long P) { return (P + LN_ROWS - 1)/LN_ROWS; }
+// Rows per warp: LN_ROWS for long matrices, fewer while the grid would be smaller than ~2 blocks (of 8 warps) per SM.
+static int ln_bwd_rows(long long P) {
+    int rows = LN_ROWS;
+    while (rows > 1 && (P + rows - 1)/rows < 2ll*148*8) rows >>= 1;
+    return rows;
+}
+static long long ln_bwd_warps(long long P) { const int r = ln_bwd_rows(P); return (P + r - 1)/r; }
 
 extern "C" size_t stv_layernorm_bwd_workspace_bytes(long long P, int C) {
     if (P <= 0 || C <= 0) return 0;
@@ -321,7 +337,7 @@ extern "C" int stv_layernorm_bwd(long long P, int C, const float* dy, const floa
         cudaFuncSetAttribute(layernorm_bwd_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         attr_done = true;
     }
-#define STV_LN_BWD(PL) layernorm_bwd_kernel<PL><<<(unsigned)blocks, 256, (size_t)8*2*C*sizeof(float), st>>>(P, C, dy, x, mean, rstd, gamma, dx, (float*)ws)
+#define STV_LN_BWD(PL) layernorm_bwd_kernel<PL><<<(unsigned)blocks, 256, (size_t)8*2*C*sizeof(float), st>>>(P, C, ln_bwd_rows(P), dy, x, mean, rstd, gamma, dx, (float*)ws)
     if (pl <= 3) STV_LN_BWD(3); else if (pl <= 4) STV_LN_BWD(4); else if (pl <= 6) STV_LN_BWD(6); else if (pl <= 8) STV_LN_BWD(8);
     else if (pl <= 12) STV_LN_BWD(12); else if (pl <= 16) STV_LN_BWD(16); else if (pl <= 24) STV_LN_BWD(24); else STV_LN_BWD(32);
 #undef STV_LN_BWD

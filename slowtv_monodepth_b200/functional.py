@@ -63,7 +63,7 @@ def grad_sink(on: bool = True) -> None:
 
 def _sink(p: Tensor | None, phys=None) -> Tensor | None:
     """`p.grad` viewed in the layout `phys` maps p to, when that view is the contiguous memory itself; else None."""
-    if not GRAD_SINK or p is None or p.grad is None or not p.grad.is_cuda or p.grad.dtype != torch.float32: return None
+    if not GRAD_SINK or p is None or not p.is_leaf or p.grad is None or not p.grad.is_cuda or p.grad.dtype != torch.float32: return None
     g = p.grad if phys is None else phys(p.grad)
     return g if g.is_contiguous() else None
 
