@@ -236,6 +236,11 @@ int stv_bn_bwd(long long M, int C, const float* dy, const float* y, const float*
                const float* gamma, int relu, float* dx, float* dres, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
                void* stream);
 
+/* 3x3 stride-2 max-pool, padding 1, channels-last (N,H,W,C) -> (N,(H-1)/2+1,(W-1)/2+1,C): the `maxpool` of the timm ResNet stem
+ * (src/networks/pose.py:40, depth.py:97). idx (same shape as y, u8) = winning tap 0..8 (first maximum in row-major order). */
+int stv_maxpool3x3s2_fwd(int N, int H, int W, int C, const float* x, float* y, uint8_t* idx, void* stream);
+int stv_maxpool3x3s2_bwd(int N, int H, int W, int C, const float* dy, const uint8_t* idx, float* dx, void* stream);
+
 /* Disparity heads: y (N,H,W) = act(bias + reflect-padded 3x3 convolution of x (N,H,W,C) with w (3,3,C)) — `outconv_i` + sigmoid of
  * the Monodepth decoder (src/networks/decoders/monodepth.py:66-69,86-87). One output channel = a dot product per pixel:
  * memory-bound, CUDA cores. C a power of two in [4,128]. Backward: dz = da*act'(y); dx (N,H,W,C) (nullable, overwritten);

@@ -82,6 +82,8 @@ _SIGNATURES = {
     'stv_bn_workspace_bytes': (C.c_size_t, [C.c_int]),
     'stv_bn_fwd': (C.c_int, [C.c_longlong, C.c_int, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     'stv_bn_bwd': (C.c_int, [C.c_longlong, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'stv_maxpool3x3s2_fwd': (C.c_int, [C.c_int]*4 + [_P, _P, _P, _P]),
+    'stv_maxpool3x3s2_bwd': (C.c_int, [C.c_int]*4 + [_P, _P, _P, _P]),
     'stv_head3x3_fwd': (C.c_int, [C.c_int]*4 + [_P, _P, _P, C.c_int, _P, _P]),
     'stv_head3x3_bwd': (C.c_int, [C.c_int]*4 + [_P, _P, _P, _P, C.c_int, _P, _P, _P, _P]),
     'stv_inv4x4': (C.c_int, [C.c_int, _P, _P, _P]),

@@ -104,19 +104,25 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_wgrad_kernel(int H, int W, int 
         // WG_U output pixels per iteration: their 7 x WG_U new window columns and WG_U gradients are loaded first (independent
         // loads in flight), then 49 x WG_U FMAs run on the (7 + WG_U - 1)-wide register window; the window shifts once per iteration.
         float win[7][6 + WG_U];  // win[ky][q] = x[yo+ky-3][xo+q-3] for the iteration starting at column xo
-        auto ld = [&](int yy, int xx) -> float {
-            return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(x + img + ((size_t)yy*W + xx)*C + c) : 0.f;
+        const float* rowp[7];    // start of input row yo+ky-3 for this channel (nullptr: outside the image -> zeros)
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+            const int yy = yo + ky - 3;
+            rowp[ky] = (yy >= 0 && yy < H) ? x + img + (size_t)yy*W*C + c : nullptr;
+        }
+        auto ld = [&](int ky, int xx) -> float {
+            return (rowp[ky] && xx >= 0 && xx < W) ? __ldg(rowp[ky] + (size_t)xx*C) : 0.f;
         };
 #pragma unroll
         for (int ky = 0; ky < 7; ++ky)
 #pragma unroll
-            for (int q = 0; q < 6; ++q) win[ky][q] = ld(yo + ky - 3, xb + q - 3);
+            for (int q = 0; q < 6; ++q) win[ky][q] = ld(ky, xb + q - 3);
         const int xe = min(xb + WG_XW, W);
         for (int xo = xb; xo < xe; xo += WG_U) {
 #pragma unroll
             for (int ky = 0; ky < 7; ++ky)
 #pragma unroll
-                for (int u = 0; u < WG_U; ++u) win[ky][6 + u] = ld(yo + ky - 3, xo + 3 + u);
+                for (int u = 0; u < WG_U; ++u) win[ky][6 + u] = ld(ky, xo + 3 + u);
             float g[WG_U];
 #pragma unroll
             for (int u = 0; u < WG_U; ++u) g[u] = xo + u < xe ? __ldg(gy + img + ((size_t)yo*W + xo + u)*C + c) : 0.f;
@@ -141,17 +147,25 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_wgrad_kernel(int H, int W, int 
     out[(size_t)49*C + c] = gsum;
 }
 
-// out[c*49 + t] = sum_blk partial[blk][t][c];  gb[c] = sum_blk partial[blk][49][c]. One warp per (t, 32-channel group).
+// out[c*49 + t] = sum_blk partial[blk][t][c];  gb[c] = sum_blk partial[blk][49][c]. A block owns 32 consecutive entries (t, c);
+// its 8 warps stride over the partial blocks (8 independent, coalesced load streams) and are combined in a fixed order.
 __global__ void __launch_bounds__(256) dwconv7_wgrad_reduce_kernel(int C, int nblk, const float* __restrict__ partial,
                                                                    float* __restrict__ gw, float* __restrict__ gb) {
-    // thread -> (t, c); blocks of 256 threads over 50*C entries; fixed-order loop over nblk (coalesced across c).
-    const int e = blockIdx.x*blockDim.x + threadIdx.x;
-    if (e >= 50*C) return;
-    const int t = e/C, c = e - t*C;
+    __shared__ double red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int e = blockIdx.x*32 + tx;
     double a = 0.0;
-    for (int b = 0; b < nblk; ++b) a += (double)partial[(size_t)b*50*C + e];
-    if (t < 49) gw[(size_t)c*49 + t] = (float)a;
-    else if (gb) gb[c] = (float)a;
+    if (e < 50*C)
+        for (int b = ty; b < nblk; b += 8) a += (double)__ldg(partial + (size_t)b*50*C + e);
+    red[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && e < 50*C) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) a += red[k][tx];
+        const int t = e/C, c = e - t*C;
+        if (t < 49) gw[(size_t)c*49 + t] = (float)a;
+        else if (gb) gb[c] = (float)a;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -232,19 +246,27 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(long long P, int C, 
     }
 }
 
-__global__ void __launch_bounds__(64) layernorm_bwd_reduce_kernel(int C, int nrows, const float* __restrict__ partial,
-                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int e = blockIdx.x*blockDim.x + threadIdx.x;
-    if (e >= 2*C) return;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four independent chains (fixed association -> deterministic)
-    int r = 0;
-    for (; r + 3 < nrows; r += 4) {
-        a0 += (double)partial[(size_t)r*2*C + e]; a1 += (double)partial[(size_t)(r + 1)*2*C + e];
-        a2 += (double)partial[(size_t)(r + 2)*2*C + e]; a3 += (double)partial[(size_t)(r + 3)*2*C + e];
+// A block owns 32 consecutive entries of [dgamma | dbeta]; its 8 warps stride over the partial rows (8 coalesced load streams in
+// flight instead of one serial chain) and are combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(int C, int nrows, const float* __restrict__ partial,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ double red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int e = blockIdx.x*32 + tx;
+    double a0 = 0.0, a1 = 0.0;
+    if (e < 2*C) {
+        int r = ty;
+        for (; r + 8 < nrows; r += 16) { a0 += (double)__ldg(partial + (size_t)r*2*C + e); a1 += (double)__ldg(partial + (size_t)(r + 8)*2*C + e); }
+        if (r < nrows) a0 += (double)__ldg(partial + (size_t)r*2*C + e);
     }
-    for (; r < nrows; ++r) a0 += (double)partial[(size_t)r*2*C + e];
-    const double a = (a0 + a1) + (a2 + a3);
-    if (e < C) dgamma[e] = (float)a; else dbeta[e - C] = (float)a;
+    red[ty][tx] = a0 + a1;
+    __syncthreads();
+    if (ty == 0 && e < 2*C) {
+        double a = red[0][tx];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) a += red[k][tx];
+        if (e < C) dgamma[e] = (float)a; else dbeta[e - C] = (float)a;
+    }
 }
 
 }  // namespace stv
@@ -262,7 +284,7 @@ extern "C" int stv_dwconv7_fwd(int N, int H, int W, int C, const float* x, const
     // Rows per block: tall strips amortise the 6-row halo; shrink them while the grid is smaller than ~2 blocks per SM.
     const long long cols = (long long)((W + DW_L - 1)/DW_L)*ncb*N;
     int rows = 32;
-    while (rows > 8 && cols*((H + rows - 1)/rows) < 2*148) rows >>= 1;
+    while (rows > 8 && cols*((H + rows - 1)/rows) < 6*148) rows >>= 1;   // blocks are only 3-4 warps: aim for >= 6 per SM
     dim3 grid(((W + DW_L - 1)/DW_L)*ncb, (H + rows - 1)/rows, N);
     if (flip) dwconv7_kernel<true><<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, rows, x, w, bias, res, y);
     else dwconv7_kernel<false><<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, rows, x, w, bias, res, y);
@@ -288,7 +310,7 @@ extern "C" int stv_dwconv7_wgrad(int N, int H, int W, int C, const float* x, con
     count_launch();
     if (int rc = check_launch("dwconv7_wgrad_kernel")) return rc;
     const int nblk = (grid.x/ncb)*grid.y*grid.z;
-    dwconv7_wgrad_reduce_kernel<<<(50*C + 255)/256, 256, 0, (cudaStream_t)stream>>>(C, nblk, (const float*)ws, gw, gb);
+    dwconv7_wgrad_reduce_kernel<<<(50*C + 31)/32, 256, 0, (cudaStream_t)stream>>>(C, nblk, (const float*)ws, gw, gb);
     count_launch();
     return check_launch("dwconv7_wgrad_reduce_kernel");
 }
@@ -343,7 +365,7 @@ extern "C" int stv_layernorm_bwd(long long P, int C, const float* dy, const floa
 #undef STV_LN_BWD
     count_launch();
     if (int rc = check_launch("layernorm_bwd_kernel")) return rc;
-    layernorm_bwd_reduce_kernel<<<(2*C + 63)/64, 64, 0, st>>>(C, (int)blocks, (const float*)ws, dgamma, dbeta);
+    layernorm_bwd_reduce_kernel<<<(2*C + 31)/32, 256, 0, st>>>(C, (int)blocks, (const float*)ws, dgamma, dbeta);
     count_launch();
     return check_launch("layernorm_bwd_reduce_kernel");
 }

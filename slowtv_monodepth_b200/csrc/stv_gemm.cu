@@ -91,7 +91,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % p.stages;
                 const uint32_t ph = (uint32_t)(it/p.stages) & 1u;
-                tc::mbar_wait(&empty[s], ph ^ 1u);
+                tc::mbar_wait_spin(&empty[s], ph ^ 1u);
                 tc::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
                 uint8_t* a = smem + (size_t)s*stage_bytes;
                 uint8_t* b = a + GEMM_A_BYTES;
@@ -132,7 +132,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % p.stages;
                 const uint32_t ph = (uint32_t)(it/p.stages) & 1u;
-                tc::mbar_wait(&full[s], ph);
+                tc::mbar_wait_spin(&full[s], ph);
                 tc::tcgen05_fence_after();
                 const uint32_t a = tc::smem_u32(smem + (size_t)s*stage_bytes), b = a + GEMM_A_BYTES;
 #pragma unroll

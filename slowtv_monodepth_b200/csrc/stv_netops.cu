@@ -293,6 +293,72 @@ __global__ void inv4x4_bwd_kernel(int n, const float* __restrict__ B, const floa
         }
 }
 
+// ---- 3x3 stride-2 max-pool (padding 1) of the ResNet stem, channels-last; 4 channels per thread -------------------------------
+// Reference: `maxpool` of the timm ResNet encoder (src/networks/pose.py:40, depth.py:97). The forward stores the winning tap
+// (0..8, first maximum in row-major window order, as ATen) per output element; the backward is a gather over the <= 4 windows
+// that contain an input pixel (deterministic, no atomics).
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(int N, int H, int W, int C, int P, int Q, const float* __restrict__ x,
+                                                          float* __restrict__ y, uint8_t* __restrict__ idx) {
+    const int c4 = C >> 2;
+    const long long total = (long long)N*P*Q*c4;
+    for (long long i = blockIdx.x*(long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x*blockDim.x) {
+        const int c = (int)(i % c4)*4;
+        long long r = i/c4;
+        const int q = (int)(r % Q); r /= Q;
+        const int p = (int)(r % P);
+        const int n = (int)(r/P);
+        float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        uchar4 bi = make_uchar4(0, 0, 0, 0);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int yy = 2*p - 1 + dy;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int xx = 2*q - 1 + dx;
+                if (xx < 0 || xx >= W) continue;
+                const float4 v = __ldg((const float4*)(x + ((size_t)(n*H + yy)*W + xx)*C + c));
+                const unsigned char t = (unsigned char)(dy*3 + dx);
+                if (v.x > best.x) { best.x = v.x; bi.x = t; }
+                if (v.y > best.y) { best.y = v.y; bi.y = t; }
+                if (v.z > best.z) { best.z = v.z; bi.z = t; }
+                if (v.w > best.w) { best.w = v.w; bi.w = t; }
+            }
+        }
+        ((float4*)y)[i] = best;
+        ((uchar4*)idx)[i] = bi;
+    }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(int N, int H, int W, int C, int P, int Q, const float* __restrict__ dy,
+                                                          const uint8_t* __restrict__ idx, float* __restrict__ dx) {
+    const int c4 = C >> 2;
+    const long long total = (long long)N*H*W*c4;
+    for (long long i = blockIdx.x*(long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x*blockDim.x) {
+        const int c = (int)(i % c4)*4;
+        long long r = i/c4;
+        const int xx = (int)(r % W); r /= W;
+        const int yy = (int)(r % H);
+        const int n = (int)(r/H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // windows p with 2p-1 <= yy <= 2p+1
+        for (int p = (yy > 0 ? (yy - 1 + 1)/2 : 0); p <= (yy + 1)/2 && p < P; ++p) {
+            const int ty = yy - (2*p - 1);
+            for (int q = (xx > 0 ? (xx - 1 + 1)/2 : 0); q <= (xx + 1)/2 && q < Q; ++q) {
+                const int t = ty*3 + (xx - (2*q - 1));
+                const size_t o = ((size_t)(n*P + p)*Q + q)*C + c;
+                const uchar4 k = *(const uchar4*)(idx + o);
+                const float4 g = __ldg((const float4*)(dy + o));
+                if (k.x == t) acc.x += g.x;
+                if (k.y == t) acc.y += g.y;
+                if (k.z == t) acc.z += g.z;
+                if (k.w == t) acc.w += g.w;
+            }
+        }
+        ((float4*)dx)[i] = acc;
+    }
+}
+
 static int rows_per_block(long long M, int C) {
     // ~4 waves of 148 SMs x 8 resident blocks, at least 64 rows per block.
     const long long col_blocks = (C + 31)/32;
@@ -397,4 +463,24 @@ extern "C" int stv_inv4x4_bwd(int n, const float* B, const float* gB, float* gA,
     inv4x4_bwd_kernel<<<(n + 63)/64, 64, 0, (cudaStream_t)stream>>>(n, B, gB, gA);
     count_launch();
     return check_launch("stv_inv4x4_bwd");
+}
+
+extern "C" int stv_maxpool3x3s2_fwd(int N, int H, int W, int C, const float* x, float* y, uint8_t* idx, void* stream) {
+    STV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && x && y && idx, "stv_maxpool3x3s2_fwd: bad arguments (C must be a multiple of 4)");
+    const int P = (H - 1)/2 + 1, Q = (W - 1)/2 + 1;
+    const long long total = (long long)N*P*Q*(C/4);
+    const int blocks = (int)((total + 255)/256 < 148ll*16 ? (total + 255)/256 : 148ll*16);
+    maxpool_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(N, H, W, C, P, Q, x, y, idx);
+    count_launch();
+    return check_launch("stv_maxpool3x3s2_fwd");
+}
+
+extern "C" int stv_maxpool3x3s2_bwd(int N, int H, int W, int C, const float* dy, const uint8_t* idx, float* dx, void* stream) {
+    STV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && dy && dx && idx, "stv_maxpool3x3s2_bwd: bad arguments (C must be a multiple of 4)");
+    const int P = (H - 1)/2 + 1, Q = (W - 1)/2 + 1;
+    const long long total = (long long)N*H*W*(C/4);
+    const int blocks = (int)((total + 255)/256 < 148ll*16 ? (total + 255)/256 : 148ll*16);
+    maxpool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(N, H, W, C, P, Q, dy, idx, dx);
+    count_launch();
+    return check_launch("stv_maxpool3x3s2_bwd");
 }

@@ -63,6 +63,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Pure spin (mbarrier.try_wait already suspends the thread in hardware for a bounded time): for the single-thread producer and
+// MMA-issuer roles, whose wake-up latency is on the critical path of the pipeline and who do not crowd anybody's issue slots.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0xFFFFu) == 0) {
+            const uint64_t now = globaltimer();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
+    }
+}
+
 // ---- proxies / fences -----------------------------------------------------------------------------------------------
 // Makes generic-proxy shared-memory writes (st.shared / cp.async) visible to the async proxy (TMA, tcgen05.mma).
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

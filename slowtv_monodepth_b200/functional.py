@@ -471,6 +471,11 @@ def act_bwd(dA: Tensor, y: Tensor, act: str | None, dbias: Tensor | None = None)
     Cc = y.shape[-1]
     M = y.numel()//Cc
     dA = _f32c(dA)
+    if act in (None, 'none'):  # identity: nothing to multiply — at most the bias gradient (column sums) is needed
+        if dbias is not None:
+            with torch.cuda.device(y.device):
+                L.check(L.lib().stv_colsum(M, Cc, Cc, L.ptr(dA), L.ptr(dbias), L.stream()), 'stv_colsum')
+        return dA
     with torch.cuda.device(y.device):
         dZ = torch.empty_like(y)
         L.check(L.lib().stv_act_bwd(M, Cc, L.ptr(dA), L.ptr(y), L.ACT[act], L.ptr(dZ), L.ptr(dbias), L.stream()), 'stv_act_bwd')
@@ -629,6 +634,36 @@ def batch_norm_nhwc(x: Tensor, gamma: Tensor, beta: Tensor, *, res: Tensor | Non
     if x.shape[-1] % 4: raise ValueError(f'batch_norm_nhwc: channels must be a multiple of 4, got {x.shape[-1]}')
     if res is not None and res.shape != x.shape: raise ValueError('batch_norm_nhwc: residual shape mismatch')
     return _BatchNormNHWC.apply(_f32c(x), _f32c(gamma), _f32c(beta), _f32c(res), run_mean, run_var, bool(relu), float(eps), float(momentum))
+
+
+class _MaxPool3x3s2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        L.require_cuda(x, what='maxpool3x3s2')
+        N, H, W, Cc = x.shape
+        with torch.cuda.device(x.device):
+            y = torch.empty((N, (H - 1)//2 + 1, (W - 1)//2 + 1, Cc), dtype=torch.float32, device=x.device)
+            idx = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
+            L.check(L.lib().stv_maxpool3x3s2_fwd(N, H, W, Cc, L.ptr(x), L.ptr(y), L.ptr(idx), L.stream()), 'stv_maxpool3x3s2_fwd')
+        ctx.save_for_backward(idx)
+        ctx.shape = (N, H, W, Cc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        idx, = ctx.saved_tensors
+        N, H, W, Cc = ctx.shape
+        dy = _f32c(dy)
+        with torch.cuda.device(dy.device):
+            dx = torch.empty(ctx.shape, dtype=torch.float32, device=dy.device)
+            L.check(L.lib().stv_maxpool3x3s2_bwd(N, H, W, Cc, L.ptr(dy), L.ptr(idx), L.ptr(dx), L.stream()), 'stv_maxpool3x3s2_bwd')
+        return dx
+
+
+def maxpool3x3s2(x: Tensor) -> Tensor:
+    """F.max_pool2d(kernel 3, stride 2, padding 1) on a channels-last (N,H,W,C) tensor, C a multiple of 4."""
+    if x.ndim != 4 or x.shape[-1] % 4: raise ValueError(f'maxpool3x3s2: expected (N,H,W,C) with C % 4 == 0, got {tuple(x.shape)}')
+    return _MaxPool3x3s2.apply(_f32c(x))
 
 
 class _Head3x3(torch.autograd.Function):

@@ -135,7 +135,7 @@ class ResNetEncoder(nn.Module):
     def forward(self, x: Tensor) -> list[Tensor]:
         if x.is_cuda:
             f0 = _bn_nhwc(_stem_conv_nhwc(x, self.conv1), self.bn1, relu=True)
-            x = F.max_pool2d(f0.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+            x = F_.maxpool3x3s2(f0)
             feats = [f0]
             for i in range(1, 5):
                 for blk in getattr(self, f'layer{i}'): x = blk.forward_nhwc(x)

@@ -115,3 +115,20 @@ def test_batchnorm_matches_torch(shape, relu, with_res):
     assert U.rel(yc, yr) < 1e-5
     assert U.rel(rmc, rm) < 1e-5 and U.rel(rvc, rv) < 1e-5
     for a, b in zip(cl, leaves): assert U.rel(a.grad, b.grad) < 2e-5
+
+
+@pytest.mark.parametrize('shape', [(2, 12, 20, 64), (1, 7, 9, 8), (3, 6, 6, 32)])
+def test_maxpool_matches_torch(shape):
+    """stv_maxpool3x3s2_fwd/bwd vs F.max_pool2d(3, 2, 1) (values, and gradients given distinct inputs)."""
+    from slowtv_monodepth_b200 import functional as F_
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(shape, generator=g)
+    gy_shape = (shape[0], (shape[1] - 1)//2 + 1, (shape[2] - 1)//2 + 1, shape[3])
+    gy = torch.randn(gy_shape, generator=g)
+    xr = x.clone().requires_grad_()
+    yr = F.max_pool2d(xr.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    yr.backward(gy)
+    xc = x.cuda().requires_grad_()
+    yc = F_.maxpool3x3s2(xc)
+    yc.backward(gy.cuda())
+    assert torch.equal(yc.cpu(), yr.detach()) and torch.allclose(xc.grad.cpu(), xr.grad, atol=1e-6)

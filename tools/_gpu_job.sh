@@ -1,4 +1,7 @@
-timeout 300 python -m pytest tests/test_nets_gpu.py tests/test_graph_gpu.py -q 2>&1 | tail -5 > gpurun_out/r14_tests.log
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r14_bench2.json 2> gpurun_out/r14_bench2.err
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r14_bench1.json 2> gpurun_out/r14_bench1.err
-tail -3 gpurun_out/r14_tests.log; cut -c1-300 gpurun_out/r14_bench2.json; tail -5 gpurun_out/r14_bench2.err; cut -c1-200 gpurun_out/r14_bench1.json
+timeout 600 python -m pytest tests -m gpu -q -s 2>&1 | grep -E "passed|failed|FAILED|Error|learn_K=|assert" | tail -25 > gpurun_out/r16_tests.log
+timeout 100 python tools/bench_dw.py > gpurun_out/r16_bench_dw.txt 2>&1
+timeout 200 python tools/bench_gemm.py > gpurun_out/r16_bench_gemm.txt 2>&1
+timeout 200 python tools/bench_conv.py > gpurun_out/r16_bench_conv.txt 2>&1
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r16_bench.json 2> gpurun_out/r16_bench.err
+timeout 200 python tools/step_profile.py --top 40 > gpurun_out/r16_step_profile.txt 2>&1
+cat gpurun_out/r16_tests.log; cut -c1-200 gpurun_out/r16_bench.json; cat gpurun_out/r16_bench_dw.txt
