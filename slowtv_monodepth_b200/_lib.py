@@ -112,6 +112,23 @@ def lib() -> C.CDLL:
     return _lib
 
 
+# Host-tensor arithmetic exists in this package ONLY as a test aid (CPU checks of parameter naming / wiring against the oracle, and
+# the gloo tests of the flat optimiser): it is never a fallback. Product code calls `require_device_path()` before touching it; the
+# CPU test-suite opts in with `host_test_mode(True)`.
+_HOST_TEST_MODE = False
+
+
+def host_test_mode(on: bool = True) -> None:
+    global _HOST_TEST_MODE
+    _HOST_TEST_MODE = bool(on)
+
+
+def require_device_path(what: str) -> None:
+    if not _HOST_TEST_MODE:
+        raise StvError(f'{what}: got host (CPU) tensors. The product path is CUDA-only (libstv kernels); there is no CPU fallback. '
+                       f'(The CPU test-suite enables the host reference arithmetic explicitly with _lib.host_test_mode(True).)')
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().stv_last_error().decode()

@@ -36,6 +36,14 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_kernel(int H, int W, int C, int
     for (int t = 0; t < 49; ++t) wr[t] = __ldg(w + (size_t)c*49 + (FLIP ? 48 - t : t));
     const float b = bias ? __ldg(bias + c) : 0.f;
     const size_t img = (size_t)n*H*W*C;
+    // Column offsets (in elements, relative to the start of an image row of this channel) of the DW_L + 6 input columns,
+    // computed once: -1 marks a column outside the image. Every load / store below is then base + 32-bit offset.
+    int coff[DW_L + 6];
+#pragma unroll
+    for (int q = 0; q < DW_L + 6; ++q) {
+        const int xx = x0 + q - 3;
+        coff[q] = (xx >= 0 && xx < W) ? xx*C : -1;
+    }
     float acc[7][DW_L];
 #pragma unroll
     for (int sl = 0; sl < 7; ++sl)
@@ -52,10 +60,7 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_kernel(int H, int W, int C, int
                 const float* row = x + img + (size_t)yin*W*C + c;
                 float v[DW_L + 6];
 #pragma unroll
-                for (int q = 0; q < DW_L + 6; ++q) {
-                    const int xx = x0 + q - 3;
-                    v[q] = (xx >= 0 && xx < W) ? __ldg(row + (size_t)xx*C) : 0.f;
-                }
+                for (int q = 0; q < DW_L + 6; ++q) v[q] = coff[q] >= 0 ? __ldg(row + coff[q]) : 0.f;
 #pragma unroll
                 for (int ky = 0; ky < 7; ++ky) {
                     const int o = i - ky;
@@ -68,13 +73,12 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_kernel(int H, int W, int C, int
             }
             const int o = i - 6;  // complete: its last input row (ky = 6) was row i
             if (o >= 0 && o < nrows) {
+                const size_t rowoff = img + (size_t)(y0 + o)*W*C + c;
 #pragma unroll
                 for (int j = 0; j < DW_L; ++j) {
-                    const int xx = x0 + j;
-                    if (xx < W) {
-                        const size_t off = img + ((size_t)(y0 + o)*W + xx)*C + c;
+                    if (coff[j + 3] >= 0) {
                         const float r = acc[(jr + 1) % 7][j];
-                        y[off] = res ? r + __ldg(res + off) : r;
+                        y[rowoff + coff[j + 3]] = res ? r + __ldg(res + rowoff + coff[j + 3]) : r;
                     }
                 }
             }
@@ -110,19 +114,19 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_wgrad_kernel(int H, int W, int 
             const int yy = yo + ky - 3;
             rowp[ky] = (yy >= 0 && yy < H) ? x + img + (size_t)yy*W*C + c : nullptr;
         }
-        auto ld = [&](int ky, int xx) -> float {
-            return (rowp[ky] && xx >= 0 && xx < W) ? __ldg(rowp[ky] + (size_t)xx*C) : 0.f;
+        // one column offset (xx*C) and validity test per column, shared by the 7 rows of the window
+        auto ldcol = [&](int xx, int q) {
+            const bool okx = xx >= 0 && xx < W;
+            const int off = xx*C;
+#pragma unroll
+            for (int ky = 0; ky < 7; ++ky) win[ky][q] = (okx && rowp[ky]) ? __ldg(rowp[ky] + off) : 0.f;
         };
 #pragma unroll
-        for (int ky = 0; ky < 7; ++ky)
-#pragma unroll
-            for (int q = 0; q < 6; ++q) win[ky][q] = ld(ky, xb + q - 3);
+        for (int q = 0; q < 6; ++q) ldcol(xb + q - 3, q);
         const int xe = min(xb + WG_XW, W);
         for (int xo = xb; xo < xe; xo += WG_U) {
 #pragma unroll
-            for (int ky = 0; ky < 7; ++ky)
-#pragma unroll
-                for (int u = 0; u < WG_U; ++u) win[ky][6 + u] = ld(ky, xo + 3 + u);
+            for (int u = 0; u < WG_U; ++u) ldcol(xo + 3 + u, 6 + u);
             float g[WG_U];
 #pragma unroll
             for (int u = 0; u < WG_U; ++u) g[u] = xo + u < xe ? __ldg(gy + img + ((size_t)yo*W + xo + u)*C + c) : 0.f;

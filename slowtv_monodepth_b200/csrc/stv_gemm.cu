@@ -18,6 +18,7 @@
 //   warps 2-9 epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> shared-memory transpose -> bias / activation /
 //             layer-scale / residual / activation-backward / column sums -> coalesced 128-bit global stores, or
 //             red.global.add.v4 when accumulating (split-K, grad buffers)
+#include <cstdlib>
 #include <mutex>
 
 #include "stv_common.cuh"
@@ -161,6 +162,166 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ---- persistent variant ------------------------------------------------------------------------------------------------------
+// Same roles, but a CTA (two resident per SM) walks a strided list of output tiles: the barriers, the TMEM allocation and the
+// tensor-map prefetch are paid once; the producer keeps streaming k-blocks of the NEXT tile into the ring while the epilogue
+// warps drain the current one; and the accumulator is double-buffered in TMEM (2 x cols columns), so the MMAs of tile j+1
+// overlap the epilogue of tile j. The epilogue stages its transposed chunks in a dedicated region (the ring stays busy).
+//   tmem_full[a]  : MMA warp -> epilogue ("accumulator a holds a finished tile"), one tcgen05.commit per tile
+//   tmem_empty[a] : epilogue -> MMA warp ("accumulator a has been read out"), one arrival per epilogue warp
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = tc::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b_bytes = p.bn*GEMM_BK*4;
+    const int stage_bytes = GEMM_A_BYTES + b_bytes;
+    float* staging = (float*)(smem + (size_t)p.stages*stage_bytes);
+    uint64_t* full = (uint64_t*)(staging + 8*EPI_WARP_FLOATS);
+    uint64_t* empty = full + GEMM_MAX_STAGES;
+    uint64_t* tmem_full = empty + GEMM_MAX_STAGES;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;            // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+    const int nt = (p.N + p.bn - 1)/p.bn, mt = (p.M + GEMM_BM - 1)/GEMM_BM;
+    const int total = nt*mt*p.splits;
+    const uint32_t acc_cols = p.bn <= 32 ? 32u : p.bn <= 64 ? 64u : 128u;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(&tmem_full[a], 1);
+            tc::mbar_init(&tmem_empty[a], 8);
+        }
+        tc::fence_barrier_init();
+    } else if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, 2*acc_cols);
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const ConvOperand& cv = p.cv;
+            int it = 0;  // k-blocks issued so far by this CTA (ring position carries over from tile to tile)
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int n0 = (t % nt)*p.bn, m0 = ((t/nt) % mt)*GEMM_BM, z = t/(nt*mt);
+                const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                int bn_ = 0, bw = 0, bh = 0, tap = 0, cb = 0;
+                int slab_c[8], slab_rs[8];
+                if (cv.mode == 1) {
+                    const int hw = cv.gridH*cv.gridW;
+                    bn_ = m0/hw;
+                    const int rem = m0 - bn_*hw, py = rem/cv.gridW, px = rem - py*cv.gridW;
+                    bw = cv.lw + px*cv.stride; bh = cv.lh + py*cv.stride;
+                    tap = kb0/cv.cblocks; cb = kb0 - tap*cv.cblocks;
+                } else if (cv.mode == 2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = n0 + 32*j, tp = col/cv.C;
+                        const bool ok = j < p.bn/32 && tp < cv.R*cv.S;
+                        slab_c[j] = ok ? col - tp*cv.C : cv.C;
+                        const int r = ok ? tp/cv.S : 0, sx = ok ? tp - r*cv.S : 0;
+                        slab_rs[j] = (r << 8) | sx;
+                    }
+                }
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it/p.stages) & 1u;
+                    tc::mbar_wait_spin(&empty[s], ph ^ 1u);
+                    tc::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+                    uint8_t* a = smem + (size_t)s*stage_bytes;
+                    uint8_t* b = a + GEMM_A_BYTES;
+                    const int k = kb*GEMM_BK;
+                    if (cv.mode == 1) {
+                        const int r = tap/cv.S, sx = tap - r*cv.S;
+                        tc::tma_load_im2col_4d(a, &tmA, &full[s], cb*GEMM_BK, bw, bh, bn_, (uint16_t)(cv.flip ? cv.S - 1 - sx : sx),
+                                               (uint16_t)(cv.flip ? cv.R - 1 - r : r));
+                        if (!p.b_mn) tc::tma_load_2d(b, &tmB, &full[s], k, n0);
+                        else
+                            for (int j = 0; j < p.bn/32; ++j)
+                                tc::tma_load_2d(b + j*SLAB_MN_BYTES, &tmB, &full[s],
+                                                ((cv.r0 + cv.tstep*r)*cv.Sfull + cv.s0 + cv.tstep*sx)*cv.b_tap_cols + n0 + 32*j, cb*GEMM_BK);
+                        if (++cb == cv.cblocks) { cb = 0; ++tap; }
+                        continue;
+                    }
+                    if (!p.a_mn) tc::tma_load_2d(a, &tmA, &full[s], k, m0);
+                    else
+                        for (int j = 0; j < GEMM_BM/32; ++j) tc::tma_load_2d(a + j*SLAB_MN_BYTES, &tmA, &full[s], m0 + 32*j, k);
+                    if (cv.mode == 2) {
+                        const int hw = cv.gridH*cv.gridW, n = k/hw, rem = k - n*hw, py = rem/cv.gridW, px = rem - py*cv.gridW;
+                        const int w = cv.lw + px*cv.stride, h = cv.lh + py*cv.stride;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < p.bn/32)
+                                tc::tma_load_im2col_4d(b + j*SLAB_MN_BYTES, &tmB, &full[s], slab_c[j], w, h, n, (uint16_t)(slab_rs[j] & 255),
+                                                       (uint16_t)(slab_rs[j] >> 8));
+                    } else if (!p.b_mn) tc::tma_load_2d(b, &tmB, &full[s], k, n0);
+                    else
+                        for (int j = 0; j < p.bn/32; ++j) tc::tma_load_2d(b + j*SLAB_MN_BYTES, &tmB, &full[s], n0 + 32*j, k);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::umma_idesc_tf32(GEMM_BM, p.bn, p.a_mn != 0, p.b_mn != 0);
+            int it = 0, j = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+                const int z = t/(nt*mt);
+                const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                const int acc = j & 1;
+                tc::mbar_wait_spin(&tmem_empty[acc], ((uint32_t)(j >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+                tc::tcgen05_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)acc*acc_cols;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it/p.stages) & 1u;
+                    tc::mbar_wait_spin(&full[s], ph);
+                    tc::tcgen05_fence_after();
+                    const uint32_t a = tc::smem_u32(smem + (size_t)s*stage_bytes), b = a + GEMM_A_BYTES;
+#pragma unroll
+                    for (int k8 = 0; k8 < GEMM_BK/8; ++k8) {
+                        const uint64_t da = p.a_mn ? tc::umma_desc_mnmajor(a, k8, SLAB_MN_BYTES) : tc::umma_desc_kmajor(a, k8);
+                        const uint64_t db = p.b_mn ? tc::umma_desc_mnmajor(b, k8, SLAB_MN_BYTES) : tc::umma_desc_kmajor(b, k8);
+                        tc::umma_tf32(d, da, db, idesc, (kb > kb0 || k8 > 0) ? 1u : 0u);
+                    }
+                    tc::umma_commit(&empty[s]);
+                }
+                tc::umma_commit(&tmem_full[acc]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const RowMap rm = {p.ldc, p.remap, p.cv.gridH, p.cv.gridW, p.oH, p.oW, p.ost, p.oa, p.ob};
+        const int ew = warp - 2;
+        int j = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+            const int n0 = (t % nt)*p.bn, m0 = ((t/nt) % mt)*GEMM_BM;
+            const int acc = j & 1;
+            tc::mbar_wait(&tmem_full[acc], (uint32_t)(j >> 1) & 1u);
+            tc::tcgen05_fence_after();
+            epilogue_tile(tmem_base + (uint32_t)acc*acc_cols, warp & 3, lane, m0, n0, p.bn, p.M, p.N, p.C, rm, p.e,
+                          staging + ew*EPI_WARP_FLOATS, (ew >> 2)*32, 64);
+            tc::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, 2*acc_cols);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -242,19 +403,54 @@ int pick_bn(int N, long long row_tiles) {
     return best;
 }
 
+static bool persistent_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* v = getenv("STV_GEMM_PERSISTENT"); on = (v && v[0] == '0') ? 0 : 1; }  // developer switch for A/B runs
+    return on != 0;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int splits, cudaStream_t stream, const char* what) {
     const int stage_bytes = GEMM_A_BYTES + p.bn*GEMM_BK*4;
+    const int nt = (p.N + p.bn - 1)/p.bn, mt = (p.M + GEMM_BM - 1)/GEMM_BM;
+    p.splits = splits;
+    if (mt > 65535) { set_error("%s: too many row tiles (%d)", what, mt); return STV_E_ARG; }
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(gemm_tf32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024);
+    });
+    if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute failed (%s)", what, cudaGetErrorString(attr_err)); return STV_E_CUDA; }
+    const long long total = (long long)nt*mt*splits;
+    if (persistent_enabled() && total < (1ll << 30)) {
+        // two resident CTAs per SM: ring + epilogue staging + barriers within ~112 KB each
+        const int staging = 8*EPI_WARP_FLOATS*4;
+        int stages = (112*1024 - staging - 2048)/stage_bytes;
+        stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
+        stages = stages < 2 ? 2 : stages;
+        p.stages = stages;
+        const size_t smem = (size_t)stages*stage_bytes + staging + 1024 /*alignment slack*/ + (2*GEMM_MAX_STAGES + 4)*8 + 16;
+        const int resident = 2*sm_count();
+        const int grid = (int)(total < resident ? total : resident);
+        gemm_tf32_persistent_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
+        count_launch();
+        return check_launch(what);
+    }
     int stages = (110*1024)/stage_bytes;                         // two resident CTAs per SM (bn <= 128 -> at least 3 stages)
     stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
     stages = stages > p.kb_per_split ? (p.kb_per_split < 2 ? 2 : p.kb_per_split) : stages;
     p.stages = stages;
     const size_t smem = (size_t)stages*stage_bytes + 1024 /*alignment slack*/ + (2*GEMM_MAX_STAGES + 1)*8 + 16;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024); });
-    if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute failed (%s)", what, cudaGetErrorString(attr_err)); return STV_E_CUDA; }
-    const dim3 grid((p.N + p.bn - 1)/p.bn, (p.M + GEMM_BM - 1)/GEMM_BM, splits);
-    if (grid.y > 65535u) { set_error("%s: too many row tiles (%u)", what, grid.y); return STV_E_ARG; }
+    const dim3 grid(nt, mt, splits);
     gemm_tf32_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
     count_launch();
     return check_launch(what);

@@ -26,7 +26,7 @@ struct ConvOperand {
 struct GemmParams {
     int M, N, K;
     int bn, stages, a_mn, b_mn;
-    int kb_total, kb_per_split;
+    int kb_total, kb_per_split, splits;
     float* C;
     long long ldc;
     stv_gemm_epi e;

@@ -11,6 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
+from .. import _lib as L_
 from .. import functional as F_
 
 __all__ = ['MonodepthDecoder']
@@ -55,6 +56,7 @@ class MonodepthDecoder(nn.Module):
 
     def forward(self, feat: list[Tensor]) -> dict[int, Tensor]:
         if feat[-1].is_cuda and self.upsample_mode == 'nearest': return self.forward_nhwc(feat)
+        L_.require_device_path('MonodepthDecoder' if not feat[-1].is_cuda else f'MonodepthDecoder(upsample_mode={self.upsample_mode!r})')
         out, act = {}, _ACT[self.out_act]
         x = feat[-1]
         for i in range(4, -1, -1):

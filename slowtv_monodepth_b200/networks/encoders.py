@@ -23,6 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
+from .. import _lib as L_
 from .. import functional as F_
 
 __all__ = ['create_encoder', 'ResNetEncoder', 'ConvNeXtEncoder', 'FeatureInfo']
@@ -141,6 +142,7 @@ class ResNetEncoder(nn.Module):
                 for blk in getattr(self, f'layer{i}'): x = blk.forward_nhwc(x)
                 feats.append(x)
             return [f.permute(0, 3, 1, 2) for f in feats]  # (N,C,H,W) views of the channels-last buffers
+        L_.require_device_path('ResNetEncoder')
         f0 = F.relu(self.bn1(_stem_conv(x, self.conv1)), inplace=True)
         x = F.max_pool2d(f0, 3, 2, 1)
         feats = [f0]
@@ -242,6 +244,7 @@ class ConvNeXtEncoder(nn.Module):
                 x = getattr(self, f'stages_{i}').forward_nhwc(x)
                 feats.append(x.permute(0, 3, 1, 2))  # (N,C,H,W) view of the channels-last buffer
             return feats
+        L_.require_device_path('ConvNeXtEncoder')
         x = self.stem_1(_stem_conv(x, self.stem_0))
         feats = []
         for i in range(4):

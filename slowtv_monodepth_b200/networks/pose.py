@@ -6,6 +6,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
+from .. import _lib as L_
 from .. import functional as F_
 from .encoders import create_encoder
 
@@ -54,6 +55,7 @@ class PoseNet(nn.Module):
 
     def forward(self, x: Tensor) -> dict:
         if x.is_cuda: return self.forward_nhwc(x)
+        L_.require_device_path('PoseNet')
         feat = self.squeeze(self.encoder(x)[-1])
         out = self.pose_eps*self.decoders['pose'](feat).mean(dim=(2, 3)).unflatten(-1, (self.n_imgs, 6))
         res = {'R': out[..., :3], 't': out[..., 3:]}

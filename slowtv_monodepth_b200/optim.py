@@ -14,6 +14,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
+from . import _lib as L_
 from . import functional as F_
 
 __all__ = ['FlatAdamW']
@@ -75,6 +76,7 @@ class FlatAdamW:
                            beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
                            step=self.step_count, grad_scale=1.0/self.world)
         else:
+            L_.require_device_path('FlatAdamW.step')
             self._step_host()
 
     @torch.no_grad()

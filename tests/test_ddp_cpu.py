@@ -31,7 +31,9 @@ def _train(model, opt, x, y, steps=3):
 
 
 def _worker(rank, world, init_file, out_dir):
+    from slowtv_monodepth_b200 import _lib
     from slowtv_monodepth_b200.optim import FlatAdamW
+    _lib.host_test_mode(True)  # spawned process: opt in to the host reference arithmetic (the product path is CUDA-only)
     dist.init_process_group('gloo', init_method=f'file://{init_file}', rank=rank, world_size=world)
     try:
         model = _model()
