@@ -134,15 +134,16 @@ int stv_smooth_bwd(const stv_smooth_cfg* cfg, const float* const* disp, const fl
 int stv_dwconv7_fwd(int N, int H, int W, int C, const float* x, const float* w, const float* bias, const float* res,
                     float* y, int flip, void* stream);
 size_t stv_dwconv7_wgrad_workspace_bytes(int N, int H, int W, int C);
-/* gw (C,49) = d/dw, gb (C) = d/dbias (nullable), from the layer input x and the output gradient gy. */
-int stv_dwconv7_wgrad(int N, int H, int W, int C, const float* x, const float* gy, float* gw, float* gb, void* ws,
+/* gw (C,49) = d/dw, gb (C) = d/dbias (nullable), from the layer input x and the output gradient gy; accumulate != 0: += . */
+int stv_dwconv7_wgrad(int N, int H, int W, int C, const float* x, const float* gy, float* gw, float* gb, int accumulate, void* ws,
                       size_t ws_bytes, void* stream);
 /* Row-wise LayerNorm of a (P, C) matrix; mean / rstd (P) are saved for the backward. */
 int stv_layernorm_fwd(long long P, int C, const float* x, const float* gamma, const float* beta, float eps, float* y,
                       float* mean, float* rstd, void* stream);
 size_t stv_layernorm_bwd_workspace_bytes(long long P, int C);
 int stv_layernorm_bwd(long long P, int C, const float* dy, const float* x, const float* mean, const float* rstd,
-                      const float* gamma, float* dx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+                      const float* gamma, float* dx, float* dgamma, float* dbeta, int accumulate /* dgamma, dbeta += */, void* ws,
+                      size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Tensor-core products of the network layers (tcgen05.mma kind::tf32 + TMA + TMEM; fp32 storage, TF32 multiply, fp32
@@ -233,8 +234,8 @@ int stv_bn_fwd(long long M, int C, const float* x, const float* gamma, const flo
                void* stream);
 /* dz = dy * (y > 0) when relu; dres = dz (nullable); dx = gamma rstd (dz - mean_m(dz) - xhat mean_m(dz xhat)); dgamma, dbeta (C). */
 int stv_bn_bwd(long long M, int C, const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
-               const float* gamma, int relu, float* dx, float* dres, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
-               void* stream);
+               const float* gamma, int relu, float* dx, float* dres, float* dgamma, float* dbeta, int accumulate /* dgamma, dbeta += */,
+               void* ws, size_t ws_bytes, void* stream);
 
 /* 3x3 stride-2 max-pool, padding 1, channels-last (N,H,W,C) -> (N,(H-1)/2+1,(W-1)/2+1,C): the `maxpool` of the timm ResNet stem
  * (src/networks/pose.py:40, depth.py:97). idx (same shape as y, u8) = winning tap 0..8 (first maximum in row-major order). */

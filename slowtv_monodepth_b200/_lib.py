@@ -66,10 +66,10 @@ _SIGNATURES = {
     'stv_smooth_bwd': (C.c_int, [C.POINTER(SmoothCfg), _P, _P, _P, _P, _P, C.c_size_t, _P]),
     'stv_dwconv7_fwd': (C.c_int, [C.c_int]*4 + [_P]*5 + [C.c_int, _P]),
     'stv_dwconv7_wgrad_workspace_bytes': (C.c_size_t, [C.c_int]*4),
-    'stv_dwconv7_wgrad': (C.c_int, [C.c_int]*4 + [_P]*5 + [C.c_size_t, _P]),
+    'stv_dwconv7_wgrad': (C.c_int, [C.c_int]*4 + [_P]*4 + [C.c_int, _P, C.c_size_t, _P]),
     'stv_layernorm_fwd': (C.c_int, [C.c_longlong, C.c_int, _P, _P, _P, C.c_float, _P, _P, _P, _P]),
     'stv_layernorm_bwd_workspace_bytes': (C.c_size_t, [C.c_longlong, C.c_int]),
-    'stv_layernorm_bwd': (C.c_int, [C.c_longlong, C.c_int] + [_P]*9 + [C.c_size_t, _P]),
+    'stv_layernorm_bwd': (C.c_int, [C.c_longlong, C.c_int] + [_P]*8 + [C.c_int, _P, C.c_size_t, _P]),
     'stv_gemm_tf32': (C.c_int, [C.c_int]*3 + [_P, C.c_longlong, C.c_int, _P, C.c_longlong, C.c_int, _P, C.c_longlong,
                                 C.POINTER(GemmEpi), C.c_int, _P]),
     'stv_conv_fprop': (C.c_int, [C.POINTER(ConvGeom), _P, _P, _P, _P, C.POINTER(GemmEpi), _P]),
@@ -81,7 +81,7 @@ _SIGNATURES = {
     'stv_colsum': (C.c_int, [C.c_longlong, C.c_int, C.c_longlong, _P, _P, _P]),
     'stv_bn_workspace_bytes': (C.c_size_t, [C.c_int]),
     'stv_bn_fwd': (C.c_int, [C.c_longlong, C.c_int, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
-    'stv_bn_bwd': (C.c_int, [C.c_longlong, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'stv_bn_bwd': (C.c_int, [C.c_longlong, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     'stv_maxpool3x3s2_fwd': (C.c_int, [C.c_int]*4 + [_P, _P, _P, _P]),
     'stv_maxpool3x3s2_bwd': (C.c_int, [C.c_int]*4 + [_P, _P, _P, _P]),
     'stv_head3x3_fwd': (C.c_int, [C.c_int]*4 + [_P, _P, _P, C.c_int, _P, _P]),

@@ -525,9 +525,9 @@ __global__ void vpad_kernel(int N, int H, int W, int C1, int C2, int Cp, int up1
                             const float* __restrict__ s2, float* __restrict__ out) {
     const int Cc = C1 + C2, c4n = Cp >> 2, Hp = H + 2*pad, Wp = W + 2*pad;
     const long long total = (long long)N*Hp*Wp*c4n;
-    for (long long idx = blockIdx.x*(long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x*blockDim.x) {
+    for (unsigned idx = blockIdx.x*blockDim.x + threadIdx.x; idx < (unsigned)total; idx += gridDim.x*blockDim.x) {  // 32-bit index math (count < 2^31, checked on the host)
         const int c = (int)(idx % c4n)*4;
-        long long r = idx/c4n;
+        unsigned r = idx/c4n;
         const int xp = (int)(r % Wp); r /= Wp;
         const int yp = (int)(r % Hp);
         const int n = (int)(r/Hp);
@@ -553,6 +553,7 @@ extern "C" int stv_vpad(const stv_conv_geom* g, const float* src1, const float* 
     STV_REQUIRE(Cp >= g->C1 + g->C2 && Cp % 4 == 0, "stv_vpad: padded channel count %d must be a multiple of 4 and >= %d", Cp, g->C1 + g->C2);
     const int pad = g->reflect ? g->pad : 0;
     const long long total = (long long)g->N*(g->H + 2*pad)*(g->W + 2*pad)*(Cp/4);
+    STV_REQUIRE(total < (1ll << 31), "stv_vpad: tensor too large");
     const int blocks = (int)((total + 255)/256 < 148ll*32 ? (total + 255)/256 : 148ll*32);
     vpad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g->N, g->H, g->W, g->C1, g->C2, Cp, g->up1, pad, src1, src2 ? src2 : src1, out);
     count_launch();

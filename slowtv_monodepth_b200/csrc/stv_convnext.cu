@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_wgrad_kernel(int H, int W, int 
 // out[c*49 + t] = sum_blk partial[blk][t][c];  gb[c] = sum_blk partial[blk][49][c]. A block owns 32 consecutive entries (t, c);
 // its 8 warps stride over the partial blocks (8 independent, coalesced load streams) and are combined in a fixed order.
 __global__ void __launch_bounds__(256) dwconv7_wgrad_reduce_kernel(int C, int nblk, const float* __restrict__ partial,
-                                                                   float* __restrict__ gw, float* __restrict__ gb) {
+                                                                   float* __restrict__ gw, float* __restrict__ gb, int accumulate) {
     __shared__ double red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int e = blockIdx.x*32 + tx;
@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_reduce_kernel(int C, int nb
 #pragma unroll
         for (int k = 1; k < 8; ++k) a += red[k][tx];
         const int t = e/C, c = e - t*C;
-        if (t < 49) gw[(size_t)c*49 + t] = (float)a;
-        else if (gb) gb[c] = (float)a;
+        if (t < 49) { float* o = gw + (size_t)c*49 + t; *o = accumulate ? *o + (float)a : (float)a; }
+        else if (gb) gb[c] = accumulate ? gb[c] + (float)a : (float)a;
     }
 }
 
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(long long P, int C, 
 // A block owns 32 consecutive entries of [dgamma | dbeta]; its 8 warps stride over the partial rows (8 coalesced load streams in
 // flight instead of one serial chain) and are combined in a fixed order (deterministic).
 __global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(int C, int nrows, const float* __restrict__ partial,
-                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
     __shared__ double red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int e = blockIdx.x*32 + tx;
@@ -269,7 +269,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_reduce_kernel(int C, int nr
         double a = red[0][tx];
 #pragma unroll
         for (int k = 1; k < 8; ++k) a += red[k][tx];
-        if (e < C) dgamma[e] = (float)a; else dbeta[e - C] = (float)a;
+        float* o = e < C ? dgamma + e : dbeta + (e - C);
+        *o = accumulate ? *o + (float)a : (float)a;
     }
 }
 
@@ -301,8 +302,8 @@ extern "C" size_t stv_dwconv7_wgrad_workspace_bytes(int N, int H, int W, int C) 
     return (size_t)N*((H + WG_RY - 1)/WG_RY)*((W + WG_XW - 1)/WG_XW)*50*C*sizeof(float);
 }
 
-extern "C" int stv_dwconv7_wgrad(int N, int H, int W, int C, const float* x, const float* gy, float* gw, float* gb, void* ws,
-                                 size_t ws_bytes, void* stream) {
+extern "C" int stv_dwconv7_wgrad(int N, int H, int W, int C, const float* x, const float* gy, float* gw, float* gb, int accumulate,
+                                 void* ws, size_t ws_bytes, void* stream) {
     STV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 1024, "stv_dwconv7_wgrad: bad shape");
     STV_REQUIRE(N <= 65535 && (H + WG_RY - 1)/WG_RY <= 65535, "stv_dwconv7_wgrad: grid too large");
     STV_REQUIRE(x && gy && gw, "stv_dwconv7_wgrad: NULL pointer");
@@ -314,7 +315,7 @@ extern "C" int stv_dwconv7_wgrad(int N, int H, int W, int C, const float* x, con
     count_launch();
     if (int rc = check_launch("dwconv7_wgrad_kernel")) return rc;
     const int nblk = (grid.x/ncb)*grid.y*grid.z;
-    dwconv7_wgrad_reduce_kernel<<<(50*C + 31)/32, 256, 0, (cudaStream_t)stream>>>(C, nblk, (const float*)ws, gw, gb);
+    dwconv7_wgrad_reduce_kernel<<<(50*C + 31)/32, 256, 0, (cudaStream_t)stream>>>(C, nblk, (const float*)ws, gw, gb, accumulate);
     count_launch();
     return check_launch("dwconv7_wgrad_reduce_kernel");
 }
@@ -345,8 +346,8 @@ extern "C" size_t stv_layernorm_bwd_workspace_bytes(long long P, int C) {
 }
 
 extern "C" int stv_layernorm_bwd(long long P, int C, const float* dy, const float* x, const float* mean, const float* rstd,
-                                 const float* gamma, float* dx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
-                                 void* stream) {
+                                 const float* gamma, float* dx, float* dgamma, float* dbeta, int accumulate, void* ws,
+                                 size_t ws_bytes, void* stream) {
     STV_REQUIRE(P > 0 && C > 0 && C <= 32*LN_MAXPL, "stv_layernorm_bwd: bad shape (C <= %d)", 32*LN_MAXPL);
     STV_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "stv_layernorm_bwd: NULL pointer");
     const size_t need = stv_layernorm_bwd_workspace_bytes(P, C);
@@ -369,7 +370,7 @@ extern "C" int stv_layernorm_bwd(long long P, int C, const float* dy, const floa
 #undef STV_LN_BWD
     count_launch();
     if (int rc = check_launch("layernorm_bwd_kernel")) return rc;
-    layernorm_bwd_reduce_kernel<<<(2*C + 31)/32, 256, 0, st>>>(C, (int)blocks, (const float*)ws, dgamma, dbeta);
+    layernorm_bwd_reduce_kernel<<<(2*C + 31)/32, 256, 0, st>>>(C, (int)blocks, (const float*)ws, dgamma, dbeta, accumulate);
     count_launch();
     return check_launch("layernorm_bwd_reduce_kernel");
 }

@@ -58,31 +58,35 @@ constexpr int EPI_LD = 36;                       // floats per staged row: 16-by
 constexpr int EPI_WARP_FLOATS = 32*EPI_LD;       // staging floats per epilogue warp
 
 // The 8 rows a lane owns in one transposed 32 x 32 chunk: epilogue chain + store, returns the lane's column sums.
-// ACT / DACT are compile-time activation codes; -1 = take them from the descriptor at run time (rare combinations).
-template <int ACT, int DACT>
+// Every template argument is a compile-time copy of a kernel-uniform descriptor field (-1 = read it at run time): the epilogue
+// warps are issue-bound on the narrow-K layers, and per-element branches on descriptor fields were ~25 of their ~54
+// instructions per output element. FULL = all 128 rows of the tile exist (no per-row bound check).
+template <int ACT, int DACT, int AUX, int GAM, int RES, int ACC, int CS, bool FULL>
 __device__ __forceinline__ float4 epilogue_rows(const stv_gemm_epi& e, float* __restrict__ C, const float* xs, const size_t (&roffs)[8],
                                                 const float4 (&pre)[8], const float4 bb, const float4 gg, int row0, int M, int n, int rsub,
                                                 int cq) {
     const int act = ACT >= 0 ? ACT : e.act, dact = DACT >= 0 ? DACT : e.dact;
+    const bool aux = AUX >= 0 ? AUX != 0 : e.aux != nullptr, gam = GAM >= 0 ? GAM != 0 : e.gamma != nullptr;
+    const bool res = RES >= 0 ? RES != 0 : e.res != nullptr, accm = ACC >= 0 ? ACC != 0 : e.accumulate != 0;
+    const bool cs_on = CS >= 0 ? CS != 0 : e.colsum != nullptr;
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int row = row0 + 4*i;
-        if (row >= M) break;
+        if (!FULL && row0 + 4*i >= M) break;
         const size_t o = roffs[i] + n;
         float4 x = *(const float4*)(xs + (4*i + rsub)*EPI_LD + cq);
         x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-        if (e.aux) *(float4*)(e.aux + o) = x;
+        if (aux) *(float4*)(e.aux + o) = x;
         if (act) { x.x = act_fwd(act, x.x); x.y = act_fwd(act, x.y); x.z = act_fwd(act, x.z); x.w = act_fwd(act, x.w); }
-        x.x *= gg.x; x.y *= gg.y; x.z *= gg.z; x.w *= gg.w;
-        if (e.res) { x.x += pre[i].x; x.y += pre[i].y; x.z += pre[i].z; x.w += pre[i].w; }
+        if (gam) { x.x *= gg.x; x.y *= gg.y; x.z *= gg.z; x.w *= gg.w; }
+        if (res) { x.x += pre[i].x; x.y += pre[i].y; x.z += pre[i].z; x.w += pre[i].w; }
         if (DACT != STV_ACT_NONE && e.dact_src) {
-            const float4 s = e.res ? __ldg((const float4*)(e.dact_src + o)) : pre[i];
+            const float4 s = res ? __ldg((const float4*)(e.dact_src + o)) : pre[i];
             x.x *= act_bwd(dact, s.x); x.y *= act_bwd(dact, s.y); x.z *= act_bwd(dact, s.z); x.w *= act_bwd(dact, s.w);
         }
-        if (e.accumulate) tc::red_add_v4(C + o, x.x, x.y, x.z, x.w);
+        if (accm) tc::red_add_v4(C + o, x.x, x.y, x.z, x.w);
         else *(float4*)(C + o) = x;
-        cs.x += x.x; cs.y += x.y; cs.z += x.z; cs.w += x.w;
+        if (cs_on) { cs.x += x.x; cs.y += x.y; cs.z += x.z; cs.w += x.w; }
     }
     return cs;
 }
@@ -120,20 +124,25 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int q, int lan
                     const int row = row0 + 4*i;
                     pre[i] = (pre_src && row < M) ? __ldg((const float4*)(pre_src + roffs[i] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                // The activation codes are kernel-uniform: dispatch once per chunk to a loop specialised on them, instead of
-                // running a switch per element (which cost ~14 % of the samples of the convolution epilogues).
+                // Descriptor fields are kernel-uniform: dispatch once per chunk to a loop specialised on the combinations the networks
+                // use (fc1, fc2, GELU' dgrad, plain store, split-K accumulate, conv + ELU / ReLU); anything else takes the generic loop.
                 float4 cs;
-#define STV_EPI_ROWS(A, D) cs = epilogue_rows<A, D>(e, C, xs, roffs, pre, bb, gg, row0, M, n, rsub, cq)
-                if (e.dact_src) {
-                    if (e.act == STV_ACT_NONE && e.dact == STV_ACT_GELU) STV_EPI_ROWS(STV_ACT_NONE, STV_ACT_GELU);
-                    else STV_EPI_ROWS(-1, -1);
-                } else switch (e.act) {
-                    case STV_ACT_NONE: STV_EPI_ROWS(STV_ACT_NONE, STV_ACT_NONE); break;
-                    case STV_ACT_RELU: STV_EPI_ROWS(STV_ACT_RELU, STV_ACT_NONE); break;
-                    case STV_ACT_GELU: STV_EPI_ROWS(STV_ACT_GELU, STV_ACT_NONE); break;
-                    case STV_ACT_ELU: STV_EPI_ROWS(STV_ACT_ELU, STV_ACT_NONE); break;
-                    default: STV_EPI_ROWS(-1, -1); break;
-                }
+                const bool full = m0 + 128 <= M;
+                const bool plain = !e.aux && !e.gamma && !e.res && !e.dact_src && !e.accumulate && !e.colsum;
+#define STV_EPI_ROWS(...) cs = full ? epilogue_rows<__VA_ARGS__, true>(e, C, xs, roffs, pre, bb, gg, row0, M, n, rsub, cq) \
+                               : epilogue_rows<__VA_ARGS__, false>(e, C, xs, roffs, pre, bb, gg, row0, M, n, rsub, cq)
+                if (plain && e.act == STV_ACT_NONE) STV_EPI_ROWS(STV_ACT_NONE, STV_ACT_NONE, 0, 0, 0, 0, 0);
+                else if (plain && e.act == STV_ACT_ELU) STV_EPI_ROWS(STV_ACT_ELU, STV_ACT_NONE, 0, 0, 0, 0, 0);
+                else if (plain && e.act == STV_ACT_RELU) STV_EPI_ROWS(STV_ACT_RELU, STV_ACT_NONE, 0, 0, 0, 0, 0);
+                else if (e.act == STV_ACT_GELU && e.aux && !e.gamma && !e.res && !e.dact_src && !e.accumulate && !e.colsum)
+                    STV_EPI_ROWS(STV_ACT_GELU, STV_ACT_NONE, 1, 0, 0, 0, 0);                                   // fc1 + bias + GELU, z saved
+                else if (e.act == STV_ACT_NONE && !e.aux && e.gamma && e.res && !e.dact_src && !e.accumulate && !e.colsum)
+                    STV_EPI_ROWS(STV_ACT_NONE, STV_ACT_NONE, 0, 1, 1, 0, 0);                                   // fc2 + bias + layer-scale + residual
+                else if (e.act == STV_ACT_NONE && !e.aux && !e.gamma && !e.res && e.dact_src && e.dact == STV_ACT_GELU && !e.accumulate)
+                    STV_EPI_ROWS(STV_ACT_NONE, STV_ACT_GELU, 0, 0, 0, 0, -1);                                  // (g W2) * GELU'(z) [+ column sums]
+                else if (e.act == STV_ACT_NONE && !e.aux && !e.gamma && !e.res && !e.dact_src && e.accumulate && !e.colsum)
+                    STV_EPI_ROWS(STV_ACT_NONE, STV_ACT_NONE, 0, 0, 0, 1, 0);                                   // split-K weight gradients
+                else STV_EPI_ROWS(-1, -1, -1, -1, -1, -1, -1);
 #undef STV_EPI_ROWS
                 if (e.colsum) {  // lanes l, l^8, l^16, l^24 hold the same 4 columns (different rows): combine, then one red per column group
                     // (all 32 lanes of the warp reach this point together when n < N for the whole warp; guard with the active mask)

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(HD_THREADS) head3x3_fwd_kernel(int N, int H, i
         const long long pix_ = (it*gridDim.x + blockIdx.x)*ppb + g;
         const bool valid = pix_ < npix;
         const long long pix = valid ? pix_ : 0;
-        const int n = (int)(pix/(H*W)), rem = (int)(pix - (long long)n*H*W), p = rem/W, q = rem - p*W;
+        const int ipix = (int)pix, n = ipix/(H*W), rem = ipix - n*H*W, p = rem/W, q = rem - p*W;  // 32-bit divisions (npix < 2^31)
         float acc = 0.f;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(HD_THREADS) head3x3_dgrad_kernel(int N, int H,
     load_taps(w, C, c, wt);
     const long long npix = (long long)N*H*W;
     for (long long pix = (long long)blockIdx.x*ppb + g; pix < npix; pix += (long long)gridDim.x*ppb) {
-        const int n = (int)(pix/(H*W)), rem = (int)(pix - (long long)n*H*W), yy = rem/W, xx = rem - yy*W;
+        const int ipix = (int)pix, n = ipix/(H*W), rem = ipix - n*H*W, yy = rem/W, xx = rem - yy*W;
         // padded coordinates (pad 1) that read input row yy: yy+1, plus 0 when yy == 1, plus H+1 when yy == H-2
         int ys[3], xs[3], ny = 0, nx = 0;
         ys[ny++] = yy + 1; if (yy == 1) ys[ny++] = 0; if (yy == H - 2) ys[ny++] = H + 1;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(HD_THREADS) head3x3_wgrad_kernel(int N, int H,
     float bsum = 0.f;
     const long long npix = (long long)N*H*W;
     for (long long pix = (long long)blockIdx.x*ppb + g; pix < npix; pix += (long long)gridDim.x*ppb) {  // no shuffles inside: ragged trip counts are fine
-        const int n = (int)(pix/(H*W)), rem = (int)(pix - (long long)n*H*W), p = rem/W, q = rem - p*W;
+        const int ipix = (int)pix, n = ipix/(H*W), rem = ipix - n*H*W, p = rem/W, q = rem - p*W;
         const float dz = __ldg(dA + pix)*act_bwd(act, __ldg(y + pix));
         bsum += dz;
 #pragma unroll
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(HD_THREADS) head3x3_wgrad_kernel(int N, int H,
 }
 
 static int head_check(int N, int H, int W, int C, const char* what) {
-    STV_REQUIRE(N > 0 && H >= 2 && W >= 2, "%s: bad image size", what);
+    STV_REQUIRE(N > 0 && H >= 2 && W >= 2 && (long long)N*H*W < (1ll << 31), "%s: bad image size", what);
     STV_REQUIRE(C >= 4 && C <= 128 && (C & (C - 1)) == 0, "%s: channels must be a power of two in [4, 128] (got %d)", what, C);
     return STV_OK;
 }

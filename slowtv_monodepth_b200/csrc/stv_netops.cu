@@ -27,9 +27,9 @@ __global__ void grad_pull_kernel(int N, int H, int W, int C, const float* __rest
     const int c4 = C >> 2;
     const long long total = (long long)N*H*W*c4;
     const int Hs = H*pool, Ws = W*pool, Hp = Hs + 2*pad, Wp = Ws + 2*pad;
-    for (long long idx = blockIdx.x*(long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x*blockDim.x) {
+    for (unsigned idx = blockIdx.x*blockDim.x + threadIdx.x; idx < (unsigned)total; idx += gridDim.x*blockDim.x) {  // 32-bit index math (count < 2^31, checked on the host)
         const int c = (int)(idx % c4)*4;
-        long long r = idx/c4;
+        unsigned r = idx/c4;
         const int x = (int)(r % W); r /= W;
         const int y = (int)(r % H);
         const int n = (int)(r/H);
@@ -99,6 +99,115 @@ __global__ void __launch_bounds__(256) colsum_kernel(long long M, int C, long lo
     }
 }
 
+// ---- vectorised row loops with per-column reductions (float4 = 4 channels per thread) ---------------------------------------------
+// A (M, C) channels-last matrix has G = C/4 column groups. G >= 32: a block owns 32 consecutive groups (lane = group) and its 8
+// warps stride over the rows. G < 32 (a power of two): one warp row covers 32/G matrix rows x all G groups, so every lane of
+// every load is useful even for 16-64 channel tensors (the decoder / ResNet layers where the scalar mapping idled most lanes).
+// Op::apply(o4, c, acc) handles the float4 at element offset 4*o4 (columns c..c+3) and adds into NACC float4 accumulators;
+// the accumulators are combined lane -> warp -> block in a fixed order and leave the block as one atomic per column and block.
+template <class Op, bool DBL>
+__global__ void __launch_bounds__(256) colred4_kernel(long long M, int C, int rows_per_block, Op op, void* __restrict__ out0,
+                                                      void* __restrict__ out1) {
+    __shared__ float red[Op::NACC][8][32][4 + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int G = C >> 2;
+    const bool wide = G >= 32;
+    const int g = wide ? blockIdx.x*32 + lane : lane & (G - 1);
+    const int rsub = wide ? 0 : lane/G, rpw = wide ? 1 : 32/G;           // row within a warp pass, rows per warp pass
+    const long long r0 = (long long)blockIdx.y*rows_per_block, r1 = min(r0 + rows_per_block, M);
+    float4 acc[Op::NACC];
+#pragma unroll
+    for (int k = 0; k < Op::NACC; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < G)
+        for (long long r = r0 + (long long)wid*rpw + rsub; r < r1; r += 8*rpw) op.apply((size_t)r*G + g, g*4, acc);
+    if (!wide)  // lanes with the same group (G apart) -> lane < G
+        for (int o = G; o < 32; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < Op::NACC; ++k) {
+                acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o); acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
+                acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, o); acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, o);
+            }
+        }
+    if (out0 == nullptr) return;
+#pragma unroll
+    for (int k = 0; k < Op::NACC; ++k) { red[k][wid][lane][0] = acc[k].x; red[k][wid][lane][1] = acc[k].y; red[k][wid][lane][2] = acc[k].z; red[k][wid][lane][3] = acc[k].w; }
+    __syncthreads();
+    const int nl = wide ? 32 : G;  // lanes holding distinct groups
+    for (int e = threadIdx.x; e < Op::NACC*nl*4; e += 256) {
+        const int k = e/(nl*4), l = (e/4) % nl, j = e & 3;
+        const int gg = wide ? blockIdx.x*32 + l : l;
+        if (gg >= G) continue;
+        void* out = k == 0 ? out0 : out1;
+        if (DBL) {
+            double v = 0.;
+#pragma unroll
+            for (int w2 = 0; w2 < 8; ++w2) v += (double)red[k][w2][l][j];
+            atomicAdd((double*)out + gg*4 + j, v);
+        } else {
+            float v = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < 8; ++w2) v += red[k][w2][l][j];
+            atomicAdd((float*)out + gg*4 + j, v);
+        }
+    }
+}
+
+__host__ __device__ inline bool colred4_ok(int C) { const int G = C >> 2; return (C & 3) == 0 && G >= 1 && (G >= 32 || (G & (G - 1)) == 0); }
+
+struct OpColSum {
+    static constexpr int NACC = 1;
+    const float* X;
+    __device__ __forceinline__ void apply(size_t o4, int, float4* acc) const {
+        const float4 v = __ldg((const float4*)X + o4);
+        acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+    }
+};
+template <int ACT>
+struct OpActBwd {
+    static constexpr int NACC = 1;
+    const float* dA; const float* Y; float* dZ;
+    __device__ __forceinline__ void apply(size_t o4, int, float4* acc) const {
+        const float4 a = __ldg((const float4*)dA + o4), y = __ldg((const float4*)Y + o4);
+        const float4 g = make_float4(a.x*act_bwd(ACT, y.x), a.y*act_bwd(ACT, y.y), a.z*act_bwd(ACT, y.z), a.w*act_bwd(ACT, y.w));
+        ((float4*)dZ)[o4] = g;
+        acc[0].x += g.x; acc[0].y += g.y; acc[0].z += g.z; acc[0].w += g.w;
+    }
+};
+struct OpBnStats {
+    static constexpr int NACC = 2;
+    const float* X;
+    __device__ __forceinline__ void apply(size_t o4, int, float4* acc) const {
+        const float4 v = __ldg((const float4*)X + o4);
+        acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+        acc[1].x = fmaf(v.x, v.x, acc[1].x); acc[1].y = fmaf(v.y, v.y, acc[1].y); acc[1].z = fmaf(v.z, v.z, acc[1].z); acc[1].w = fmaf(v.w, v.w, acc[1].w);
+    }
+};
+struct OpBnBwdReduce {
+    static constexpr int NACC = 2;
+    const float* dY; const float* Y; const float* X; const float* mean; const float* rstd; int relu;
+    __device__ __forceinline__ void apply(size_t o4, int c, float4* acc) const {
+        float4 g = __ldg((const float4*)dY + o4);
+        if (relu) {
+            const float4 y = __ldg((const float4*)Y + o4);
+            g.x = y.x > 0.f ? g.x : 0.f; g.y = y.y > 0.f ? g.y : 0.f; g.z = y.z > 0.f ? g.z : 0.f; g.w = y.w > 0.f ? g.w : 0.f;
+        }
+        const float4 x = __ldg((const float4*)X + o4), m = __ldg((const float4*)(mean + c)), r = __ldg((const float4*)(rstd + c));
+        acc[0].x += g.x; acc[0].y += g.y; acc[0].z += g.z; acc[0].w += g.w;
+        acc[1].x = fmaf(g.x, (x.x - m.x)*r.x, acc[1].x); acc[1].y = fmaf(g.y, (x.y - m.y)*r.y, acc[1].y);
+        acc[1].z = fmaf(g.z, (x.z - m.z)*r.z, acc[1].z); acc[1].w = fmaf(g.w, (x.w - m.w)*r.w, acc[1].w);
+    }
+};
+
+// Launch geometry of colred4_kernel: grid.x = 32-group column blocks (1 when G < 32), grid.y = row blocks.
+static void colred4_grid(long long M, int C, dim3& grid, int& rpb) {
+    const int G = C >> 2, colb = G >= 32 ? (G + 31)/32 : 1;
+    long long want = (4ll*148*8 + colb - 1)/colb;   // ~4 waves of 8 resident blocks per SM
+    rpb = (int)((M + want - 1)/want);
+    const int min_rows = G >= 32 ? 64 : 64*(32/G);
+    if (rpb < min_rows) rpb = min_rows;
+    grid = dim3(colb, (unsigned)((M + rpb - 1)/rpb));
+}
+
 // ---- train-mode BatchNorm over the rows of a channels-last (M, C) matrix (M = N*H*W) ------------------------------------------
 // Reference: the nn.BatchNorm2d layers of the timm ResNet encoder (src/networks/pose.py:40, depth.py:97), batch statistics
 // per GPU (no SyncBN, api/train/train.py:105-119). Statistics are accumulated in double (block partials -> atomicAdd(double)).
@@ -149,7 +258,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(long long total4, int C, 
                                                        const float* __restrict__ beta, const float* __restrict__ res, int relu,
                                                        float* __restrict__ Y) {
     const int c4 = C >> 2;
-    for (long long i = blockIdx.x*(long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x*blockDim.x) {
+    for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < (unsigned)total4; i += gridDim.x*blockDim.x) {  // 32-bit index math (count < 2^31, checked on the host)
         const int c = (int)(i % c4)*4;
         const float4 x = __ldg((const float4*)X + i), m = __ldg((const float4*)(mean + c)), r = __ldg((const float4*)(rstd + c));
         const float4 g = __ldg((const float4*)(gamma + c)), b = __ldg((const float4*)(beta + c));
@@ -199,12 +308,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(long long total4, lon
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ gamma, const double* __restrict__ sums, int relu,
                                                            float* __restrict__ dX, float* __restrict__ dRes, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta) {
+                                                           float* __restrict__ dbeta, int accumulate) {
     const int c4 = C >> 2;
     const float invM = 1.f/(float)M;
     if (blockIdx.x == 0)
-        for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta[c] = (float)sums[c]; dgamma[c] = (float)sums[C + c]; }
-    for (long long i = blockIdx.x*(long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x*blockDim.x) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)sums[c];
+            dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)sums[C + c];
+        }
+    for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < (unsigned)total4; i += gridDim.x*blockDim.x) {  // 32-bit index math (count < 2^31, checked on the host)
         const int c = (int)(i % c4)*4;
         float4 g = __ldg((const float4*)dY + i);
         if (relu) {
@@ -301,9 +413,9 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(int N, int H, int W, i
                                                           float* __restrict__ y, uint8_t* __restrict__ idx) {
     const int c4 = C >> 2;
     const long long total = (long long)N*P*Q*c4;
-    for (long long i = blockIdx.x*(long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x*blockDim.x) {
+    for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x*blockDim.x) {  // 32-bit index math (count < 2^31, checked on the host)
         const int c = (int)(i % c4)*4;
-        long long r = i/c4;
+        unsigned r = i/c4;
         const int q = (int)(r % Q); r /= Q;
         const int p = (int)(r % P);
         const int n = (int)(r/P);
@@ -334,9 +446,9 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(int N, int H, int W, i
                                                           const uint8_t* __restrict__ idx, float* __restrict__ dx) {
     const int c4 = C >> 2;
     const long long total = (long long)N*H*W*c4;
-    for (long long i = blockIdx.x*(long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x*blockDim.x) {
+    for (unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x*blockDim.x) {  // 32-bit index math (count < 2^31, checked on the host)
         const int c = (int)(i % c4)*4;
-        long long r = i/c4;
+        unsigned r = i/c4;
         const int xx = (int)(r % W); r /= W;
         const int yy = (int)(r % H);
         const int n = (int)(r/H);
@@ -378,6 +490,7 @@ extern "C" int stv_grad_pull(int N, int H, int W, int C, const float* src, int C
     STV_REQUIRE(C % 4 == 0 && Cs % 4 == 0 && c_off % 4 == 0 && c_off + C <= Cs, "stv_grad_pull: channel slice [%d, %d) of %d must be 4-aligned", c_off, c_off + C, Cs);
     STV_REQUIRE((pool == 1 || pool == 2) && pad >= 0 && pad < H*pool && pad < W*pool, "stv_grad_pull: bad pool / pad");
     const long long total = (long long)N*H*W*(C/4);
+    STV_REQUIRE(total < (1ll << 31) && (long long)N*(H*pool + 2*pad)*(W*pool + 2*pad)*(Cs/4) < (1ll << 31), "stv_grad_pull: tensor too large");
     const int blocks = (int)((total + 255)/256 < 148ll*32 ? (total + 255)/256 : 148ll*32);
     grad_pull_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(N, H, W, C, src, Cs, c_off, pad, pool, dst, accumulate);
     count_launch();
@@ -386,9 +499,23 @@ extern "C" int stv_grad_pull(int N, int H, int W, int C, const float* src, int C
 
 extern "C" int stv_act_bwd(long long M, int C, const float* dA, const float* Y, int act, float* dZ, float* dbias, void* stream) {
     STV_REQUIRE(M > 0 && C > 0 && dA && Y && dZ, "stv_act_bwd: empty tensor / null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (colred4_ok(C) && (((uintptr_t)dA | (uintptr_t)Y | (uintptr_t)dZ) & 15) == 0) {
+        dim3 grid; int rpb;
+        colred4_grid(M, C, grid, rpb);
+        switch (act) {
+            case STV_ACT_RELU: colred4_kernel<OpActBwd<STV_ACT_RELU>, false><<<grid, 256, 0, st>>>(M, C, rpb, {dA, Y, dZ}, dbias, nullptr); break;
+            case STV_ACT_ELU: colred4_kernel<OpActBwd<STV_ACT_ELU>, false><<<grid, 256, 0, st>>>(M, C, rpb, {dA, Y, dZ}, dbias, nullptr); break;
+            case STV_ACT_SIGMOID: colred4_kernel<OpActBwd<STV_ACT_SIGMOID>, false><<<grid, 256, 0, st>>>(M, C, rpb, {dA, Y, dZ}, dbias, nullptr); break;
+            case STV_ACT_GELU: colred4_kernel<OpActBwd<STV_ACT_GELU>, false><<<grid, 256, 0, st>>>(M, C, rpb, {dA, Y, dZ}, dbias, nullptr); break;
+            case STV_ACT_NONE: colred4_kernel<OpActBwd<STV_ACT_NONE>, false><<<grid, 256, 0, st>>>(M, C, rpb, {dA, Y, dZ}, dbias, nullptr); break;
+            default: STV_REQUIRE(false, "stv_act_bwd: unknown activation %d", act);
+        }
+        count_launch();
+        return check_launch("stv_act_bwd");
+    }
     const int rpb = rows_per_block(M, C);
     const dim3 grid((C + 31)/32, (unsigned)((M + rpb - 1)/rpb));
-    cudaStream_t st = (cudaStream_t)stream;
     switch (act) {
         case STV_ACT_NONE: act_bwd_kernel<STV_ACT_NONE><<<grid, 256, 0, st>>>(M, C, dA, Y, dZ, dbias, rpb); break;
         case STV_ACT_RELU: act_bwd_kernel<STV_ACT_RELU><<<grid, 256, 0, st>>>(M, C, dA, Y, dZ, dbias, rpb); break;
@@ -403,6 +530,13 @@ extern "C" int stv_act_bwd(long long M, int C, const float* dA, const float* Y, 
 
 extern "C" int stv_colsum(long long M, int C, long long ld, const float* X, float* out, void* stream) {
     STV_REQUIRE(M > 0 && C > 0 && ld >= C && X && out, "stv_colsum: empty tensor / null pointer");
+    if (ld == C && colred4_ok(C) && ((uintptr_t)X & 15) == 0) {
+        dim3 grid; int rpb4;
+        colred4_grid(M, C, grid, rpb4);
+        colred4_kernel<OpColSum, false><<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, rpb4, {X}, out, nullptr);
+        count_launch();
+        return check_launch("stv_colsum");
+    }
     const int rpb = rows_per_block(M, C);
     const dim3 grid((C + 31)/32, (unsigned)((M + rpb - 1)/rpb));
     colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, ld, X, out, rpb);
@@ -421,11 +555,18 @@ extern "C" int stv_bn_fwd(long long M, int C, const float* x, const float* gamma
     cudaStream_t st = (cudaStream_t)stream;
     double* sums = (double*)ws;
     if (cudaMemsetAsync(sums, 0, stv_bn_workspace_bytes(C), st) != cudaSuccess) return check_launch("stv_bn_fwd(memset)");
-    const int rpb = rows_per_block(M, C);
-    const dim3 grid((C + 31)/32, (unsigned)((M + rpb - 1)/rpb));
-    bn_stats_kernel<<<grid, 256, 0, st>>>(M, C, x, sums, rpb);
+    if (colred4_ok(C)) {
+        dim3 grid; int rpb;
+        colred4_grid(M, C, grid, rpb);
+        colred4_kernel<OpBnStats, true><<<grid, 256, 0, st>>>(M, C, rpb, {x}, sums, sums + C);
+    } else {
+        const int rpb = rows_per_block(M, C);
+        const dim3 grid((C + 31)/32, (unsigned)((M + rpb - 1)/rpb));
+        bn_stats_kernel<<<grid, 256, 0, st>>>(M, C, x, sums, rpb);
+    }
     bn_finalize_kernel<<<(C + 127)/128, 128, 0, st>>>(M, C, sums, eps, momentum, mean, rstd, run_mean, run_var);
     const long long total4 = M*(C/4);
+    STV_REQUIRE(total4 < (1ll << 31), "stv_bn_fwd: tensor too large");
     const int blocks = (int)((total4 + 255)/256 < 148ll*16 ? (total4 + 255)/256 : 148ll*16);
     bn_apply_kernel<<<blocks, 256, 0, st>>>(total4, C, x, mean, rstd, gamma, beta, res, relu, y);
     count_launch(3);
@@ -433,20 +574,27 @@ extern "C" int stv_bn_fwd(long long M, int C, const float* x, const float* gamma
 }
 
 extern "C" int stv_bn_bwd(long long M, int C, const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
-                          const float* gamma, int relu, float* dx, float* dres, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
-                          void* stream) {
+                          const float* gamma, int relu, float* dx, float* dres, float* dgamma, float* dbeta, int accumulate, void* ws,
+                          size_t ws_bytes, void* stream) {
     STV_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && dy && x && mean && rstd && gamma && dx && dgamma && dbeta && (!relu || y),
                 "stv_bn_bwd: bad arguments (C must be a multiple of 4)");
     STV_REQUIRE(ws && ws_bytes >= stv_bn_workspace_bytes(C), "stv_bn_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     double* sums = (double*)ws;
     if (cudaMemsetAsync(sums, 0, stv_bn_workspace_bytes(C), st) != cudaSuccess) return check_launch("stv_bn_bwd(memset)");
-    const int rpb = rows_per_block(M, C);
-    const dim3 grid((C + 31)/32, (unsigned)((M + rpb - 1)/rpb));
-    bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(M, C, dy, y, x, mean, rstd, relu, sums, rpb);
+    if (colred4_ok(C)) {
+        dim3 grid; int rpb;
+        colred4_grid(M, C, grid, rpb);
+        colred4_kernel<OpBnBwdReduce, true><<<grid, 256, 0, st>>>(M, C, rpb, {dy, y, x, mean, rstd, relu}, sums, sums + C);
+    } else {
+        const int rpb = rows_per_block(M, C);
+        const dim3 grid((C + 31)/32, (unsigned)((M + rpb - 1)/rpb));
+        bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(M, C, dy, y, x, mean, rstd, relu, sums, rpb);
+    }
     const long long total4 = M*(C/4);
+    STV_REQUIRE(total4 < (1ll << 31), "stv_bn_bwd: tensor too large");
     const int blocks = (int)((total4 + 255)/256 < 148ll*16 ? (total4 + 255)/256 : 148ll*16);
-    bn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(total4, M, C, dy, y, x, mean, rstd, gamma, sums, relu, dx, dres, dgamma, dbeta);
+    bn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(total4, M, C, dy, y, x, mean, rstd, gamma, sums, relu, dx, dres, dgamma, dbeta, accumulate);
     count_launch(2);
     return check_launch("stv_bn_bwd");
 }
@@ -469,6 +617,7 @@ extern "C" int stv_maxpool3x3s2_fwd(int N, int H, int W, int C, const float* x, 
     STV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && x && y && idx, "stv_maxpool3x3s2_fwd: bad arguments (C must be a multiple of 4)");
     const int P = (H - 1)/2 + 1, Q = (W - 1)/2 + 1;
     const long long total = (long long)N*P*Q*(C/4);
+    STV_REQUIRE((long long)N*H*W*(C/4) < (1ll << 31), "stv_maxpool3x3s2_fwd: tensor too large");
     const int blocks = (int)((total + 255)/256 < 148ll*16 ? (total + 255)/256 : 148ll*16);
     maxpool_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(N, H, W, C, P, Q, x, y, idx);
     count_launch();
@@ -479,6 +628,7 @@ extern "C" int stv_maxpool3x3s2_bwd(int N, int H, int W, int C, const float* dy,
     STV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && dy && dx && idx, "stv_maxpool3x3s2_bwd: bad arguments (C must be a multiple of 4)");
     const int P = (H - 1)/2 + 1, Q = (W - 1)/2 + 1;
     const long long total = (long long)N*H*W*(C/4);
+    STV_REQUIRE(total < (1ll << 31), "stv_maxpool3x3s2_bwd: tensor too large");
     const int blocks = (int)((total + 255)/256 < 148ll*16 ? (total + 255)/256 : 148ll*16);
     maxpool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(N, H, W, C, P, Q, dy, idx, dx);
     count_launch();

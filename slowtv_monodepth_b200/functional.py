@@ -351,6 +351,8 @@ class _DwConv7(torch.autograd.Function):
             L.check(L.lib().stv_dwconv7_fwd(N, H, W, Cc, L.ptr(x), L.ptr(w), L.ptr(b), None, L.ptr(y), 0, L.stream()), 'stv_dwconv7_fwd')
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
+        ctx.w_sink, ctx.b_sink = _sink(w), _sink(b)
+        if b is not None and (ctx.w_sink is None or ctx.b_sink is None): ctx.w_sink = ctx.b_sink = None  # one accumulate flag for both
         return y
 
     @staticmethod
@@ -365,11 +367,13 @@ class _DwConv7(torch.autograd.Function):
                 gx = torch.empty_like(x)
                 L.check(lib.stv_dwconv7_fwd(N, H, W, Cc, L.ptr(gy), L.ptr(w), None, None, L.ptr(gx), 1, L.stream()), 'stv_dwconv7_fwd(flip)')
             if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-                gw = torch.empty_like(w)
-                gb = torch.empty(Cc, dtype=torch.float32, device=dev) if ctx.has_bias else None
+                sink = ctx.w_sink is not None
+                gw = ctx.w_sink if sink else torch.empty_like(w)
+                gb = (ctx.b_sink if sink else torch.empty(Cc, dtype=torch.float32, device=dev)) if ctx.has_bias else None
                 ws = _ws(lib.stv_dwconv7_wgrad_workspace_bytes(N, H, W, Cc), dev)
-                L.check(lib.stv_dwconv7_wgrad(N, H, W, Cc, L.ptr(x), L.ptr(gy), L.ptr(gw), L.ptr(gb), L.ptr(ws), ws.numel(), L.stream()),
-                        'stv_dwconv7_wgrad')
+                L.check(lib.stv_dwconv7_wgrad(N, H, W, Cc, L.ptr(x), L.ptr(gy), L.ptr(gw), L.ptr(gb), int(sink), L.ptr(ws), ws.numel(),
+                                              L.stream()), 'stv_dwconv7_wgrad')
+                if sink: gw = gb = None  # accumulated in place into weight.grad / bias.grad
         return gx, gw, gb
 
 
@@ -392,6 +396,8 @@ class _LayerNorm(torch.autograd.Function):
             L.check(L.lib().stv_layernorm_fwd(P, Cc, L.ptr(x), L.ptr(gamma), L.ptr(beta), eps, L.ptr(y), L.ptr(mean), L.ptr(rstd),
                                               L.stream()), 'stv_layernorm_fwd')
         ctx.save_for_backward(x, mean, rstd, gamma)
+        ctx.g_sink, ctx.b_sink = _sink(gamma), _sink(beta)
+        if ctx.g_sink is None or ctx.b_sink is None: ctx.g_sink = ctx.b_sink = None
         return y
 
     @staticmethod
@@ -401,12 +407,14 @@ class _LayerNorm(torch.autograd.Function):
         P = x.numel()//Cc
         gy = _f32c(gy)
         lib, dev = L.lib(), x.device
+        sink = ctx.g_sink is not None
         with torch.cuda.device(dev):
-            gx, gg, gb = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(gamma)
+            gx = torch.empty_like(x)
+            gg, gb = (ctx.g_sink, ctx.b_sink) if sink else (torch.empty_like(gamma), torch.empty_like(gamma))
             ws = _ws(lib.stv_layernorm_bwd_workspace_bytes(P, Cc), dev)
             L.check(lib.stv_layernorm_bwd(P, Cc, L.ptr(gy), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), L.ptr(gx), L.ptr(gg),
-                                          L.ptr(gb), L.ptr(ws), ws.numel(), L.stream()), 'stv_layernorm_bwd')
-        return gx, gg, gb, None
+                                          L.ptr(gb), int(sink), L.ptr(ws), ws.numel(), L.stream()), 'stv_layernorm_bwd')
+        return (gx, None, None, None) if sink else (gx, gg, gb, None)
 
 
 def layer_norm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-6) -> Tensor:
@@ -607,6 +615,8 @@ class _BatchNormNHWC(torch.autograd.Function):
                                    L.ptr(rstd), L.ptr(run_mean), L.ptr(run_var), L.ptr(ws), ws.numel(), L.stream()), 'stv_bn_fwd')
         ctx.save_for_backward(x, y, mean, rstd, gamma)
         ctx.relu, ctx.has_res = relu, res is not None
+        ctx.g_sink, ctx.b_sink = _sink(gamma), _sink(beta)
+        if ctx.g_sink is None or ctx.b_sink is None: ctx.g_sink = ctx.b_sink = None
         return y
 
     @staticmethod
@@ -619,11 +629,13 @@ class _BatchNormNHWC(torch.autograd.Function):
         with torch.cuda.device(dev):
             dx = torch.empty_like(x)
             dres = torch.empty_like(x) if ctx.has_res and ctx.relu else None
-            dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+            sink = ctx.g_sink is not None
+            dgamma, dbeta = (ctx.g_sink, ctx.b_sink) if sink else (torch.empty_like(gamma), torch.empty_like(gamma))
             ws = _ws(lib.stv_bn_workspace_bytes(Cc), dev)
             L.check(lib.stv_bn_bwd(M, Cc, L.ptr(dy), L.ptr(y), L.ptr(x), L.ptr(mean), L.ptr(rstd), L.ptr(gamma), int(ctx.relu), L.ptr(dx),
-                                   L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), ws.numel(), L.stream()), 'stv_bn_bwd')
+                                   L.ptr(dres), L.ptr(dgamma), L.ptr(dbeta), int(sink), L.ptr(ws), ws.numel(), L.stream()), 'stv_bn_bwd')
         if ctx.has_res and not ctx.relu: dres = dy
+        if sink: dgamma = dbeta = None
         return dx, dgamma, dbeta, dres, None, None, None, None, None
 
 
@@ -756,6 +768,7 @@ class _ConvNeXtMlp(torch.autograd.Function):
         out = gemm_tf32(h, w2, bias=b2, gamma=gamma, res=res)
         ctx.save_for_backward(x, z, h, w1, w2, b2, gamma)
         ctx.w1_sink, ctx.b1_sink = _sink(w1), _sink(b1)
+        ctx.tail_sinks = (_sink(w2), _sink(b2), _sink(gamma))
         return out
 
     @staticmethod
@@ -775,6 +788,12 @@ class _ConvNeXtMlp(torch.autograd.Function):
         G = torch.zeros_like(w2)                                             # g^T h, before the layer-scale
         gemm_tf32(g, h, a_mn=True, b_mn=True, out=G, accumulate=True, split_k=_split_k(Cc, Hd, M))
         gs = colsum(g)
+        w2s, b2s, gas = ctx.tail_sinks
+        if w2s is not None and b2s is not None and gas is not None:  # accumulate straight into the flat gradient buffer
+            w2s.addcmul_(G, gamma[:, None])
+            b2s.addcmul_(gamma, gs)
+            gas.add_((w2*G).sum(1)).addcmul_(b2, gs)
+            return (dx, g if ctx.needs_input_grad[1] else None, dw1, db1, None, None, None)
         return (dx, g if ctx.needs_input_grad[1] else None, dw1, db1, G*gamma[:, None], gamma*gs, (w2*G).sum(1) + b2*gs)
 
 
