@@ -56,21 +56,28 @@ typedef struct {
 } stv_photo_cfg;
 
 size_t stv_photo_workspace_bytes(const stv_photo_cfg* cfg);
+/* Bytes of the optional coefficient planes (S,b,9,H,W) handed from stv_photo_fwd to stv_photo_bwd (use_min only). */
+size_t stv_photo_coef_bytes(const stv_photo_cfg* cfg);
 
 /* loss (device scalar) = mean over (S,b,H,W) of the reduced, auto-masked photometric error.
  * depth: S pointers to (b,1,H,W) upsampled depth maps; tgt (b,3,H,W); supp (n,b,3,H,W); T (n,b,4,4); K, Kinv (b,4,4);
  * noise: NULL or (S,b,H,W) standard-normal samples replacing randn_like (reconstruction.py:72);
  * sel (S,b,H,W) u8: per-pixel decision (support index | STV_SEL_STATIC | STV_SEL_MEAN), consumed by the backward;
- * warp0: NULL or (n,b,3,H,W) warped support frames at scale 0 (handlers.py:66). */
+ * warp0: NULL or (n,b,3,H,W) warped support frames at scale 0 (handlers.py:66);
+ * coef: NULL, or (use_min only) stv_photo_coef_bytes() of device memory that receives, per (scale, pixel), the nine
+ *   numbers d SSIMError_c / d(sum x, sum x^2, sum xy) of the support frame the pixel selected (undefined where the
+ *   static frame won; `sel` masks them): what autograd would keep of photometric.py:40-50 for the backward pass. */
 int stv_photo_fwd(const stv_photo_cfg* cfg, const float* const* depth, const float* tgt, const float* supp,
                   const float* T, const float* K, const float* Kinv, const float* noise,
-                  float* loss, uint8_t* sel, float* warp0, void* ws, size_t ws_bytes, void* stream);
+                  float* loss, uint8_t* sel, float* warp0, float* coef, void* ws, size_t ws_bytes, void* stream);
 
 /* Backward of stv_photo_fwd w.r.t. depth, T, K and Kinv. grad_loss: device scalar dL/dloss.
  * g_depth: S pointers to (b,1,H,W) (overwritten); gT (n,b,4,4) (overwritten; row 3 = 0);
- * gK, gKinv (b,4,4) nullable (overwritten; only the 3x3 block is non-zero). */
+ * gK, gKinv (b,4,4) nullable (overwritten; only the 3x3 block is non-zero).
+ * coef: the planes stv_photo_fwd wrote (lean path: masked 3x3 box sums + the pixel's own sampler/projection chain), or NULL
+ *   (the kernel then re-warps a halo-2 tile and rebuilds the SSIM window sums itself; required when !use_min). */
 int stv_photo_bwd(const stv_photo_cfg* cfg, const float* const* depth, const float* tgt, const float* supp,
-                  const float* T, const float* K, const float* Kinv, const uint8_t* sel, const float* grad_loss,
+                  const float* T, const float* K, const float* Kinv, const uint8_t* sel, const float* coef, const float* grad_loss,
                   float* const* g_depth, float* gT, float* gK, float* gKinv, void* ws, size_t ws_bytes, void* stream);
 
 /* compute_photo (reconstruction.py:79-96) on its own: pred (n,b,3,H,W) vs target (b,3,H,W) -> err (b,1,H,W).

@@ -53,8 +53,9 @@ _SIGNATURES = {
     'stv_last_error': (C.c_char_p, []),
     'stv_launch_count': (C.c_ulonglong, []),
     'stv_photo_workspace_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
-    'stv_photo_fwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
-    'stv_photo_bwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'stv_photo_coef_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
+    'stv_photo_fwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'stv_photo_bwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     'stv_photo_error': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P]),
     'stv_view_synth_fwd': (C.c_int, [C.c_int]*4 + [_P]*9),
     'stv_view_synth_workspace_bytes': (C.c_size_t, [C.c_int]*4),

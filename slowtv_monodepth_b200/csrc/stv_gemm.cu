@@ -358,6 +358,23 @@ int make_tmap_2d(CUtensorMap* tm, const float* base, long long rows, long long c
     return STV_OK;
 }
 
+int make_tmap_3d(CUtensorMap* tm, const float* base, long long W, long long H, long long planes, int bw, int bh, int bp) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the CUDA driver"); return STV_E_CUDA; }
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)W*4, (cuuint64_t)W*H*4};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bp};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for a (%lld,%lld,%lld) tensor, box (%d,%d,%d), base %p", (int)r, planes, H, W, bp, bh, bw,
+                  (const void*)base);
+        return STV_E_CUDA;
+    }
+    return STV_OK;
+}
+
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
                                    const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

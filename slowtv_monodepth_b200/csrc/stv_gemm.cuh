@@ -39,6 +39,8 @@ int make_tmap_2d(CUtensorMap* tm, const float* base, long long rows, long long c
 // to [lw, W + uw) x [lh, H + uh) and stepped by `stride`; out-of-image pixels / channels read as zeros.
 int make_tmap_im2col(CUtensorMap* tm, const float* base, int N, int H, int W, int C, int lw, int lh, int uw, int uh, int stride,
                      int pixels, int mn_major);
+// Dense fp32 (planes, H, W) tensor read as un-swizzled boxes {bw, bh, bp} (W % 4 == 0, bw % 4 == 0); zero OOB fill.
+int make_tmap_3d(CUtensorMap* tm, const float* base, long long W, long long H, long long planes, int bw, int bh, int bp);
 int pick_bn(int N, long long row_tiles);
 // Fills p.stages, launches grid (ceil(M/128), ceil(N/bn), splits). p.bn, p.kb_total, p.kb_per_split must be set.
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int splits, cudaStream_t stream, const char* what);

@@ -14,6 +14,7 @@
 // between neighbouring pixels) + 1 B decision byte per scale; see DESIGN.md for the roofline accounting.
 #include "stv_common.cuh"
 #include "stv_f2.cuh"
+#include "stv_gemm.cuh"
 
 namespace stv {
 
@@ -38,6 +39,9 @@ struct PhotoParams {
     float* partial;   // fwd: one float per block; bwd: n_acc floats per (block, k)
     uint8_t* sel;
     float* warp0;
+    float* coef;             // fwd out: (S,b,9,H,W) masked d err/d(S1,S2,S3) per channel of the SELECTED support (nullable)
+    const float* coef_in;    // bwd in
+    int coef_tma;            // bwd: coefficient tiles arrive by TMA (row pitch 16-byte granular)
     cudaTextureObject_t supp_tex;  // supp viewed as one (n*b*3*H) x W single-channel texture (0 = not available)
 };
 
@@ -176,9 +180,36 @@ __device__ __forceinline__ void ssim_pair(f2 S1, f2 S2, f2 S3, f2 T1, f2 T2, flo
     e1 = __saturatef(fmaf(-0.5f*hi2(num), rcp_fast(hi2(den)), 0.5f));
 }
 
-// Photometric error of the thread's FRUN centres for one support frame.
+// Same, plus d err/d(S1,S2,S3) of both pixels (zero where the clamp is active, as ssim_err_grad) sharing num/den/rcp:
+//   r = A1 A2/(B1 B2);  a = k (r mx (B2-B1) - my (A2-A1))/(B1 B2);  b = k r /(2 B2);  c = -k A1/(B1 B2),  k = 1/9.
+__device__ __forceinline__ void ssim_pair_coef(f2 S1, f2 S2, f2 S3, f2 T1, f2 T2, float& e0, float& e1, f2& ca, f2& cb, f2& cc) {
+    const f2 k = splat2(1.f/9.f), two = splat2(2.f), nk = splat2(-1.f/9.f), neg = splat2(-1.f);
+    const f2 mx = S1*k, my = T1*k;
+    const f2 mxy = mx*my, mxx = mx*mx, myy = my*my;
+    const f2 nsxx = fma2(S2, nk, mxx), nsyy = fma2(T2, nk, myy), nsxy = fma2(S3, nk, mxy);
+    const f2 A1 = fma2(two, mxy, splat2(STV_C1)), A2 = fma2(splat2(-2.f), nsxy, splat2(STV_C2));
+    const f2 B1 = mxx + myy + splat2(STV_C1), B2 = fma2(neg, nsxx + nsyy, splat2(STV_C2));
+    const f2 num = A1*A2, den = B1*B2;
+    const f2 iD = mk2(rcp_fast(lo2(den)), rcp_fast(hi2(den)));
+    const f2 r = num*iD;
+    e0 = __saturatef(fmaf(-0.5f, lo2(r), 0.5f));
+    e1 = __saturatef(fmaf(-0.5f, hi2(r), 0.5f));
+    const f2 kid = iD*k;
+    const f2 dA = fma2(A1, neg, A2), dB = fma2(B1, neg, B2);
+    const f2 a = kid*fma2(my*dA, neg, (r*mx)*dB);
+    const f2 b = (kid*splat2(0.5f))*(r*B1);
+    const f2 c = kid*(A1*neg);
+    const bool v0 = fabsf(lo2(r)) <= 1.f, v1 = fabsf(hi2(r)) <= 1.f;  // un-clamped error inside [0,1]; NaN -> false
+    ca = mk2(v0 ? lo2(a) : 0.f, v1 ? hi2(a) : 0.f);
+    cb = mk2(v0 ? lo2(b) : 0.f, v1 ? hi2(b) : 0.f);
+    cc = mk2(v0 ? lo2(c) : 0.f, v1 ? hi2(c) : 0.f);
+}
+
+// Photometric error of the thread's FRUN centres for one support frame (COEF: plus the SSIM coefficients per channel,
+// coef[c*3 + q][pixel], un-scaled).
+template <bool COEF>
 __device__ __forceinline__ void photo_run_t(const TileT* sw, const TileT* st, int top, int col, const f2 (*T1)[FNP],
-                                            const f2 (*T2)[FNP], float w_ssim, float w_l1, float* ek) {
+                                            const f2 (*T2)[FNP], float w_ssim, float w_l1, float* ek, float (*coef)[FRUN]) {
 #pragma unroll
     for (int j = 0; j < FRUN; ++j) ek[j] = 0.f;
     const float ws = w_ssim*(1.f/3.f), wl = w_l1*(1.f/3.f);
@@ -190,7 +221,13 @@ __device__ __forceinline__ void photo_run_t(const TileT* sw, const TileT* st, in
 #pragma unroll
             for (int j = 0; j < FNP; ++j) {
                 float e0, e1;
-                ssim_pair(w.S1[j], w.S2[j], w.S3[j], T1[c][j], T2[c][j], e0, e1);
+                if (COEF) {
+                    f2 ca, cb, cc;
+                    ssim_pair_coef(w.S1[j], w.S2[j], w.S3[j], T1[c][j], T2[c][j], e0, e1, ca, cb, cc);
+                    coef[c*3 + 0][2*j] = lo2(ca); coef[c*3 + 0][2*j + 1] = hi2(ca);
+                    coef[c*3 + 1][2*j] = lo2(cb); coef[c*3 + 1][2*j + 1] = hi2(cb);
+                    coef[c*3 + 2][2*j] = lo2(cc); coef[c*3 + 2][2*j + 1] = hi2(cc);
+                } else ssim_pair(w.S1[j], w.S2[j], w.S3[j], T1[c][j], T2[c][j], e0, e1);
                 ek[2*j] = fmaf(ws, e0, ek[2*j]);
                 ek[2*j + 1] = fmaf(ws, e1, ek[2*j + 1]);
             }
@@ -288,7 +325,7 @@ __global__ void __launch_bounds__(FNT) photo_error_kernel(PhotoParams p, const f
         load_tile3_t(sw, pred + ((size_t)k*p.b + i)*3*HW, ty0 - 1, tx0 - 1, H, W);
         __syncthreads();
         float ek[FRUN];
-        photo_run_t(sw, st, top, lx, T1, T2, p.w_ssim, p.w_l1, ek);
+        photo_run_t<false>(sw, st, top, lx, T1, T2, p.w_ssim, p.w_l1, ek, nullptr);
 #pragma unroll
         for (int j = 0; j < FRUN; ++j) ered[j] = p.use_min ? fminf(ered[j], ek[j]) : ered[j] + ek[j];
         __syncthreads();
@@ -307,8 +344,11 @@ __global__ void __launch_bounds__(FNT) photo_error_kernel(PhotoParams p, const f
 #ifndef STV_FWD_MINB
 #define STV_FWD_MINB 4  // measured on B200 at 8x384x640, n=2, S=4: (TH, NT, MINB) = (8, 256, 4) is the fastest of six variants
 #endif
-template <bool TEX>
-__global__ void __launch_bounds__(FNT, STV_FWD_MINB) photo_fwd_kernel(PhotoParams p) {
+#ifndef STV_FWD_MINB_COEF
+#define STV_FWD_MINB_COEF 3
+#endif
+template <bool TEX, bool COEF>
+__global__ void __launch_bounds__(FNT, COEF ? STV_FWD_MINB_COEF : STV_FWD_MINB) photo_fwd_kernel(PhotoParams p) {
     __shared__ __align__(16) float st[3][FPW][FPH];
     __shared__ __align__(16) float sw[3][FPW][FPH];
     __shared__ float red[32];
@@ -365,6 +405,9 @@ __global__ void __launch_bounds__(FNT, STV_FWD_MINB) photo_fwd_kernel(PhotoParam
         }
     }
 
+    // COEF: the SSIM coefficients of a support frame are stored whenever it becomes the pixel's running minimum (a later
+    // winner overwrites them in L2); pixels the static frame wins keep stale values that the backward masks out by `sel`.
+    float* const coefp = COEF ? p.coef + ((size_t)s*p.b + i)*9*HW : nullptr;
     const bool want_warp = p.warp0 != nullptr && s == 0;
     for (int k = 0; k < p.n; ++k) {
         Cam cam;
@@ -397,11 +440,29 @@ __global__ void __launch_bounds__(FNT, STV_FWD_MINB) photo_fwd_kernel(PhotoParam
         }
         // phase 2: photometric error, reduce over support frames (first index wins ties, as torch.min)
         float ek[FRUN];
-        photo_run_t(sw, st, top, lx, T1, T2, p.w_ssim, p.w_l1, ek);
+        float cur[COEF ? 9 : 1][FRUN];
+        if (COEF) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+#pragma unroll
+                for (int j = 0; j < FRUN; ++j) cur[q][j] = 0.f;
+            }
+        }
+        photo_run_t<COEF>(sw, st, top, lx, T1, T2, p.w_ssim, p.w_l1, ek, cur);
 #pragma unroll
         for (int j = 0; j < FRUN; ++j) {
-            if (p.use_min) { if (ek[j] < ered[j]) { ered[j] = ek[j]; ksel[j] = k; } }
-            else ered[j] += ek[j];
+            if (p.use_min) {
+                if (ek[j] < ered[j]) {
+                    ered[j] = ek[j]; ksel[j] = k;
+                    if (COEF) {
+                        const int y = ty0 + top + j, x = tx0 + lx;
+                        if (y < H && x < W) {
+#pragma unroll
+                            for (int q = 0; q < 9; ++q) coefp[(size_t)q*HW + y*W + x] = cur[q][j];
+                        }
+                    }
+                }
+            } else ered[j] += ek[j];
         }
         __syncthreads();
     }
@@ -441,6 +502,9 @@ __global__ void reduce_mean_kernel(const float* __restrict__ partial, int n, dou
 // ---------------------------------------------------------------------------------------------------------------------
 // Backward. grid = (tiles, b, S); dynamic shared memory.
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef STV_BWD_MINB
+#define STV_BWD_MINB 3
+#endif
 constexpr int N_ACC_T = 12, N_ACC_K = 15;  // dT (3x4) | dK rows 0-1 (2x3) + dKinv (3x3)
 
 struct BwdSmem {
@@ -653,6 +717,248 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(PhotoParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward from the forward's coefficient planes (use_min). grid = (tiles, b, S), tile = TH x TW as above.
+//
+// The forward left, per (scale, pixel q), the nine numbers d err_c/d(S1,S2,S3) of the support frame that pixel selected
+// (undefined where the static frame won: masked by `sel`). The gradient w.r.t. the warped pixel p of support k is then
+//     gw_c(p) = g [ sum_{q in N(p), sel(q)=k} m(p,q) (A_c(q) + 2 w_c(p) B_c(q) + t_c(p) C_c(q)) ] + [sel(p)=k] g_l1 sign(w_c - t_c)
+// (m = reflection multiplicity of the 3x3 window), i.e. a masked 3x3 box sum of nine planes — no halo re-warp and no SSIM
+// re-evaluation — followed by the sampler / projection chain of the pixel itself. Each thread owns CR vertically
+// consecutive pixels of one column per pass; a block walks its TH rows in TH/(CR*NT/TW) passes.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int CR = 2;                       // pixels per thread per pass
+constexpr int CPASS_ROWS = CR*(NT/TW);      // rows per pass (8)
+constexpr int CXO = 3;                      // smem column of the tile's left halo: a TMA box must START on a 16-byte boundary of the
+constexpr int PW1T = TW + 8;                // row (measured: x % 4 != 0 faults on sm_100a), so the box spans x0-4 .. x0+TW+3
+static_assert(TH % CPASS_ROWS == 0, "coefficient backward: tile height must be a multiple of the pass height");
+
+struct CoefSmem {
+    float sc[9][PH1][PW1T];  // coefficient planes, tile + halo 1 (zero outside the image) — one TMA box {PW1T, PH1, 9}
+    uint8_t ssel[PH1][PW1 + 2];
+    float red[NT/32][N_ACC_T + N_ACC_K];
+    Cam cam;
+    uint64_t bar;
+};
+constexpr uint32_t COEF_BOX_BYTES = 9*PH1*PW1T*sizeof(float);
+
+template <bool NEED_K, bool TEX>
+__global__ void __launch_bounds__(NT, STV_BWD_MINB) photo_bwd_coef_kernel(const __grid_constant__ CUtensorMap tm_coef, PhotoParams p) {
+    __shared__ __align__(128) CoefSmem sm;
+    constexpr int NACC = N_ACC_T + (NEED_K ? N_ACC_K : 0);
+    const int tile = blockIdx.x, i = blockIdx.y, s = blockIdx.z;
+    const int tx0 = (tile % p.tiles_x)*TW, ty0 = (tile/p.tiles_x)*TH;
+    const int H = p.H, W = p.W, HW = H*W;
+    const float sx = (float)W/(float)(W - 1), sy = (float)H/(float)(H - 1);
+    const float g0 = __ldg(p.grad_loss)/((float)p.S*(float)p.b*(float)HW);
+    const float g = g0*p.w_ssim*(1.f/3.f), gl = g0*p.w_l1*(1.f/3.f);  // channel means of the SSIM / L1 terms
+    const bool tma = p.coef_tma != 0;
+
+    // coefficient planes of tile + halo 1: one TMA box (out-of-image elements are zero-filled by the copy engine), or plain loads
+    // when the row pitch is not 16-byte granular
+    if (tma) {
+        if (threadIdx.x == 0) {
+            tc::mbar_init(&sm.bar, 1);
+            tc::fence_barrier_init();
+            tc::mbar_arrive_expect_tx(&sm.bar, COEF_BOX_BYTES);
+            tc::tma_load_3d(&sm.sc[0][0][0], &tm_coef, &sm.bar, tx0 - 1 - CXO, ty0 - 1, (s*p.b + i)*9);
+        }
+    } else {
+        const float* __restrict__ cp = p.coef_in + ((size_t)s*p.b + i)*9*HW;
+        for (int q = threadIdx.x; q < PH1*PW1; q += NT) {
+            const int py = q/PW1, px = q - py*PW1;
+            const int y = ty0 - 1 + py, x = tx0 - 1 + px;
+            const bool in = y >= 0 && y < H && x >= 0 && x < W;
+            const int o = in ? y*W + x : 0;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) sm.sc[c][py][px + CXO] = in ? __ldg(cp + (size_t)c*HW + o) : 0.f;
+        }
+    }
+    {   // decisions of tile + halo 1
+        const uint8_t* __restrict__ selp = p.sel_in + ((size_t)s*p.b + i)*HW;
+        for (int q = threadIdx.x; q < PH1*PW1; q += NT) {
+            const int py = q/PW1, px = q - py*PW1;
+            const int y = ty0 - 1 + py, x = tx0 - 1 + px;
+            const bool in = y >= 0 && y < H && x >= 0 && x < W;
+            sm.ssel[py][px] = in ? selp[y*W + x] : (uint8_t)STV_SEL_STATIC;
+        }
+    }
+
+    const int lx = threadIdx.x & (TW - 1), trow = (threadIdx.x/TW)*CR;
+    const int x = tx0 + lx;
+    const float mxl = (x == 1) ? 2.f : 1.f, mxr = (x == W - 2) ? 2.f : 1.f;
+    const float* __restrict__ dp = p.depth[s] + (size_t)i*HW;
+    const float* __restrict__ tg = p.tgt + (size_t)i*3*HW;
+    float* __restrict__ gdp = p.g_depth[s] + (size_t)i*HW;
+    const Cam& cam = sm.cam;
+
+    for (int k = 0; k < p.n; ++k) {
+        if (threadIdx.x < 32) {  // camera constants of (k, i) -> shared memory (read back as broadcasts; keeps ~27 registers free)
+            const float* __restrict__ Tm = p.T + ((size_t)k*p.b + i)*16;
+            const float* __restrict__ Km = p.K + (size_t)i*16;
+            const float* __restrict__ Ki = p.Kinv + (size_t)i*16;
+            const int t = threadIdx.x;
+            if (t < 9) { sm.cam.R[t] = __ldg(Tm + (t/3)*4 + t % 3); sm.cam.Ki[t] = __ldg(Ki + (t/3)*4 + t % 3); }
+            else if (t < 12) sm.cam.t[t - 9] = __ldg(Tm + (t - 9)*4 + 3);
+            else if (t < 15) sm.cam.K0[t - 12] = __ldg(Km + (t - 12));
+            else if (t < 18) sm.cam.K1[t - 15] = __ldg(Km + 4 + (t - 15));
+        }
+        __syncthreads();
+        if (k == 0 && tma) tc::mbar_wait(&sm.bar, 0);
+        const int plane0 = (k*p.b + i)*3;
+        const float* __restrict__ sp = p.supp + (size_t)plane0*HW;
+        float acc[NACC];
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) acc[q] = 0.f;
+
+#pragma unroll 1
+        for (int pass = 0; pass < TH/CPASS_ROWS; ++pass) {
+            const int top = pass*CPASS_ROWS + trow;   // tile row of the first pixel == smem row of its upper neighbour
+            // masked, multiplicity-weighted window weights of the (CR+2) x 3 centres around the run
+            float mw[CR + 2][3];
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < CR + 2; ++r) {
+                const uint8_t* sr = &sm.ssel[top + r][lx];
+                mw[r][0] = sr[0] == k ? mxl : 0.f;
+                mw[r][1] = sr[1] == k ? 1.f : 0.f;
+                mw[r][2] = sr[2] == k ? mxr : 0.f;
+                any = any || sr[0] == k || sr[1] == k || sr[2] == k;
+            }
+            float gdv[CR];
+#pragma unroll
+            for (int j = 0; j < CR; ++j) gdv[j] = 0.f;
+            if (any && x < W) {
+                // the pixels' own depth: requested before the box sums, consumed after them
+                float dj[CR];
+#pragma unroll
+                for (int j = 0; j < CR; ++j) dj[j] = __ldg(dp + min(ty0 + top + j, H - 1)*W + x);
+                float cs[9][CR];  // window sums of the nine planes at the thread's pixels
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    float h[CR + 2];
+#pragma unroll
+                    for (int r = 0; r < CR + 2; ++r) {
+                        const float* ra = &sm.sc[c][top + r][lx + CXO];
+                        h[r] = fmaf(mw[r][0], ra[0], fmaf(mw[r][2], ra[2], mw[r][1]*ra[1]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < CR; ++j) {
+                        const int y = ty0 + top + j;
+                        const float myu = (y == 1) ? 2.f : 1.f, myd = (y == H - 2) ? 2.f : 1.f;
+                        cs[c][j] = fmaf(myu, h[j], fmaf(myd, h[j + 2], h[j + 1]));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < CR; ++j) {
+                    const int y = ty0 + top + j;
+                    if (y >= H) continue;
+                    const int o = y*W + x;
+                    const float d = dj[j];
+                    Proj pr;
+                    project(cam, (float)x, (float)y, d, sx, sy, pr);
+                    const float mxc = (float)(W - 1), myc = (float)(H - 1);
+                    const float bx = (pr.ix > 0.f && pr.ix < mxc) ? 1.f : 0.f, by = (pr.iy > 0.f && pr.iy < myc) ? 1.f : 0.f;
+                    const float cx = fminf(fmaxf(pr.ix, 0.f), mxc), cy = fminf(fmaxf(pr.iy, 0.f), myc);
+                    const float x0f = floorf(cx), y0f = floorf(cy);
+                    const float wx = cx - x0f, wy = cy - y0f;
+                    const bool own = sm.ssel[top + 1 + j][lx + 1] == k;
+                    float ta[3], tb[3], tcx[3], td[3], tv[3];  // taps (x0,y0) (x1,y0) (x0,y1) (x1,y1), target
+                    if (TEX) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float4 t4 = tex2Dgather<float4>(p.supp_tex, x0f + 1.f, y0f + 1.f + (float)((plane0 + c)*H), 0);
+                            ta[c] = t4.w; tb[c] = t4.z; tcx[c] = t4.x; td[c] = t4.y;
+                        }
+                    } else {
+                        const int x0 = (int)x0f, y0 = (int)y0f, x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float* q = sp + c*HW;
+                            ta[c] = __ldg(q + y0*W + x0); tb[c] = __ldg(q + y0*W + x1); tcx[c] = __ldg(q + y1*W + x0); td[c] = __ldg(q + y1*W + x1);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) tv[c] = __ldg(tg + c*HW + o);
+                    float gix = 0.f, giy = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float top_ = fmaf(wx, tb[c] - ta[c], ta[c]), bot = fmaf(wx, td[c] - tcx[c], tcx[c]);
+                        const float wv = fmaf(wy, bot - top_, top_);
+                        const float dx = fmaf(wy, (td[c] - tcx[c]) - (tb[c] - ta[c]), tb[c] - ta[c]), dy = bot - top_;
+                        float gwv = g*fmaf(2.f*wv, cs[c*3 + 1][j], fmaf(tv[c], cs[c*3 + 2][j], cs[c*3 + 0][j]));
+                        if (own) {
+                            const float df = wv - tv[c];
+                            gwv += df > 0.f ? gl : (df < 0.f ? -gl : 0.f);
+                        }
+                        gix = fmaf(gwv, dx, gix);
+                        giy = fmaf(gwv, dy, giy);
+                    }
+                    const float gqx = gix*bx*sx, gqy = giy*by*sy;
+                    float gn[3];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) gn[r] = fmaf(cam.K0[r], gqx, cam.K1[r]*gqy);
+                    float gQ[3];
+                    float gz = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) { gQ[r] = gn[r]*pr.inv; gz = fmaf(gn[r], pr.Q[r], gz); }
+                    if (pr.Q[2] >= STV_MIN_Z) gQ[2] -= gz*pr.inv*pr.inv;
+                    float gP[3];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) gP[r] = fmaf(cam.R[r], gQ[0], fmaf(cam.R[3 + r], gQ[1], cam.R[6 + r]*gQ[2]));
+                    gdv[j] = fmaf(gP[0], pr.ray[0], fmaf(gP[1], pr.ray[1], gP[2]*pr.ray[2]));
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        acc[r*4 + 0] = fmaf(gQ[r], pr.P[0], acc[r*4 + 0]);
+                        acc[r*4 + 1] = fmaf(gQ[r], pr.P[1], acc[r*4 + 1]);
+                        acc[r*4 + 2] = fmaf(gQ[r], pr.P[2], acc[r*4 + 2]);
+                        acc[r*4 + 3] += gQ[r];
+                    }
+                    if (NEED_K) {
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            acc[12 + r] = fmaf(gqx, pr.nrm[r], acc[12 + r]);
+                            acc[15 + r] = fmaf(gqy, pr.nrm[r], acc[15 + r]);
+                            const float gr = gP[r]*d;
+                            acc[18 + r*3 + 0] = fmaf(gr, (float)x, acc[18 + r*3 + 0]);
+                            acc[18 + r*3 + 1] = fmaf(gr, (float)y, acc[18 + r*3 + 1]);
+                            acc[18 + r*3 + 2] += gr;
+                        }
+                    }
+                }
+            }
+            // d loss / d depth: the first support frame writes, later ones accumulate (same thread, same address)
+            if (x < W) {
+#pragma unroll
+                for (int j = 0; j < CR; ++j) {
+                    const int y = ty0 + top + j;
+                    if (y < H) {
+                        float* q = gdp + y*W + x;
+                        if (k == 0) *q = gdv[j];
+                        else if (gdv[j] != 0.f) *q += gdv[j];
+                    }
+                }
+            }
+        }
+        // block reduction of the pose / intrinsics partials for this support frame
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) {
+            const float v = warp_sum(acc[q]);
+            if (lane == 0) sm.red[wid][q] = v;
+        }
+        __syncthreads();  // also: every thread is done with sm.cam of this support frame
+        if (threadIdx.x >= 32 && threadIdx.x < 32 + NACC) {  // (warp 0 goes on to load the next camera)
+            const int q = threadIdx.x - 32;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < NT/32; ++w) v += sm.red[w][q];
+            const size_t blk = ((size_t)blockIdx.z*gridDim.y + blockIdx.y)*gridDim.x + blockIdx.x;
+            p.partial[(blk*p.n + k)*(N_ACC_T + N_ACC_K) + q] = v;
+        }
+    }
+}
+
 // Sums the per-block partials in a fixed order (double accumulation).
 //   gT[k,i,r,c]   (r<3)   = sum_{s,tile} partial[((s*b+i)*tiles+tile)*n + k][r*4+c]
 //   gK[i,r,c]     (r<2)   = sum_{s,tile,k} partial[...][12 + r*3 + c]
@@ -801,6 +1107,11 @@ extern "C" size_t stv_photo_workspace_bytes(const stv_photo_cfg* c) {
     return e0 + (part_fwd > part_bwd ? part_fwd : part_bwd);
 }
 
+extern "C" size_t stv_photo_coef_bytes(const stv_photo_cfg* c) {
+    if (check_cfg(c) != STV_OK) return 0;
+    return (size_t)c->S*c->b*9*c->H*c->W*sizeof(float);
+}
+
 extern "C" int stv_photo_error(const stv_photo_cfg* c, const float* pred, const float* tgt, float* err, void* stream) {
     if (int rc = check_cfg(c)) return rc;
     STV_REQUIRE(pred && tgt && err, "stv_photo_error: NULL pointer");
@@ -816,7 +1127,7 @@ extern "C" int stv_photo_error(const stv_photo_cfg* c, const float* pred, const 
 
 extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, const float* tgt, const float* supp,
                              const float* T, const float* K, const float* Kinv, const float* noise, float* loss,
-                             uint8_t* sel, float* warp0, void* ws, size_t ws_bytes, void* stream) {
+                             uint8_t* sel, float* warp0, float* coef, void* ws, size_t ws_bytes, void* stream) {
     if (int rc = check_cfg(c)) return rc;
     STV_REQUIRE(depth && tgt && supp && T && K && Kinv && loss && sel, "stv_photo_fwd: NULL pointer");
     for (int s = 0; s < c->S; ++s) STV_REQUIRE(depth[s] != nullptr, "stv_photo_fwd: depth[%d] is NULL", s);
@@ -835,6 +1146,8 @@ extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, 
     p.e0 = e0;
     p.partial = (float*)((char*)ws + align256((size_t)c->b*c->H*c->W*sizeof(float)));
     p.sel = sel; p.warp0 = warp0;
+    STV_REQUIRE(coef == nullptr || c->use_min, "stv_photo_fwd: coefficient planes need use_min (one selected support per pixel)");
+    p.coef = coef;
     const int tiles = p.tiles_x*p.tiles_y;
     if (c->use_automask) {
         photo_error_kernel<<<dim3(tiles, c->b), FNT, 0, st>>>(p, supp, e0);
@@ -842,8 +1155,14 @@ extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, 
         if (int rc = check_launch("photo_error_kernel")) return rc;
     }
     p.supp_tex = supp_texture(supp, c->n*c->b*3*c->H, c->W);
-    if (p.supp_tex) photo_fwd_kernel<true><<<dim3(tiles, c->b, c->S), FNT, 0, st>>>(p);
-    else photo_fwd_kernel<false><<<dim3(tiles, c->b, c->S), FNT, 0, st>>>(p);
+    const dim3 grid(tiles, c->b, c->S);
+    if (coef) {
+        if (p.supp_tex) photo_fwd_kernel<true, true><<<grid, FNT, 0, st>>>(p);
+        else photo_fwd_kernel<false, true><<<grid, FNT, 0, st>>>(p);
+    } else {
+        if (p.supp_tex) photo_fwd_kernel<true, false><<<grid, FNT, 0, st>>>(p);
+        else photo_fwd_kernel<false, false><<<grid, FNT, 0, st>>>(p);
+    }
     count_launch();
     if (int rc = check_launch("photo_fwd_kernel")) return rc;
     const int nblk = tiles*c->b*c->S;
@@ -853,7 +1172,7 @@ extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, 
 }
 
 extern "C" int stv_photo_bwd(const stv_photo_cfg* c, const float* const* depth, const float* tgt, const float* supp,
-                             const float* T, const float* K, const float* Kinv, const uint8_t* sel,
+                             const float* T, const float* K, const float* Kinv, const uint8_t* sel, const float* coef,
                              const float* grad_loss, float* const* g_depth, float* gT, float* gK, float* gKinv, void* ws,
                              size_t ws_bytes, void* stream) {
     if (int rc = check_cfg(c)) return rc;
@@ -880,7 +1199,24 @@ extern "C" int stv_photo_bwd(const stv_photo_cfg* c, const float* const* depth, 
         attr_done = true;
     }
     dim3 grid(tiles, c->b, c->S);
-    if (need_k) photo_bwd_kernel<true><<<grid, NT, sizeof(BwdSmem), st>>>(p);
+    if (coef) {  // lean path: box-filter adjoint of the forward's coefficient planes
+        STV_REQUIRE(c->use_min, "stv_photo_bwd: coefficient planes need use_min");
+        p.coef_in = coef;
+        p.supp_tex = supp_texture(supp, c->n*c->b*3*c->H, c->W);
+        CUtensorMap tm{};
+        static const bool no_tma = getenv("STV_NO_COEF_TMA") != nullptr;  // developer switch: plain loads of the coefficient tiles
+        p.coef_tma = (!no_tma && c->W % 4 == 0 && ((uintptr_t)coef % 16) == 0) ? 1 : 0;
+        if (p.coef_tma) {
+            if (int rc = make_tmap_3d(&tm, coef, c->W, c->H, (long long)c->S*c->b*9, PW1T, PH1, 9)) return rc;
+        }
+        if (p.supp_tex) {
+            if (need_k) photo_bwd_coef_kernel<true, true><<<grid, NT, 0, st>>>(tm, p);
+            else photo_bwd_coef_kernel<false, true><<<grid, NT, 0, st>>>(tm, p);
+        } else {
+            if (need_k) photo_bwd_coef_kernel<true, false><<<grid, NT, 0, st>>>(tm, p);
+            else photo_bwd_coef_kernel<false, false><<<grid, NT, 0, st>>>(tm, p);
+        }
+    } else if (need_k) photo_bwd_kernel<true><<<grid, NT, sizeof(BwdSmem), st>>>(p);
     else photo_bwd_kernel<false><<<grid, NT, sizeof(BwdSmem), st>>>(p);
     count_launch();
     if (int rc = check_launch("photo_bwd_kernel")) return rc;

@@ -96,6 +96,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// 3-D tiled load: box origin (x, y, z), x the contiguous coordinate; out-of-bounds elements (negative coordinates included) are
+// zero-filled.
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+
 // im2col-mode load from a channels-last (N,H,W,C) tensor map: `pixelsPerColumn` base pixels starting at (n, h, w) — walking W,
 // then H, then N inside the map's bounding box with its traversal strides — each read at the filter-tap offset (off_h, off_w),
 // channels c .. c+31; pixels / channels outside the tensor are zero-filled. Rows land as a TMA box does (128 B, swizzled).

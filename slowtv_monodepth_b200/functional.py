@@ -18,18 +18,25 @@ __all__ = ['photo_loss', 'photo_error', 'smooth_loss', 'disp_to_depth', 'view_sy
 # Optional per-call device timing of the fused loss kernels (bench.py's roofline figures): when enabled, a pair of CUDA
 # events brackets each library call on the launching stream; `kernel_timings()` resolves them after a synchronize.
 _TIMING: dict[str, list] | None = None
+_TIMING_DETAIL = False
 
 
-def enable_kernel_timing(on: bool = True) -> None:
-    global _TIMING
+def enable_kernel_timing(on: bool = True, detail: bool = False) -> None:
+    """detail=True keys every call by entry point AND problem shape (tools/gemm_breakdown.py)."""
+    global _TIMING, _TIMING_DETAIL
     _TIMING = {} if on else None
+    _TIMING_DETAIL = bool(on and detail)
 
 
 class _timed:
-    def __init__(self, name: str): self.name = name
+    def __init__(self, name: str, detail=None): self.name, self.detail = name, detail
 
     def __enter__(self):
         if _TIMING is not None:
+            if _TIMING_DETAIL and self.detail is not None:
+                d = self.detail
+                if isinstance(d, L.ConvGeom): d = ' '.join(f'{k}={getattr(d, k)}' for k, _ in d._fields_)
+                self.name = f'{self.name} {d}'
             self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             self.ev[0].record()
 
@@ -81,13 +88,20 @@ def _ws(nbytes: int, device) -> Tensor:
 # ---------------------------------------------------------------------------------------------------------------------
 # Fused view-synthesis photometric loss
 # ---------------------------------------------------------------------------------------------------------------------
+PHOTO_COEF = True  # developer switch (parity tests exercise both backward kernels)
+
+
 class _PhotoLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg: L.PhotoCfg, want_warp: bool, tgt, supp, T, K, Kinv, noise, *depths):
         L.require_cuda(tgt, supp, T, K, Kinv, noise, *depths, what='photo_loss')
         lib, dev = L.lib(), tgt.device
         b, n, S, H, W = cfg.b, cfg.n, cfg.S, cfg.H, cfg.W
+        # Lean backward (min-reprojection only): the forward hands over the SSIM coefficient planes of the selected support
+        # frame, so the backward is a masked box filter + the pixel's own sampler/projection chain (no halo re-warp).
+        want_coef = bool(cfg.use_min) and PHOTO_COEF and any(ctx.needs_input_grad[4:7] + ctx.needs_input_grad[8:])
         with torch.cuda.device(dev):
+            coef = torch.empty((S, b, 9, H, W), dtype=torch.float32, device=dev) if want_coef else None
             loss = torch.empty((), dtype=torch.float32, device=dev)
             sel = torch.empty((S, b, H, W), dtype=torch.uint8, device=dev)
             warp0 = torch.empty((n, b, 3, H, W), dtype=torch.float32, device=dev) if want_warp else None
@@ -95,9 +109,9 @@ class _PhotoLoss(torch.autograd.Function):
             ws = _ws(nws, dev)
             with _timed('stv_photo_fwd'):
                 L.check(lib.stv_photo_fwd(C.byref(cfg), L.ptr_array(depths), L.ptr(tgt), L.ptr(supp), L.ptr(T), L.ptr(K),
-                                          L.ptr(Kinv), L.ptr(noise), L.ptr(loss), L.ptr(sel), L.ptr(warp0), L.ptr(ws),
+                                          L.ptr(Kinv), L.ptr(noise), L.ptr(loss), L.ptr(sel), L.ptr(warp0), L.ptr(coef), L.ptr(ws),
                                           ws.numel(), L.stream()), 'stv_photo_fwd')
-        ctx.cfg, ctx.nws = cfg, nws
+        ctx.cfg, ctx.nws, ctx.coef = cfg, nws, coef
         ctx.save_for_backward(tgt, supp, T, K, Kinv, sel, *depths)
         ctx.mark_non_differentiable(sel)
         if warp0 is None: warp0 = torch.empty(0, device=dev)
@@ -121,7 +135,7 @@ class _PhotoLoss(torch.autograd.Function):
             ws = _ws(ctx.nws, dev)
             with _timed('stv_photo_bwd'):
                 L.check(lib.stv_photo_bwd(C.byref(cfg), L.ptr_array(depths), L.ptr(tgt), L.ptr(supp), L.ptr(T), L.ptr(K),
-                                          L.ptr(Kinv), L.ptr(sel), L.ptr(g_loss), L.ptr_array(g_depths), L.ptr(gT), L.ptr(gK),
+                                          L.ptr(Kinv), L.ptr(sel), L.ptr(ctx.coef), L.ptr(g_loss), L.ptr_array(g_depths), L.ptr(gT), L.ptr(gK),
                                           L.ptr(gKi), L.ptr(ws), ws.numel(), L.stream()), 'stv_photo_bwd')
         return (None, None, None, None, gT if need_T else None, gK if need_K else None, gKi if need_Ki else None, None,
                 *[g if ctx.needs_input_grad[8 + j] else None for j, g in enumerate(g_depths)])
@@ -454,7 +468,7 @@ def gemm_tf32(A: Tensor, B: Tensor, *, a_mn: bool = False, b_mn: bool = False, o
             if t is not None and (t.shape != (N,) or not t.is_contiguous()): raise ValueError('gemm_tf32: bias / gamma / colsum must be contiguous (N,).')
         epi = L.GemmEpi(bias=L.ptr(bias), aux=L.ptr(aux), gamma=L.ptr(gamma), res=L.ptr(res), dact_src=L.ptr(dact_src), colsum=L.ptr(colsum),
                         act=L.ACT[act], dact=L.ACT[dact], accumulate=int(accumulate))
-        with _timed('stv_gemm_tf32'):
+        with _timed('stv_gemm_tf32', (M, N, K, 'a_mn' if a_mn else '', 'b_mn' if b_mn else '', f'sk{split_k}')):
             L.check(L.lib().stv_gemm_tf32(M, N, K, L.ptr(A), A.stride(0), int(a_mn), L.ptr(B), B.stride(0), int(b_mn), L.ptr(out),
                                           out.stride(0), C.byref(epi), int(split_k), L.stream()), 'stv_gemm_tf32')
     return out
@@ -538,7 +552,7 @@ class _Conv2dNHWC(torch.autograd.Function):
                 if Cp != Cin: w_phys = torch.nn.functional.pad(w_phys, (0, Cp - Cin))
             y = torch.empty((g.N, P, Q, g.Cout), dtype=torch.float32, device=dev)
             epi = L.GemmEpi(bias=L.ptr(b), act=L.ACT[act])
-            with _timed('stv_conv_fprop'):
+            with _timed('stv_conv_fprop', g):
                 L.check(lib.stv_conv_fprop(C.byref(g), L.ptr(src1), L.ptr(src2), L.ptr(w_phys), L.ptr(y), C.byref(epi), L.stream()),
                         'stv_conv_fprop')
         ctx.save_for_backward(src1, src2, w_phys, y)
@@ -567,14 +581,14 @@ class _Conv2dNHWC(torch.autograd.Function):
             dw = None
             if ctx.needs_input_grad[2]:
                 dw = ctx.w_sink if ctx.w_sink is not None else torch.zeros_like(wq)
-                with _timed('stv_conv_wgrad'):
+                with _timed('stv_conv_wgrad', g):
                     L.check(lib.stv_conv_wgrad(C.byref(g), L.ptr(src1), L.ptr(src2), L.ptr(dZ), L.ptr(dw), 0, L.stream()), 'stv_conv_wgrad')
                 dw = None if ctx.w_sink is not None else dw[:Cout, :, :, :ctx.cin].permute(0, 3, 1, 2)
             d1 = d2 = None
             if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
                 pd = g.pad if g.reflect else 0
                 dv = torch.empty((g.N, g.H + 2*pd, g.W + 2*pd, Cin), dtype=torch.float32, device=dev)
-                with _timed('stv_conv_dgrad'):
+                with _timed('stv_conv_dgrad', g):
                     L.check(lib.stv_conv_dgrad(C.byref(g), L.ptr(dZ), L.ptr(wq), L.ptr(dv), None, L.stream()), 'stv_conv_dgrad')
                 if ctx.virt is not None:  # dv is the gradient of the materialised (padded) virtual input
                     shape1, shape2, c1, pv, pool = ctx.virt
