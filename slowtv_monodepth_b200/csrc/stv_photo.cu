@@ -345,10 +345,10 @@ __global__ void __launch_bounds__(FNT) photo_error_kernel(PhotoParams p, const f
 #define STV_FWD_MINB 4  // measured on B200 at 8x384x640, n=2, S=4: (TH, NT, MINB) = (8, 256, 4) is the fastest of six variants
 #endif
 #ifndef STV_FWD_MINB_COEF
-#define STV_FWD_MINB_COEF 3
+#define STV_FWD_MINB_COEF 4  // measured (config 3): 2 -> 0.62 ms, 3 -> 0.53, 4 -> 0.51: residency beats the 150 B of spills
 #endif
-template <bool TEX, bool COEF>
-__global__ void __launch_bounds__(FNT, COEF ? STV_FWD_MINB_COEF : STV_FWD_MINB) photo_fwd_kernel(PhotoParams p) {
+template <bool TEX, bool COEF, int MINB = (COEF ? STV_FWD_MINB_COEF : STV_FWD_MINB)>
+__global__ void __launch_bounds__(FNT, MINB) photo_fwd_kernel(PhotoParams p) {
     __shared__ __align__(16) float st[3][FPW][FPH];
     __shared__ __align__(16) float sw[3][FPW][FPH];
     __shared__ float red[32];
@@ -1157,8 +1157,11 @@ extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, 
     p.supp_tex = supp_texture(supp, c->n*c->b*3*c->H, c->W);
     const dim3 grid(tiles, c->b, c->S);
     if (coef) {
-        if (p.supp_tex) photo_fwd_kernel<true, true><<<grid, FNT, 0, st>>>(p);
-        else photo_fwd_kernel<false, true><<<grid, FNT, 0, st>>>(p);
+        static const int minb = getenv("STV_FWD_MINB_COEF") ? atoi(getenv("STV_FWD_MINB_COEF")) : 0;  // developer sweep
+        if (!p.supp_tex) photo_fwd_kernel<false, true><<<grid, FNT, 0, st>>>(p);
+        else if (minb == 2) photo_fwd_kernel<true, true, 2><<<grid, FNT, 0, st>>>(p);
+        else if (minb == 4) photo_fwd_kernel<true, true, 4><<<grid, FNT, 0, st>>>(p);
+        else photo_fwd_kernel<true, true><<<grid, FNT, 0, st>>>(p);
     } else {
         if (p.supp_tex) photo_fwd_kernel<true, false><<<grid, FNT, 0, st>>>(p);
         else photo_fwd_kernel<false, false><<<grid, FNT, 0, st>>>(p);
