@@ -229,6 +229,13 @@ int stv_grad_pull(int N, int H, int W, int C, const float* src, int Cs, int c_of
 int stv_act_bwd(long long M, int C, const float* da, const float* y, int act, float* dz, float* dbias, void* stream);
 /* out[c] += sum_m x[m*ld + c] */
 int stv_colsum(long long M, int C, long long ld, const float* x, float* out, void* stream);
+/* Parameter gradients behind the ConvNeXt layer-scale (timm ConvNeXtBlock: x + gamma * fc2(...), encoder built at
+ * src/networks/depth.py:97). G = g^T h (C, Hd), gs = column sums of g (C), w2 (C, Hd):
+ *   dw2 += gamma[:,None]*G;  db2 += gamma*gs;  dgamma += sum_j w2[c,j]*G[c,j] + b2*gs.   (all accumulated in place) */
+int stv_ls_tail(int C, int Hd, const float* G, const float* w2, const float* b2, const float* gamma, const float* gs,
+                float* dw2, float* db2, float* dgamma, void* stream);
+/* out[c,j] = w[c,j] * gamma[c]  (layer-scale folded into fc2 for the data gradient) */
+int stv_rowscale(int C, int Hd, const float* w, const float* gamma, float* out, void* stream);
 
 /* Train-mode BatchNorm over the M = N*H*W rows of a channels-last (M, C) matrix, fused with the residual add and ReLU that
  * follow it in a ResNet BasicBlock: y = [relu]((x - mean_c) * rstd_c * gamma_c + beta_c [+ res]). Replaces the cuDNN batch-norm

@@ -480,6 +480,41 @@ static int rows_per_block(long long M, int C) {
     return (int)rpb;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// ConvNeXt block, parameter gradients behind the layer-scale: with out = res + gamma * (h W2^T + b2), G = g^T h (C x Hd) and
+// gs = column sums of g (C):  dW2 += gamma[:,None] * G;  db2 += gamma * gs;  dgamma += sum_j W2[c,j] G[c,j] + b2 * gs.
+// One warp per output channel c (one launch instead of five ATen launches per block). w2g = gamma[:,None] * W2 (forward fold).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ls_tail_kernel(int C, int Hd, const float* __restrict__ G, const float* __restrict__ w2,
+                                                      const float* __restrict__ b2, const float* __restrict__ gamma,
+                                                      const float* __restrict__ gs, float* __restrict__ dw2, float* __restrict__ db2,
+                                                      float* __restrict__ dgamma) {
+    const int c = blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= C) return;
+    const float ga = __ldg(gamma + c);
+    const float* g = G + (size_t)c*Hd;
+    const float* w = w2 + (size_t)c*Hd;
+    float* d = dw2 + (size_t)c*Hd;
+    float dot = 0.f;
+    for (int j = lane; j < Hd; j += 32) {
+        const float gv = g[j];
+        dot = fmaf(__ldg(w + j), gv, dot);
+        d[j] = fmaf(ga, gv, d[j]);
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) {
+        const float s = __ldg(gs + c);
+        db2[c] = fmaf(ga, s, db2[c]);
+        dgamma[c] += fmaf(__ldg(b2 + c), s, dot);
+    }
+}
+
+__global__ void __launch_bounds__(256) rowscale_kernel(long long n, int Hd, const float* __restrict__ w, const float* __restrict__ gamma,
+                                                       float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < n) out[i] = w[i]*__ldg(gamma + i/Hd);
+}
+
 }  // namespace stv
 
 using namespace stv;
@@ -633,4 +668,21 @@ extern "C" int stv_maxpool3x3s2_bwd(int N, int H, int W, int C, const float* dy,
     maxpool_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(N, H, W, C, P, Q, dy, idx, dx);
     count_launch();
     return check_launch("stv_maxpool3x3s2_bwd");
+}
+
+extern "C" int stv_ls_tail(int C, int Hd, const float* G, const float* w2, const float* b2, const float* gamma, const float* gs,
+                           float* dw2, float* db2, float* dgamma, void* stream) {
+    STV_REQUIRE(C > 0 && Hd > 0, "stv_ls_tail: bad shape (C=%d Hd=%d)", C, Hd);
+    STV_REQUIRE(G && w2 && b2 && gamma && gs && dw2 && db2 && dgamma, "stv_ls_tail: NULL pointer");
+    ls_tail_kernel<<<(C + 7)/8, 256, 0, (cudaStream_t)stream>>>(C, Hd, G, w2, b2, gamma, gs, dw2, db2, dgamma);
+    count_launch();
+    return check_launch("ls_tail_kernel");
+}
+
+extern "C" int stv_rowscale(int C, int Hd, const float* w, const float* gamma, float* out, void* stream) {
+    STV_REQUIRE(C > 0 && Hd > 0 && w && gamma && out, "stv_rowscale: bad arguments");
+    const long long n = (long long)C*Hd;
+    rowscale_kernel<<<(unsigned)((n + 255)/256), 256, 0, (cudaStream_t)stream>>>(n, Hd, w, gamma, out);
+    count_launch();
+    return check_launch("rowscale_kernel");
 }

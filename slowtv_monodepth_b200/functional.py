@@ -357,8 +357,9 @@ def view_synth(inp: Tensor, depth: Tensor, T: Tensor, K: Tensor, K_inv: Tensor |
 # ---------------------------------------------------------------------------------------------------------------------
 class _DwConv7(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, link=None):
         L.require_cuda(x, w, b, what='dwconv7')
+        ctx.link = link
         N, H, W, Cc = x.shape
         with torch.cuda.device(x.device):
             y = torch.empty_like(x)
@@ -377,9 +378,12 @@ class _DwConv7(torch.autograd.Function):
         lib, dev = L.lib(), x.device
         gx = gw = gb = None
         with torch.cuda.device(dev):
+            # ConvNeXt block: the gradient of the residual branch (left in `link` by _ConvNeXtMlp.backward, which always runs
+            # first) is added by the data-gradient kernel itself instead of a separate autograd accumulation pass.
+            g_res = ctx.link.pop('g_res', None) if ctx.link is not None else None
             if ctx.needs_input_grad[0]:
                 gx = torch.empty_like(x)
-                L.check(lib.stv_dwconv7_fwd(N, H, W, Cc, L.ptr(gy), L.ptr(w), None, None, L.ptr(gx), 1, L.stream()), 'stv_dwconv7_fwd(flip)')
+                L.check(lib.stv_dwconv7_fwd(N, H, W, Cc, L.ptr(gy), L.ptr(w), None, L.ptr(g_res), L.ptr(gx), 1, L.stream()), 'stv_dwconv7_fwd(flip)')
             if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
                 sink = ctx.w_sink is not None
                 gw = ctx.w_sink if sink else torch.empty_like(w)
@@ -388,13 +392,13 @@ class _DwConv7(torch.autograd.Function):
                 L.check(lib.stv_dwconv7_wgrad(N, H, W, Cc, L.ptr(x), L.ptr(gy), L.ptr(gw), L.ptr(gb), int(sink), L.ptr(ws), ws.numel(),
                                               L.stream()), 'stv_dwconv7_wgrad')
                 if sink: gw = gb = None  # accumulated in place into weight.grad / bias.grad
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
-def dwconv7(x: Tensor, weight: Tensor, bias: Tensor | None) -> Tensor:
+def dwconv7(x: Tensor, weight: Tensor, bias: Tensor | None, link: dict | None = None) -> Tensor:
     """Depthwise 7x7 convolution, padding 3, on a channels-last (N,H,W,C) tensor; weight (C,1,7,7)."""
     if x.ndim != 4 or weight.shape != (x.shape[-1], 1, 7, 7): raise ValueError(f'dwconv7: bad shapes {tuple(x.shape)}, {tuple(weight.shape)}')
-    return _DwConv7.apply(_f32c(x), _f32c(weight), _f32c(bias))
+    return _DwConv7.apply(_f32c(x), _f32c(weight), _f32c(bias), link)
 
 
 class _LayerNorm(torch.autograd.Function):
@@ -774,7 +778,8 @@ class _ConvNeXtMlp(torch.autograd.Function):
     Two tcgen05 GEMMs forward (bias+GELU and bias+layer-scale+residual fused into their epilogues) and four backward
     (GELU' fused into the fc2 data gradient; both weight gradients as split-K products accumulated with red.global.add)."""
     @staticmethod
-    def forward(ctx, x, res, w1, b1, w2, b2, gamma):
+    def forward(ctx, x, res, w1, b1, w2, b2, gamma, link=None):
+        ctx.link = link
         M, Cc = x.shape
         z = torch.empty((M, w1.shape[0]), dtype=torch.float32, device=x.device)
         h = torch.empty_like(z)
@@ -791,7 +796,10 @@ class _ConvNeXtMlp(torch.autograd.Function):
         g = _f32c(g)
         M, Cc = x.shape
         Hd = w1.shape[0]
-        w2g = w2*gamma[:, None]                                              # (C, 4C): layer-scale folded into fc2
+        lib = L.lib()
+        with torch.cuda.device(g.device):
+            w2g = torch.empty_like(w2)                                       # (C, 4C): layer-scale folded into fc2
+            L.check(lib.stv_rowscale(Cc, Hd, L.ptr(w2), L.ptr(gamma), L.ptr(w2g), L.stream()), 'stv_rowscale')
         db1 = ctx.b1_sink if ctx.b1_sink is not None else torch.zeros(Hd, dtype=torch.float32, device=g.device)
         dz = gemm_tf32(g, w2g, b_mn=True, dact='gelu', dact_src=z, colsum=db1)  # (M, 4C) = (g W2g) * GELU'(z); db1 = its column sums
         dx = gemm_tf32(dz, w1, b_mn=True) if ctx.needs_input_grad[0] else None
@@ -803,19 +811,25 @@ class _ConvNeXtMlp(torch.autograd.Function):
         gemm_tf32(g, h, a_mn=True, b_mn=True, out=G, accumulate=True, split_k=_split_k(Cc, Hd, M))
         gs = colsum(g)
         w2s, b2s, gas = ctx.tail_sinks
-        if w2s is not None and b2s is not None and gas is not None:  # accumulate straight into the flat gradient buffer
-            w2s.addcmul_(G, gamma[:, None])
-            b2s.addcmul_(gamma, gs)
-            gas.add_((w2*G).sum(1)).addcmul_(b2, gs)
-            return (dx, g if ctx.needs_input_grad[1] else None, dw1, db1, None, None, None)
-        return (dx, g if ctx.needs_input_grad[1] else None, dw1, db1, G*gamma[:, None], gamma*gs, (w2*G).sum(1) + b2*gs)
+        sunk = w2s is not None and b2s is not None and gas is not None
+        if sunk: dw2, db2, dga = w2s, b2s, gas                               # accumulate straight into the flat gradient buffer
+        else: dw2, db2, dga = torch.zeros_like(w2), torch.zeros_like(b2), torch.zeros_like(gamma)
+        with torch.cuda.device(g.device):
+            L.check(lib.stv_ls_tail(Cc, Hd, L.ptr(G), L.ptr(w2), L.ptr(b2), L.ptr(gamma), L.ptr(gs), L.ptr(dw2), L.ptr(db2), L.ptr(dga),
+                                    L.stream()), 'stv_ls_tail')
+        g_res = g if ctx.needs_input_grad[1] else None
+        if g_res is not None and ctx.link is not None:  # handed to the block's depthwise data-gradient kernel (see _DwConv7.backward)
+            ctx.link['g_res'] = g_res
+            g_res = None
+        if sunk: return (dx, g_res, dw1, db1, None, None, None, None)
+        return (dx, g_res, dw1, db1, dw2, db2, dga, None)
 
 
-def convnext_mlp(x: Tensor, res: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, gamma: Tensor) -> Tensor:
+def convnext_mlp(x: Tensor, res: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, gamma: Tensor, link: dict | None = None) -> Tensor:
     """x, res: (M, C) contiguous rows (channels-last pixels); w1 (4C, C), w2 (C, 4C). -> (M, C)."""
     if x.ndim != 2 or res.shape != x.shape or w1.shape[1] != x.shape[1] or w2.shape != w1.shape[::-1]:
         raise ValueError(f'convnext_mlp: bad shapes {tuple(x.shape)}, {tuple(res.shape)}, {tuple(w1.shape)}, {tuple(w2.shape)}')
-    return _ConvNeXtMlp.apply(_f32c(x), _f32c(res), _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2), _f32c(gamma))
+    return _ConvNeXtMlp.apply(_f32c(x), _f32c(res), _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2), _f32c(gamma), link)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -191,11 +191,14 @@ class ConvNeXtBlock(nn.Module):
     def forward_nhwc(self, xl: Tensor) -> Tensor:
         """xl (N,H,W,C) channels-last. libstv kernels: depthwise 7x7 (fwd / dgrad / wgrad), LayerNorm (fwd / bwd) and the
         pointwise MLP as tcgen05 TF32 GEMMs with bias+GELU / bias+layer-scale+residual epilogues."""
-        y = F_.dwconv7(xl, self.conv_dw.weight, self.conv_dw.bias)
+        # `link` carries the residual-branch gradient from the MLP's backward to the depthwise data-gradient kernel, which adds
+        # it in its epilogue (xl feeds both): one pass less over the activation than autograd's own accumulation.
+        link = {} if xl.requires_grad and xl.is_contiguous() else None
+        y = F_.dwconv7(xl, self.conv_dw.weight, self.conv_dw.bias, link)
         y = F_.layer_norm(y, self.norm.weight, self.norm.bias, self.norm.eps)
         c = xl.shape[-1]
         out = F_.convnext_mlp(y.view(-1, c), xl.reshape(-1, c), self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight,
-                              self.mlp.fc2.bias, self.gamma)
+                              self.mlp.fc2.bias, self.gamma, link)
         return out.view(xl.shape)
 
 

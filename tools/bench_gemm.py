@@ -6,7 +6,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 from slowtv_monodepth_b200 import functional as F_
 
-ap = argparse.ArgumentParser(); ap.add_argument('--b', type=int, default=8); ap.add_argument('--only', default=''); a = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument('--b', type=int, default=8); ap.add_argument('--only', default=''); ap.add_argument('--once', action='store_true', help='run every case once, ours only (ncu captures)'); a = ap.parse_args()
 torch.backends.cuda.matmul.allow_tf32 = True
 dev = 'cuda'
 
@@ -40,5 +40,7 @@ for st, (C, hw) in enumerate([(96, 96*160), (192, 48*80), (384, 24*40), (768, 12
         ('G=g^T.h', C, Hd, M, lambda: F_.gemm_tf32(g, h, a_mn=True, b_mn=True, out=G, accumulate=True, split_k=F_._split_k(C, Hd, M)), lambda: g.t() @ h, 4*(M*Hd + M*C)),
     ]
     for name, m, n, k, ours, ref, nbytes in cases:
+        if a.once:
+            ours(); torch.cuda.synchronize(); print(f'st{st} {name}'); continue
         t, tr = timeit(ours), timeit(ref)
         print(f'st{st} {name:18s} {m:7d} {n:5d} {k:7d} | {t:7.3f} {2*m*n*k/t/1e9:6.1f} {nbytes/t/1e6:6.0f} | {tr:7.3f}')
