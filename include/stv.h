@@ -227,6 +227,18 @@ int stv_grad_pull(int N, int H, int W, int C, const float* src, int Cs, int c_of
                   void* stream);
 /* dz[m,c] = da[m,c] * act'(y[m,c]) (y = activation OUTPUT; pre-activation for GELU); dbias[c] += sum_m dz[m,c] (nullable). */
 int stv_act_bwd(long long M, int C, const float* da, const float* y, int act, float* dz, float* dbias, void* stream);
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Aspect-ratio augmentation (src/core/aspect_ratio.py:36-186, called from training_step, src/core/trainer.py:106): bilinear
+ * resampling of (P, H, W) fp32 planes to (P, oh, ow) with separable sample positions.
+ *   STV_RESAMPLE_GRID   ix = ax*j + bx, iy = ay*i + by (pixel units), zero padding: kornia.center_crop(mode='bilinear',
+ *                       align_corners=False) = warp_affine -> F.affine_grid + F.grid_sample (crop_aug, aspect_ratio.py:82)
+ *   STV_RESAMPLE_INTERP F.interpolate(size, mode='bilinear', align_corners=False) with ax = W/ow, ay = H/oh (resize_aug, :139)
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define STV_RESAMPLE_GRID 0
+#define STV_RESAMPLE_INTERP 1
+int stv_resample_bilinear(long long P, int H, int W, int oh, int ow, float ax, float bx, float ay, float by, int mode,
+                          const float* src, float* dst, void* stream);
+
 /* out[c] += sum_m x[m*ld + c] */
 int stv_colsum(long long M, int C, long long ld, const float* x, float* out, void* stream);
 /* Parameter gradients behind the ConvNeXt layer-scale (timm ConvNeXtBlock: x + gamma * fc2(...), encoder built at

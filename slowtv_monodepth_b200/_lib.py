@@ -80,6 +80,7 @@ _SIGNATURES = {
     'stv_grad_pull': (C.c_int, [C.c_int]*4 + [_P] + [C.c_int]*4 + [_P, C.c_int, _P]),
     'stv_act_bwd': (C.c_int, [C.c_longlong, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     'stv_colsum': (C.c_int, [C.c_longlong, C.c_int, C.c_longlong, _P, _P, _P]),
+    'stv_resample_bilinear': (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _P, _P, _P]),
     'stv_ls_tail': (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'stv_rowscale': (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P]),
     'stv_bn_workspace_bytes': (C.c_size_t, [C.c_int]),

@@ -833,6 +833,33 @@ def convnext_mlp(x: Tensor, res: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# Bilinear resampling (aspect-ratio augmentation)
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def resample_bilinear(x: Tensor, size: tuple[int, int], *, mode: str, ax: float = 0., bx: float = 0., ay: float = 0., by: float = 0.) -> Tensor:
+    """(..., H, W) fp32 -> (..., oh, ow) on the libstv kernel (include/stv.h: stv_resample_bilinear). No autograd (augmentation).
+
+    mode 'interp': F.interpolate(size, mode='bilinear', align_corners=False).
+    mode 'grid':   sample positions ix = ax*j + bx, iy = ay*i + by in pixel units, zero padding (affine_grid + grid_sample)."""
+    L.require_cuda(x, what='resample_bilinear')
+    if x.ndim < 2: raise ValueError(f'resample_bilinear: expected (..., H, W), got {tuple(x.shape)}')
+    if mode not in ('interp', 'grid'): raise ValueError(f'resample_bilinear: unknown mode {mode!r}')
+    x = _f32c(x)
+    H, W = x.shape[-2:]
+    oh, ow = int(size[0]), int(size[1])
+    if oh <= 0 or ow <= 0: raise ValueError(f'resample_bilinear: bad output size {size}')
+    P = x.numel()//(H*W)
+    with torch.cuda.device(x.device):
+        out = torch.empty((*x.shape[:-2], oh, ow), dtype=torch.float32, device=x.device)
+        if mode == 'interp': ax, ay, bx, by = W/ow, H/oh, 0., 0.
+        for p0 in range(0, P, 65535):  # gridDim.z limit
+            pn = min(65535, P - p0)
+            L.check(L.lib().stv_resample_bilinear(pn, H, W, oh, ow, ax, bx, ay, by, 1 if mode == 'interp' else 0,
+                                                  x.data_ptr() + p0*H*W*4, out.data_ptr() + p0*oh*ow*4, L.stream()), 'stv_resample_bilinear')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # Optimiser step
 # ---------------------------------------------------------------------------------------------------------------------
 @torch.no_grad()

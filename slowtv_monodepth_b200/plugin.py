@@ -6,12 +6,13 @@
 
 `install()` (a) triggers the reference's lazy registrations so the originals exist, (b) re-registers the B200 classes under
 the same keys with `overwrite=True` (registry.py:131-132), and (c) rebinds the names the trainer resolves at call time:
-`src.core.handlers.image_recon / disp_smooth` (trainer.py:389,437) and `src.core.trainer.ViewSynth` (trainer.py:168).
+`src.core.handlers.image_recon / disp_smooth` (trainer.py:389,437), `src.core.trainer.ViewSynth` (trainer.py:168) and
+`src.core.trainer.aspect_ratio_aug` (trainer.py:12,54-60; the GPU augmentation of SURVEY 8f).
 The reference tree itself is not modified. Requires the reference to be importable (`src` on sys.path).
 """
 from __future__ import annotations
 
-from . import geometry, handlers, losses, networks, regularizers
+from . import aspect_ratio, geometry, handlers, losses, networks, regularizers
 
 __all__ = ['install', 'uninstall', 'REPLACED']
 
@@ -44,6 +45,9 @@ def install(nets: bool = True, loss: bool = True) -> None:
         ref_handlers.image_recon = handlers.image_recon
         ref_handlers.disp_smooth = handlers.disp_smooth
         ref_trainer.ViewSynth = geometry.ViewSynth
+    # MonoDepthModule.__init__ binds `aspect_ratio_aug` by name from src.core.trainer (trainer.py:12,54-60)
+    _saved.setdefault(('attr', 'aspect_ratio_aug'), ref_trainer.aspect_ratio_aug)
+    ref_trainer.aspect_ratio_aug = aspect_ratio.aspect_ratio_aug
 
 
 def uninstall() -> None:
