@@ -21,7 +21,7 @@ from .losses import ReconstructionLoss
 from .networks import DepthNet, PoseNet
 from .regularizers import SmoothReg
 
-__all__ = ['MonoDepthStep', 'GraphedTrainStep', 'default_cfg']
+__all__ = ['MonoDepthStep', 'GraphedTrainStep', 'ShapeCachedTrainStep', 'default_cfg']
 
 NET_REG = {'depth': DepthNet, 'pose': PoseNet}
 LOSS_REG = {'img_recon': ReconstructionLoss, 'disp_smooth': SmoothReg}
@@ -127,7 +127,7 @@ class GraphedTrainStep:
 
     The auto-mask tie-break noise seed (a host integer, advanced per call in eager mode) is frozen at capture time: the noise
     PATTERN then repeats every step — it only decides exact ties between the warped and the static error."""
-    def __init__(self, model: MonoDepthStep, opt, example_batch, warmup: int = 3):
+    def __init__(self, model: MonoDepthStep, opt, example_batch, warmup: int = 3, pool=None):
         self.model, self.opt = model, opt
         x, y, _ = example_batch
         clone = lambda d: {k: (v.clone() if torch.is_tensor(v) and v.is_cuda else v) for k, v in d.items()}
@@ -138,7 +138,7 @@ class GraphedTrainStep:
             for _ in range(max(warmup, 1)): self._fwd_bwd()   # lazy one-time initialisation must not happen under capture
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, pool=pool):
             self.loss = self._fwd_bwd()
 
     def _fwd_bwd(self) -> Tensor:
@@ -190,3 +190,32 @@ class GraphedTrainStep:
         self._consumed[j].record(cur)
         self._slot_r += 1
         return self.run()
+
+
+class ShapeCachedTrainStep:
+    """Graph replay under the aspect-ratio augmentation (src/core/aspect_ratio.py; trainer.py:106), which changes the image
+    size from step to step: one captured graph per distinct (b, n, H, W), built the first time a shape is seen and replayed
+    afterwards. `sample_resize` only emits multiples of 32 with a bounded pixel count, so a run visits a few dozen shapes.
+    The graphs never run concurrently and therefore share ONE private memory pool (the largest shape sets its size); libstv
+    kernels are shape-agnostic (no per-shape compilation), so a new shape costs one eager warm-up + one capture.
+
+    `max_graphs` bounds the cache (least recently used shape is dropped)."""
+    def __init__(self, model: MonoDepthStep, opt, warmup: int = 2, max_graphs: int = 64):
+        self.model, self.opt, self.warmup, self.max_graphs = model, opt, warmup, max_graphs
+        self.steps: dict[tuple, GraphedTrainStep] = {}
+        self.pool = None
+
+    @staticmethod
+    def key(batch) -> tuple:
+        x = batch[0]
+        return (tuple(x['imgs'].shape), tuple(x['supp_imgs'].shape), tuple(int(i) for i in x['supp_idxs']))
+
+    def run(self, batch) -> Tensor:
+        k = self.key(batch)
+        step = self.steps.pop(k, None)
+        if step is None:
+            if len(self.steps) >= self.max_graphs: self.steps.pop(next(iter(self.steps)))
+            step = GraphedTrainStep(self.model, self.opt, batch, warmup=self.warmup, pool=self.pool)
+            if self.pool is None: self.pool = step.graph.pool()
+        self.steps[k] = step  # most recently used last
+        return step.run(batch)
