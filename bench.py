@@ -304,7 +304,7 @@ def main() -> None:
             'gpu_launches': launches,
             'roofline': {'kernel': 'fused photometric loss, stv_photo_fwd + stv_photo_bwd', 'bound': 'hbm', 'achieved': round(ach, 1),
                          'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(ach/peak, 4),
-                         'traffic': 614.0e6, 'traffic_source': 'ncu --set full dram__bytes_read+write, fwd 303.6 MB + bwd 310.4 MB (profiles/r1a_loss_ncu_full_summary.txt)',
+                         'traffic': 1252.0e6, 'traffic_source': 'ncu --set full dram__bytes_read+write: fwd 343 + 297 MB, bwd 579 + 33 MB (profiles/r1f_loss_ncu_full_summary.txt); the 2x over the algorithmic bytes is the (S,b,9,H,W) SSIM coefficient planes the forward hands to the backward (283 MB written, re-read with a 1-pixel halo) — traded for a 2.4x shorter backward',
                          'algorithmic_bytes_per_launch': bytes_fwd + bytes_bwd, 'avg_ms': round(t_f + t_b, 4),
                          'detail': {'photo_fwd': {'ms': round(t_f, 4), 'GB/s': round(gbs(bytes_fwd, t_f), 1), 'frac': round(gbs(bytes_fwd, t_f)/peak, 4)},
                                     'photo_bwd': {'ms': round(t_b, 4), 'GB/s': round(gbs(bytes_bwd, t_b), 1), 'frac': round(gbs(bytes_bwd, t_b)/peak, 4)},

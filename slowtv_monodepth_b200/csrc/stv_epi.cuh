@@ -2,13 +2,16 @@
 #pragma once
 #include "stv_common.cuh"
 #include "stv_tc.cuh"
+#include "stv_f2.cuh"
 
 namespace stv {
 
-// Branch-free erf (Abramowitz & Stegun 7.1.26, |abs err| <= 1.5e-7) given e = exp(-u*u): one MUFU.RCP + 5 FMA. erff() costs ~3x
+// Branch-free erf (Abramowitz & Stegun 7.1.26, |abs err| <= 1.5e-7) given e = exp(-u*u): one bare MUFU.RCP (rcp.approx, <= 1 ulp;
+// __frcp_rn adds a Newton fix-up and a special-case branch, ~7 more instructions per element for accuracy the polynomial lacks) + 5 FMA. erff() costs ~3x
 // the instructions and branches on |u|, which serialises the four elements of a float4 in the epilogue warps.
 __device__ __forceinline__ float erf_fast(float u, float e) {
-    const float t = __frcp_rn(fmaf(0.3275911f, fabsf(u), 1.f));
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, fabsf(u), 1.f)));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
@@ -40,6 +43,47 @@ __device__ __forceinline__ float act_bwd(int act, float s) {
         case STV_ACT_SIGMOID: return s*(1.f - s);
         default: return 1.f;
     }
+}
+
+// ---- packed (two elements per instruction) GELU / GELU' for the float4 epilogue ------------------------------------------------
+// The GELU epilogues are issue-bound (fc1 / GELU'-dgrad of the ConvNeXt MLP: ~2x the time of their plain siblings at equal
+// bytes and flops), so the polynomial, the products and the final blend run as FFMA2 / FMUL2 on element pairs; only the two
+// MUFU ops (rcp, ex2) and the sign/abs bit operations stay per element. Same A&S 7.1.26 formulation as erf_fast.
+__device__ __forceinline__ f2 abs2(f2 a) { f2 r; r.v = a.v & 0x7FFFFFFF7FFFFFFFull; return r; }
+__device__ __forceinline__ f2 copysign2(f2 mag, f2 sgn) { f2 r; r.v = mag.v | (sgn.v & 0x8000000080000000ull); return r; }  // mag >= 0
+__device__ __forceinline__ float ex2_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// erf(u) for u = x/sqrt(2) and e = exp(-u^2), both packed.
+__device__ __forceinline__ void erf_exp2(f2 x, f2& erf, f2& e) {
+    const f2 u = x*splat2(0.70710678118654752f);
+    const f2 d = fma2(splat2(0.3275911f), abs2(u), splat2(1.f));
+    const f2 t = mk2(rcp_fast(lo2(d)), rcp_fast(hi2(d)));
+    const f2 a = (u*u)*splat2(-1.4426950408889634f);                      // -u^2 * log2(e)
+    e = mk2(ex2_fast(lo2(a)), ex2_fast(hi2(a)));
+    f2 p = fma2(splat2(-1.061405429f), t, splat2(1.453152027f));          // negated polynomial: r = 1 - poly(t) * e
+    p = fma2(p, t, splat2(-1.421413741f));
+    p = fma2(p, t, splat2(0.284496736f));
+    p = fma2(p, t, splat2(-0.254829592f));
+    erf = copysign2(fma2(p*t, e, splat2(1.f)), u);
+}
+__device__ __forceinline__ f2 gelu2(f2 x) {
+    f2 erf, e;
+    erf_exp2(x, erf, e);
+    const f2 hx = x*splat2(0.5f);
+    return fma2(hx, erf, hx);
+}
+__device__ __forceinline__ f2 gelu_grad2(f2 s) {  // Phi(s) + s*phi(s)
+    f2 erf, e;
+    erf_exp2(s, erf, e);
+    return fma2(s*splat2(0.3989422804014327f), e, fma2(splat2(0.5f), erf, splat2(0.5f)));
+}
+__device__ __forceinline__ void gelu4(float4& x) {
+    const f2 a = gelu2(mk2(x.x, x.y)), b = gelu2(mk2(x.z, x.w));
+    x = make_float4(lo2(a), hi2(a), lo2(b), hi2(b));
+}
+__device__ __forceinline__ void mul_gelu_grad4(float4& x, const float4 s) {
+    const f2 a = mk2(x.x, x.y)*gelu_grad2(mk2(s.x, s.y)), b = mk2(x.z, x.w)*gelu_grad2(mk2(s.z, s.w));
+    x = make_float4(lo2(a), hi2(a), lo2(b), hi2(b));
 }
 
 // Output row -> element offset. Plain GEMM / convolution outputs are row-major (row*ldc). A stride-s data gradient is computed
@@ -77,12 +121,14 @@ __device__ __forceinline__ float4 epilogue_rows(const stv_gemm_epi& e, float* __
         float4 x = *(const float4*)(xs + (4*i + rsub)*EPI_LD + cq);
         x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
         if (aux) *(float4*)(e.aux + o) = x;
-        if (act) { x.x = act_fwd(act, x.x); x.y = act_fwd(act, x.y); x.z = act_fwd(act, x.z); x.w = act_fwd(act, x.w); }
+        if (ACT == STV_ACT_GELU) gelu4(x);
+        else if (act) { x.x = act_fwd(act, x.x); x.y = act_fwd(act, x.y); x.z = act_fwd(act, x.z); x.w = act_fwd(act, x.w); }
         if (gam) { x.x *= gg.x; x.y *= gg.y; x.z *= gg.z; x.w *= gg.w; }
         if (res) { x.x += pre[i].x; x.y += pre[i].y; x.z += pre[i].z; x.w += pre[i].w; }
         if (DACT != STV_ACT_NONE && e.dact_src) {
             const float4 s = res ? __ldg((const float4*)(e.dact_src + o)) : pre[i];
-            x.x *= act_bwd(dact, s.x); x.y *= act_bwd(dact, s.y); x.z *= act_bwd(dact, s.z); x.w *= act_bwd(dact, s.w);
+            if (DACT == STV_ACT_GELU) mul_gelu_grad4(x, s);
+            else { x.x *= act_bwd(dact, s.x); x.y *= act_bwd(dact, s.y); x.z *= act_bwd(dact, s.z); x.w *= act_bwd(dact, s.w); }
         }
         if (accm) tc::red_add_v4(C + o, x.x, x.y, x.z, x.w);
         else *(float4*)(C + o) = x;
