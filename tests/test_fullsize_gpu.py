@@ -1,0 +1,65 @@
+"""GPU, BASELINE.json's FULL sizes (where the CPU oracle would take minutes): size-independent properties of the loss stack.
+
+  * two independent implementations agree: the lean backward fed by the forward's coefficient planes vs. the self-contained
+    backward that re-warps and rebuilds the SSIM sums (different kernels, different tiling, different data flow);
+  * linearity of the backward in the incoming gradient; bit-identical repeat runs (fixed-order reductions, no float atomics);
+  * the decision bytes and the loss value do not depend on whether the coefficient planes are requested;
+  * the resampling kernel against ATen's at the augmentation's real sizes.
+Shapes: configs[2] (b=8, n=2, S=4, 384x640), configs[3] (n=4), configs[4] (b=4, 512x1024)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CASES = {'config3': (8, 2, 4, (384, 640)), 'config4_n4': (4, 4, 4, (384, 640)), 'config5_hr': (4, 2, 4, (512, 1024))}
+
+
+def _run(d, coef: bool, scale: float = 1.0):
+    from slowtv_monodepth_b200 import functional as F_, geometry as G
+    F_.PHOTO_COEF = coef
+    try:
+        disps = [x.clone().requires_grad_() for x in d['disps']]
+        aa, t, K = (d[k].clone().requires_grad_() for k in ('aa', 't', 'K'))
+        H, W = d['imgs'].shape[-2:]
+        depths = [G.upsample_to_depth(x, (H, W), 0.1, 100.)[1] for x in disps]
+        loss, sel, _ = F_.photo_loss(depths, d['imgs'], d['supp_imgs'], G.T_from_AAt(aa, t), K, noise_seed=7)
+        (loss*scale).backward()
+        torch.cuda.synchronize()
+        return loss.detach(), sel, [x.grad for x in disps], aa.grad, t.grad, K.grad
+    finally:
+        F_.PHOTO_COEF = True
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_photometric_pair_properties_at_full_size(name):
+    from slowtv_monodepth_b200 import synthetic as syn
+    b, n, S, shape = CASES[name]
+    d = syn.make_loss_inputs(b, n, S, shape, seed=3)
+    d = {k: ([x.cuda() for x in v] if isinstance(v, list) else v.cuda()) for k, v in d.items()}
+    rel = lambda a, r: ((a.double() - r.double()).norm()/r.double().norm().clamp(min=1e-30)).item()
+
+    lean, full = _run(d, True), _run(d, False)
+    assert torch.isfinite(lean[0]) and torch.equal(lean[0], full[0]) and torch.equal(lean[1], full[1])   # same forward, same decisions
+    for s in range(S): assert rel(lean[2][s], full[2][s]) < 1e-4, (s, rel(lean[2][s], full[2][s]))       # d/d disparity (the parity bar; measured 3e-5: rcp.approx vs. exact division in the SSIM coefficients)
+    for j, what in ((3, 'aa'), (4, 't'), (5, 'K')): assert rel(lean[j], full[j]) < 1e-4, (what, rel(lean[j], full[j]))
+
+    again = _run(d, True)
+    for j in (3, 4, 5): assert torch.equal(lean[j], again[j])                                               # deterministic
+    for s in range(S): assert torch.equal(lean[2][s], again[2][s])
+
+    twice = _run(d, True, scale=2.0)                                                                        # linear in dL/dloss
+    for s in range(S): assert rel(twice[2][s], 2*lean[2][s]) < 1e-6
+    assert rel(twice[4], 2*lean[4]) < 1e-6
+
+
+def test_resample_at_augmentation_sizes():
+    import torch.nn.functional as F
+    from slowtv_monodepth_b200 import aspect_ratio as AR, functional as F_
+    x = torch.rand(16, 3, 384, 640, device='cuda')
+    crop = AR.center_crop(x, (245, 588))
+    assert crop.shape == (16, 3, 245, 588)
+    out = F_.resample_bilinear(crop, (256, 704), mode='interp')
+    want = F.interpolate(crop, size=(256, 704), mode='bilinear', align_corners=False)
+    assert (out - want).abs().max().item() < 1e-4
+    # the crop samples strictly inside the image: every output is a convex combination of inputs
+    assert crop.min().item() >= 0 and crop.max().item() <= 1
