@@ -239,6 +239,13 @@ int stv_act_bwd(long long M, int C, const float* da, const float* y, int act, fl
 int stv_resample_bilinear(long long P, int H, int W, int oh, int ow, float ax, float bx, float ay, float by, int mode,
                           const float* src, float* dst, void* stream);
 
+/* Logging statistics (src/core/trainer.py:486-503 `summarize_depth`: `.mean().item()` / `.std().item()` per up-sampled
+ * disparity / depth map, 16 host syncs per logging step): mean and unbiased standard deviation of k <= STV_STATS_MAX device
+ * tensors in one launch pair. out (k,2) fp32 = {mean, std}; ws >= stv_mean_std_workspace_bytes(k). No host synchronisation. */
+#define STV_STATS_MAX 16
+size_t stv_mean_std_workspace_bytes(int k);
+int stv_mean_std(int k, const float* const* tensors, const long long* counts, float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* out[c] += sum_m x[m*ld + c] */
 int stv_colsum(long long M, int C, long long ld, const float* x, float* out, void* stream);
 /* Parameter gradients behind the ConvNeXt layer-scale (timm ConvNeXtBlock: x + gamma * fc2(...), encoder built at

@@ -81,6 +81,8 @@ _SIGNATURES = {
     'stv_act_bwd': (C.c_int, [C.c_longlong, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     'stv_colsum': (C.c_int, [C.c_longlong, C.c_int, C.c_longlong, _P, _P, _P]),
     'stv_resample_bilinear': (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _P, _P, _P]),
+    'stv_mean_std_workspace_bytes': (C.c_size_t, [C.c_int]),
+    'stv_mean_std': (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
     'stv_ls_tail': (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'stv_rowscale': (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P]),
     'stv_bn_workspace_bytes': (C.c_size_t, [C.c_int]),

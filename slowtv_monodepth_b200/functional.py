@@ -860,6 +860,28 @@ def resample_bilinear(x: Tensor, size: tuple[int, int], *, mode: str, ax: float 
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# Logging statistics
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def mean_std(tensors: list[Tensor]) -> Tensor:
+    """(k,2) device tensor {mean, unbiased std} of k fp32 device tensors in one launch pair (include/stv.h: stv_mean_std). No sync:
+    read it back with ONE `.cpu()` when logging (the reference's summarize_depth syncs once per statistic, trainer.py:486-503)."""
+    if not tensors: raise ValueError('mean_std: no tensors')
+    L.require_cuda(*tensors, what='mean_std')
+    ts = [_f32c(t) for t in tensors]
+    dev = ts[0].device
+    with torch.cuda.device(dev):
+        out = torch.empty((len(ts), 2), dtype=torch.float32, device=dev)
+        for k0 in range(0, len(ts), 16):
+            part = ts[k0:k0 + 16]
+            ws = _ws(L.lib().stv_mean_std_workspace_bytes(len(part)), dev)
+            counts = (C.c_longlong*len(part))(*[t.numel() for t in part])
+            L.check(L.lib().stv_mean_std(len(part), L.ptr_array(part), counts, out.data_ptr() + k0*8, L.ptr(ws), ws.numel(), L.stream()),
+                    'stv_mean_std')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # Optimiser step
 # ---------------------------------------------------------------------------------------------------------------------
 @torch.no_grad()

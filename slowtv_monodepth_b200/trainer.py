@@ -21,7 +21,7 @@ from .losses import ReconstructionLoss
 from .networks import DepthNet, PoseNet
 from .regularizers import SmoothReg
 
-__all__ = ['MonoDepthStep', 'GraphedTrainStep', 'ShapeCachedTrainStep', 'default_cfg']
+__all__ = ['MonoDepthStep', 'GraphedTrainStep', 'ShapeCachedTrainStep', 'StepSummary', 'summarize', 'default_cfg']
 
 NET_REG = {'depth': DepthNet, 'pose': PoseNet}
 LOSS_REG = {'img_recon': ReconstructionLoss, 'disp_smooth': SmoothReg}
@@ -114,6 +114,39 @@ class MonoDepthStep(nn.Module):
         fwd = self.forward_postprocess(fwd, x, y)
         loss, loss_dict = self.forward_loss(fwd, x, y, want_maps=want_maps or mode != 'train')
         return loss, loss_dict, fwd
+
+
+class StepSummary:
+    """Names + ONE device vector of the step's logging scalars; `to_host()` is the only synchronisation."""
+    def __init__(self, names: list[str], values: Tensor): self.names, self.values = names, values
+
+    def to_host(self) -> dict[str, float]:
+        return dict(zip(self.names, self.values.detach().cpu().tolist()))
+
+
+@torch.no_grad()
+def summarize(fwd: dict) -> StepSummary:
+    """The reference's `summarize_depth` / `summarize_pose` / `summarize_K` (src/core/trainer.py:486-529, same keys) without their
+    ~28 `.item()` synchronisations: the eight full-resolution maps go through one multi-tensor kernel (stv_mean_std), the
+    pose / intrinsics statistics are a handful of tiny device ops, and everything lands in one vector."""
+    names, parts = [], []
+    maps, map_names = [], []
+    for key in ('disp', 'depth'):
+        for k, v in fwd.get(f'{key}_up', {}).items():
+            maps.append(v); map_names += [f'{key}_mean_{k}', f'{key}_std_{k}']
+    if maps:
+        names += map_names; parts.append(F_.mean_std(maps).flatten())
+    for k, v in fwd.items():
+        if not (isinstance(k, str) and k.startswith('T_')): continue
+        ts = v[..., :3, 3].pow(2).sum(-1).sqrt()
+        tr = v[..., :3, :3].diagonal(dim1=-2, dim2=-1).mean(dim=-1)
+        names += [f'{k}_t_mean', f'{k}_t_std', f'{k}_R_mean', f'{k}_R_std']
+        parts.append(torch.stack([ts.mean(), ts.std(), tr.mean(), tr.std()]))
+    if 'K' in fwd and 'fs' in fwd:
+        names += ['fx', 'fy', 'cx', 'cy']
+        parts.append(torch.stack([fwd['fs'][..., 0].mean(), fwd['fs'][..., 1].mean(), fwd['cs'][..., 0].mean(), fwd['cs'][..., 1].mean()]))
+    vals = torch.cat([p.float() for p in parts]) if parts else torch.empty(0)
+    return StepSummary(names, vals)
 
 
 class GraphedTrainStep:

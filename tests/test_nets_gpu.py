@@ -132,3 +132,30 @@ def test_maxpool_matches_torch(shape):
     yc = F_.maxpool3x3s2(xc)
     yc.backward(gy.cuda())
     assert torch.equal(yc.cpu(), yr.detach()) and torch.allclose(xc.grad.cpu(), xr.grad, atol=1e-6)
+
+
+@pytest.mark.parametrize('shapes', [[(8, 1, 384, 640)]*8, [(3, 1, 37, 53), (1, 5), (2, 3, 4, 5, 6)], [(1, 1, 33, 65)]*17])
+def test_mean_std_matches_torch(shapes):
+    """stv_mean_std (the logging statistics of trainer.py:486-503) vs torch.mean / torch.std (unbiased), incl. a map far from zero."""
+    from slowtv_monodepth_b200 import functional as F_
+    torch.manual_seed(0)
+    ts = [torch.rand(s, device='cuda')*(1 + 30*(i % 3)) + 40*(i % 2) for i, s in enumerate(shapes)]
+    got = F_.mean_std(ts).cpu().double()
+    want = torch.tensor([[t.double().mean().item(), t.double().std().item()] for t in ts], dtype=torch.float64)
+    assert torch.allclose(got, want, rtol=2e-6, atol=1e-7), (got - want).abs().max()
+
+
+def test_step_summary_has_the_reference_keys_and_values():
+    from slowtv_monodepth_b200 import synthetic as syn
+    from slowtv_monodepth_b200.trainer import MonoDepthStep, default_cfg, summarize
+    torch.manual_seed(0)
+    model = MonoDepthStep(default_cfg('resnet18', 'resnet18', learn_K=True)).cuda().train()
+    batch = syn.make_batch(2, 2, (64, 96), seed=0, device='cuda')
+    with torch.no_grad(): _, _, fwd = model.step(batch)
+    got = summarize(fwd).to_host()
+    for s in range(4):
+        for key in ('disp', 'depth'):
+            v = fwd[f'{key}_up'][s]
+            assert abs(got[f'{key}_mean_{s}'] - v.mean().item()) <= 1e-5*abs(v.mean().item()) + 1e-7
+            assert abs(got[f'{key}_std_{s}'] - v.std().item()) <= 1e-4*abs(v.std().item()) + 1e-7
+    assert {'T_-1_t_mean', 'T_1_R_std', 'fx', 'cy'} <= set(got)
