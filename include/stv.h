@@ -278,10 +278,10 @@ int stv_maxpool3x3s2_bwd(int N, int H, int W, int C, const float* dy, const uint
 /* Disparity heads: y (N,H,W) = act(bias + reflect-padded 3x3 convolution of x (N,H,W,C) with w (3,3,C)) — `outconv_i` + sigmoid of
  * the Monodepth decoder (src/networks/decoders/monodepth.py:66-69,86-87). One output channel = a dot product per pixel:
  * memory-bound, CUDA cores. C a power of two in [4,128]. Backward: dz = da*act'(y); dx (N,H,W,C) (nullable, overwritten);
- * dw (3,3,C) and db (1) (nullable, atomically accumulated). */
+ * dw (3,3,C) and db (1) (nullable, atomically accumulated); dz_ws: N*H*W floats of scratch (receives dz). */
 int stv_head3x3_fwd(int N, int H, int W, int C, const float* x, const float* w, const float* bias, int act, float* y, void* stream);
 int stv_head3x3_bwd(int N, int H, int W, int C, const float* x, const float* w, const float* da, const float* y, int act, float* dx,
-                    float* dw, float* db, void* stream);
+                    float* dw, float* db, float* dz_ws, void* stream);
 
 /* Batched 4x4 inverse B = A^-1 (n matrices, row-major) and its backward gA = -B^T gB B^T: `K.inverse()` of ViewSynth.forward
  * (src/tools/geometry.py:383) and `T.inverse()` of the backward poses (src/core/trainer.py:253). Stream-ordered, no host sync

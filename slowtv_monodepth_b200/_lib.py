@@ -91,7 +91,7 @@ _SIGNATURES = {
     'stv_maxpool3x3s2_fwd': (C.c_int, [C.c_int]*4 + [_P, _P, _P, _P]),
     'stv_maxpool3x3s2_bwd': (C.c_int, [C.c_int]*4 + [_P, _P, _P, _P]),
     'stv_head3x3_fwd': (C.c_int, [C.c_int]*4 + [_P, _P, _P, C.c_int, _P, _P]),
-    'stv_head3x3_bwd': (C.c_int, [C.c_int]*4 + [_P, _P, _P, _P, C.c_int, _P, _P, _P, _P]),
+    'stv_head3x3_bwd': (C.c_int, [C.c_int]*4 + [_P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
     'stv_inv4x4': (C.c_int, [C.c_int, _P, _P, _P]),
     'stv_inv4x4_bwd': (C.c_int, [C.c_int, _P, _P, _P, _P]),
     'stv_adamw_step': (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_size_t] + [C.c_float]*6 + [C.c_int, _P]),

@@ -719,8 +719,9 @@ class _Head3x3(torch.autograd.Function):
             dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
             dw = torch.zeros_like(w_phys) if ctx.needs_input_grad[1] else None
             db = torch.zeros(1, dtype=torch.float32, device=x.device) if ctx.has_bias and dw is not None else None
+            dz = torch.empty((N, H, W), dtype=torch.float32, device=x.device)  # scratch: dA * act'(y), shared by both gradient kernels
             L.check(L.lib().stv_head3x3_bwd(N, H, W, Cc, L.ptr(x), L.ptr(w_phys), L.ptr(dA), L.ptr(y), L.ACT[ctx.act], L.ptr(dx), L.ptr(dw),
-                                            L.ptr(db), L.stream()), 'stv_head3x3_bwd')
+                                            L.ptr(db), L.ptr(dz), L.stream()), 'stv_head3x3_bwd')
         return dx, None if dw is None else dw.permute(0, 3, 1, 2), db, None
 
 

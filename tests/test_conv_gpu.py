@@ -108,7 +108,8 @@ def test_activation_forward_backward(act):
         assert err < 2e-3, f'{name}: rel err {err.item():.3e}'
 
 
-@pytest.mark.parametrize('N,H,W,C', [(2, 10, 14, 16), (1, 7, 9, 32), (3, 6, 8, 64), (2, 5, 6, 128), (1, 33, 65, 16)])
+@pytest.mark.parametrize('N,H,W,C', [(2, 10, 14, 16), (1, 7, 9, 32), (3, 6, 8, 64), (2, 5, 6, 128), (1, 33, 65, 16), (1, 3, 3, 16), (2, 4, 5, 8),
+                                     (1, 2, 2, 16), (2, 64, 300, 16), (1, 24, 37, 128)])
 def test_head3x3_matches_conv2d(N, H, W, C):
     """stv_head3x3_fwd/bwd (one-channel reflect-padded 3x3 conv + sigmoid on the CUDA cores) vs torch in float64."""
     gen = torch.Generator(device='cuda').manual_seed(C + H)
