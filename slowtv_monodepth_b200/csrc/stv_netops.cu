@@ -118,8 +118,20 @@ __global__ void __launch_bounds__(256) colred4_kernel(long long M, int C, int ro
     float4 acc[Op::NACC];
 #pragma unroll
     for (int k = 0; k < Op::NACC; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g < G)
-        for (long long r = r0 + (long long)wid*rpw + rsub; r < r1; r += 8*rpw) op.apply((size_t)r*G + g, g*4, acc);
+    if (g < G) {
+        // four rows per trip in straight-line code: their loads are independent (read-only path), so a thread keeps 4-12 requests in
+        // flight instead of 1-3 — these reductions were latency-bound at ~2.5x their HBM time (BatchNorm statistics / backward
+        // sums, r1f profile). A `#pragma unroll` alone keeps the bound check between the copies and hoists nothing.
+        const long long step = 8*rpw;
+        long long r = r0 + (long long)wid*rpw + rsub;
+        for (; r + 3*step < r1; r += 4*step) {
+            op.apply((size_t)r*G + g, g*4, acc);
+            op.apply((size_t)(r + step)*G + g, g*4, acc);
+            op.apply((size_t)(r + 2*step)*G + g, g*4, acc);
+            op.apply((size_t)(r + 3*step)*G + g, g*4, acc);
+        }
+        for (; r < r1; r += step) op.apply((size_t)r*G + g, g*4, acc);
+    }
     if (!wide)  // lanes with the same group (G apart) -> lane < G
         for (int o = G; o < 32; o <<= 1) {
 #pragma unroll
