@@ -194,6 +194,43 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(long long P, int C, 
     if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
 }
 
+// Register-resident variant (C % 4 == 0, C <= 128*NV): a lane holds its NV float4 of the row, so the row is read from memory ONCE
+// (all loads issued up front) and the three passes (mean, variance, normalise) run on registers.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(long long P, int C, float eps, const float* __restrict__ x,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= P) return;
+    const int c4 = C >> 2;
+    const float4* xr = (const float4*)(x + row*C);
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = lane + 32*i < c4 ? __ldg(xr + lane + 32*i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mu = warp_sum(s)/(float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (lane + 32*i < c4) {
+            const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+            q += fmaf(a, a, b*b) + fmaf(c, c, d*d);
+        }
+    const float rs = rsqrtf(warp_sum(q)/(float)C + eps);
+    float4* yr = (float4*)(y + row*C);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (lane + 32*i < c4) {
+            const float4 g = __ldg((const float4*)gamma + lane + 32*i), b = __ldg((const float4*)beta + lane + 32*i);
+            yr[lane + 32*i] = make_float4(fmaf((v[i].x - mu)*rs, g.x, b.x), fmaf((v[i].y - mu)*rs, g.y, b.y),
+                                          fmaf((v[i].z - mu)*rs, g.z, b.z), fmaf((v[i].w - mu)*rs, g.w, b.w));
+        }
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+}
+
 // dx = rstd * (dy*gamma - mean_c(dy*gamma) - xhat * mean_c(dy*gamma*xhat));  dgamma = sum_rows dy*xhat;  dbeta = sum_rows dy.
 // Each warp walks `rows` (<= LN_ROWS) consecutive rows and keeps its lanes' dgamma/dbeta slices in registers (C <= 32*LN_MAXPL).
 // `rows` shrinks for short matrices (the deep ConvNeXt stages have only 2-8 k rows) so that the grid still covers the SMs.
@@ -326,7 +363,14 @@ extern "C" int stv_layernorm_fwd(long long P, int C, const float* x, const float
     STV_REQUIRE(x && gamma && beta && y && mean && rstd, "stv_layernorm_fwd: NULL pointer");
     const long long blocks = (P + 7)/8;
     STV_REQUIRE(blocks < (1ll << 31), "stv_layernorm_fwd: too many rows");
-    layernorm_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P, C, eps, x, gamma, beta, y, mean, rstd);
+    const bool vec = C % 4 == 0 && C <= 1024 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
+    const int nv = (C/4 + 31)/32;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec && nv <= 1) layernorm_fwd_vec_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(P, C, eps, x, gamma, beta, y, mean, rstd);
+    else if (vec && nv == 2) layernorm_fwd_vec_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(P, C, eps, x, gamma, beta, y, mean, rstd);
+    else if (vec && nv <= 4) layernorm_fwd_vec_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(P, C, eps, x, gamma, beta, y, mean, rstd);
+    else if (vec && nv <= 8) layernorm_fwd_vec_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(P, C, eps, x, gamma, beta, y, mean, rstd);
+    else layernorm_fwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(P, C, eps, x, gamma, beta, y, mean, rstd);
     count_launch();
     return check_launch("layernorm_fwd_kernel");
 }

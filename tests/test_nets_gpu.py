@@ -30,7 +30,7 @@ def test_dwconv7_matches_oracle(shape):
     assert U.rel(xc.grad, xr.grad) < 1e-5 and U.rel(wc.grad, wr.grad) < 1e-5 and U.rel(bc.grad, br.grad) < 1e-5
 
 
-@pytest.mark.parametrize('P,C', [(100, 96), (37, 33), (64, 768), (50, 1024), (9, 160)])
+@pytest.mark.parametrize('P,C', [(100, 96), (37, 33), (64, 768), (50, 1024), (9, 160), (33, 192), (21, 384), (17, 512), (40, 4)])
 def test_layernorm_matches_oracle(P, C):
     from slowtv_monodepth_b200 import functional as F_
     g = torch.Generator().manual_seed(1)
