@@ -4,8 +4,10 @@
 // committing with .multicast::cluster to both CTAs. It answers, before the product kernel is touched:
 //   (1) do our UMMA descriptors / instruction descriptor carry over to M = 256, (2) which CTA holds which half of B,
 //   (3) does the leader-barrier transaction accounting (peer CTA's TMA -> leader's mbarrier) behave as CUTLASS documents.
+//   (4) with `stages` < K/32: does a smem ring shared by the pair work when the leader's multicast commit releases stage s in BOTH
+//       CTAs (each producer waits on its own empty[s]; the leader alone posts expect_tx for the bytes of both CTAs).
 // STATUS: compiles for sm_100a; NOT YET RUN (written after the round-1 GPU budget was spent). Expected output: "max |err|" ~1e-3
-// (TF32-exact inputs: expect 0) and "mismatches=0". usage: timeout 20 ./cta2_gemm_probe [N=128] [K=64]   (ALWAYS under a timeout: a
+// (TF32-exact inputs: expect 0) and "mismatches=0". usage: timeout 20 ./cta2_gemm_probe [N=128] [K=64] [stages=K/32]   (ALWAYS under a timeout: a
 // wrong barrier protocol hangs the pair)
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -50,21 +52,21 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int BK = 32, THREADS = 128, MAXKB = 8;
+constexpr int BK = 32, THREADS = 128, MAXST = 8;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS)
-cta2_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C, int N, int K) {
+cta2_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C, int N, int K, int stages) {
     extern __shared__ uint8_t raw[];
     uint8_t* smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int kb_total = K/BK, halfN = N/2;
     const uint32_t a_bytes = 128*BK*4, b_bytes = (uint32_t)halfN*BK*4, stage = a_bytes + b_bytes;
-    __shared__ uint64_t full[MAXKB], done;
+    __shared__ uint64_t full[MAXST], empty[MAXST], done;
     __shared__ uint32_t tmem_slot;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kb_total; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(&done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -78,32 +80,40 @@ cta2_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
 
+    // Producer (thread 0 of BOTH CTAs): this CTA's 128 rows of A and N/2 rows of B per k-block into ring stage kb % stages.
+    // The stage is free again once the leader's multicast commit has arrived on THIS CTA's empty[s].
     if (warp == 0 && lane == 0) {
-        // producer (both CTAs): this CTA's 128 rows of A and N/2 rows of B for every k-block (no stage reuse in the probe)
         for (int kb = 0; kb < kb_total; ++kb) {
-            if (rank == 0) mbar_expect_tx(&full[kb], 2*stage);   // bytes of BOTH CTAs arrive on the leader's barrier
-            uint8_t* a = smem + (size_t)kb*stage;
-            tma_load_2d_2sm(a, &tmA, &full[kb], kb*BK, (int)rank*128);
-            tma_load_2d_2sm(a + a_bytes, &tmB, &full[kb], kb*BK, (int)rank*halfN);
+            const int s = kb % stages;
+            mbar_wait(&empty[s], (uint32_t)((kb/stages) & 1) ^ 1u);   // first pass: passes immediately (fresh barrier, parity 1)
+            if (rank == 0) mbar_expect_tx(&full[s], 2*stage);          // bytes of BOTH CTAs arrive on the leader's barrier
+            uint8_t* a = smem + (size_t)s*stage;
+            tma_load_2d_2sm(a, &tmA, &full[s], kb*BK, (int)rank*128);
+            tma_load_2d_2sm(a + a_bytes, &tmB, &full[s], kb*BK, (int)rank*halfN);
         }
-        if (rank == 0) {   // leader: MMA for the pair
-            const uint32_t idesc = idesc_tf32(256, N);
-            for (int kb = 0; kb < kb_total; ++kb) {
-                mbar_wait(&full[kb], 0);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a = smem_u32(smem + (size_t)kb*stage), b = a + a_bytes;
-                for (int k8 = 0; k8 < BK/8; ++k8) {
-                    const uint64_t da = umma_desc_kmajor(a, k8), db = umma_desc_kmajor(b, k8);
-                    const uint32_t accum = (kb > 0 || k8 > 0) ? 1u : 0u;
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                                 ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
-                }
+    }
+    // MMA issuer (thread 32 of the LEADER): separate warp, so that the producer above can run ahead through the ring
+    if (warp == 1 && lane == 0 && rank == 0) {
+        const uint32_t idesc = idesc_tf32(256, N);
+        for (int kb = 0; kb < kb_total; ++kb) {
+            const int s = kb % stages;
+            mbar_wait(&full[s], (uint32_t)(kb/stages) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a = smem_u32(smem + (size_t)s*stage), b = a + a_bytes;
+            for (int k8 = 0; k8 < BK/8; ++k8) {
+                const uint64_t da = umma_desc_kmajor(a, k8), db = umma_desc_kmajor(b, k8);
+                const uint32_t accum = (kb > 0 || k8 > 0) ? 1u : 0u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
             }
-            // arrive on `done` in BOTH CTAs once every MMA above has completed
+            // release stage s in BOTH CTAs once these MMAs have read it
             asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                         ::"r"(smem_u32(&done)), "h"((uint16_t)0b11) : "memory");
+                         ::"r"(smem_u32(&empty[s])), "h"((uint16_t)0b11) : "memory");
         }
+        // arrive on `done` in BOTH CTAs once every MMA above has completed
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&done)), "h"((uint16_t)0b11) : "memory");
     }
     __syncwarp();
     // epilogue (both CTAs): warp w drains TMEM lanes 32w..32w+31 = rows rank*128 + 32w + lane
@@ -144,7 +154,9 @@ static int make_map(CUtensorMap* tm, const float* base, int rows, int cols, int 
 
 int main(int argc, char** argv) {
     const int N = argc > 1 ? atoi(argv[1]) : 128, K = argc > 2 ? atoi(argv[2]) : 64, M = 256;
-    if (N % 32 || N > 256 || K % BK || K/BK > MAXKB) { printf("need N %% 32 == 0, N <= 256, K %% 32 == 0, K <= %d\n", BK*MAXKB); return 1; }
+    int stages = argc > 3 ? atoi(argv[3]) : K/BK;
+    if (stages > MAXST) stages = MAXST;
+    if (N % 32 || N > 256 || K % BK || stages < 1) { printf("need N %% 32 == 0, N <= 256, K %% 32 == 0, stages >= 1\n"); return 1; }
     std::vector<float> A((size_t)M*K), B((size_t)N*K), Cc((size_t)M*N);
     srand(1);
     auto tf32ish = [] { return (float)((rand() % 17) - 8)/8.f; };   // exactly representable in TF32: the product must be exact
@@ -156,11 +168,11 @@ int main(int argc, char** argv) {
     cudaMemset(dC, 0xFF, Cc.size()*4);
     CUtensorMap tmA, tmB;
     if (make_map(&tmA, dA, M, K, 128) || make_map(&tmB, dB, N, K, N/2)) { printf("tensor map encode failed\n"); return 1; }
-    const size_t smem = (size_t)(K/BK)*(128*BK*4 + (N/2)*BK*4) + 1024;
+    const size_t smem = (size_t)stages*(128*BK*4 + (N/2)*BK*4) + 1024;
     cudaFuncSetAttribute(cta2_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cta2_gemm<<<2, THREADS, smem>>>(tmA, tmB, dC, N, K);
+    cta2_gemm<<<2, THREADS, smem>>>(tmA, tmB, dC, N, K, stages);
     const cudaError_t e = cudaDeviceSynchronize();
-    printf("M=256 N=%d K=%d: run=%s ", N, K, cudaGetErrorString(e));
+    printf("M=256 N=%d K=%d stages=%d: run=%s ", N, K, stages, cudaGetErrorString(e));
     if (e == cudaSuccess) {
         cudaMemcpy(Cc.data(), dC, Cc.size()*4, cudaMemcpyDeviceToHost);
         int bad = 0; double worst = 0;
