@@ -26,6 +26,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.stv_version() >= 100
 
 
+def test_library_exports_nothing_undeclared():
+    """The reverse direction: every stv_* function the shared library defines is part of the documented ABI (include/stv.h)."""
+    import shutil
+    import subprocess
+    from slowtv_monodepth_b200 import _build
+    nm = shutil.which('nm')
+    if nm is None: pytest.skip('binutils nm not available')
+    out = subprocess.run([nm, '-D', '--defined-only', str(_build.LIB)], capture_output=True, text=True, check=True).stdout
+    exported = sorted({ln.split()[2] for ln in out.splitlines() if len(ln.split()) == 3 and ln.split()[1] == 'T' and ln.split()[2].startswith('stv_')})
+    assert exported == _declared()
+
+
 def test_invalid_arguments_are_rejected_without_a_gpu():
     from slowtv_monodepth_b200 import _lib as L
     lib = L.lib()
