@@ -17,7 +17,40 @@ import torch.nn as nn
 from . import _lib as L_
 from . import functional as F_
 
-__all__ = ['FlatAdamW']
+__all__ = ['FlatAdamW', 'LRSchedule']
+
+
+class LRSchedule:
+    """Per-epoch learning rate of the reference's chained schedulers, in closed form.
+
+    Reference: `configure_optimizers` (src/core/trainer.py:85-94) wraps every entry of `cfg['scheduler']` (src/tools/parsers.py:246-269;
+    KBR: `steplr` {step_size 40, gamma 0.1} + `linear` {start_factor 0.1, total_iters 4}, cfg/kbr/default.yaml:97-103) in one
+    `torch.optim.lr_scheduler.ChainedScheduler`, stepped once per epoch by Lightning. The chained recursive updates multiply out
+    to  lr(e) = base * gamma^floor(e/step_size) * (start + (end - start) * min(e, total_iters)/total_iters).
+    FlatAdamW's learning rate is a host scalar handed to the kernel, so `apply(opt, epoch)` is all a training loop needs."""
+    def __init__(self, base_lr: float, cfg: dict | None):
+        self.base_lr, self.factors = float(base_lr), []
+        for name, kw in (cfg or {}).items():
+            if kw is None: continue
+            if name == 'steplr':
+                step, gamma = int(kw['step_size']), float(kw.get('gamma', 0.1))
+                if step <= 0: raise ValueError(f'steplr: step_size must be positive (got {step})')
+                self.factors.append(lambda e, step=step, gamma=gamma: gamma**(e//step))
+            elif name == 'linear':
+                start, end, total = float(kw.get('start_factor', 1/3)), float(kw.get('end_factor', 1.0)), int(kw.get('total_iters', 5))
+                if not 0 < start <= 1 or not 0 <= end <= 1: raise ValueError('linear: factors must lie in (0, 1] / [0, 1]')
+                self.factors.append(lambda e, start=start, end=end, total=total: start + (end - start)*min(e, total)/total)
+            else:
+                raise KeyError(f'Unsupported scheduler "{name}" (steplr | linear).')
+
+    def lr(self, epoch: int) -> float:
+        out = self.base_lr
+        for f in self.factors: out *= f(int(epoch))
+        return out
+
+    def apply(self, opt: 'FlatAdamW', epoch: int) -> float:
+        opt.lr = self.lr(epoch)
+        return opt.lr
 
 
 class FlatAdamW:

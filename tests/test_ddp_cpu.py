@@ -74,3 +74,26 @@ def test_flat_adamw_matches_torch_adamw():
         opt2.zero_grad(); ((m2(x) - y)**2).mean().backward(); opt2.step()
     for (n, a), b in zip(m1.named_parameters(), m2.parameters()):
         assert torch.allclose(a, b, atol=1e-6, rtol=1e-5), n
+
+
+def test_lr_schedule_matches_the_reference_chained_schedulers():
+    """`LRSchedule` (closed form) vs torch's ChainedScheduler([StepLR, LinearLR]) stepped per epoch, as the reference builds it
+    (src/core/trainer.py:85-94 with cfg/kbr/default.yaml's scheduler block)."""
+    import pytest
+    import torch
+    from torch.optim.lr_scheduler import ChainedScheduler, LinearLR, StepLR
+    from slowtv_monodepth_b200.optim import LRSchedule
+    for cfg in ({'steplr': {'step_size': 40, 'gamma': 0.1}, 'linear': {'start_factor': 0.1, 'total_iters': 4}},
+                {'steplr': {'step_size': 3, 'gamma': 0.5}}, {'linear': {'start_factor': 0.25, 'end_factor': 0.75, 'total_iters': 6}}, {}):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.AdamW([p], lr=1e-4)
+        scheds = []
+        if 'steplr' in cfg: scheds.append(StepLR(opt, **cfg['steplr']))
+        if 'linear' in cfg: scheds.append(LinearLR(opt, **cfg['linear']))
+        chained = ChainedScheduler(scheds) if scheds else None
+        ours = LRSchedule(1e-4, cfg)
+        for epoch in range(100):
+            assert ours.lr(epoch) == pytest.approx(opt.param_groups[0]['lr'], rel=1e-9), (cfg, epoch)
+            opt.step()
+            if chained: chained.step()
+    with pytest.raises(KeyError): LRSchedule(1e-4, {'cosine': {}})
