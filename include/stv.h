@@ -62,13 +62,16 @@ size_t stv_photo_coef_bytes(const stv_photo_cfg* cfg);
 /* loss (device scalar) = mean over (S,b,H,W) of the reduced, auto-masked photometric error.
  * depth: S pointers to (b,1,H,W) upsampled depth maps; tgt (b,3,H,W); supp (n,b,3,H,W); T (n,b,4,4); K, Kinv (b,4,4);
  * noise: NULL or (S,b,H,W) standard-normal samples replacing randn_like (reconstruction.py:72);
+ * noise_step: NULL or a DEVICE counter: when the noise is drawn in-kernel (noise == NULL, noise_seed != 0) the effective seed is
+ *   noise_seed + *noise_step and the call advances *noise_step by one, stream-ordered after its last reader — a captured CUDA
+ *   graph therefore draws fresh noise on every replay, as torch.randn_like does every step;
  * sel (S,b,H,W) u8: per-pixel decision (support index | STV_SEL_STATIC | STV_SEL_MEAN), consumed by the backward;
  * warp0: NULL or (n,b,3,H,W) warped support frames at scale 0 (handlers.py:66);
  * coef: NULL, or (use_min only) stv_photo_coef_bytes() of device memory that receives, per (scale, pixel), the nine
  *   numbers d SSIMError_c / d(sum x, sum x^2, sum xy) of the support frame the pixel selected (undefined where the
  *   static frame won; `sel` masks them): what autograd would keep of photometric.py:40-50 for the backward pass. */
 int stv_photo_fwd(const stv_photo_cfg* cfg, const float* const* depth, const float* tgt, const float* supp,
-                  const float* T, const float* K, const float* Kinv, const float* noise,
+                  const float* T, const float* K, const float* Kinv, const float* noise, unsigned long long* noise_step,
                   float* loss, uint8_t* sel, float* warp0, float* coef, void* ws, size_t ws_bytes, void* stream);
 
 /* Backward of stv_photo_fwd w.r.t. depth, T, K and Kinv. grad_loss: device scalar dL/dloss.

@@ -37,12 +37,12 @@ class OracleTrainer(nn.Module):
             fwd['K'] = OL.resize_K(K, x['imgs'].shape[-2:])
         return fwd
 
-    def loss(self, batch, noise=None):
+    def loss(self, batch, noise=None, forced_sel=None):
         x, y, _ = batch
         fwd = self.forward_nets(x)
         disps = [fwd['disp'][s] for s in sorted(fwd['disp'])]
         loss, out = OL.loss_stack(disps, y['imgs'], y['supp_imgs'], fwd['Ts'], fwd.get('K', y['K']), self.min_depth,
-                                  self.max_depth, self.w_recon, self.w_smooth, noise=noise)
+                                  self.max_depth, self.w_recon, self.w_smooth, noise=noise, forced_sel=forced_sel)
         return loss, out, fwd
 
     def train_step(self, batch, noise=None):

@@ -54,7 +54,7 @@ _SIGNATURES = {
     'stv_launch_count': (C.c_ulonglong, []),
     'stv_photo_workspace_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
     'stv_photo_coef_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
-    'stv_photo_fwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'stv_photo_fwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     'stv_photo_bwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     'stv_photo_error': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P]),
     'stv_view_synth_fwd': (C.c_int, [C.c_int]*4 + [_P]*9),
@@ -159,7 +159,7 @@ def require_cuda(*ts: torch.Tensor | None, what: str = 'stv') -> None:
         if t is None: continue
         if not t.is_cuda:
             raise StvError(f'{what}: expected CUDA tensors, got a {t.device} tensor (there is no CPU fallback).')
-        if t.dtype != torch.float32 and t.dtype != torch.uint8:
+        if t.dtype not in (torch.float32, torch.uint8, torch.int64):
             raise ValueError(f'{what}: expected float32 tensors, got {t.dtype}.')
 
 

@@ -36,6 +36,7 @@ struct PhotoParams {
     float* g_depth[STV_MAX_SCALES];
     const float *tgt, *supp, *T, *K, *Kinv, *noise, *e0, *grad_loss;
     const uint8_t* sel_in;
+    const unsigned long long* step;  // device-side call counter added to `seed` (advanced by the loss reduction kernel)
     float* partial;   // fwd: one float per block; bwd: n_acc floats per (block, k)
     uint8_t* sel;
     float* warp0;
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(FNT, MINB) photo_fwd_kernel(PhotoParams p) {
 
     // Identity error (+ tie-break noise) of the thread's centres: requested now, consumed after the support-frame loop.
     float e0v[FRUN];
+    const uint64_t seed = p.seed ? p.seed + (p.step ? *p.step : 0ull) : 0ull;
     {
         const int x = min(tx0 + lx, W - 1);
 #pragma unroll
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(FNT, MINB) photo_fwd_kernel(PhotoParams p) {
             if (p.use_automask) {
                 e0v[j] = __ldg(p.e0 + pix);
                 if (p.noise) e0v[j] = fmaf(STV_EPS32, __ldg(p.noise + nidx), e0v[j]);
-                else if (p.seed) e0v[j] = fmaf(STV_EPS32, hash_normal(p.seed, nidx), e0v[j]);
+                else if (seed) e0v[j] = fmaf(STV_EPS32, hash_normal(seed, nidx), e0v[j]);
             }
         }
     }
@@ -486,7 +488,8 @@ __global__ void __launch_bounds__(FNT, MINB) photo_fwd_kernel(PhotoParams p) {
 }
 
 // loss = sum(partials) / count, accumulated in double in a fixed order. One block.
-__global__ void reduce_mean_kernel(const float* __restrict__ partial, int n, double inv_count, float* __restrict__ out) {
+__global__ void reduce_mean_kernel(const float* __restrict__ partial, int n, double inv_count, float* __restrict__ out,
+                                   unsigned long long* step) {
     __shared__ double sh[256];
     double a = 0.0;
     for (int q = threadIdx.x; q < n; q += blockDim.x) a += (double)partial[q];
@@ -496,7 +499,10 @@ __global__ void reduce_mean_kernel(const float* __restrict__ partial, int n, dou
         if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = (float)(sh[0]*inv_count);
+    if (threadIdx.x == 0) {
+        *out = (float)(sh[0]*inv_count);
+        if (step) *step += 1ull;  // every reader of this call's value ran before this kernel (stream order)
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1126,8 +1132,9 @@ extern "C" int stv_photo_error(const stv_photo_cfg* c, const float* pred, const 
 }
 
 extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, const float* tgt, const float* supp,
-                             const float* T, const float* K, const float* Kinv, const float* noise, float* loss,
-                             uint8_t* sel, float* warp0, float* coef, void* ws, size_t ws_bytes, void* stream) {
+                             const float* T, const float* K, const float* Kinv, const float* noise,
+                             unsigned long long* noise_step, float* loss, uint8_t* sel, float* warp0, float* coef, void* ws,
+                             size_t ws_bytes, void* stream) {
     if (int rc = check_cfg(c)) return rc;
     STV_REQUIRE(depth && tgt && supp && T && K && Kinv && loss && sel, "stv_photo_fwd: NULL pointer");
     for (int s = 0; s < c->S; ++s) STV_REQUIRE(depth[s] != nullptr, "stv_photo_fwd: depth[%d] is NULL", s);
@@ -1141,7 +1148,7 @@ extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, 
     fill_params(p, c);
     use_fwd_tiles(p);
     for (int s = 0; s < c->S; ++s) p.depth[s] = depth[s];
-    p.tgt = tgt; p.supp = supp; p.T = T; p.K = K; p.Kinv = Kinv; p.noise = noise;
+    p.tgt = tgt; p.supp = supp; p.T = T; p.K = K; p.Kinv = Kinv; p.noise = noise; p.step = noise_step;
     float* e0 = (float*)ws;
     p.e0 = e0;
     p.partial = (float*)((char*)ws + align256((size_t)c->b*c->H*c->W*sizeof(float)));
@@ -1169,7 +1176,8 @@ extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, 
     count_launch();
     if (int rc = check_launch("photo_fwd_kernel")) return rc;
     const int nblk = tiles*c->b*c->S;
-    reduce_mean_kernel<<<1, 256, 0, st>>>(p.partial, nblk, 1.0/((double)c->S*c->b*c->H*c->W), loss);
+    reduce_mean_kernel<<<1, 256, 0, st>>>(p.partial, nblk, 1.0/((double)c->S*c->b*c->H*c->W), loss,
+                                          (c->use_automask && noise == nullptr && c->noise_seed) ? noise_step : nullptr);
     count_launch();
     return check_launch("reduce_mean_kernel");
 }

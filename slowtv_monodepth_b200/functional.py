@@ -93,13 +93,13 @@ PHOTO_COEF = True  # developer switch (parity tests exercise both backward kerne
 
 class _PhotoLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, cfg: L.PhotoCfg, want_warp: bool, tgt, supp, T, K, Kinv, noise, *depths):
-        L.require_cuda(tgt, supp, T, K, Kinv, noise, *depths, what='photo_loss')
+    def forward(ctx, cfg: L.PhotoCfg, want_warp: bool, tgt, supp, T, K, Kinv, noise, noise_step, *depths):
+        L.require_cuda(tgt, supp, T, K, Kinv, noise, noise_step, *depths, what='photo_loss')
         lib, dev = L.lib(), tgt.device
         b, n, S, H, W = cfg.b, cfg.n, cfg.S, cfg.H, cfg.W
         # Lean backward (min-reprojection only): the forward hands over the SSIM coefficient planes of the selected support
         # frame, so the backward is a masked box filter + the pixel's own sampler/projection chain (no halo re-warp).
-        want_coef = bool(cfg.use_min) and PHOTO_COEF and any(ctx.needs_input_grad[4:7] + ctx.needs_input_grad[8:])
+        want_coef = bool(cfg.use_min) and PHOTO_COEF and any(ctx.needs_input_grad[4:7] + ctx.needs_input_grad[9:])
         with torch.cuda.device(dev):
             coef = torch.empty((S, b, 9, H, W), dtype=torch.float32, device=dev) if want_coef else None
             loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -109,7 +109,7 @@ class _PhotoLoss(torch.autograd.Function):
             ws = _ws(nws, dev)
             with _timed('stv_photo_fwd'):
                 L.check(lib.stv_photo_fwd(C.byref(cfg), L.ptr_array(depths), L.ptr(tgt), L.ptr(supp), L.ptr(T), L.ptr(K),
-                                          L.ptr(Kinv), L.ptr(noise), L.ptr(loss), L.ptr(sel), L.ptr(warp0), L.ptr(coef), L.ptr(ws),
+                                          L.ptr(Kinv), L.ptr(noise), L.ptr(noise_step), L.ptr(loss), L.ptr(sel), L.ptr(warp0), L.ptr(coef), L.ptr(ws),
                                           ws.numel(), L.stream()), 'stv_photo_fwd')
         ctx.cfg, ctx.nws, ctx.coef = cfg, nws, coef
         ctx.save_for_backward(tgt, supp, T, K, Kinv, sel, *depths)
@@ -122,9 +122,9 @@ class _PhotoLoss(torch.autograd.Function):
     def backward(ctx, g_loss, _g_sel, _g_warp):
         tgt, supp, T, K, Kinv, sel, *depths = ctx.saved_tensors
         cfg, lib, dev = ctx.cfg, L.lib(), tgt.device
-        need_d = any(ctx.needs_input_grad[8:])
+        need_d = any(ctx.needs_input_grad[9:])
         need_T, need_K, need_Ki = ctx.needs_input_grad[4], ctx.needs_input_grad[5], ctx.needs_input_grad[6]
-        if not (need_d or need_T or need_K or need_Ki): return (None,)*(8 + len(depths))
+        if not (need_d or need_T or need_K or need_Ki): return (None,)*(9 + len(depths))
         with torch.cuda.device(dev):
             g_loss = g_loss.to(torch.float32).contiguous()
             g_depths = [torch.empty_like(d) for d in depths]
@@ -137,8 +137,8 @@ class _PhotoLoss(torch.autograd.Function):
                 L.check(lib.stv_photo_bwd(C.byref(cfg), L.ptr_array(depths), L.ptr(tgt), L.ptr(supp), L.ptr(T), L.ptr(K),
                                           L.ptr(Kinv), L.ptr(sel), L.ptr(ctx.coef), L.ptr(g_loss), L.ptr_array(g_depths), L.ptr(gT), L.ptr(gK),
                                           L.ptr(gKi), L.ptr(ws), ws.numel(), L.stream()), 'stv_photo_bwd')
-        return (None, None, None, None, gT if need_T else None, gK if need_K else None, gKi if need_Ki else None, None,
-                *[g if ctx.needs_input_grad[8 + j] else None for j, g in enumerate(g_depths)])
+        return (None, None, None, None, gT if need_T else None, gK if need_K else None, gKi if need_Ki else None, None, None,
+                *[g if ctx.needs_input_grad[9 + j] else None for j, g in enumerate(g_depths)])
 
 
 def _photo_cfg(b, n, S, H, W, loss_name, use_min, use_automask, noise_seed) -> L.PhotoCfg:
@@ -151,12 +151,14 @@ def _photo_cfg(b, n, S, H, W, loss_name, use_min, use_automask, noise_seed) -> L
 
 def photo_loss(depths: list[Tensor], tgt: Tensor, supp: Tensor, T: Tensor, K: Tensor, K_inv: Tensor | None = None, *,
                loss_name: str = 'ssim', use_min: bool = True, use_automask: bool = True, noise: Tensor | None = None,
-               noise_seed: int = 0, want_warp: bool = False):
+               noise_seed: int = 0, noise_step: Tensor | None = None, want_warp: bool = False):
     """Fused warp + photometric loss over all scales and support frames.
 
     depths: S x (b,1,H,W); tgt (b,3,H,W); supp (n,b,3,H,W); T (n,b,4,4); K (b,4,4); K_inv (b,4,4) or None (= K^-1,
     differentiable, as `ViewSynth.forward` does with `K.inverse()`, src/tools/geometry.py:383).
-    noise: None or (S*b,1,H,W) explicit tie-break noise (parity tests); otherwise `noise_seed != 0` draws it in-kernel.
+    noise: None or (S*b,1,H,W) explicit tie-break noise (parity tests); otherwise `noise_seed != 0` draws it in-kernel with the
+    effective seed noise_seed + noise_step[0]; `noise_step` (one int64 on the device, optional) is advanced by the call itself, so
+    every call — and every replay of a captured CUDA graph — draws fresh noise (torch.randn_like, reconstruction.py:72).
     -> loss (), sel (S,b,H,W) uint8, warp0 (n,b,3,H,W) | None.
     """
     S = len(depths)
@@ -169,10 +171,12 @@ def photo_loss(depths: list[Tensor], tgt: Tensor, supp: Tensor, T: Tensor, K: Te
         if d.shape != (b, 1, H, W): raise ValueError(f'Invalid depth shape. ({tuple(d.shape)} vs. {(b, 1, H, W)})')
     if noise is not None and noise.numel() != S*b*H*W:
         raise ValueError(f'Invalid noise shape. ({tuple(noise.shape)} vs. {(S*b, 1, H, W)})')
+    if noise_step is not None and (noise_step.dtype != torch.int64 or noise_step.numel() != 1):
+        raise ValueError('noise_step must be a single int64 element on the device.')
     if K_inv is None: K_inv = inv4x4(K)
     cfg = _photo_cfg(b, n, S, H, W, loss_name, use_min, use_automask, noise_seed)
     loss, sel, warp0 = _PhotoLoss.apply(cfg, want_warp, _f32c(tgt), _f32c(supp), _f32c(T), _f32c(K), _f32c(K_inv),
-                                        _f32c(noise), *[_f32c(d) for d in depths])
+                                        _f32c(noise), noise_step, *[_f32c(d) for d in depths])
     return loss, sel, (warp0 if want_warp else None)
 
 

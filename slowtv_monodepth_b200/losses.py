@@ -31,8 +31,11 @@ class ReconstructionLoss(nn.Module):
         if loss_name not in {'ssim', 'l1'}:
             raise KeyError(f'loss_name="{loss_name}" is not provided by the B200 photometric kernels (ssim | l1).')
         self.loss_name, self.use_min, self.use_automask, self.mask_name = loss_name, use_min, use_automask, mask_name
-        self.noise_seed = 0x5107  # Base seed of the in-kernel tie-break noise; advanced every call.
-        self._calls = 0
+        self.noise_seed = 0x5107  # Base seed of the in-kernel tie-break noise (reconstruction.py:72 draws randn_like per call).
+        # Device-side call counter added to the seed: the kernels advance it themselves, so eager calls AND replays of a captured
+        # CUDA graph draw fresh noise every step. Created on first use on the inputs' device (before any graph capture: the
+        # runners warm up eagerly first). Tests set it (`noise_step.fill_(k)`) to reproduce a particular draw.
+        self.noise_step: Tensor | None = None
 
     def compute_photo(self, pred: Tensor, target: Tensor, mask: Tensor | None = None) -> Tensor:
         """pred (*n,b,3,h,w), target (b,3,h,w) -> (b,1,h,w). Forward only (used for automasks and `depth_regr`)."""
@@ -42,12 +45,15 @@ class ReconstructionLoss(nn.Module):
     def fused(self, depths: list[Tensor], target: Tensor, source: Tensor, T: Tensor, K: Tensor, K_inv: Tensor | None = None,
               noise: Tensor | None = None, want_warp: bool = False):
         """Warp + loss in one kernel. -> (loss, {'automask': (S,b,1,H,W) bool}, sel, warp0)."""
-        self._calls += 1
+        if self.use_automask and noise is None and (self.noise_step is None or self.noise_step.device != target.device):
+            self.noise_step = torch.zeros(1, dtype=torch.int64, device=target.device)
         loss, sel, warp0 = F_.photo_loss(depths, target, source, T, K, K_inv, loss_name=self.loss_name, use_min=self.use_min,
                                          use_automask=self.use_automask, noise=noise,
-                                         noise_seed=(self.noise_seed + self._calls) if self.use_automask else 0,
+                                         noise_seed=self.noise_seed if self.use_automask else 0,
+                                         noise_step=self.noise_step if (self.use_automask and noise is None) else None,
                                          want_warp=want_warp)
         ld = {'automask': (sel != 255).unsqueeze(2)} if self.use_automask else {}
+        self.last_sel = sel  # (S,b,H,W) uint8 per-pixel decisions of the most recent call (diagnostics / parity tests)
         return loss, ld, sel, warp0
 
     def forward(self, pred: Tensor, target: Tensor, source: Tensor | None = None, mask: Tensor | None = None):

@@ -54,6 +54,15 @@ class LRSchedule:
 
 
 class FlatAdamW:
+    """Every trainable parameter in one flat fp32 buffer + fused AdamW + one gradient all-reduce.
+
+    Differences from torch.optim.AdamW worth knowing: a parameter that took no part in the step has a ZERO gradient here (the
+    buffer is zeroed, never set to None), so it still receives weight decay, where torch skips `grad is None` parameters; on
+    the hot path every parameter of both networks is used every step (the unused half of the pose head's output channels gets an
+    exact-zero, not-None gradient in the reference too), so the two agree — `tests/test_optim_gpu.py` holds the kernel to
+    torch.optim.AdamW with timm's no-decay groups.
+    With world > 1 the constructor broadcasts rank 0's parameters (DDP's initial sync); `broadcast_buffers()` does the same for
+    module buffers (BatchNorm running statistics) and should be called after loading a checkpoint on one rank."""
     def __init__(self, module: nn.Module, lr: float = 1e-4, weight_decay: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  channels_last: bool = True):
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
@@ -90,6 +99,15 @@ class FlatAdamW:
         self.step_count = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._work = None
+        self._module = module
+        if self.world > 1: dist.broadcast(self.flat, 0)
+
+    def broadcast_buffers(self, src: int = 0) -> None:
+        """Rank `src`'s parameters and module buffers to every rank (after a checkpoint load on one rank)."""
+        if self.world <= 1: return
+        dist.broadcast(self.flat, src)
+        for buf in self._module.buffers():
+            if buf.numel(): dist.broadcast(buf, src)
 
     def zero_grad(self) -> None:
         """Gradients are accumulated in place into the flat buffer, so they are zeroed (one memset), not set to None."""

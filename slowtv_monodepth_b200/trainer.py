@@ -92,12 +92,12 @@ class MonoDepthStep(nn.Module):
         return fwd
 
     # -- trainer.py:350-472 ------------------------------------------------------------------------------------------
-    def forward_loss(self, fwd: dict, x: dict, y: dict, want_maps: bool = False):
+    def forward_loss(self, fwd: dict, x: dict, y: dict, want_maps: bool = False, noise: Tensor | None = None):
         loss, loss_dict = 0., {}
         for k, crit in self.losses.items():
             if k == 'img_recon':
                 l, ld = H.image_recon(crit, None, depths=fwd['depth_up'], masks=None, imgs=y['imgs'], supp_imgs=y['supp_imgs'],
-                                      Ts=fwd['Ts'], Ks=fwd.get('K', y['K']), want_warp=want_maps)
+                                      Ts=fwd['Ts'], Ks=fwd.get('K', y['K']), want_warp=want_maps, noise=noise)
             elif k == 'disp_smooth':
                 l, ld = H.disp_smooth(crit, fwd['disp'], y['imgs'], want_maps=want_maps)
             else:
@@ -108,11 +108,12 @@ class MonoDepthStep(nn.Module):
         return loss, loss_dict
 
     # -- trainer.py:115-190 ------------------------------------------------------------------------------------------
-    def step(self, batch, mode: str = 'train', want_maps: bool = False):
+    def step(self, batch, mode: str = 'train', want_maps: bool = False, noise: Tensor | None = None):
+        """`noise`: explicit auto-mask tie-break noise (S*b,1,H,W) replacing the per-step draw (parity tests)."""
         x, y, m = batch
         fwd = self.forward(x)
         fwd = self.forward_postprocess(fwd, x, y)
-        loss, loss_dict = self.forward_loss(fwd, x, y, want_maps=want_maps or mode != 'train')
+        loss, loss_dict = self.forward_loss(fwd, x, y, want_maps=want_maps or mode != 'train', noise=noise)
         return loss, loss_dict, fwd
 
 

@@ -1,4 +1,6 @@
-"""GPU, BASELINE.json's FULL sizes (where the CPU oracle would take minutes): size-independent properties of the loss stack.
+"""GPU, BASELINE.json's FULL sizes: (a) the loss stack against the float64 oracle at the image sizes / support-frame counts of
+configs[2], [3] and [4] (batch 1-2: the oracle needs a few seconds per case) with the protocol of tests/test_loss_gpu.py;
+(b) at the full batch, size-independent properties of the loss stack.
 
   * two independent implementations agree: the lean backward fed by the forward's coefficient planes vs. the self-contained
     backward that re-warps and rebuilds the SSIM sums (different kernels, different tiling, different data flow);
@@ -16,6 +18,24 @@ CASES = {'config3': (8, 2, 4, (384, 640)), 'config4_n4': (4, 4, 4, (384, 640)), 
          # odd width: rows are not 16-byte granular, so the support frames cannot be bound as a texture and the coefficient tiles
          # cannot travel by TMA — the plain-load variants of the forward and of both backward kernels run instead
          'ragged_37x53': (3, 2, 2, (37, 53)), 'ragged_50x66_n3': (2, 3, 3, (50, 66))}
+
+
+ORACLE_CASES = {'config3_384x640_n2': (2, 2, 4, (384, 640)), 'config4_384x640_n4': (1, 4, 4, (384, 640)),
+                'config5_512x1024_n2': (1, 2, 4, (512, 1024))}
+
+
+@pytest.mark.parametrize('name', ORACLE_CASES)
+def test_loss_stack_matches_oracle_at_full_size(name):
+    """Same bars as the small golden cases: loss 1e-5, pose / intrinsics gradients 1e-4, per-pixel gradients 1e-4 on >= 85 % of
+    the pixels of every scale, decisions equal to the oracle's except inside float32 rounding of a tie."""
+    from slowtv_monodepth_b200 import synthetic as syn
+    from tests import util as U
+    b, n, S, shape = ORACLE_CASES[name]
+    inp = syn.make_loss_inputs(b, n, S, shape, seed=11)
+    cfg = dict(b=b, n=n, S=S, shape=shape)
+    got = U.run_cuda(inp, cfg)
+    torch.cuda.synchronize()
+    U.check_loss_stack(inp, cfg, got)
 
 
 def _run(d, coef: bool, scale: float = 1.0):

@@ -16,12 +16,15 @@ def test_graphed_step_matches_eager():
     b1 = syn.make_batch(2, 2, (64, 96), seed=1, device='cuda')
     g = GraphedTrainStep(model, opt, b0)
     # replay on a NEW batch, then the same batch eagerly: the flat gradient buffers must agree
+    crit = model.losses['img_recon']
     g.load(b1)
+    crit.noise_step.fill_(41)   # the tie-break noise is seeded by a DEVICE counter that every call (and replay) advances
     g.graph.replay()
     torch.cuda.synchronize()
+    assert crit.noise_step.item() == 42   # the replay drew its noise and advanced the counter, like randn_like would
     loss_g, grad_g = g.loss.clone(), opt.grad.clone()
     opt.zero_grad()
-    model.losses['img_recon']._calls -= 1  # same tie-break noise seed as the captured call
+    crit.noise_step.fill_(41)   # same draw for the eager step
     loss_e, _, _ = model.step(b1)
     loss_e.backward()
     torch.cuda.synchronize()
@@ -54,10 +57,12 @@ def test_shape_cached_graphs_follow_the_aspect_ratio_augmentation():
     # replay of a cached shape (graph only, no optimiser step) == eager step on the same batch with the same parameters
     b = batches[0]
     step = runner.steps[runner.key(b)]
+    crit = model.losses['img_recon']
+    crit.noise_step.fill_(7)
     step.load(b); step.graph.replay(); torch.cuda.synchronize()
     loss_g, grad_g = step.loss.clone(), opt.grad.clone()
     opt.zero_grad()
-    model.losses['img_recon']._calls -= 1
+    crit.noise_step.fill_(7)    # same tie-break draw as the replay (the counter lives on the device, shared by every graph)
     loss_e, _, _ = model.step(b)
     loss_e.backward()
     torch.cuda.synchronize()

@@ -14,8 +14,11 @@ The reference's float32 run differs from its float64 run by ~1e-2 on d/d dispari
 (tests/test_oracle_golden.py::test_fp32_reference_noise_floor), so the check is split:
   (1) decisions equal the oracle's except where the oracle's margin is < 2e-5, and on < 0.5 % of the pixels;
   (2) the oracle is re-run with the kernel's decisions forced (oracle/loss.py `forced_sel`); values and pose/intrinsics
-      gradients must then agree to the tolerances above; per-pixel gradient maps are compared on the pixels that are not
-      within rounding of a type-(b) event (tests/util.py::unstable_pixels; they must be < 5 % of the pixels).
+      gradients must then agree to the tolerances above; the full-resolution per-pixel gradient maps (d/d depth_up) are compared
+      on the pixels whose 3x3 neighbourhood holds no type-(b) event (tests/util.py::unstable_pixels) — at least 85 % of every
+      scale's pixels must take part (asserted) — and the low-resolution d/d disparity on EVERY pixel, against the oracle's own
+      vector-Jacobian product of the bilinear upsample + to_scaled applied to the kernel's full-resolution maps plus the
+      oracle's smoothness gradient (both event-free), tests/util.py::check_pixel_gradients.
 The oracle runs with float32's eps (`util.eps32`), i.e. it is the exact-arithmetic version of the float32 reference.
 """
 import numpy as np
@@ -40,44 +43,7 @@ def test_loss_stack_matches_oracle(name, coef, monkeypatch):
     if coef and not cfg.get('use_min', True): pytest.skip('coefficient planes need min-reprojection; covered by recompute-bwd')
     got = U.run_cuda(inp, cfg)
     torch.cuda.synchronize()
-    sel = got['sel'].cpu()
-    S, b = cfg['S'], cfg['b']
-    use_min, use_auto = cfg.get('use_min', True), cfg.get('use_automask', True)
-
-    with U.eps32():
-        bad, cands = U.unstable_pixels(inp, cfg)
-        # (1) decisions
-        free = U.run_oracle(inp, cfg, torch.float64)
-        if use_min or use_auto:
-            osel = free['sel']
-            if not use_min: osel = torch.where(osel == 255, osel, torch.full_like(osel, 254))
-            diff = sel != osel
-            top2 = cands.topk(2, dim=1, largest=False)[0]
-            margin = top2[:, 1:2] - top2[:, 0:1]
-            assert diff.float().mean().item() < 5e-3, f'{diff.float().mean().item():.4%} decisions differ'
-            assert (margin[diff] < 2e-5).all(), f'decision flipped with margin {margin[diff].max().item():.3e}'
-
-        # (2) values and gradients given the kernel's decisions
-        if not use_min and use_auto:
-            pytest.skip('mean-reduction + automask has no forced-decision mode in the oracle; covered by (1) and the golden test')
-        want = U.run_oracle(inp, cfg, torch.float64, forced_sel=sel if use_min else None)
-
-    assert bad.float().mean().item() < 0.05, f'{bad.float().mean().item():.2%} unstable pixels'
-    assert U.rel(got['loss_recon'], want['loss_recon']) < TOL_LOSS
-    assert U.rel(got['loss_smooth'], want['loss_smooth']) < TOL_LOSS
-    for k in ('g_aa', 'g_t', 'g_K'):
-        assert U.rel(got[k], want[k]) < TOL_GRAD, f'{k}: {U.rel(got[k], want[k]):.3e}'
-    for s in range(S):
-        good = ~bad[s*b:(s + 1)*b]
-        # A flipped type-(b) event changes the SSIM/L1 gradient of its 3x3 neighbourhood: dilate by one pixel.
-        good = ~(torch.nn.functional.max_pool2d((~good).float(), 3, 1, 1) > 0)
-        e = U.rel_masked(got[f'g_depth{s}'], want[f'g_depth{s}'], good)
-        assert e < TOL_GRAD, f'g_depth{s}: {e:.3e}'
-        good_lr = ~U.footprint(~good, 2**s)
-        e = U.rel_masked(got[f'g_disp{s}'], want[f'g_disp{s}'], good_lr)
-        assert e < TOL_GRAD, f'g_disp{s}: {e:.3e}'
-    for k in ('warp0', 'depth_up0', 'disp_grad', 'image_grad'):
-        assert U.rel(got[k], want[k]) < 1e-5, f'{k}: {U.rel(got[k], want[k]):.3e}'
+    U.check_loss_stack(inp, cfg, got, TOL_LOSS, TOL_GRAD)
 
 
 @pytest.mark.parametrize('name', U.LOSS_CASES)

@@ -53,19 +53,39 @@ def run_oracle(inp: dict, cfg: dict, dtype=torch.float64, forced_sel=None, w_smo
     Ts = OL.T_from_AAt(aa, t)
     H, W = d['imgs'].shape[-2:]
     mn, mx = cfg.get('min_depth', 0.1), cfg.get('max_depth', 100.)
-    depths = [OL.disp_to_depth(OL.resize_bilinear(x, (H, W)), mn, mx) for x in disps]
+    disps_up = [OL.resize_bilinear(x, (H, W)) for x in disps]
+    depths = [OL.disp_to_depth(x, mn, mx) for x in disps_up]
     l_rec, o = OL.image_recon(depths, d['imgs'], d['supp_imgs'], Ts, K, cfg.get('use_min', True), cfg.get('use_automask', True),
                               d['noise'], loss_name=cfg.get('loss_name', 'ssim'), forced_sel=forced_sel)
     l_sm, o2 = OL.disp_smooth(disps, d['imgs'], True)
-    for x in depths: x.retain_grad()
+    for x in depths + disps_up: x.retain_grad()
     (l_rec + w_smooth*l_sm).backward()
     out = dict(loss_recon=l_rec.detach(), loss_smooth=l_sm.detach(), g_aa=aa.grad, g_t=t.grad, g_K=K.grad,
                warp0=o['supp_imgs_warp'].detach(), sel=o['sel'], err=o['err'].detach(), depth_up0=depths[0].detach(),
                disp_grad=o2['disp_grad'].detach(), image_grad=o2['image_grad'].detach())
     for s, x in enumerate(disps): out[f'g_disp{s}'] = x.grad
     for s, x in enumerate(depths): out[f'g_depth{s}'] = x.grad
+    for s, x in enumerate(disps_up): out[f'g_dispup{s}'] = x.grad if x.grad is not None else disps[s].grad  # scale 0 is not resized
     if 'automask' in o: out['automask0'] = o['automask']
     return out
+
+
+def oracle_pull_to_disp(inp: dict, cfg: dict, g_full: list, kind: str = 'depth', w_smooth: float = 1e-3) -> list:
+    """d loss / d disp_s given the full-resolution gradient maps `g_full[s]` w.r.t. depth_up ('depth') or disp_up ('disp'): the
+    vector-Jacobian product of the oracle's bilinear upsample (+ to_scaled / to_inv) plus the oracle's smoothness gradient.
+    Both are free of discrete events, so the product's low-resolution gradients can be held to this on EVERY pixel."""
+    d = cast(inp, torch.float64)
+    H, W = d['imgs'].shape[-2:]
+    mn, mx = cfg.get('min_depth', 0.1), cfg.get('max_depth', 100.)
+    disps = [x.clone().requires_grad_() for x in d['disps']]
+    l_sm, _ = OL.disp_smooth(disps, d['imgs'], True)
+    total = w_smooth*l_sm
+    for x, g in zip(disps, g_full):
+        up = OL.resize_bilinear(x, (H, W))
+        if kind == 'depth': up = OL.disp_to_depth(up, mn, mx)
+        total = total + (up*g.detach().double().cpu()).sum()
+    total.backward()
+    return [x.grad for x in disps]
 
 
 def unstable_pixels(inp: dict, cfg: dict, tol_val: float = 4e-6, tol_pos: float = 5e-4):
@@ -113,6 +133,26 @@ def footprint(bad: torch.Tensor, f: int) -> torch.Tensor:
     return F.max_pool2d(x, kernel_size=f, stride=f) > 0
 
 
+def check_pixel_gradients(inp: dict, cfg: dict, got: dict, want: dict, bad: torch.Tensor, tol: float, min_frac: float = 0.85) -> None:
+    """(1) full-resolution maps d loss/d depth_up (or d/d disp_up, `got['up_kind']`) on the stable pixels, which must be at least
+    `min_frac` of every scale; (2) low-resolution d loss/d disp_s on every pixel against the oracle's pull-back of those maps."""
+    import torch.nn.functional as F
+    S, b = cfg['S'], cfg['b']
+    kind = got.get('up_kind', 'depth')
+    key = 'g_depth' if kind == 'depth' else 'g_dispup'
+    for s in range(S):
+        good = ~bad[s*b:(s + 1)*b]
+        good = ~(F.max_pool2d((~good).float(), 3, 1, 1) > 0)  # a flipped event changes the SSIM/L1 gradient of its 3x3 neighbourhood
+        frac = good.float().mean().item()
+        assert frac >= min_frac, f'scale {s}: only {frac:.1%} of the pixels are compared'
+        e = rel_masked(got[f'g_up{s}'], want[f'{key}{s}'], good)
+        assert e < tol, f'{key}{s}: {e:.3e} on {frac:.1%} of the pixels'
+    pulled = oracle_pull_to_disp(inp, cfg, [got[f'g_up{s}'] for s in range(S)], kind)
+    for s in range(S):
+        e = rel(got[f'g_disp{s}'], pulled[s])
+        assert e < 0.1*tol, f'g_disp{s} vs the oracle pull-back of the full-resolution map: {e:.3e}'
+
+
 def rel_masked(a, b, good) -> float:
     a, b = a.detach().double().cpu()*good, b.detach().double().cpu()*good
     return ((a - b).norm()/b.norm().clamp(min=1e-30)).item()
@@ -141,6 +181,42 @@ def run_cuda(inp: dict, cfg: dict, w_smooth: float = 1e-3, device='cuda') -> dic
                warp0=o['supp_imgs_warp'], depth_up0=depths[0].detach(), disp_grad=o2['disp_grad'], image_grad=o2['image_grad'],
                sel=sel.flatten(0, 1).unsqueeze(1))
     for s, x in enumerate(disps): out[f'g_disp{s}'] = x.grad
-    for s, x in depths.items(): out[f'g_depth{s}'] = x.grad
+    for s, x in depths.items(): out[f'g_up{s}'] = x.grad
+    out['up_kind'] = 'depth'
     if 'automask' in o: out['automask0'] = o['automask']
     return out
+
+
+def check_loss_stack(inp: dict, cfg: dict, got: dict, tol_loss: float = 1e-5, tol_grad: float = 1e-4) -> None:
+    """The parity protocol of tests/test_loss_gpu.py (see its docstring) for one set of inputs and one CUDA result."""
+    import pytest
+    sel = got['sel'].cpu()
+    S, b = cfg['S'], cfg['b']
+    use_min, use_auto = cfg.get('use_min', True), cfg.get('use_automask', True)
+
+    with eps32():
+        bad, cands = unstable_pixels(inp, cfg)
+        # (1) decisions
+        free = run_oracle(inp, cfg, torch.float64)
+        if use_min or use_auto:
+            osel = free['sel']
+            if not use_min: osel = torch.where(osel == 255, osel, torch.full_like(osel, 254))
+            diff = sel != osel
+            top2 = cands.topk(2, dim=1, largest=False)[0]
+            margin = top2[:, 1:2] - top2[:, 0:1]
+            assert diff.float().mean().item() < 5e-3, f'{diff.float().mean().item():.4%} decisions differ'
+            assert (margin[diff] < 2e-5).all(), f'decision flipped with margin {margin[diff].max().item():.3e}'
+
+        # (2) values and gradients given the kernel's decisions
+        if not use_min and use_auto:
+            pytest.skip('mean-reduction + automask has no forced-decision mode in the oracle; covered by (1) and the golden test')
+        want = run_oracle(inp, cfg, torch.float64, forced_sel=sel if use_min else None)
+
+    assert bad.float().mean().item() < 0.05, f'{bad.float().mean().item():.2%} unstable pixels'
+    assert rel(got['loss_recon'], want['loss_recon']) < tol_loss
+    assert rel(got['loss_smooth'], want['loss_smooth']) < tol_loss
+    for k in ('g_aa', 'g_t', 'g_K'):
+        assert rel(got[k], want[k]) < tol_grad, f'{k}: {rel(got[k], want[k]):.3e}'
+    check_pixel_gradients(inp, cfg, got, want, bad, tol_grad)
+    for k in ('warp0', 'depth_up0', 'disp_grad', 'image_grad'):
+        assert rel(got[k], want[k]) < 1e-5, f'{k}: {rel(got[k], want[k]):.3e}'
