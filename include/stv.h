@@ -88,6 +88,19 @@ int stv_photo_bwd(const stv_photo_cfg* cfg, const float* const* depth, const flo
 int stv_photo_error(const stv_photo_cfg* cfg /* b,n,H,W,w_ssim,w_l1,use_min */, const float* pred, const float* tgt,
                     float* err, void* stream);
 
+/* ReconstructionLoss.forward on ALREADY WARPED frames (src/losses/reconstruction.py:98-126; what a caller of the registered
+ * `img_recon` class gets when it warps elsewhere, e.g. the virtual-stereo branch src/core/trainer.py:394-399), and its gradient
+ * w.r.t. those frames. cfg: b, n, H, W, w_ssim, w_l1, use_min, use_automask, noise_seed (S is ignored).
+ * pred (n,b,3,H,W); tgt (b,3,H,W); source (n,b,3,H,W) un-warped frames (required when use_automask, reconstruction.py:121);
+ * noise NULL | (b,1,H,W); noise_step as in stv_photo_fwd; loss: device scalar = mean over (b,H,W); sel (b,H,W) u8 decisions;
+ * err: NULL | (b,1,H,W) the reduced, auto-masked error map. Cold path: plain one-thread-per-pixel kernels. */
+size_t stv_recon_workspace_bytes(const stv_photo_cfg* cfg);
+int stv_recon_fwd(const stv_photo_cfg* cfg, const float* pred, const float* tgt, const float* source, const float* noise,
+                  unsigned long long* noise_step, float* loss, uint8_t* sel, float* err, void* ws, size_t ws_bytes, void* stream);
+/* g_pred (n,b,3,H,W) (overwritten) = grad_loss * d loss / d pred given the decisions `sel` of the forward call. */
+int stv_recon_bwd(const stv_photo_cfg* cfg, const float* pred, const float* tgt, const uint8_t* sel, const float* grad_loss,
+                  float* g_pred, void* stream);
+
 /* ViewSynth.forward (src/tools/geometry.py:366-391) on its own: input (B,C,H,W), depth (B,1,H,W), T,K,Kinv (B,4,4) ->
  * warp (B,C,H,W), depth_warp (B,1,H,W), mask_valid (B,1,H,W) u8. Any C; used by the stand-alone ViewSynth module. */
 int stv_view_synth_fwd(int B, int C, int H, int W, const float* input, const float* depth, const float* T,

@@ -1,10 +1,9 @@
-"""Import shim for the REAL reference tree (jspenmar/slowtv_monodepth at /root/reference).
+"""Import shim for the REAL reference (jspenmar/slowtv_monodepth): the source tree at /root/reference in the build container,
+or its byte-compiled build `oracle/_ref/` (oracle/build_ref.py) on the GPU box, where the source tree does not exist.
 
-TEST INFRASTRUCTURE ONLY. This module is used by `oracle/make_golden.py` (and by the optional
-`-m "not gpu"` cross-checks that skip when the reference tree is absent) to execute the reference's own
-PyTorch code on CPU inside the build container, so that the oracle restatement in `oracle/` can be pinned
-and golden vectors can be generated. It never travels to the GPU box (the reference tree does not exist
-there) and nothing in the product package imports it.
+TEST INFRASTRUCTURE ONLY. Used by `oracle/make_golden.py`, by the tests that execute the reference's own PyTorch code (CPU
+cross-checks here; `tests/test_plugin_gpu.py` on the GPU box) and by `bench.py --impl reference`. Nothing in the product
+package imports it.
 
 The reference has import-time dependencies that are not installed here (matplotlib, skimage, kornia, timm,
 torchmetrics, lmdb, pytorch_lightning). They are only needed for plotting / logging / data loading, none of
@@ -21,11 +20,48 @@ import sys
 import types
 from pathlib import Path
 
-REF_ROOT = Path(os.environ.get('STV_REFERENCE_ROOT', '/root/reference'))
+SRC_ROOT = Path(os.environ.get('STV_REFERENCE_ROOT', '/root/reference'))
+BUILT_ROOT = Path(__file__).resolve().parent/'_ref'
+
+
+def _root() -> Path | None:
+    if (SRC_ROOT/'src'/'tools'/'geometry.py').is_file(): return SRC_ROOT
+    if (BUILT_ROOT/'src'/'tools'/'geometry.pyc').is_file(): return BUILT_ROOT
+    return None
+
+
+REF_ROOT = _root() or SRC_ROOT
 
 
 def available() -> bool:
-    return (REF_ROOT/'src'/'tools'/'geometry.py').is_file()
+    return _root() is not None
+
+
+def kind() -> str:
+    """'source' (the reference tree itself), 'bytecode' (oracle/_ref built from it) or 'absent'."""
+    r = _root()
+    return 'absent' if r is None else ('source' if r == SRC_ROOT else 'bytecode')
+
+
+def load_cfg(*names: str) -> dict:
+    """The reference's experiment configurations, merged in order like `src.utils.io.load_merge_yaml` (api/train/train.py:29)."""
+    import json
+    load()
+    from src.utils import io
+    if kind() == 'source':
+        return io.load_merge_yaml(*[SRC_ROOT/'cfg'/n for n in names])
+    cfgs = json.loads((BUILT_ROOT/'cfg.json').read_text())
+    out: dict = {}
+    for n in names: out = _merge(out, cfgs[n])
+    return out
+
+
+def _merge(old: dict, new: dict) -> dict:
+    """Recursive dict merge, new values win (the rule of src/utils/io.py:134-161)."""
+    out = dict(old)
+    for k, v in new.items():
+        out[k] = _merge(out[k], v) if (isinstance(v, dict) and isinstance(out.get(k), dict)) else v
+    return out
 
 
 def _try(name: str) -> bool:
@@ -99,7 +135,7 @@ _LOADED = False
 def load():
     """Make `import src` resolve to the reference tree. Returns the imported `src` package."""
     global _LOADED
-    if not available(): raise FileNotFoundError(f'Reference tree not found at {REF_ROOT}')
+    if not available(): raise FileNotFoundError(f'Reference not found: neither {SRC_ROOT} nor the built {BUILT_ROOT}')
     sys.dont_write_bytecode = True  # The reference tree is read-only.
     if not _LOADED:
         install_stubs()

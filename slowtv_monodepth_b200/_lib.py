@@ -57,6 +57,9 @@ _SIGNATURES = {
     'stv_photo_fwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     'stv_photo_bwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     'stv_photo_error': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P]),
+    'stv_recon_workspace_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
+    'stv_recon_fwd': (C.c_int, [C.POINTER(PhotoCfg)] + [_P]*9 + [C.c_size_t, _P]),
+    'stv_recon_bwd': (C.c_int, [C.POINTER(PhotoCfg)] + [_P]*6),
     'stv_view_synth_fwd': (C.c_int, [C.c_int]*4 + [_P]*9),
     'stv_view_synth_workspace_bytes': (C.c_size_t, [C.c_int]*4),
     'stv_view_synth_bwd': (C.c_int, [C.c_int]*4 + [_P]*13 + [C.c_size_t, _P]),

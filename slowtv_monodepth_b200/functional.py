@@ -193,6 +193,48 @@ def photo_error(pred: Tensor, target: Tensor, *, loss_name: str = 'ssim', use_mi
     return err
 
 
+class _ReconLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg: L.PhotoCfg, pred, tgt, source, noise, noise_step):
+        L.require_cuda(pred, tgt, source, noise, noise_step, what='recon_loss')
+        lib, dev = L.lib(), pred.device
+        with torch.cuda.device(dev):
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            sel = torch.empty((cfg.b, cfg.H, cfg.W), dtype=torch.uint8, device=dev)
+            ws = _ws(lib.stv_recon_workspace_bytes(C.byref(cfg)), dev)
+            L.check(lib.stv_recon_fwd(C.byref(cfg), L.ptr(pred), L.ptr(tgt), L.ptr(source), L.ptr(noise), L.ptr(noise_step), L.ptr(loss),
+                                      L.ptr(sel), None, L.ptr(ws), ws.numel(), L.stream()), 'stv_recon_fwd')
+        ctx.cfg = cfg
+        ctx.save_for_backward(pred, tgt, sel)
+        ctx.mark_non_differentiable(sel)
+        return loss, sel
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_sel):
+        pred, tgt, sel = ctx.saved_tensors
+        if not ctx.needs_input_grad[1]: return (None,)*6
+        with torch.cuda.device(pred.device):
+            g = torch.empty_like(pred)
+            L.check(L.lib().stv_recon_bwd(C.byref(ctx.cfg), L.ptr(pred), L.ptr(tgt), L.ptr(sel), L.ptr(g_loss.to(torch.float32).contiguous()),
+                                          L.ptr(g), L.stream()), 'stv_recon_bwd')
+        return None, g, None, None, None, None
+
+
+def recon_loss(pred: Tensor, target: Tensor, source: Tensor | None = None, *, loss_name: str = 'ssim', use_min: bool = False,
+               use_automask: bool = False, noise: Tensor | None = None, noise_seed: int = 0, noise_step: Tensor | None = None):
+    """`ReconstructionLoss.forward` on already warped frames (src/losses/reconstruction.py:98-126), differentiable in `pred`.
+    pred (n,b,3,H,W) | (b,3,H,W); target (b,3,H,W); source like pred (needed when use_automask) -> loss (), sel (b,H,W) uint8."""
+    if pred.ndim == 4: pred = pred[None]
+    if source is not None and source.ndim == 4: source = source[None]
+    n, b, c, H, W = pred.shape
+    if c != 3 or target.shape != (b, 3, H, W): raise ValueError(f'Invalid shapes. ({tuple(pred.shape)} vs. {tuple(target.shape)})')
+    if use_automask and source is None: raise ValueError("Must provide the original 'source' images when automasking...")
+    if source is not None and source.shape != pred.shape: raise ValueError(f'Invalid source shape. ({tuple(source.shape)} vs. {tuple(pred.shape)})')
+    cfg = _photo_cfg(b, n, 1, H, W, loss_name, use_min, use_automask, noise_seed)
+    return _ReconLoss.apply(cfg, _f32c(pred), _f32c(target.detach()), _f32c(None if source is None else source.detach()),
+                            _f32c(noise), noise_step)
+
+
 class _Inv4x4(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A):

@@ -1,8 +1,9 @@
 """Photometric reconstruction loss — host-side mirror of `src/losses/{photometric,reconstruction}.py` (reference).
 
 `ReconstructionLoss` keeps the reference's constructor and `forward` / `compute_photo` contracts. The training hot path
-never calls `forward` on already-warped images: `slowtv_monodepth_b200.handlers.image_recon` hands the un-warped support
-frames, depths and poses to the fused libstv kernel (`fused()` below), so the warped frames never exist in HBM.
+does not call `forward` on already-warped images: `slowtv_monodepth_b200.handlers.image_recon` hands the un-warped support
+frames, depths and poses to the fused libstv kernel (`fused()` below), so the warped frames never exist in HBM; `forward`
+(stv_recon_fwd / stv_recon_bwd) serves every other caller of the registered class.
 """
 from __future__ import annotations
 
@@ -45,8 +46,7 @@ class ReconstructionLoss(nn.Module):
     def fused(self, depths: list[Tensor], target: Tensor, source: Tensor, T: Tensor, K: Tensor, K_inv: Tensor | None = None,
               noise: Tensor | None = None, want_warp: bool = False):
         """Warp + loss in one kernel. -> (loss, {'automask': (S,b,1,H,W) bool}, sel, warp0)."""
-        if self.use_automask and noise is None and (self.noise_step is None or self.noise_step.device != target.device):
-            self.noise_step = torch.zeros(1, dtype=torch.int64, device=target.device)
+        if self.use_automask and noise is None: self._step_counter(target)
         loss, sel, warp0 = F_.photo_loss(depths, target, source, T, K, K_inv, loss_name=self.loss_name, use_min=self.use_min,
                                          use_automask=self.use_automask, noise=noise,
                                          noise_seed=self.noise_seed if self.use_automask else 0,
@@ -56,7 +56,22 @@ class ReconstructionLoss(nn.Module):
         self.last_sel = sel  # (S,b,H,W) uint8 per-pixel decisions of the most recent call (diagnostics / parity tests)
         return loss, ld, sel, warp0
 
-    def forward(self, pred: Tensor, target: Tensor, source: Tensor | None = None, mask: Tensor | None = None):
-        raise NotImplementedError(
-            'ReconstructionLoss.forward on pre-warped images is not part of the B200 hot path: the warp is fused into the '
-            'loss kernel. Call slowtv_monodepth_b200.handlers.image_recon (installed over src.core.handlers.image_recon).')
+    def _step_counter(self, like: Tensor) -> Tensor:
+        if self.noise_step is None or self.noise_step.device != like.device:
+            self.noise_step = torch.zeros(1, dtype=torch.int64, device=like.device)
+        return self.noise_step
+
+    def forward(self, pred: Tensor, target: Tensor, source: Tensor | None = None, mask: Tensor | None = None, *,
+                noise: Tensor | None = None):
+        """Reference contract (reconstruction.py:98-126) on ALREADY WARPED frames: pred (*n,b,3,h,w), target (b,3,h,w),
+        source (*n,b,3,h,w) -> (loss, {'automask': (b,1,h,w) bool}); differentiable in `pred` (stv_recon_fwd / stv_recon_bwd).
+        The training hot path does not come through here — `handlers.image_recon` fuses the warp into the loss kernel — but
+        everything else that calls the registered `img_recon` class directly does (e.g. the virtual-stereo branch,
+        src/core/trainer.py:394-399)."""
+        if mask is not None: raise ValueError('Weighting masks are not supported by the B200 photometric kernels.')
+        if self.use_automask and source is None: raise ValueError("Must provide the original 'source' images when automasking...")
+        draw = self.use_automask and noise is None
+        loss, sel = F_.recon_loss(pred, target, source if self.use_automask else None, loss_name=self.loss_name, use_min=self.use_min,
+                                  use_automask=self.use_automask, noise=noise, noise_seed=self.noise_seed if draw else 0,
+                                  noise_step=self._step_counter(target) if draw else None)
+        return loss, ({'automask': (sel != 255).unsqueeze(1)} if self.use_automask else {})
