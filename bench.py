@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the SlowTV-monodepth training hot path on B200 (one JSON line on stdout from rank 0).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5] [--api auto|plugin|native]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-A "step" is one full training step of BASELINE.json config 3 (ConvNeXt-T depth + ResNet-18 pose, 384x640, batch 8 per GPU,
-2 support frames, 4 scales, min-reprojection + automask + edge-aware smoothness, AdamW): networks forward, fused loss,
-backward, gradient all-reduce (N > 1), optimiser step. Synthetic video triplets, random-init weights.
+A "step" is one full training step of a BASELINE.json configuration — default configs[2] (ConvNeXt-T depth + ResNet-18 pose,
+384x640, batch 8 per GPU, 2 support frames, 4 scales, min-reprojection + automask + edge-aware smoothness, AdamW), the one the
+metric is quoted on; --config selects the others: networks forward, fused loss, backward, gradient all-reduce (N > 1),
+optimiser step. Synthetic video triplets, random-init weights. By default the step is driven THROUGH THE REFERENCE'S OWN MODULE
+(`MonoDepthModule(cfg).step`, built by its registry after `plugin.install()`) when the reference build (oracle/_ref) is present.
 
   value  images/s over all ranks, inputs resident in HBM before the timed region (CUDA events, max over ranks)
   e2e    the same metric through the public API with HOST (pinned) batches: H2D copy of every step's batch and a D2H
          read of the loss inside the timed region
   roofline      fused photometric loss (forward + backward entry points), algorithmic bytes (148 + 164 B per
                 target pixel for n=2, S=4) over the live CUDA-event duration of those calls, vs MEASURED_PEAKS.json
-  cpu_baseline  the oracle port of the reference step (oracle/step.py, PyTorch CPU, all host threads) on a bounded sample
+  roofline_tensor  all tcgen05 products of the step vs the cuBLAS TF32 peak measured on this GPU in the same run
+  gpu_torch_baseline  the library path (torch.nn + ATen: cuDNN / cuBLAS TF32) of the same step on the same GPU
+  cpu_baseline  the reference's own step on the host cores (bounded sample)
 
-`--impl reference` times that CPU port alone (the reference is pure Python/PyTorch and its tree is not present on the GPU
-box, so the arm executes the oracle restatement of it; rank 0 only).
+`--impl reference` times the reference's own CPU step alone: its unmodified modules from the byte-compiled build oracle/_ref
+(the source tree does not exist on the GPU box), or the oracle port when that build is absent; rank 0 only.
 """
 from __future__ import annotations
 
@@ -34,22 +38,40 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-SHAPE, BATCH, N_SUPP, N_SCALES = (384, 640), 8, 2, 4
-DEPTH_ENC, POSE_ENC = 'convnext_tiny', 'resnet18'
-WORKLOAD = 'configs[2]: ConvNeXt-T depth + ResNet-18 pose (KBR default), 384x640, batch 8/GPU, 2 support frames, S=4'
+N_SCALES = 4
+# BASELINE.json configs (SURVEY 8d "Configs -> concrete shapes"); gflop = forward GFLOP per image (x3 for forward + both gradients).
+CONFIGS = {
+    'c2': dict(depth='resnet18', pose='resnet18', shape=(192, 640), batch=12, n=2, learn_K=False, gflop=8.9 + 7.1 + 2*10.3,
+               label='configs[1]: ResNet-18 depth + ResNet-18 pose, 192x640, batch 12, 2 support frames, S=4'),
+    'c3': dict(depth='convnext_tiny', pose='resnet18', shape=(384, 640), batch=8, n=2, learn_K=False, gflop=43.6 + 14.0 + 2*20.7,
+               label='configs[2]: ConvNeXt-T depth + ResNet-18 pose (KBR default), 384x640, batch 8/GPU, 2 support frames, S=4'),
+    'c4': dict(depth='convnext_tiny', pose='resnet18', shape=(384, 640), batch=8, n=4, learn_K=True, gflop=43.6 + 14.0 + 4*20.7,
+               label='configs[3]: learned intrinsics + 4-scale loss + auto-mask, ConvNeXt-T, 384x640, batch 8/GPU, 4 support frames'),
+    'c5': dict(depth='convnext_base', pose='resnet18', shape=(512, 1024), batch=4, n=2, learn_K=False, gflop=320.9 + 34.1 + 2*44.1,
+               label='configs[4]: HR stress, ConvNeXt-B depth, 512x1024, batch 4/GPU, 2 support frames, S=4'),
+}
 CPU_BATCH = 2
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=BATCH)
+    ap.add_argument('--config', default='c3', choices=sorted(CONFIGS), help='BASELINE.json configuration (default c3 = configs[2], the one the metric is quoted on)')
+    ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the configuration\'s)')
+    ap.add_argument('--api', default='auto', choices=['auto', 'plugin', 'native'],
+                    help="plugin: the reference's own MonoDepthModule built through its registry after plugin.install() (needs oracle/_ref); "
+                         'native: slowtv_monodepth_b200.trainer.MonoDepthStep; auto: plugin when the reference build is present')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-torch-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='enqueue every step eagerly instead of replaying the captured CUDA graph')
-    return ap.parse_args()
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.cfg = cfg
+    if args.batch <= 0: args.batch = cfg['batch']
+    return args
 
 
 def peaks() -> tuple[float, str]:
@@ -62,14 +84,14 @@ def peaks() -> tuple[float, str]:
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU arm: oracle port of the reference step
 # ---------------------------------------------------------------------------------------------------------------------
-def reference_cfg(batch: int) -> dict:
+def reference_cfg(batch: int, c: dict) -> dict:
     """The reference's own experiment configuration of the benchmarked workload: cfg/abl_learn_K/default.yaml (ConvNeXt-T depth +
     ResNet-18 pose) with the KBR loss / depth-range / optimiser settings (cfg/kbr/default.yaml), random init."""
     from oracle import ref_shim
     cfg = ref_shim.load_cfg('abl_learn_K/default.yaml')
     kbr = ref_shim.load_cfg('kbr/default.yaml')
-    cfg['net']['depth'].update(enc_name=DEPTH_ENC, pretrained=False)
-    cfg['net']['pose'].update(enc_name=POSE_ENC, pretrained=False, learn_K=False)
+    cfg['net']['depth'].update(enc_name=c['depth'], pretrained=False)
+    cfg['net']['pose'].update(enc_name=c['pose'], pretrained=False, learn_K=c['learn_K'])
     cfg['loss'] = {k: kbr['loss'][k] for k in ('img_recon', 'disp_smooth')}
     cfg['optimizer'] = {'type': 'adamw', 'lr': 1e-4, 'weight_decay': 1e-3}
     cfg['scheduler'] = None
@@ -79,7 +101,7 @@ def reference_cfg(batch: int) -> dict:
     return cfg
 
 
-def cpu_reference(steps: int, warmup: int, batch: int = CPU_BATCH, budget_s: float = 200.0) -> dict:
+def cpu_reference(c: dict, steps: int, warmup: int, batch: int = CPU_BATCH, budget_s: float = 200.0) -> dict:
     """The reference step on the host cores. With the reference build present (oracle/_ref, or /root/reference in the build
     container) this is the REFERENCE'S OWN code — `MonoDepthModule(cfg).step(batch)` built through its registry / parsers, its
     own handlers / ViewSynth / losses, `loss.backward()`, the AdamW its `parsers.get_opt` builds — with only the absent third-party
@@ -92,13 +114,13 @@ def cpu_reference(steps: int, warmup: int, batch: int = CPU_BATCH, budget_s: flo
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    batches = [syn.make_batch(batch, N_SUPP, SHAPE, seed=s) for s in range(2)]
+    batches = [syn.make_batch(batch, c['n'], c['shape'], seed=s) for s in range(2)]
     if ref_shim.available():
         warnings.filterwarnings('ignore')
         ref_shim.load()
         import src.core.trainer as rt
         from src.tools import parsers
-        cfg = reference_cfg(batch)
+        cfg = reference_cfg(batch, c)
         module = rt.MonoDepthModule(cfg).train()
         if not torch.cuda.is_available():  # build container only: the module's timers call torch.cuda.synchronize()
             from src.utils import MultiLevelTimer
@@ -114,7 +136,7 @@ def cpu_reference(steps: int, warmup: int, batch: int = CPU_BATCH, budget_s: flo
         what = f"the reference's own MonoDepthModule.step + backward + AdamW ({ref_shim.kind()} build; timm/Lightning stubbed)"
     else:
         from oracle.step import OracleTrainer
-        tr = OracleTrainer(DEPTH_ENC, POSE_ENC).train()
+        tr = OracleTrainer(c['depth'], c['pose'], learn_K=c['learn_K']).train()
         train_step = tr.train_step
         kind = 'port'
         what = 'oracle port of the reference step (oracle/step.py)'
@@ -135,12 +157,12 @@ def cpu_reference(steps: int, warmup: int, batch: int = CPU_BATCH, budget_s: flo
 def run_reference_arm(args, out) -> None:
     if int(os.environ.get('RANK', '0')) != 0: return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    r = cpu_reference(steps, warmup)
+    r = cpu_reference(args.cfg, steps, warmup)
     line = {
         'impl': 'reference', 'metric': 'training images/sec', 'value': round(r['value'], 4), 'unit': 'images/s',
         'n_gpus': args.gpus, 'steps': r['steps_done'], 'warmup': warmup, 'ms_per_step': round(r['ms_per_step'], 2),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'cpu_batch_per_step': r['batch'], 'requested_steps': args.steps,
+        'config': {'workload': args.cfg['label'], 'cpu_batch_per_step': r['batch'], 'requested_steps': args.steps,
                    'requested_warmup': args.warmup,
                    'note': 'per-image rate at a reduced batch (BASELINE.md section 3); median of the timed steps; the run stops early only past a 200 s budget'},
         'cpu_baseline': {'value': round(r['value'], 4), 'unit': 'images/s', 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']},
@@ -204,16 +226,64 @@ def _claim_stdout():
     return os.fdopen(saved, 'w')
 
 
+def measured_tf32_peak(dev) -> float:
+    """TFLOP/s of cuBLAS TF32 on this GPU, measured now: torch.matmul fp32 8192^3 with TF32 enabled, best of 6 (CUDA events)."""
+    n = 8192
+    a, b = torch.randn(n, n, device=dev), torch.randn(n, n, device=dev)
+    best = float('inf')
+    for i in range(8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record()
+        torch.cuda.synchronize()
+        if i >= 2: best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0*n**3/1e12/(best/1e3)
+
+
+def photo_traffic() -> tuple[float | None, str]:
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r2_photo_traffic.json, written by
+    tools/ncu_traffic.py from `ncu --set full`), or None when no capture of this build has been committed."""
+    f = ROOT/'profiles'/'r2_photo_traffic.json'
+    if not f.is_file(): return None, 'no committed ncu capture (profiles/r2_photo_traffic.json)'
+    d = json.loads(f.read_text())
+    return float(d['dram_bytes_per_step']), d.get('source', str(f.name))
+
+
+def torch_gpu_baseline(c: dict, batch: int, dev, steps: int = 10, warmup: int = 3) -> dict:
+    """The library path on the same box: the oracle port of the reference step (plain torch.nn modules + ATen ops: cuDNN / cuBLAS
+    TF32, cudnn.benchmark, torch.optim.AdamW) run eagerly on this GPU — what the reference itself would execute here."""
+    from oracle.step import OracleTrainer
+    from slowtv_monodepth_b200 import synthetic as syn
+    torch.manual_seed(0)
+    tr = OracleTrainer(c['depth'], c['pose'], learn_K=c['learn_K']).to(dev).train()
+    bs = [syn.make_batch(batch, c['n'], c['shape'], seed=900 + s, device=dev) for s in range(2)]
+    for i in range(warmup): tr.train_step(bs[i % 2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps): tr.train_step(bs[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)/steps
+    del tr, bs
+    torch.cuda.empty_cache()
+    return {'value': round(batch/(ms/1e3), 2), 'unit': 'images/s', 'ms_per_step': round(ms, 3), 'steps': steps,
+            'what': 'oracle port of the reference step as torch.nn modules + ATen ops on this GPU (cuDNN/cuBLAS TF32, cudnn.benchmark, '
+                    'torch.optim.AdamW), eager, inputs resident'}
+
+
 def main() -> None:
     args = parse()
     out = _claim_stdout()
     if args.impl == 'reference': return run_reference_arm(args, out)
 
     import torch.distributed as dist
+    from oracle import ref_shim
     from slowtv_monodepth_b200 import _lib as L, functional as F_, synthetic as syn
     from slowtv_monodepth_b200.optim import FlatAdamW
-    from slowtv_monodepth_b200.trainer import GraphedTrainStep, MonoDepthStep, default_cfg
+    from slowtv_monodepth_b200.trainer import GraphedTrainStep, MonoDepthStep, default_cfg, gradient_buckets
 
+    c = args.cfg
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank, local = int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
     if not torch.cuda.is_available(): raise SystemExit('bench.py needs a CUDA device (no CPU fallback for --impl ours).')
@@ -228,15 +298,28 @@ def main() -> None:
     torch.set_float32_matmul_precision('high')
 
     L.lib()  # fail loudly if libstv.so is missing
-    b, (H, W) = args.batch, SHAPE
-    torch.manual_seed(1234)  # identical initial weights on every rank (DDP broadcast equivalent)
-    model = MonoDepthStep(default_cfg(DEPTH_ENC, POSE_ENC)).to(dev).train()
-    model = model.to(memory_format=torch.channels_last)
-    opt = FlatAdamW(model.nets, lr=1e-4, weight_decay=1e-3)
+    b, (H, W), n_supp = args.batch, c['shape'], c['n']
+    torch.manual_seed(1234)  # identical initial weights on every rank (FlatAdamW also broadcasts rank 0's, like DDP)
+    use_plugin = args.api == 'plugin' or (args.api == 'auto' and ref_shim.available())
+    if use_plugin:
+        # The drop-in: the REFERENCE'S OWN module, built by its own parsers through its registry after plugin.install(); its own
+        # step / forward_loss / handlers call sites run, with the B200 classes behind them.
+        import warnings
+        warnings.filterwarnings('ignore')
+        from slowtv_monodepth_b200 import plugin
+        ref_shim.load()
+        plugin.install()
+        import src.core.trainer as rt
+        model = rt.MonoDepthModule(reference_cfg(b, c)).to(dev).train()
+        api = f"plugin: the reference's MonoDepthModule(cfg).step via src.registry after plugin.install() ({ref_shim.kind()} build of the reference)"
+    else:
+        model = MonoDepthStep(default_cfg(c['depth'], c['pose'], learn_K=c['learn_K'])).to(dev).train()
+        api = 'native: slowtv_monodepth_b200.trainer.MonoDepthStep.step'
+    opt = FlatAdamW(model.nets, lr=1e-4, weight_decay=1e-3, buckets=gradient_buckets(model.nets))
     n_params = opt.flat.numel()
 
     # Distinct batches per rank (DistributedSampler equivalent): seed = base + rank. Two batches are rotated.
-    host = [syn.make_batch(b, N_SUPP, SHAPE, seed=100*rank + s, pin=True) for s in range(2)]
+    host = [syn.make_batch(b, n_supp, c['shape'], seed=100*rank + s, pin=True) for s in range(2)]
     to_dev = lambda bt: ({k: (v.to(dev, non_blocking=True) if k != 'supp_idxs' else v) for k, v in bt[0].items()},
                          {k: v.to(dev, non_blocking=True) for k, v in bt[1].items()}, {})
     resident = [to_dev(bt) for bt in host]
@@ -244,7 +327,7 @@ def main() -> None:
 
     def eager_step(batch):
         opt.zero_grad()
-        loss, _, _ = model.step(batch)
+        loss = model.step(batch)[0]
         loss.backward()
         opt.all_reduce_async()
         opt.step()
@@ -255,7 +338,7 @@ def main() -> None:
     eager_step(resident[1])
     torch.cuda.synchronize()
     F_.reset_kernel_timings()
-    TIMED_STEPS = 3
+    TIMED_STEPS = 5
     for i in range(TIMED_STEPS): eager_step(resident[i % 2])
     torch.cuda.synchronize()
     kt = F_.kernel_timings()
@@ -264,7 +347,9 @@ def main() -> None:
     if not args.no_graph:
         try:
             graphed = GraphedTrainStep(model, opt, resident[0])
-            graph_note = 'CUDA graph replay of zero_grad+fwd+loss+bwd, then all-reduce + AdamW'
+            graph_note = 'CUDA graph replay of fwd+loss+bwd' + (' + per-bucket NCCL all-reduce overlapped inside the graph' if graphed.overlap
+                                                                  else (', then all-reduce' if world > 1 else '')) + ', then AdamW'
+            if world > 1 and not graphed.overlap and hasattr(graphed, 'overlap_error'): graph_note += f' (overlap capture failed: {graphed.overlap_error})'
         except Exception as e:  # keep the benchmark alive: report the eager number and say why
             torch.cuda.synchronize()
             graph_note = f'eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})'
@@ -327,47 +412,55 @@ def main() -> None:
     if rank == 0:
         peak, peak_src = peaks()
         px = b*H*W
-        bytes_fwd, bytes_bwd = (12 + 12*N_SUPP + 12*N_SUPP*N_SCALES + 4*N_SCALES)*px, (12 + 12*N_SUPP + 12*N_SUPP*N_SCALES + 8*N_SCALES)*px
+        per_px_fwd = 12 + 12*n_supp + 12*n_supp*N_SCALES + 4*N_SCALES    # target + identity supports + gathered supports + depth
+        per_px_bwd = per_px_fwd + 4*N_SCALES                              # + d loss/d depth_up written
+        bytes_fwd, bytes_bwd = per_px_fwd*px, per_px_bwd*px
         mean = lambda v: sum(v)/max(len(v), 1)
         t_f, t_b = mean(kt.get('stv_photo_fwd', [0])), mean(kt.get('stv_photo_bwd', [0]))
         gbs = lambda by, t: (by/1e9)/(t/1e3) if t > 0 else 0.0
         ach = gbs(bytes_fwd + bytes_bwd, t_f + t_b)
-        # Tensor-core kernel (every Linear / convolution product of the networks): algorithmic FLOPs of config 3 from SURVEY 8d
-        # (forward 43.6 + 14.0 + 2 x 20.7 GFLOP per image, x3 for forward + both gradients) over the summed live duration of
-        # the stv_gemm_tf32 / stv_conv_* calls of one step; peak = TF32 dense = half the measured bf16 figure.
+        traffic, traffic_src = photo_traffic() if args.config == 'c3' else (None, 'captured for configs[2] only')
+        # Tensor-core kernel (every Linear / convolution product of the networks): algorithmic FLOPs from SURVEY 8d (forward GFLOP
+        # per image x3 for forward + both gradients) over the summed live duration of the stv_gemm_tf32 / stv_conv_* calls of one
+        # step; peak = cuBLAS TF32 measured on this GPU just now.
         tc_ms = sum(sum(kt.get(k, [])) for k in ('stv_gemm_tf32', 'stv_conv_fprop', 'stv_conv_dgrad', 'stv_conv_wgrad'))/TIMED_STEPS
-        tc_flops = 3*(43.6 + 14.0 + N_SUPP*20.7)*1e9*b*(H*W)/(384*640)
-        pk = json.loads((ROOT/'MEASURED_PEAKS.json').read_text()) if (ROOT/'MEASURED_PEAKS.json').is_file() else {}
-        tc_peak = float(pk.get('bf16_tflops_sustained', 1400.0))/2
+        tc_flops = 3*c['gflop']*1e9*b
+        tc_peak = measured_tf32_peak(dev)
         tc_ach = tc_flops/1e12/(tc_ms/1e3) if tc_ms > 0 else 0.0
+        loss_ms = {k: round(mean(kt.get(k, [0])), 4) for k in ('stv_photo_fwd', 'stv_photo_bwd', 'stv_smooth_fwd', 'stv_smooth_bwd')}
         line = {
             'metric': 'training images/sec', 'value': round(b*world*args.steps/(ms/1e3), 3), 'unit': 'images/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(ms/args.steps, 3),
             'host_enqueue_ms_per_step': round(host_ms, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'global_batch': b*world, 'per_gpu_batch': b, 'parallelism': f'dp{world}', 'launch': graph_note,
-                       'params': n_params, 'optimizer': 'adamw(lr=1e-4, wd=1e-3), fused flat-buffer kernel',
-                       'l2_policy': 'inputs larger than L2: two rotating 141 MB batches + multi-GB activations per step',
+            'config': {'workload': c['label'], 'config': args.config, 'api': api, 'global_batch': b*world, 'per_gpu_batch': b,
+                       'parallelism': f'dp{world}', 'launch': graph_note,
+                       'params': n_params, 'optimizer': 'adamw(lr=1e-4, wd=1e-3), fused flat-buffer kernel per gradient bucket',
+                       'l2_policy': f'inputs larger than L2: two rotating {h2d_bytes/1e6:.0f} MB batches + multi-GB activations per step',
                        'numerics': 'fp32 storage, TF32 tensor-core matmul/conv (reference: precision 32, matmul high), fp32 loss kernels'},
             'clocks': clocks,
             'e2e': {'value': round(b*world*args.steps/(ms_e2e/1e3), 3), 'unit': 'images/s', 'ms_per_step': round(ms_e2e/args.steps, 3),
-                    'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'last_loss': last.get('loss')},
+                    'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'last_loss': last.get('loss'), 'api': api},
             'gpu_launches': launches,
-            'roofline': {'kernel': 'fused photometric loss, stv_photo_fwd + stv_photo_bwd', 'bound': 'hbm', 'achieved': round(ach, 1),
+            'roofline': {'kernel': 'fused photometric loss: stv_photo_fused_fwd (loss + unit gradients in one sweep) + stv_photo_fused_bwd',
+                         'bound': 'hbm', 'achieved': round(ach, 1),
                          'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(ach/peak, 4),
-                         'traffic': 1252.0e6, 'traffic_source': 'ncu --set full dram__bytes_read+write: fwd 343 + 297 MB, bwd 579 + 33 MB (profiles/r1f_loss_ncu_full_summary.txt); the 2x over the algorithmic bytes is the (S,b,9,H,W) SSIM coefficient planes the forward hands to the backward (283 MB written, re-read with a 1-pixel halo) — traded for a 2.4x shorter backward',
-                         'algorithmic_bytes_per_launch': bytes_fwd + bytes_bwd, 'avg_ms': round(t_f + t_b, 4),
-                         'detail': {'photo_fwd': {'ms': round(t_f, 4), 'GB/s': round(gbs(bytes_fwd, t_f), 1), 'frac': round(gbs(bytes_fwd, t_f)/peak, 4)},
-                                    'photo_bwd': {'ms': round(t_b, 4), 'GB/s': round(gbs(bytes_bwd, t_b), 1), 'frac': round(gbs(bytes_bwd, t_b)/peak, 4)},
-                                    'smooth_fwd_ms': round(mean(kt.get('stv_smooth_fwd', [0])), 4),
-                                    'smooth_bwd_ms': round(mean(kt.get('stv_smooth_bwd', [0])), 4)}},
+                         'traffic': traffic, 'traffic_source': traffic_src,
+                         'algorithmic_bytes_per_launch': bytes_fwd + bytes_bwd, 'algorithmic_bytes_per_pixel': per_px_fwd + per_px_bwd,
+                         'avg_ms': round(t_f + t_b, 4),
+                         'detail': {'photo_fwd_ms': loss_ms['stv_photo_fwd'], 'photo_bwd_ms': loss_ms['stv_photo_bwd'],
+                                    'smooth_fwd_ms': loss_ms['stv_smooth_fwd'], 'smooth_bwd_ms': loss_ms['stv_smooth_bwd'],
+                                    'loss_stack_ms': round(sum(loss_ms.values()), 4)}},
         }
         line['roofline_tensor'] = {
             'kernel': 'gemm_tf32_kernel (tcgen05 kind::tf32 + TMA/TMA-im2col + TMEM): all Linear / convolution fwd, dgrad, wgrad of the step',
-            'bound': 'tensor', 'achieved': round(tc_ach, 1), 'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': round(tc_ach/tc_peak, 4),
-            'peak_source': 'TF32 dense = MEASURED_PEAKS.json bf16_tflops_sustained / 2', 'algorithmic_flops_per_step': tc_flops,
+            'bound': 'tensor', 'achieved': round(tc_ach, 1), 'peak': round(tc_peak, 1), 'unit': 'TFLOP/s', 'frac': round(tc_ach/tc_peak, 4),
+            'peak_source': 'measured now: torch.matmul fp32 8192^3 with TF32 enabled (cuBLAS), best of 6', 'algorithmic_flops_per_step': tc_flops,
             'ms_per_step_in_kernel_calls': round(tc_ms, 3)}
+        if world == 1 and not args.no_torch_baseline:
+            try: line['gpu_torch_baseline'] = torch_gpu_baseline(c, b, dev)
+            except Exception as e: line['gpu_torch_baseline'] = {'unavailable': f'{type(e).__name__}: {str(e)[:160]}'}
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference(steps=5, warmup=2, budget_s=60.0)
+            r = cpu_reference(c, steps=5, warmup=2, budget_s=60.0)
             line['cpu_baseline'] = {'value': round(r['value'], 4), 'unit': 'images/s', 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']}
         print(json.dumps(line), file=out, flush=True)
     if world > 1: dist.destroy_process_group()

@@ -56,8 +56,6 @@ typedef struct {
 } stv_photo_cfg;
 
 size_t stv_photo_workspace_bytes(const stv_photo_cfg* cfg);
-/* Bytes of the optional coefficient planes (S,b,9,H,W) handed from stv_photo_fwd to stv_photo_bwd (use_min only). */
-size_t stv_photo_coef_bytes(const stv_photo_cfg* cfg);
 
 /* loss (device scalar) = mean over (S,b,H,W) of the reduced, auto-masked photometric error.
  * depth: S pointers to (b,1,H,W) upsampled depth maps; tgt (b,3,H,W); supp (n,b,3,H,W); T (n,b,4,4); K, Kinv (b,4,4);
@@ -66,27 +64,69 @@ size_t stv_photo_coef_bytes(const stv_photo_cfg* cfg);
  *   noise_seed + *noise_step and the call advances *noise_step by one, stream-ordered after its last reader — a captured CUDA
  *   graph therefore draws fresh noise on every replay, as torch.randn_like does every step;
  * sel (S,b,H,W) u8: per-pixel decision (support index | STV_SEL_STATIC | STV_SEL_MEAN), consumed by the backward;
- * warp0: NULL or (n,b,3,H,W) warped support frames at scale 0 (handlers.py:66);
- * coef: NULL, or (use_min only) stv_photo_coef_bytes() of device memory that receives, per (scale, pixel), the nine
- *   numbers d SSIMError_c / d(sum x, sum x^2, sum xy) of the support frame the pixel selected (undefined where the
- *   static frame won; `sel` masks them): what autograd would keep of photometric.py:40-50 for the backward pass. */
+ * warp0: NULL or (n,b,3,H,W) warped support frames at scale 0 (handlers.py:66).
+ * Two-pass formulation, any reduction (min / mean) and any n <= STV_MAX_SUPPORT; the default configuration (min-reprojection,
+ * n <= STV_FUSED_MAX_SUPPORT) is served by the single-pass stv_photo_fused_fwd below. */
 int stv_photo_fwd(const stv_photo_cfg* cfg, const float* const* depth, const float* tgt, const float* supp,
                   const float* T, const float* K, const float* Kinv, const float* noise, unsigned long long* noise_step,
-                  float* loss, uint8_t* sel, float* warp0, float* coef, void* ws, size_t ws_bytes, void* stream);
+                  float* loss, uint8_t* sel, float* warp0, void* ws, size_t ws_bytes, void* stream);
 
 /* Backward of stv_photo_fwd w.r.t. depth, T, K and Kinv. grad_loss: device scalar dL/dloss.
  * g_depth: S pointers to (b,1,H,W) (overwritten); gT (n,b,4,4) (overwritten; row 3 = 0);
  * gK, gKinv (b,4,4) nullable (overwritten; only the 3x3 block is non-zero).
- * coef: the planes stv_photo_fwd wrote (lean path: masked 3x3 box sums + the pixel's own sampler/projection chain), or NULL
- *   (the kernel then re-warps a halo-2 tile and rebuilds the SSIM window sums itself; required when !use_min). */
+ * Self-contained: re-warps a halo-2 tile per support frame and rebuilds the SSIM window sums. */
 int stv_photo_bwd(const stv_photo_cfg* cfg, const float* const* depth, const float* tgt, const float* supp,
-                  const float* T, const float* K, const float* Kinv, const uint8_t* sel, const float* coef, const float* grad_loss,
+                  const float* T, const float* K, const float* Kinv, const uint8_t* sel, const float* grad_loss,
                   float* const* g_depth, float* gT, float* gK, float* gKinv, void* ws, size_t ws_bytes, void* stream);
 
 /* compute_photo (reconstruction.py:79-96) on its own: pred (n,b,3,H,W) vs target (b,3,H,W) -> err (b,1,H,W).
  * Forward only (used for the identity/static error and by `depth_regr`, src/core/trainer.py:430). */
 int stv_photo_error(const stv_photo_cfg* cfg /* b,n,H,W,w_ssim,w_l1,use_min */, const float* pred, const float* tgt,
                     float* err, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Single-pass fused photometric loss (min-reprojection, <= STV_FUSED_MAX_SUPPORT support frames): same inputs and semantics as
+ * stv_photo_fwd, but the loss AND its gradients come out of ONE sweep (the loss is a mean, so d loss/d(.) is known up to the
+ * scalar dL/dloss as soon as a pixel's decision is taken) — no SSIM coefficient planes or re-warp between a forward and a
+ * backward kernel. The kernel can also consume the network's low-resolution sigmoid disparities directly, fusing
+ * ops.interpolate_like + to_scaled (src/core/trainer.py:320-321) into the sweep.
+ *   src->mode STV_PHOTO_SRC_DEPTH: maps[s] = (b,1,H,W) up-sampled depth (what handlers.image_recon receives, handlers.py:48);
+ *   src->mode STV_PHOTO_SRC_DISP:  maps[s] = (b,1,h[s],w[s]) sigmoid disparity; depth = to_inv(to_scaled(upsample(disp))) with
+ *                                  min_depth / max_depth (<= 0: unset -> to_inv only).
+ * supp_tex: 0, or a handle from stv_tex_create(supp, n*b*3*H, W) (2x2 gathers through the texture unit; same results).
+ * g_unit: NULL (forward only), or S pointers to (b,1,H,W) receiving d loss/d(up-sampled map) for dL/dloss = 1 (mode DEPTH: d/d depth;
+ *   mode DISP: d/d up-sampled disparity); gpart: stv_photo_fused_partial_bytes() of device memory receiving per-strip moment sums
+ *   of the pose / intrinsics gradients. Both are handed unchanged to stv_photo_fused_bwd.
+ * Everything else as stv_photo_fwd (loss, sel, warp0, noise, noise_step, ws >= stv_photo_fused_workspace_bytes()).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define STV_FUSED_MAX_SUPPORT 4
+#define STV_PHOTO_SRC_DEPTH 0
+#define STV_PHOTO_SRC_DISP 1
+typedef struct {
+    int mode;
+    int h[STV_MAX_SCALES], w[STV_MAX_SCALES];
+    float min_depth, max_depth;
+} stv_photo_src;
+
+size_t stv_photo_fused_workspace_bytes(const stv_photo_cfg* cfg);
+size_t stv_photo_fused_partial_bytes(const stv_photo_cfg* cfg);
+int stv_photo_fused_fwd(const stv_photo_cfg* cfg, const stv_photo_src* src, const float* const* maps, const float* tgt,
+                        const float* supp, unsigned long long supp_tex, const float* T, const float* K, const float* Kinv,
+                        const float* noise, unsigned long long* noise_step, float* loss, uint8_t* sel, float* warp0,
+                        float* const* g_unit, float* gpart, void* ws, size_t ws_bytes, void* stream);
+/* Backward of stv_photo_fused_fwd: nothing is recomputed. g_maps[s] (nullable array; overwritten) = grad_loss * g_unit[s] pulled back
+ * to the layout of maps[s] (mode DISP: through the adjoint of the bilinear up-sampling, deterministic gathers; mode DEPTH: as is;
+ * g_maps[s] may alias g_unit[s] in mode DEPTH). gT (n,b,4,4) (nullable), gK, gKinv (b,4,4) (nullable) from gpart, scaled by
+ * grad_loss (device scalar). ws >= stv_photo_fused_bwd_workspace_bytes(). */
+size_t stv_photo_fused_bwd_workspace_bytes(const stv_photo_cfg* cfg, const stv_photo_src* src);
+int stv_photo_fused_bwd(const stv_photo_cfg* cfg, const stv_photo_src* src, const float* grad_loss, const float* const* g_unit,
+                        const float* gpart, const float* T, const float* Kinv, float* const* g_maps, float* gT, float* gK,
+                        float* gKinv, void* ws, size_t ws_bytes, void* stream);
+/* Texture view of a (rows, W) fp32 plane stack for the 2x2 gathers of the photometric kernels. *handle = 0 when the buffer cannot
+ * be bound (alignment / size limits): the kernels then use plain loads. The CALLER owns the handle (create it outside CUDA-graph
+ * capture, destroy it when the buffer goes away); the library keeps no cache. */
+int stv_tex_create(const float* ptr, long long rows, int W, unsigned long long* handle);
+int stv_tex_destroy(unsigned long long handle);
 
 /* ReconstructionLoss.forward on ALREADY WARPED frames (src/losses/reconstruction.py:98-126; what a caller of the registered
  * `img_recon` class gets when it warps elsewhere, e.g. the virtual-stereo branch src/core/trainer.py:394-399), and its gradient
@@ -121,9 +161,11 @@ int stv_view_synth_bwd(int B, int C, int H, int W, const float* input, const flo
  * ------------------------------------------------------------------------------------------------------------------ */
 int stv_disp_to_depth_fwd(int b, int h, int w, int H, int W, float min_depth, float max_depth, const float* disp,
                           float* disp_up, float* depth_up, void* stream);
-/* g_disp (b,1,h,w) = d(depth_up)/d(disp)^T g_depth_up [+ d(disp_up)/d(disp)^T g_disp_up when non-NULL]. Deterministic gather. */
+/* g_disp (b,1,h,w) = d(depth_up)/d(disp)^T g_depth_up [+ d(disp_up)/d(disp)^T g_disp_up]; either gradient may be NULL.
+ * Two separable deterministic gathers (rows, then columns); ws >= stv_disp_to_depth_bwd_workspace_bytes(). */
+size_t stv_disp_to_depth_bwd_workspace_bytes(int b, int h, int w, int H, int W);
 int stv_disp_to_depth_bwd(int b, int h, int w, int H, int W, float min_depth, float max_depth, const float* disp,
-                          const float* g_depth_up, const float* g_disp_up, float* g_disp, void* stream);
+                          const float* g_depth_up, const float* g_disp_up, float* g_disp, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Edge-aware smoothness: replaces handlers.disp_smooth (src/core/handlers.py:262-281) = per scale

@@ -3,8 +3,10 @@
 TEST INFRASTRUCTURE. The reference (jspenmar/slowtv_monodepth) is pure Python, its tree (`/root/reference`) exists only in the
 build container, and its sources must not be copied into this repository. What CAN travel to the GPU box is a *built* artefact,
 exactly like a compiled `.so`: this script byte-compiles the reference's hot-path packages from the sources where they lie
-(`py_compile`, no source text is written anywhere) into `oracle/_ref/src/**.pyc` (sourceless import layout), and dumps the
-experiment configurations the benchmarks name as parsed JSON (`oracle/_ref/cfg.json`). `oracle/_ref/` is git-ignored (never
+(`py_compile`, no source text is written anywhere) into ONE archive `oracle/_ref/ref_build.zip` holding `src/**.pyc` in the
+sourceless import layout (imported through zipimport; a single binary file, because directory trees of `*.pyc` are commonly
+filtered out when a work tree is shipped), and dumps the experiment configurations the benchmarks name as parsed JSON
+(`oracle/_ref/cfg.json`). `oracle/_ref/` is git-ignored (never
 enters history) and not gpurun-ignored (ships with the snapshot). `__graft_entry__.build()` runs this when `/root/reference`
 is present; on the GPU box the prebuilt files are used as they are.
 
@@ -20,11 +22,14 @@ import json
 import py_compile
 import shutil
 import sys
+import tempfile
+import zipfile
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 REF = Path('/root/reference')
 OUT = ROOT/'oracle'/'_ref'
+ARCHIVE = 'ref_build.zip'
 SKIP = ('external_libs/dgp', 'external_libs/midas', 'external_libs/newcrfs')
 CFGS = ['default.yaml', 'kbr/default.yaml', 'abl_learn_K/default.yaml', 'benchmark/default.yaml', 'benchmark/monodepth2_M.yaml']
 
@@ -43,16 +48,18 @@ def build(force: bool = False) -> Path | None:
     st = stamp()
     if not force and (OUT/'STAMP').is_file() and (OUT/'STAMP').read_text() == st: return OUT
     if OUT.exists(): shutil.rmtree(OUT)
+    OUT.mkdir(parents=True)
     n = 0
-    for f in sorted((REF/'src').rglob('*.py')):
-        rel = f.relative_to(REF)
-        if any(s in rel.as_posix() for s in SKIP): continue
-        dst = (OUT/rel).with_suffix('.pyc')
-        dst.parent.mkdir(parents=True, exist_ok=True)
-        # dfile: tracebacks keep pointing at the reference's own file:line
-        py_compile.compile(str(f), cfile=str(dst), dfile=str(f), doraise=True, optimize=0,
-                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
-        n += 1
+    with tempfile.TemporaryDirectory() as tmp, zipfile.ZipFile(OUT/ARCHIVE, 'w', zipfile.ZIP_DEFLATED) as zf:
+        for f in sorted((REF/'src').rglob('*.py')):
+            rel = f.relative_to(REF)
+            if any(s in rel.as_posix() for s in SKIP): continue
+            dst = Path(tmp)/'m.pyc'
+            # dfile: tracebacks keep pointing at the reference's own file:line
+            py_compile.compile(str(f), cfile=str(dst), dfile=str(f), doraise=True, optimize=0,
+                               invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+            zf.write(dst, rel.with_suffix('.pyc').as_posix())
+            n += 1
     import yaml
     cfgs = {c: yaml.safe_load((REF/'cfg'/c).read_text()) for c in CFGS if (REF/'cfg'/c).is_file()}
     (OUT/'cfg.json').write_text(json.dumps(cfgs))

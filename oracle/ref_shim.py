@@ -22,11 +22,12 @@ from pathlib import Path
 
 SRC_ROOT = Path(os.environ.get('STV_REFERENCE_ROOT', '/root/reference'))
 BUILT_ROOT = Path(__file__).resolve().parent/'_ref'
+BUILT_ARCHIVE = BUILT_ROOT/'ref_build.zip'   # src/**.pyc, imported through zipimport (oracle/build_ref.py)
 
 
 def _root() -> Path | None:
     if (SRC_ROOT/'src'/'tools'/'geometry.py').is_file(): return SRC_ROOT
-    if (BUILT_ROOT/'src'/'tools'/'geometry.pyc').is_file(): return BUILT_ROOT
+    if BUILT_ARCHIVE.is_file(): return BUILT_ARCHIVE
     return None
 
 

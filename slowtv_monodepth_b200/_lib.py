@@ -29,6 +29,10 @@ class PhotoCfg(C.Structure):
                 ('noise_seed', C.c_uint64), ('depth_stride_s', C.c_int64)]
 
 
+class PhotoSrc(C.Structure):
+    _fields_ = [('mode', C.c_int), ('h', C.c_int*MAX_SCALES), ('w', C.c_int*MAX_SCALES), ('min_depth', C.c_float), ('max_depth', C.c_float)]
+
+
 class GemmEpi(C.Structure):
     _fields_ = [('bias', C.c_void_p), ('aux', C.c_void_p), ('gamma', C.c_void_p), ('res', C.c_void_p), ('dact_src', C.c_void_p),
                 ('colsum', C.c_void_p), ('act', C.c_int), ('dact', C.c_int), ('accumulate', C.c_int)]
@@ -53,10 +57,16 @@ _SIGNATURES = {
     'stv_last_error': (C.c_char_p, []),
     'stv_launch_count': (C.c_ulonglong, []),
     'stv_photo_workspace_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
-    'stv_photo_coef_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
-    'stv_photo_fwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
-    'stv_photo_bwd': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    'stv_photo_fwd': (C.c_int, [C.POINTER(PhotoCfg)] + [_P]*12 + [C.c_size_t, _P]),
+    'stv_photo_bwd': (C.c_int, [C.POINTER(PhotoCfg)] + [_P]*13 + [C.c_size_t, _P]),
     'stv_photo_error': (C.c_int, [C.POINTER(PhotoCfg), _P, _P, _P, _P]),
+    'stv_photo_fused_workspace_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
+    'stv_photo_fused_partial_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
+    'stv_photo_fused_fwd': (C.c_int, [C.POINTER(PhotoCfg), C.POINTER(PhotoSrc), _P, _P, _P, C.c_ulonglong] + [_P]*11 + [C.c_size_t, _P]),
+    'stv_photo_fused_bwd_workspace_bytes': (C.c_size_t, [C.POINTER(PhotoCfg), C.POINTER(PhotoSrc)]),
+    'stv_photo_fused_bwd': (C.c_int, [C.POINTER(PhotoCfg), C.POINTER(PhotoSrc)] + [_P]*10 + [C.c_size_t, _P]),
+    'stv_tex_create': (C.c_int, [_P, C.c_longlong, C.c_int, C.POINTER(C.c_ulonglong)]),
+    'stv_tex_destroy': (C.c_int, [C.c_ulonglong]),
     'stv_recon_workspace_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
     'stv_recon_fwd': (C.c_int, [C.POINTER(PhotoCfg)] + [_P]*9 + [C.c_size_t, _P]),
     'stv_recon_bwd': (C.c_int, [C.POINTER(PhotoCfg)] + [_P]*6),
@@ -64,7 +74,8 @@ _SIGNATURES = {
     'stv_view_synth_workspace_bytes': (C.c_size_t, [C.c_int]*4),
     'stv_view_synth_bwd': (C.c_int, [C.c_int]*4 + [_P]*13 + [C.c_size_t, _P]),
     'stv_disp_to_depth_fwd': (C.c_int, [C.c_int]*5 + [C.c_float]*2 + [_P]*4),
-    'stv_disp_to_depth_bwd': (C.c_int, [C.c_int]*5 + [C.c_float]*2 + [_P]*5),
+    'stv_disp_to_depth_bwd_workspace_bytes': (C.c_size_t, [C.c_int]*5),
+    'stv_disp_to_depth_bwd': (C.c_int, [C.c_int]*5 + [C.c_float]*2 + [_P]*5 + [C.c_size_t, _P]),
     'stv_smooth_workspace_bytes': (C.c_size_t, [C.POINTER(SmoothCfg)]),
     'stv_smooth_fwd': (C.c_int, [C.POINTER(SmoothCfg), _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     'stv_smooth_bwd': (C.c_int, [C.POINTER(SmoothCfg), _P, _P, _P, _P, _P, C.c_size_t, _P]),

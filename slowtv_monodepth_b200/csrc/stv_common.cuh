@@ -25,6 +25,9 @@ int check_launch(const char* what);
         }                                          \
     } while (0)
 
+// Identity (static) photometric error min_k photo(supp_k, tgt) for the auto-mask -> e0 (b,H,W); defined in stv_photo.cu.
+int photo_identity_error(const stv_photo_cfg* c, const float* tgt, const float* supp, float* e0, cudaStream_t st);
+
 // ---- small device helpers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ int reflect_idx(int i, int n) {  // nn.ReflectionPad2d(1): -1 -> 1, n -> n-2
     i = i < 0 ? -i : i;

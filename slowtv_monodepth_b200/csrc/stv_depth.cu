@@ -37,51 +37,6 @@ __global__ void __launch_bounds__(256) disp_to_depth_fwd_kernel(int h, int w, in
     depth_up[o] = to_depth(v, ds, dprime);
 }
 
-// Gather form of the adjoint: every low-res pixel visits the output pixels whose taps include it.
-__global__ void __launch_bounds__(256) disp_to_depth_bwd_kernel(int h, int w, int H, int W, DepthScale ds,
-                                                                const float* __restrict__ disp,
-                                                                const float* __restrict__ g_depth_up,
-                                                                const float* __restrict__ g_disp_up,
-                                                                float* __restrict__ g_disp) {
-    const int xl = blockIdx.x*blockDim.x + threadIdx.x, yl = blockIdx.y, i = blockIdx.z;
-    if (xl >= w) return;
-    const float ry = (float)h/(float)H, rx = (float)w/(float)W;
-    // Output rows whose floor(src) is yl-1 or yl: src in [yl-1, yl+1)  (plus the clamp-to-0 rows when yl == 0)
-    const int Ylo = yl == 0 ? 0 : max(0, (int)floorf(((float)yl - 0.5f)/ry - 0.5f) - 1);
-    const int Yhi = min(H - 1, (int)ceilf(((float)yl + 1.5f)/ry - 0.5f) + 1);
-    const int Xlo = xl == 0 ? 0 : max(0, (int)floorf(((float)xl - 0.5f)/rx - 0.5f) - 1);
-    const int Xhi = min(W - 1, (int)ceilf(((float)xl + 1.5f)/rx - 0.5f) + 1);
-    const float* p = disp + (size_t)i*h*w;
-    float acc = 0.f;
-    for (int Y = Ylo; Y <= Yhi; ++Y) {
-        int y0, y1; float ly;
-        lin_tap(Y, ry, h, y0, y1, ly);
-        const float wy = (y0 == yl ? 1.f - ly : 0.f) + (y1 == yl ? ly : 0.f);
-        if (wy == 0.f) continue;
-        for (int X = Xlo; X <= Xhi; ++X) {
-            int x0, x1; float lx;
-            lin_tap(X, rx, w, x0, x1, lx);
-            const float wx = (x0 == xl ? 1.f - lx : 0.f) + (x1 == xl ? lx : 0.f);
-            if (wx == 0.f) continue;
-            const size_t o = (size_t)i*H*W + (size_t)Y*W + X;
-            float gup = g_disp_up ? __ldg(g_disp_up + o) : 0.f;
-            if (g_depth_up) {
-                // recompute the upsampled disparity of this output pixel for d depth / d disp'
-                const float v = (1.f - ly)*((1.f - lx)*__ldg(p + y0*w + x0) + lx*__ldg(p + y0*w + x1)) +
-                                ly*((1.f - lx)*__ldg(p + y1*w + x0) + lx*__ldg(p + y1*w + x1));
-                float dprime;
-                to_depth(v, ds, dprime);
-                if (dprime > 0.f && dprime >= STV_EPS32) {
-                    const float inv = 1.0f/dprime;
-                    gup = fmaf(-__ldg(g_depth_up + o)*inv*inv, ds.scaled ? ds.mul : 1.f, gup);
-                }
-            }
-            acc = fmaf(wy*wx, gup, acc);
-        }
-    }
-    g_disp[(size_t)i*h*w + (size_t)yl*w + xl] = acc;
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // Stand-alone ViewSynth (src/tools/geometry.py:366-391) for arbitrary channel counts. grid = (ceil(HW/256), B)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -224,18 +179,6 @@ extern "C" int stv_disp_to_depth_fwd(int b, int h, int w, int H, int W, float mi
                                                                                          disp, disp_up, depth_up);
     count_launch();
     return check_launch("disp_to_depth_fwd_kernel");
-}
-
-extern "C" int stv_disp_to_depth_bwd(int b, int h, int w, int H, int W, float min_depth, float max_depth, const float* disp,
-                                     const float* g_depth_up, const float* g_disp_up, float* g_disp, void* stream) {
-    STV_REQUIRE(b > 0 && h > 0 && w > 0 && H > 0 && W > 0, "stv_disp_to_depth_bwd: bad shape");
-    STV_REQUIRE(b <= 65535 && h <= 65535, "stv_disp_to_depth_bwd: b/h exceed grid limits");
-    STV_REQUIRE(disp && g_disp && (g_depth_up || g_disp_up), "stv_disp_to_depth_bwd: NULL pointer");
-    const int bx = w >= 256 ? 256 : (w >= 128 ? 128 : (w >= 64 ? 64 : 32));
-    disp_to_depth_bwd_kernel<<<dim3((w + bx - 1)/bx, h, b), bx, 0, (cudaStream_t)stream>>>(h, w, H, W, make_scale(min_depth, max_depth),
-                                                                                          disp, g_depth_up, g_disp_up, g_disp);
-    count_launch();
-    return check_launch("disp_to_depth_bwd_kernel");
 }
 
 extern "C" int stv_view_synth_fwd(int B, int C, int H, int W, const float* input, const float* depth, const float* T,

@@ -14,7 +14,6 @@
 // between neighbouring pixels) + 1 B decision byte per scale; see DESIGN.md for the roofline accounting.
 #include "stv_common.cuh"
 #include "stv_f2.cuh"
-#include "stv_gemm.cuh"
 
 namespace stv {
 
@@ -723,248 +722,6 @@ __global__ void __launch_bounds__(NT, 2) photo_bwd_kernel(PhotoParams p) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Backward from the forward's coefficient planes (use_min). grid = (tiles, b, S), tile = TH x TW as above.
-//
-// The forward left, per (scale, pixel q), the nine numbers d err_c/d(S1,S2,S3) of the support frame that pixel selected
-// (undefined where the static frame won: masked by `sel`). The gradient w.r.t. the warped pixel p of support k is then
-//     gw_c(p) = g [ sum_{q in N(p), sel(q)=k} m(p,q) (A_c(q) + 2 w_c(p) B_c(q) + t_c(p) C_c(q)) ] + [sel(p)=k] g_l1 sign(w_c - t_c)
-// (m = reflection multiplicity of the 3x3 window), i.e. a masked 3x3 box sum of nine planes — no halo re-warp and no SSIM
-// re-evaluation — followed by the sampler / projection chain of the pixel itself. Each thread owns CR vertically
-// consecutive pixels of one column per pass; a block walks its TH rows in TH/(CR*NT/TW) passes.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int CR = 2;                       // pixels per thread per pass
-constexpr int CPASS_ROWS = CR*(NT/TW);      // rows per pass (8)
-constexpr int CXO = 3;                      // smem column of the tile's left halo: a TMA box must START on a 16-byte boundary of the
-constexpr int PW1T = TW + 8;                // row (measured: x % 4 != 0 faults on sm_100a), so the box spans x0-4 .. x0+TW+3
-static_assert(TH % CPASS_ROWS == 0, "coefficient backward: tile height must be a multiple of the pass height");
-
-struct CoefSmem {
-    float sc[9][PH1][PW1T];  // coefficient planes, tile + halo 1 (zero outside the image) — one TMA box {PW1T, PH1, 9}
-    uint8_t ssel[PH1][PW1 + 2];
-    float red[NT/32][N_ACC_T + N_ACC_K];
-    Cam cam;
-    uint64_t bar;
-};
-constexpr uint32_t COEF_BOX_BYTES = 9*PH1*PW1T*sizeof(float);
-
-template <bool NEED_K, bool TEX>
-__global__ void __launch_bounds__(NT, STV_BWD_MINB) photo_bwd_coef_kernel(const __grid_constant__ CUtensorMap tm_coef, PhotoParams p) {
-    __shared__ __align__(128) CoefSmem sm;
-    constexpr int NACC = N_ACC_T + (NEED_K ? N_ACC_K : 0);
-    const int tile = blockIdx.x, i = blockIdx.y, s = blockIdx.z;
-    const int tx0 = (tile % p.tiles_x)*TW, ty0 = (tile/p.tiles_x)*TH;
-    const int H = p.H, W = p.W, HW = H*W;
-    const float sx = (float)W/(float)(W - 1), sy = (float)H/(float)(H - 1);
-    const float g0 = __ldg(p.grad_loss)/((float)p.S*(float)p.b*(float)HW);
-    const float g = g0*p.w_ssim*(1.f/3.f), gl = g0*p.w_l1*(1.f/3.f);  // channel means of the SSIM / L1 terms
-    const bool tma = p.coef_tma != 0;
-
-    // coefficient planes of tile + halo 1: one TMA box (out-of-image elements are zero-filled by the copy engine), or plain loads
-    // when the row pitch is not 16-byte granular
-    if (tma) {
-        if (threadIdx.x == 0) {
-            tc::mbar_init(&sm.bar, 1);
-            tc::fence_barrier_init();
-            tc::mbar_arrive_expect_tx(&sm.bar, COEF_BOX_BYTES);
-            tc::tma_load_3d(&sm.sc[0][0][0], &tm_coef, &sm.bar, tx0 - 1 - CXO, ty0 - 1, (s*p.b + i)*9);
-        }
-    } else {
-        const float* __restrict__ cp = p.coef_in + ((size_t)s*p.b + i)*9*HW;
-        for (int q = threadIdx.x; q < PH1*PW1; q += NT) {
-            const int py = q/PW1, px = q - py*PW1;
-            const int y = ty0 - 1 + py, x = tx0 - 1 + px;
-            const bool in = y >= 0 && y < H && x >= 0 && x < W;
-            const int o = in ? y*W + x : 0;
-#pragma unroll
-            for (int c = 0; c < 9; ++c) sm.sc[c][py][px + CXO] = in ? __ldg(cp + (size_t)c*HW + o) : 0.f;
-        }
-    }
-    {   // decisions of tile + halo 1
-        const uint8_t* __restrict__ selp = p.sel_in + ((size_t)s*p.b + i)*HW;
-        for (int q = threadIdx.x; q < PH1*PW1; q += NT) {
-            const int py = q/PW1, px = q - py*PW1;
-            const int y = ty0 - 1 + py, x = tx0 - 1 + px;
-            const bool in = y >= 0 && y < H && x >= 0 && x < W;
-            sm.ssel[py][px] = in ? selp[y*W + x] : (uint8_t)STV_SEL_STATIC;
-        }
-    }
-
-    const int lx = threadIdx.x & (TW - 1), trow = (threadIdx.x/TW)*CR;
-    const int x = tx0 + lx;
-    const float mxl = (x == 1) ? 2.f : 1.f, mxr = (x == W - 2) ? 2.f : 1.f;
-    const float* __restrict__ dp = p.depth[s] + (size_t)i*HW;
-    const float* __restrict__ tg = p.tgt + (size_t)i*3*HW;
-    float* __restrict__ gdp = p.g_depth[s] + (size_t)i*HW;
-    const Cam& cam = sm.cam;
-
-    for (int k = 0; k < p.n; ++k) {
-        if (threadIdx.x < 32) {  // camera constants of (k, i) -> shared memory (read back as broadcasts; keeps ~27 registers free)
-            const float* __restrict__ Tm = p.T + ((size_t)k*p.b + i)*16;
-            const float* __restrict__ Km = p.K + (size_t)i*16;
-            const float* __restrict__ Ki = p.Kinv + (size_t)i*16;
-            const int t = threadIdx.x;
-            if (t < 9) { sm.cam.R[t] = __ldg(Tm + (t/3)*4 + t % 3); sm.cam.Ki[t] = __ldg(Ki + (t/3)*4 + t % 3); }
-            else if (t < 12) sm.cam.t[t - 9] = __ldg(Tm + (t - 9)*4 + 3);
-            else if (t < 15) sm.cam.K0[t - 12] = __ldg(Km + (t - 12));
-            else if (t < 18) sm.cam.K1[t - 15] = __ldg(Km + 4 + (t - 15));
-        }
-        __syncthreads();
-        if (k == 0 && tma) tc::mbar_wait(&sm.bar, 0);
-        const int plane0 = (k*p.b + i)*3;
-        const float* __restrict__ sp = p.supp + (size_t)plane0*HW;
-        float acc[NACC];
-#pragma unroll
-        for (int q = 0; q < NACC; ++q) acc[q] = 0.f;
-
-#pragma unroll 1
-        for (int pass = 0; pass < TH/CPASS_ROWS; ++pass) {
-            const int top = pass*CPASS_ROWS + trow;   // tile row of the first pixel == smem row of its upper neighbour
-            // masked, multiplicity-weighted window weights of the (CR+2) x 3 centres around the run
-            float mw[CR + 2][3];
-            bool any = false;
-#pragma unroll
-            for (int r = 0; r < CR + 2; ++r) {
-                const uint8_t* sr = &sm.ssel[top + r][lx];
-                mw[r][0] = sr[0] == k ? mxl : 0.f;
-                mw[r][1] = sr[1] == k ? 1.f : 0.f;
-                mw[r][2] = sr[2] == k ? mxr : 0.f;
-                any = any || sr[0] == k || sr[1] == k || sr[2] == k;
-            }
-            float gdv[CR];
-#pragma unroll
-            for (int j = 0; j < CR; ++j) gdv[j] = 0.f;
-            if (any && x < W) {
-                // the pixels' own depth: requested before the box sums, consumed after them
-                float dj[CR];
-#pragma unroll
-                for (int j = 0; j < CR; ++j) dj[j] = __ldg(dp + min(ty0 + top + j, H - 1)*W + x);
-                float cs[9][CR];  // window sums of the nine planes at the thread's pixels
-#pragma unroll
-                for (int c = 0; c < 9; ++c) {
-                    float h[CR + 2];
-#pragma unroll
-                    for (int r = 0; r < CR + 2; ++r) {
-                        const float* ra = &sm.sc[c][top + r][lx + CXO];
-                        h[r] = fmaf(mw[r][0], ra[0], fmaf(mw[r][2], ra[2], mw[r][1]*ra[1]));
-                    }
-#pragma unroll
-                    for (int j = 0; j < CR; ++j) {
-                        const int y = ty0 + top + j;
-                        const float myu = (y == 1) ? 2.f : 1.f, myd = (y == H - 2) ? 2.f : 1.f;
-                        cs[c][j] = fmaf(myu, h[j], fmaf(myd, h[j + 2], h[j + 1]));
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < CR; ++j) {
-                    const int y = ty0 + top + j;
-                    if (y >= H) continue;
-                    const int o = y*W + x;
-                    const float d = dj[j];
-                    Proj pr;
-                    project(cam, (float)x, (float)y, d, sx, sy, pr);
-                    const float mxc = (float)(W - 1), myc = (float)(H - 1);
-                    const float bx = (pr.ix > 0.f && pr.ix < mxc) ? 1.f : 0.f, by = (pr.iy > 0.f && pr.iy < myc) ? 1.f : 0.f;
-                    const float cx = fminf(fmaxf(pr.ix, 0.f), mxc), cy = fminf(fmaxf(pr.iy, 0.f), myc);
-                    const float x0f = floorf(cx), y0f = floorf(cy);
-                    const float wx = cx - x0f, wy = cy - y0f;
-                    const bool own = sm.ssel[top + 1 + j][lx + 1] == k;
-                    float ta[3], tb[3], tcx[3], td[3], tv[3];  // taps (x0,y0) (x1,y0) (x0,y1) (x1,y1), target
-                    if (TEX) {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float4 t4 = tex2Dgather<float4>(p.supp_tex, x0f + 1.f, y0f + 1.f + (float)((plane0 + c)*H), 0);
-                            ta[c] = t4.w; tb[c] = t4.z; tcx[c] = t4.x; td[c] = t4.y;
-                        }
-                    } else {
-                        const int x0 = (int)x0f, y0 = (int)y0f, x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float* q = sp + c*HW;
-                            ta[c] = __ldg(q + y0*W + x0); tb[c] = __ldg(q + y0*W + x1); tcx[c] = __ldg(q + y1*W + x0); td[c] = __ldg(q + y1*W + x1);
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) tv[c] = __ldg(tg + c*HW + o);
-                    float gix = 0.f, giy = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float top_ = fmaf(wx, tb[c] - ta[c], ta[c]), bot = fmaf(wx, td[c] - tcx[c], tcx[c]);
-                        const float wv = fmaf(wy, bot - top_, top_);
-                        const float dx = fmaf(wy, (td[c] - tcx[c]) - (tb[c] - ta[c]), tb[c] - ta[c]), dy = bot - top_;
-                        float gwv = g*fmaf(2.f*wv, cs[c*3 + 1][j], fmaf(tv[c], cs[c*3 + 2][j], cs[c*3 + 0][j]));
-                        if (own) {
-                            const float df = wv - tv[c];
-                            gwv += df > 0.f ? gl : (df < 0.f ? -gl : 0.f);
-                        }
-                        gix = fmaf(gwv, dx, gix);
-                        giy = fmaf(gwv, dy, giy);
-                    }
-                    const float gqx = gix*bx*sx, gqy = giy*by*sy;
-                    float gn[3];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) gn[r] = fmaf(cam.K0[r], gqx, cam.K1[r]*gqy);
-                    float gQ[3];
-                    float gz = 0.f;
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) { gQ[r] = gn[r]*pr.inv; gz = fmaf(gn[r], pr.Q[r], gz); }
-                    if (pr.Q[2] >= STV_MIN_Z) gQ[2] -= gz*pr.inv*pr.inv;
-                    float gP[3];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) gP[r] = fmaf(cam.R[r], gQ[0], fmaf(cam.R[3 + r], gQ[1], cam.R[6 + r]*gQ[2]));
-                    gdv[j] = fmaf(gP[0], pr.ray[0], fmaf(gP[1], pr.ray[1], gP[2]*pr.ray[2]));
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        acc[r*4 + 0] = fmaf(gQ[r], pr.P[0], acc[r*4 + 0]);
-                        acc[r*4 + 1] = fmaf(gQ[r], pr.P[1], acc[r*4 + 1]);
-                        acc[r*4 + 2] = fmaf(gQ[r], pr.P[2], acc[r*4 + 2]);
-                        acc[r*4 + 3] += gQ[r];
-                    }
-                    if (NEED_K) {
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) {
-                            acc[12 + r] = fmaf(gqx, pr.nrm[r], acc[12 + r]);
-                            acc[15 + r] = fmaf(gqy, pr.nrm[r], acc[15 + r]);
-                            const float gr = gP[r]*d;
-                            acc[18 + r*3 + 0] = fmaf(gr, (float)x, acc[18 + r*3 + 0]);
-                            acc[18 + r*3 + 1] = fmaf(gr, (float)y, acc[18 + r*3 + 1]);
-                            acc[18 + r*3 + 2] += gr;
-                        }
-                    }
-                }
-            }
-            // d loss / d depth: the first support frame writes, later ones accumulate (same thread, same address)
-            if (x < W) {
-#pragma unroll
-                for (int j = 0; j < CR; ++j) {
-                    const int y = ty0 + top + j;
-                    if (y < H) {
-                        float* q = gdp + y*W + x;
-                        if (k == 0) *q = gdv[j];
-                        else if (gdv[j] != 0.f) *q += gdv[j];
-                    }
-                }
-            }
-        }
-        // block reduction of the pose / intrinsics partials for this support frame
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-        for (int q = 0; q < NACC; ++q) {
-            const float v = warp_sum(acc[q]);
-            if (lane == 0) sm.red[wid][q] = v;
-        }
-        __syncthreads();  // also: every thread is done with sm.cam of this support frame
-        if (threadIdx.x >= 32 && threadIdx.x < 32 + NACC) {  // (warp 0 goes on to load the next camera)
-            const int q = threadIdx.x - 32;
-            float v = 0.f;
-#pragma unroll
-            for (int w = 0; w < NT/32; ++w) v += sm.red[w][q];
-            const size_t blk = ((size_t)blockIdx.z*gridDim.y + blockIdx.y)*gridDim.x + blockIdx.x;
-            p.partial[(blk*p.n + k)*(N_ACC_T + N_ACC_K) + q] = v;
-        }
-    }
-}
-
 // Sums the per-block partials in a fixed order (double accumulation).
 //   gT[k,i,r,c]   (r<3)   = sum_{s,tile} partial[((s*b+i)*tiles+tile)*n + k][r*4+c]
 //   gK[i,r,c]     (r<2)   = sum_{s,tile,k} partial[...][12 + r*3 + c]
@@ -1037,70 +794,14 @@ static void use_fwd_tiles(PhotoParams& p) { p.tiles_x = (p.W + FTW - 1)/FTW; p.t
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// ---- texture view of the support frames -------------------------------------------------------------------------------
-// The (n,b,3,H,W) support tensor is bound as ONE single-channel float texture of n*b*3*H rows x W columns (pitch W*4), so the
-// sampler's 2x2 footprint is one TLD4 per channel with hardware address clamping in x. Texture objects are cached per
-// (device, pointer, shape): PyTorch's caching allocator hands the same buffers back every step, so steady state creates none.
-#include <cstdlib>
-#include <mutex>
-#include <unordered_map>
-namespace {
-struct TexKey {
-    int dev; const void* ptr; int rows, W;
-    bool operator==(const TexKey& o) const { return dev == o.dev && ptr == o.ptr && rows == o.rows && W == o.W; }
-};
-struct TexKeyHash {
-    size_t operator()(const TexKey& k) const {
-        return std::hash<const void*>()(k.ptr) ^ (std::hash<long long>()(((long long)k.rows << 32) | (unsigned)k.W)*31 + k.dev);
-    }
-};
-struct TexEntry { cudaTextureObject_t tex; unsigned long long stamp; };
-std::mutex g_tex_mu;
-std::unordered_map<TexKey, TexEntry, TexKeyHash> g_tex;
-unsigned long long g_tex_clock = 0;
-constexpr size_t TEX_CACHE_MAX = 64;
-}  // namespace
-
-// Returns 0 when the buffer cannot be bound (alignment / size limits): callers then use the plain-load kernels.
-static cudaTextureObject_t supp_texture(const float* supp, int rows, int W) {
-    static const bool disabled = getenv("STV_NO_TEX") != nullptr;  // developer switch: force the plain-load kernels
-    if (disabled) return 0;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    static thread_local int prop_dev = -1;
-    static thread_local size_t tex_align = 512, pitch_align = 32;
-    static thread_local int max_w = 0, max_h = 0;
-    if (prop_dev != dev) {
-        cudaDeviceProp pr;
-        if (cudaGetDeviceProperties(&pr, dev) != cudaSuccess) return 0;
-        tex_align = pr.textureAlignment; pitch_align = pr.texturePitchAlignment;
-        max_w = pr.maxTexture2DLinear[0]; max_h = pr.maxTexture2DLinear[1];
-        prop_dev = dev;
-    }
-    const size_t pitch = (size_t)W*sizeof(float);
-    if (((uintptr_t)supp % tex_align) != 0 || (pitch % pitch_align) != 0 || W > max_w || rows > max_h || rows >= (1 << 23)) return 0;
-    std::lock_guard<std::mutex> lock(g_tex_mu);
-    const TexKey key{dev, supp, rows, W};
-    auto it = g_tex.find(key);
-    if (it != g_tex.end()) { it->second.stamp = ++g_tex_clock; return it->second.tex; }
-    cudaResourceDesc rd{};
-    rd.resType = cudaResourceTypePitch2D;
-    rd.res.pitch2D.devPtr = const_cast<float*>(supp);
-    rd.res.pitch2D.desc = cudaCreateChannelDesc<float>();
-    rd.res.pitch2D.width = W; rd.res.pitch2D.height = rows; rd.res.pitch2D.pitchInBytes = pitch;
-    cudaTextureDesc td{};
-    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-    td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
-    cudaTextureObject_t tex = 0;
-    if (cudaCreateTextureObject(&tex, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); return 0; }
-    if (g_tex.size() >= TEX_CACHE_MAX) {  // evict the least recently used view (long idle by construction)
-        auto old = g_tex.begin();
-        for (auto j = g_tex.begin(); j != g_tex.end(); ++j) if (j->second.stamp < old->second.stamp) old = j;
-        cudaDestroyTextureObject(old->second.tex);
-        g_tex.erase(old);
-    }
-    g_tex[key] = TexEntry{tex, ++g_tex_clock};
-    return tex;
+int stv::photo_identity_error(const stv_photo_cfg* c, const float* tgt, const float* supp, float* e0, cudaStream_t st) {
+    PhotoParams p{};
+    fill_params(p, c);
+    use_fwd_tiles(p);
+    p.tgt = tgt;
+    photo_error_kernel<<<dim3(p.tiles_x*p.tiles_y, c->b), FNT, 0, st>>>(p, supp, e0);
+    count_launch();
+    return check_launch("photo_error_kernel");
 }
 
 extern "C" size_t stv_photo_workspace_bytes(const stv_photo_cfg* c) {
@@ -1111,11 +812,6 @@ extern "C" size_t stv_photo_workspace_bytes(const stv_photo_cfg* c) {
     const size_t part_fwd = align256(tiles_f*c->b*c->S*sizeof(float));
     const size_t part_bwd = align256(tiles_b*c->b*c->S*c->n*(N_ACC_T + N_ACC_K)*sizeof(float));
     return e0 + (part_fwd > part_bwd ? part_fwd : part_bwd);
-}
-
-extern "C" size_t stv_photo_coef_bytes(const stv_photo_cfg* c) {
-    if (check_cfg(c) != STV_OK) return 0;
-    return (size_t)c->S*c->b*9*c->H*c->W*sizeof(float);
 }
 
 extern "C" int stv_photo_error(const stv_photo_cfg* c, const float* pred, const float* tgt, float* err, void* stream) {
@@ -1133,7 +829,7 @@ extern "C" int stv_photo_error(const stv_photo_cfg* c, const float* pred, const 
 
 extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, const float* tgt, const float* supp,
                              const float* T, const float* K, const float* Kinv, const float* noise,
-                             unsigned long long* noise_step, float* loss, uint8_t* sel, float* warp0, float* coef, void* ws,
+                             unsigned long long* noise_step, float* loss, uint8_t* sel, float* warp0, void* ws,
                              size_t ws_bytes, void* stream) {
     if (int rc = check_cfg(c)) return rc;
     STV_REQUIRE(depth && tgt && supp && T && K && Kinv && loss && sel, "stv_photo_fwd: NULL pointer");
@@ -1153,26 +849,14 @@ extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, 
     p.e0 = e0;
     p.partial = (float*)((char*)ws + align256((size_t)c->b*c->H*c->W*sizeof(float)));
     p.sel = sel; p.warp0 = warp0;
-    STV_REQUIRE(coef == nullptr || c->use_min, "stv_photo_fwd: coefficient planes need use_min (one selected support per pixel)");
-    p.coef = coef;
     const int tiles = p.tiles_x*p.tiles_y;
     if (c->use_automask) {
         photo_error_kernel<<<dim3(tiles, c->b), FNT, 0, st>>>(p, supp, e0);
         count_launch();
         if (int rc = check_launch("photo_error_kernel")) return rc;
     }
-    p.supp_tex = supp_texture(supp, c->n*c->b*3*c->H, c->W);
     const dim3 grid(tiles, c->b, c->S);
-    if (coef) {
-        static const int minb = getenv("STV_FWD_MINB_COEF") ? atoi(getenv("STV_FWD_MINB_COEF")) : 0;  // developer sweep
-        if (!p.supp_tex) photo_fwd_kernel<false, true><<<grid, FNT, 0, st>>>(p);
-        else if (minb == 2) photo_fwd_kernel<true, true, 2><<<grid, FNT, 0, st>>>(p);
-        else if (minb == 4) photo_fwd_kernel<true, true, 4><<<grid, FNT, 0, st>>>(p);
-        else photo_fwd_kernel<true, true><<<grid, FNT, 0, st>>>(p);
-    } else {
-        if (p.supp_tex) photo_fwd_kernel<true, false><<<grid, FNT, 0, st>>>(p);
-        else photo_fwd_kernel<false, false><<<grid, FNT, 0, st>>>(p);
-    }
+    photo_fwd_kernel<false, false><<<grid, FNT, 0, st>>>(p);
     count_launch();
     if (int rc = check_launch("photo_fwd_kernel")) return rc;
     const int nblk = tiles*c->b*c->S;
@@ -1183,7 +867,7 @@ extern "C" int stv_photo_fwd(const stv_photo_cfg* c, const float* const* depth, 
 }
 
 extern "C" int stv_photo_bwd(const stv_photo_cfg* c, const float* const* depth, const float* tgt, const float* supp,
-                             const float* T, const float* K, const float* Kinv, const uint8_t* sel, const float* coef,
+                             const float* T, const float* K, const float* Kinv, const uint8_t* sel,
                              const float* grad_loss, float* const* g_depth, float* gT, float* gK, float* gKinv, void* ws,
                              size_t ws_bytes, void* stream) {
     if (int rc = check_cfg(c)) return rc;
@@ -1210,24 +894,7 @@ extern "C" int stv_photo_bwd(const stv_photo_cfg* c, const float* const* depth, 
         attr_done = true;
     }
     dim3 grid(tiles, c->b, c->S);
-    if (coef) {  // lean path: box-filter adjoint of the forward's coefficient planes
-        STV_REQUIRE(c->use_min, "stv_photo_bwd: coefficient planes need use_min");
-        p.coef_in = coef;
-        p.supp_tex = supp_texture(supp, c->n*c->b*3*c->H, c->W);
-        CUtensorMap tm{};
-        static const bool no_tma = getenv("STV_NO_COEF_TMA") != nullptr;  // developer switch: plain loads of the coefficient tiles
-        p.coef_tma = (!no_tma && c->W % 4 == 0 && ((uintptr_t)coef % 16) == 0) ? 1 : 0;
-        if (p.coef_tma) {
-            if (int rc = make_tmap_3d(&tm, coef, c->W, c->H, (long long)c->S*c->b*9, PW1T, PH1, 9)) return rc;
-        }
-        if (p.supp_tex) {
-            if (need_k) photo_bwd_coef_kernel<true, true><<<grid, NT, 0, st>>>(tm, p);
-            else photo_bwd_coef_kernel<false, true><<<grid, NT, 0, st>>>(tm, p);
-        } else {
-            if (need_k) photo_bwd_coef_kernel<true, false><<<grid, NT, 0, st>>>(tm, p);
-            else photo_bwd_coef_kernel<false, false><<<grid, NT, 0, st>>>(tm, p);
-        }
-    } else if (need_k) photo_bwd_kernel<true><<<grid, NT, sizeof(BwdSmem), st>>>(p);
+    if (need_k) photo_bwd_kernel<true><<<grid, NT, sizeof(BwdSmem), st>>>(p);
     else photo_bwd_kernel<false><<<grid, NT, sizeof(BwdSmem), st>>>(p);
     count_launch();
     if (int rc = check_launch("photo_bwd_kernel")) return rc;

@@ -88,20 +88,22 @@ def _ws(nbytes: int, device) -> Tensor:
 # ---------------------------------------------------------------------------------------------------------------------
 # Fused view-synthesis photometric loss
 # ---------------------------------------------------------------------------------------------------------------------
-PHOTO_COEF = True  # developer switch (parity tests exercise both backward kernels)
+# Developer switches (parity / property tests): route min-reprojection through the two-pass kernels as well; keep a reference to
+# the single-pass kernel's full-resolution unit-gradient maps of the most recent call.
+PHOTO_FORCE_TWO_PASS = False
+KEEP_UNIT_GRADS = False
+LAST_UNIT_GRADS = None
 
 
 class _PhotoLoss(torch.autograd.Function):
+    """Two-pass formulation (stv_photo_fwd + stv_photo_bwd; the backward re-warps a halo-2 tile and rebuilds the SSIM sums):
+    any reduction (mean / min), any number of support frames. The default configuration goes through `_PhotoFused`."""
     @staticmethod
     def forward(ctx, cfg: L.PhotoCfg, want_warp: bool, tgt, supp, T, K, Kinv, noise, noise_step, *depths):
         L.require_cuda(tgt, supp, T, K, Kinv, noise, noise_step, *depths, what='photo_loss')
         lib, dev = L.lib(), tgt.device
         b, n, S, H, W = cfg.b, cfg.n, cfg.S, cfg.H, cfg.W
-        # Lean backward (min-reprojection only): the forward hands over the SSIM coefficient planes of the selected support
-        # frame, so the backward is a masked box filter + the pixel's own sampler/projection chain (no halo re-warp).
-        want_coef = bool(cfg.use_min) and PHOTO_COEF and any(ctx.needs_input_grad[4:7] + ctx.needs_input_grad[9:])
         with torch.cuda.device(dev):
-            coef = torch.empty((S, b, 9, H, W), dtype=torch.float32, device=dev) if want_coef else None
             loss = torch.empty((), dtype=torch.float32, device=dev)
             sel = torch.empty((S, b, H, W), dtype=torch.uint8, device=dev)
             warp0 = torch.empty((n, b, 3, H, W), dtype=torch.float32, device=dev) if want_warp else None
@@ -109,9 +111,9 @@ class _PhotoLoss(torch.autograd.Function):
             ws = _ws(nws, dev)
             with _timed('stv_photo_fwd'):
                 L.check(lib.stv_photo_fwd(C.byref(cfg), L.ptr_array(depths), L.ptr(tgt), L.ptr(supp), L.ptr(T), L.ptr(K),
-                                          L.ptr(Kinv), L.ptr(noise), L.ptr(noise_step), L.ptr(loss), L.ptr(sel), L.ptr(warp0), L.ptr(coef), L.ptr(ws),
+                                          L.ptr(Kinv), L.ptr(noise), L.ptr(noise_step), L.ptr(loss), L.ptr(sel), L.ptr(warp0), L.ptr(ws),
                                           ws.numel(), L.stream()), 'stv_photo_fwd')
-        ctx.cfg, ctx.nws, ctx.coef = cfg, nws, coef
+        ctx.cfg, ctx.nws = cfg, nws
         ctx.save_for_backward(tgt, supp, T, K, Kinv, sel, *depths)
         ctx.mark_non_differentiable(sel)
         if warp0 is None: warp0 = torch.empty(0, device=dev)
@@ -135,10 +137,91 @@ class _PhotoLoss(torch.autograd.Function):
             ws = _ws(ctx.nws, dev)
             with _timed('stv_photo_bwd'):
                 L.check(lib.stv_photo_bwd(C.byref(cfg), L.ptr_array(depths), L.ptr(tgt), L.ptr(supp), L.ptr(T), L.ptr(K),
-                                          L.ptr(Kinv), L.ptr(sel), L.ptr(ctx.coef), L.ptr(g_loss), L.ptr_array(g_depths), L.ptr(gT), L.ptr(gK),
+                                          L.ptr(Kinv), L.ptr(sel), L.ptr(g_loss), L.ptr_array(g_depths), L.ptr(gT), L.ptr(gK),
                                           L.ptr(gKi), L.ptr(ws), ws.numel(), L.stream()), 'stv_photo_bwd')
         return (None, None, None, None, gT if need_T else None, gK if need_K else None, gKi if need_Ki else None, None, None,
                 *[g if ctx.needs_input_grad[9 + j] else None for j, g in enumerate(g_depths)])
+
+
+# Texture views of the support frames for the 2x2 gathers: handles are created by the library on request and OWNED HERE (the
+# library keeps no state). Keyed by (device, address, shape): torch's caching allocator hands the same buffers back every step
+# and CUDA-graph runners use static input buffers, so steady state creates none; least-recently-used views are destroyed.
+_TEX: dict[tuple, int] = {}
+_TEX_MAX = 64
+
+
+def _tex_handle(supp: Tensor) -> int:
+    rows, W = supp.numel()//supp.shape[-1], supp.shape[-1]
+    key = (supp.device.index, supp.data_ptr(), rows, W)
+    h = _TEX.pop(key, None)
+    if h is None:
+        out = C.c_ulonglong(0)
+        with torch.cuda.device(supp.device):
+            L.check(L.lib().stv_tex_create(L.ptr(supp), rows, W, C.byref(out)), 'stv_tex_create')
+        h = int(out.value)
+        if len(_TEX) >= _TEX_MAX:
+            old = next(iter(_TEX))
+            L.lib().stv_tex_destroy(_TEX.pop(old))
+    _TEX[key] = h  # most recently used last
+    return h
+
+
+class _PhotoFused(torch.autograd.Function):
+    """Single-pass kernel (stv_photo_fused_fwd): the loss and its UNIT gradients in one sweep; the backward only scales them
+    (and pulls the per-pixel maps back through the bilinear up-sampling when the kernel consumed low-resolution disparities)."""
+    @staticmethod
+    def forward(ctx, cfg: L.PhotoCfg, src: L.PhotoSrc, want_warp: bool, tgt, supp, T, K, Kinv, noise, noise_step, *maps):
+        L.require_cuda(tgt, supp, T, K, Kinv, noise, noise_step, *maps, what='photo_loss')
+        lib, dev = L.lib(), tgt.device
+        b, n, S, H, W = cfg.b, cfg.n, cfg.S, cfg.H, cfg.W
+        grad = any(ctx.needs_input_grad[5:8] + ctx.needs_input_grad[10:])
+        with torch.cuda.device(dev):
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            sel = torch.empty((S, b, H, W), dtype=torch.uint8, device=dev)
+            warp0 = torch.empty((n, b, 3, H, W), dtype=torch.float32, device=dev) if want_warp else None
+            g_unit = [torch.empty((b, 1, H, W), dtype=torch.float32, device=dev) for _ in range(S)] if grad else None
+            gpart = _ws(lib.stv_photo_fused_partial_bytes(C.byref(cfg)), dev) if grad else None
+            ws = _ws(lib.stv_photo_fused_workspace_bytes(C.byref(cfg)), dev)
+            with _timed('stv_photo_fwd'):
+                L.check(lib.stv_photo_fused_fwd(C.byref(cfg), C.byref(src), L.ptr_array(maps), L.ptr(tgt), L.ptr(supp), _tex_handle(supp),
+                                                L.ptr(T), L.ptr(K), L.ptr(Kinv), L.ptr(noise), L.ptr(noise_step), L.ptr(loss), L.ptr(sel),
+                                                L.ptr(warp0), L.ptr_array(g_unit) if grad else None, L.ptr(gpart), L.ptr(ws), ws.numel(),
+                                                L.stream()), 'stv_photo_fused_fwd')
+        ctx.cfg, ctx.src, ctx.shapes = cfg, src, [m.shape for m in maps]
+        if KEEP_UNIT_GRADS:
+            global LAST_UNIT_GRADS
+            LAST_UNIT_GRADS = g_unit
+        ctx.save_for_backward(T, Kinv, gpart, *(g_unit or []))
+        ctx.mark_non_differentiable(sel)
+        if warp0 is None: warp0 = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(warp0)
+        return loss, sel, warp0
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_sel, _g_warp):
+        T, Kinv, gpart, *g_unit = ctx.saved_tensors
+        cfg, src, lib, dev = ctx.cfg, ctx.src, L.lib(), T.device
+        nmap = len(ctx.shapes)
+        need_m = any(ctx.needs_input_grad[10:])
+        need_T, need_K, need_Ki = ctx.needs_input_grad[5], ctx.needs_input_grad[6], ctx.needs_input_grad[7]
+        if not (need_m or need_T or need_K or need_Ki) or gpart is None: return (None,)*(10 + nmap)
+        with torch.cuda.device(dev):
+            g_loss = g_loss.to(torch.float32).contiguous()
+            g_maps = [torch.empty(sh, dtype=torch.float32, device=dev) for sh in ctx.shapes] if need_m else None
+            want_p = need_T or need_K or need_Ki
+            gT = torch.empty_like(T) if want_p else None
+            gK = torch.empty_like(Kinv) if (need_K or need_Ki) else None
+            gKi = torch.empty_like(Kinv) if (need_K or need_Ki) else None
+            ws = _ws(lib.stv_photo_fused_bwd_workspace_bytes(C.byref(cfg), C.byref(src)), dev)
+            with _timed('stv_photo_bwd'):
+                L.check(lib.stv_photo_fused_bwd(C.byref(cfg), C.byref(src), L.ptr(g_loss), L.ptr_array(g_unit), L.ptr(gpart), L.ptr(T), L.ptr(Kinv),
+                                                L.ptr_array(g_maps) if need_m else None, L.ptr(gT), L.ptr(gK), L.ptr(gKi), L.ptr(ws),
+                                                ws.numel(), L.stream()), 'stv_photo_fused_bwd')
+        return (None, None, None, None, None, gT if need_T else None, gK if need_K else None, gKi if need_Ki else None, None, None,
+                *[g if ctx.needs_input_grad[10 + j] else None for j, g in enumerate(g_maps or [None]*nmap)])
+
+
+FUSED_MAX_SUPPORT = 4
 
 
 def _photo_cfg(b, n, S, H, W, loss_name, use_min, use_automask, noise_seed) -> L.PhotoCfg:
@@ -151,11 +234,15 @@ def _photo_cfg(b, n, S, H, W, loss_name, use_min, use_automask, noise_seed) -> L
 
 def photo_loss(depths: list[Tensor], tgt: Tensor, supp: Tensor, T: Tensor, K: Tensor, K_inv: Tensor | None = None, *,
                loss_name: str = 'ssim', use_min: bool = True, use_automask: bool = True, noise: Tensor | None = None,
-               noise_seed: int = 0, noise_step: Tensor | None = None, want_warp: bool = False):
+               noise_seed: int = 0, noise_step: Tensor | None = None, want_warp: bool = False,
+               disp_size: tuple[int, int] | None = None, min_depth: float | None = None, max_depth: float | None = None):
     """Fused warp + photometric loss over all scales and support frames.
 
-    depths: S x (b,1,H,W); tgt (b,3,H,W); supp (n,b,3,H,W); T (n,b,4,4); K (b,4,4); K_inv (b,4,4) or None (= K^-1,
-    differentiable, as `ViewSynth.forward` does with `K.inverse()`, src/tools/geometry.py:383).
+    depths: S x (b,1,H,W) up-sampled depth maps — or, with `disp_size=(H, W)`, S x (b,1,h_s,w_s) sigmoid disparities straight
+    from the network: the bilinear up-sampling (ops.interpolate_like) and to_scaled / to_inv with `min_depth` / `max_depth` are then
+    done inside the kernel and the gradient comes back at the disparities' own resolution (src/core/trainer.py:320-321 fused away).
+    tgt (b,3,H,W); supp (n,b,3,H,W); T (n,b,4,4); K (b,4,4); K_inv (b,4,4) or None (= K^-1, differentiable, as
+    `ViewSynth.forward` does with `K.inverse()`, src/tools/geometry.py:383).
     noise: None or (S*b,1,H,W) explicit tie-break noise (parity tests); otherwise `noise_seed != 0` draws it in-kernel with the
     effective seed noise_seed + noise_step[0]; `noise_step` (one int64 on the device, optional) is advanced by the call itself, so
     every call — and every replay of a captured CUDA graph — draws fresh noise (torch.randn_like, reconstruction.py:72).
@@ -167,16 +254,27 @@ def photo_loss(depths: list[Tensor], tgt: Tensor, supp: Tensor, T: Tensor, K: Te
     if supp.shape != (n, b, 3, H, W): raise ValueError(f'Invalid support frames shape. ({tuple(supp.shape)} vs. {(n, b, 3, H, W)})')
     if T.shape != (n, b, 4, 4): raise ValueError(f'Invalid transforms shape. ({tuple(T.shape)} vs. {(n, b, 4, 4)})')
     if K.shape != (b, 4, 4): raise ValueError(f'Invalid intrinsics shape. ({tuple(K.shape)} vs. {(b, 4, 4)})')
+    if S > L.MAX_SCALES: raise ValueError(f'At most {L.MAX_SCALES} scales are supported, got {S}.')
+    from_disp = disp_size is not None
+    if from_disp and tuple(disp_size) != (H, W): raise ValueError(f'disp_size {tuple(disp_size)} does not match the frames {(H, W)}.')
     for d in depths:
-        if d.shape != (b, 1, H, W): raise ValueError(f'Invalid depth shape. ({tuple(d.shape)} vs. {(b, 1, H, W)})')
+        if from_disp:
+            if d.ndim != 4 or d.shape[:2] != (b, 1): raise ValueError(f'Invalid disparity shape. ({tuple(d.shape)} vs. {(b, 1, "h", "w")})')
+        elif d.shape != (b, 1, H, W): raise ValueError(f'Invalid depth shape. ({tuple(d.shape)} vs. {(b, 1, H, W)})')
     if noise is not None and noise.numel() != S*b*H*W:
         raise ValueError(f'Invalid noise shape. ({tuple(noise.shape)} vs. {(S*b, 1, H, W)})')
     if noise_step is not None and (noise_step.dtype != torch.int64 or noise_step.numel() != 1):
         raise ValueError('noise_step must be a single int64 element on the device.')
     if K_inv is None: K_inv = inv4x4(K)
     cfg = _photo_cfg(b, n, S, H, W, loss_name, use_min, use_automask, noise_seed)
-    loss, sel, warp0 = _PhotoLoss.apply(cfg, want_warp, _f32c(tgt), _f32c(supp), _f32c(T), _f32c(K), _f32c(K_inv),
-                                        _f32c(noise), noise_step, *[_f32c(d) for d in depths])
+    args = (_f32c(tgt), _f32c(supp), _f32c(T), _f32c(K), _f32c(K_inv), _f32c(noise), noise_step)
+    if use_min and n <= FUSED_MAX_SUPPORT and not PHOTO_FORCE_TWO_PASS:
+        src = L.PhotoSrc(mode=1 if from_disp else 0, min_depth=float(min_depth or 0), max_depth=float(max_depth or 0))
+        for j, d in enumerate(depths): src.h[j], src.w[j] = (d.shape[2], d.shape[3]) if from_disp else (H, W)
+        loss, sel, warp0 = _PhotoFused.apply(cfg, src, want_warp, *args, *[_f32c(d) for d in depths])
+    else:
+        if from_disp: depths = [disp_to_depth(d, (H, W), min_depth, max_depth)[1] for d in depths]
+        loss, sel, warp0 = _PhotoLoss.apply(cfg, want_warp, *args, *[_f32c(d) for d in depths])
     return loss, sel, (warp0 if want_warp else None)
 
 
@@ -339,8 +437,9 @@ class _DispToDepth(torch.autograd.Function):
         b, _, h, w = disp.shape
         with torch.cuda.device(disp.device):
             g = torch.empty_like(disp)
+            ws = _ws(L.lib().stv_disp_to_depth_bwd_workspace_bytes(b, h, w, H, W), disp.device)
             L.check(L.lib().stv_disp_to_depth_bwd(b, h, w, H, W, mn, mx, L.ptr(disp), L.ptr(_f32c(g_depth_up)),
-                                                  L.ptr(_f32c(g_disp_up)), L.ptr(g), L.stream()), 'stv_disp_to_depth_bwd')
+                                                  L.ptr(_f32c(g_disp_up)), L.ptr(g), L.ptr(ws), ws.numel(), L.stream()), 'stv_disp_to_depth_bwd')
         return g, None, None, None, None
 
 
@@ -350,7 +449,11 @@ def disp_to_depth(disp: Tensor, size: tuple[int, int], min_depth: float | None, 
     if (min_depth or max_depth):
         if not min_depth or min_depth <= 0: raise ValueError(f'Min depth must be greater than 0. ({min_depth})')
         if max_depth and max_depth < min_depth: raise ValueError(f'Max depth must be greater than min. ({max_depth} vs. {min_depth})')
-    return _DispToDepth.apply(_f32c(disp), int(size[0]), int(size[1]), float(min_depth or 0), float(max_depth or 0))
+    disp_up, depth_up = _DispToDepth.apply(_f32c(disp), int(size[0]), int(size[1]), float(min_depth or 0), float(max_depth or 0))
+    # Provenance tag: `handlers.image_recon` hands the network's disparity straight to the fused loss kernel when every depth map it
+    # receives was produced here (same range), instead of reading these up-sampled copies and differentiating through them.
+    depth_up._stv_src = (disp, (int(size[0]), int(size[1])), min_depth or None, max_depth or None)
+    return disp_up, depth_up
 
 
 # ---------------------------------------------------------------------------------------------------------------------

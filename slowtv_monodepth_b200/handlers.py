@@ -10,18 +10,40 @@ from .regularizers import SmoothReg
 __all__ = ['image_recon', 'disp_smooth']
 
 
+def _disparity_sources(depths: dict[int, Tensor], size) -> tuple | None:
+    """(disparities, (min_depth, max_depth)) when every depth map is the tagged output of `functional.disp_to_depth` for this
+    image size and one depth range — the loss kernel then starts from the disparities themselves."""
+    tags = [getattr(d, '_stv_src', None) for d in depths.values()]
+    if not tags or any(t is None for t in tags): return None
+    if any(t[1] != tuple(size) or t[2:] != tags[0][2:] for t in tags): return None
+    return [t[0] for t in tags], tags[0][2:]
+
+
 def image_recon(crit: ReconstructionLoss, synth, depths: dict[int, Tensor], masks, imgs: Tensor, supp_imgs: Tensor,
-                Ts: Tensor, Ks: Tensor, *, noise: Tensor | None = None, want_warp: bool = True):
+                Ts: Tensor, Ks: Tensor, *, noise: Tensor | None = None, want_warp: bool = True,
+                disps: dict[int, Tensor] | None = None, depth_range: tuple | None = None):
     """Reference: src/core/handlers.py:14-67.
 
     Same arguments and return contract. `synth` is accepted for signature compatibility and unused: the reference expands
     depths / frames / poses to n*S*b virtual images (189 MB of copies at b=8, 384x640) and warps them through ~60 ATen
     launches; here one kernel reads the originals once per (scale, support) and never materialises the warped frames.
     -> (loss, {'supp_imgs_warp': (n,b,3,H,W) at scale 0, 'automask': (b,1,H,W) bool at scale 0})
+
+    Beyond the reference's arguments: `disps` + `depth_range=(min_depth, max_depth)` hand over the network's low-resolution
+    disparities instead of `depths` (the kernel up-samples and converts them itself, trainer.py:320-321). When `depths` are the
+    tagged outputs of `functional.disp_to_depth` (what the installed `forward_postprocess` produces) the same shortcut is taken
+    automatically, so the reference's own `forward_loss` call site (trainer.py:389-393) gets it unchanged.
     """
     if masks is not None: raise ValueError('Predicted photometric masks are not supported by the B200 loss kernels.')
-    keys = list(depths)
-    loss, ld, sel, warp0 = crit.fused([depths[k] for k in keys], imgs, supp_imgs, Ts, Ks, noise=noise, want_warp=want_warp)
+    if disps is None and crit.use_min and depths is not None:
+        found = _disparity_sources(depths, imgs.shape[-2:])
+        if found is not None: disps, depth_range = dict(zip(depths, found[0])), found[1]
+    if disps is not None and (crit.use_min or depths is None):
+        loss, ld, sel, warp0 = crit.fused(list(disps.values()), imgs, supp_imgs, Ts, Ks, noise=noise, want_warp=want_warp,
+                                          from_disp=tuple(depth_range or (None, None)))
+    else:
+        keys = list(depths)
+        loss, ld, sel, warp0 = crit.fused([depths[k] for k in keys], imgs, supp_imgs, Ts, Ks, noise=noise, want_warp=want_warp)
     out = {k: v[0] for k, v in ld.items()}  # Only scale 0 (handlers.py:64-65).
     if want_warp: out['supp_imgs_warp'] = warp0
     return loss, out

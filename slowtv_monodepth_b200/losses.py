@@ -44,14 +44,17 @@ class ReconstructionLoss(nn.Module):
         return F_.photo_error(pred, target, loss_name=self.loss_name, use_min=self.use_min)
 
     def fused(self, depths: list[Tensor], target: Tensor, source: Tensor, T: Tensor, K: Tensor, K_inv: Tensor | None = None,
-              noise: Tensor | None = None, want_warp: bool = False):
-        """Warp + loss in one kernel. -> (loss, {'automask': (S,b,1,H,W) bool}, sel, warp0)."""
+              noise: Tensor | None = None, want_warp: bool = False, from_disp: tuple | None = None):
+        """Warp + loss in one kernel. -> (loss, {'automask': (S,b,1,H,W) bool}, sel, warp0).
+        from_disp = (min_depth, max_depth): `depths` are the network's low-resolution sigmoid disparities; up-sampling and
+        disparity -> depth happen inside the kernel."""
         if self.use_automask and noise is None: self._step_counter(target)
         loss, sel, warp0 = F_.photo_loss(depths, target, source, T, K, K_inv, loss_name=self.loss_name, use_min=self.use_min,
                                          use_automask=self.use_automask, noise=noise,
                                          noise_seed=self.noise_seed if self.use_automask else 0,
                                          noise_step=self.noise_step if (self.use_automask and noise is None) else None,
-                                         want_warp=want_warp)
+                                         want_warp=want_warp, **({} if from_disp is None else dict(
+                                             disp_size=tuple(target.shape[-2:]), min_depth=from_disp[0], max_depth=from_disp[1])))
         ld = {'automask': (sel != 255).unsqueeze(2)} if self.use_automask else {}
         self.last_sel = sel  # (S,b,H,W) uint8 per-pixel decisions of the most recent call (diagnostics / parity tests)
         return loss, ld, sel, warp0

@@ -77,6 +77,7 @@ class MonodepthDecoder(nn.Module):
         for i in range(4, -1, -1):
             c0, c1 = self.layer(f'upconv_{i}_0').conv, self.layer(f'upconv_{i}_1').conv
             x = F_.conv2d_nhwc(x, c0.weight, c0.bias, pad=1, reflect=True, act='elu')
+            if i == 4: self.first_node = x.grad_fn   # the decoder's last node in backward: its gradients are final after it
             skip = f[self.enc_sc.index(2**i)] if self.use_skip and 2**i in self.enc_sc else None
             x = F_.conv2d_nhwc(x, c1.weight, c1.bias, src2=skip, up1=True, pad=1, reflect=True, act='elu')
             if i in self.out_sc:

@@ -107,7 +107,9 @@ class BasicBlock(nn.Module):
     def forward_nhwc(self, x: Tensor) -> Tensor:
         """x (N,H,W,C) channels-last; convolutions are libstv tcgen05 implicit GEMMs."""
         s = self.conv1.stride[0]
-        y = _bn_nhwc(F_.conv2d_nhwc(x, self.conv1.weight, None, stride=s, pad=1), self.bn1, relu=True)
+        c1 = F_.conv2d_nhwc(x, self.conv1.weight, None, stride=s, pad=1)
+        self.first_node = c1.grad_fn   # created before the shortcut's node: the block's last node to run in backward
+        y = _bn_nhwc(c1, self.bn1, relu=True)
         sc = x if self.downsample is None else _bn_nhwc(F_.conv2d_nhwc(x, self.downsample[0].weight, None, stride=s), self.downsample[1])
         return _bn_nhwc(F_.conv2d_nhwc(y, self.conv2.weight, None, pad=1), self.bn2, relu=True, res=sc)
 
@@ -135,11 +137,17 @@ class ResNetEncoder(nn.Module):
 
     def forward(self, x: Tensor) -> list[Tensor]:
         if x.is_cuda:
-            f0 = _bn_nhwc(_stem_conv_nhwc(x, self.conv1), self.bn1, relu=True)
+            # `marks`: autograd node of the first operation of each part; when it has run in backward, every gradient of that part
+            # (and of everything after it in the forward order) is final — FlatAdamW starts that bucket's all-reduce from it.
+            y = _stem_conv_nhwc(x, self.conv1)
+            self.marks = {'stem': y.grad_fn}
+            f0 = _bn_nhwc(y, self.bn1, relu=True)
             x = F_.maxpool3x3s2(f0)
             feats = [f0]
             for i in range(1, 5):
-                for blk in getattr(self, f'layer{i}'): x = blk.forward_nhwc(x)
+                for j, blk in enumerate(getattr(self, f'layer{i}')):
+                    x = blk.forward_nhwc(x)
+                    if j == 0: self.marks[f'layer{i}'] = blk.first_node
                 feats.append(x)
             return [f.permute(0, 3, 1, 2) for f in feats]  # (N,C,H,W) views of the channels-last buffers
         L_.require_device_path('ResNetEncoder')
@@ -211,13 +219,15 @@ class ConvNeXtStage(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         return self.blocks(self.downsample(x))
 
-    def forward_nhwc(self, x: Tensor) -> Tensor:
+    def forward_nhwc(self, x: Tensor, want_mark: bool = False):
+        mark = None
         if not isinstance(self.downsample, nn.Identity):
             ln, conv = self.downsample[0], self.downsample[1]
             x = F_.layer_norm(x, ln.weight, ln.bias, ln.eps)
+            mark = x.grad_fn
             x = F_.conv2d_nhwc(x, conv.weight, conv.bias, stride=2)
         for blk in self.blocks: x = blk.forward_nhwc(x)
-        return x
+        return (x, mark) if want_mark else x   # stage 0 has no first op of its own (mark None): it completes with the stem
 
 
 class ConvNeXtEncoder(nn.Module):
@@ -241,10 +251,12 @@ class ConvNeXtEncoder(nn.Module):
     def forward(self, x: Tensor) -> list[Tensor]:
         if x.is_cuda:
             x = _stem_conv_nhwc(x, self.stem_0)
+            self.marks = {'stem': x.grad_fn}   # see ResNetEncoder.forward
             x = F_.layer_norm(x, self.stem_1.weight, self.stem_1.bias, self.stem_1.eps)
             feats = []
             for i in range(4):
-                x = getattr(self, f'stages_{i}').forward_nhwc(x)
+                st = getattr(self, f'stages_{i}')
+                x, self.marks[f'stages_{i}'] = st.forward_nhwc(x, want_mark=True)
                 feats.append(x.permute(0, 3, 1, 2))  # (N,C,H,W) view of the channels-last buffer
             return feats
         L_.require_device_path('ConvNeXtEncoder')

@@ -64,17 +64,32 @@ class FlatAdamW:
     With world > 1 the constructor broadcasts rank 0's parameters (DDP's initial sync); `broadcast_buffers()` does the same for
     module buffers (BatchNorm running statistics) and should be called after loading a checkpoint on one rank."""
     def __init__(self, module: nn.Module, lr: float = 1e-4, weight_decay: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 channels_last: bool = True):
+                 channels_last: bool = True, buckets: list[str] | None = None):
+        """buckets: parameter-name prefixes in the order their gradients COMPLETE during backward (e.g. ['pose.',
+        'depth.decoders.', 'depth.encoder.stages_3', ...]); parameters matching no prefix form a last bucket. Each bucket is one
+        contiguous slice of the flat buffers (its decayed parameters first), so a bucket is one all-reduce + one AdamW launch and
+        `bucket_ready(j)` can start bucket j's all-reduce while backward is still producing the later ones."""
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         if not named: raise ValueError('No trainable parameters.')
         no_decay = lambda n, p: p.ndim <= 1 or n.endswith('.bias')  # timm `param_groups_weight_decay`
-        self.params = [p for n, p in named if not no_decay(n, p)] + [p for n, p in named if no_decay(n, p)]
-        dev = self.params[0].device
-        # Every parameter starts on a 16-byte boundary (TMA / 128-bit loads read weights and biases in place); the decayed
-        # block is padded as a whole so that [0, n_decay) stays one contiguous range. Padding elements stay zero.
+        prefixes = list(buckets or [])
+        which = lambda n: next((j for j, pre in enumerate(prefixes) if n.startswith(pre)), len(prefixes))
+        groups: list[list] = [[] for _ in range(len(prefixes) + 1)]
+        for n, p in named: groups[which(n)].append((n, p))
+        groups = [g for g in groups if g]
+        dev = named[0][1].device
+        # Every parameter starts on a 16-byte boundary (TMA / 128-bit loads read weights and biases in place); padding stays zero.
         al = lambda n: (n + 3)//4*4
-        self.n_decay = sum(al(p.numel()) for n, p in named if not no_decay(n, p))
-        total = sum(al(p.numel()) for p in self.params)
+        self.params, self.buckets = [], []   # buckets: (start, size, n_decay) in elements of the flat buffers
+        total = 0
+        for g in groups:
+            dec = [p for n, p in g if not no_decay(n, p)]
+            nod = [p for n, p in g if no_decay(n, p)]
+            n_dec, n_all = sum(al(p.numel()) for p in dec), sum(al(p.numel()) for p in dec + nod)
+            self.buckets.append((total, n_all, n_dec))
+            self.params += dec + nod
+            total += n_all
+        self.n_decay = self.buckets[0][2] if len(self.buckets) == 1 else None
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros_like(self.flat)
@@ -98,7 +113,8 @@ class FlatAdamW:
         self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
         self.step_count = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self._work = None
+        self._works: list = []
+        self._reduced: set[int] = set()
         self._module = module
         if self.world > 1: dist.broadcast(self.flat, 0)
 
@@ -113,29 +129,45 @@ class FlatAdamW:
         """Gradients are accumulated in place into the flat buffer, so they are zeroed (one memset), not set to None."""
         self.grad.zero_()
 
-    def all_reduce_async(self):
-        """Sum-all-reduce of the flat gradient buffer (the 1/world scale is folded into the optimiser kernel)."""
-        if self.world > 1: self._work = dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, async_op=True)
+    def bucket_ready(self, j: int) -> None:
+        """Start the sum-all-reduce of bucket j (its gradients are final). Called from autograd hooks while backward is still
+        running the networks whose gradients complete later; the collective runs on NCCL's own stream, ordered after the kernels
+        enqueued so far, so it overlaps with the rest of backward (and is captured with it when the step is a CUDA graph)."""
+        if self.world <= 1 or j in self._reduced or j >= len(self.buckets): return
+        start, n, _ = self.buckets[j]
+        self._reduced.add(j)
+        self._works.append(dist.all_reduce(self.grad[start:start + n], op=dist.ReduceOp.SUM, async_op=True))
 
-    def step(self) -> None:
-        if self._work is not None:
-            self._work.wait()
-            self._work = None
+    def all_reduce_async(self):
+        """Sum-all-reduce of every bucket not started yet (the 1/world scale is folded into the optimiser kernel)."""
+        for j in range(len(self.buckets)): self.bucket_ready(j)
+
+    def wait_all_reduce(self) -> None:
+        """Make the current stream wait for the outstanding all-reduces (no host synchronisation with NCCL)."""
+        for w in self._works: w.wait()
+        self._works.clear()
+        self._reduced.clear()
+
+    def step(self, grad_scale: float = 1.0) -> None:
+        """grad_scale: extra factor on the gradient (1/k after accumulating k micro-batches, as Lightning divides the loss)."""
+        self.wait_all_reduce()
         self.step_count += 1
         if self.flat.is_cuda:
-            F_.adamw_step_(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, n_decay=self.n_decay, lr=self.lr,
-                           beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
-                           step=self.step_count, grad_scale=1.0/self.world)
+            for start, n, n_dec in self.buckets:
+                sl = slice(start, start + n)
+                F_.adamw_step_(self.flat[sl], self.grad[sl], self.exp_avg[sl], self.exp_avg_sq[sl], n_decay=n_dec, lr=self.lr,
+                               beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
+                               step=self.step_count, grad_scale=grad_scale/self.world)
         else:
             L_.require_device_path('FlatAdamW.step')
-            self._step_host()
+            self._step_host(grad_scale)
 
     @torch.no_grad()
-    def _step_host(self) -> None:
+    def _step_host(self, grad_scale: float = 1.0) -> None:
         """Host-tensor arithmetic used only by the CPU (gloo) tests of the multi-process logic; same update rule."""
         b1, b2 = self.betas
-        g = self.grad/self.world
-        self.flat[:self.n_decay].mul_(1 - self.lr*self.weight_decay)
+        g = self.grad*(grad_scale/self.world)
+        for start, n, n_dec in self.buckets: self.flat[start:start + n_dec].mul_(1 - self.lr*self.weight_decay)
         self.exp_avg.mul_(b1).add_(g, alpha=1 - b1)
         self.exp_avg_sq.mul_(b2).addcmul_(g, g, value=1 - b2)
         bc1, bc2 = 1 - b1**self.step_count, 1 - b2**self.step_count

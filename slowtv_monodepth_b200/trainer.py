@@ -21,7 +21,8 @@ from .losses import ReconstructionLoss
 from .networks import DepthNet, PoseNet
 from .regularizers import SmoothReg
 
-__all__ = ['MonoDepthStep', 'GraphedTrainStep', 'ShapeCachedTrainStep', 'StepSummary', 'summarize', 'default_cfg']
+__all__ = ['MonoDepthStep', 'GraphedTrainStep', 'ShapeCachedTrainStep', 'StepSummary', 'summarize', 'default_cfg', 'gradient_buckets',
+           'register_bucket_hooks']
 
 NET_REG = {'depth': DepthNet, 'pose': PoseNet}
 LOSS_REG = {'img_recon': ReconstructionLoss, 'disp_smooth': SmoothReg}
@@ -80,14 +81,20 @@ class MonoDepthStep(nn.Module):
                 K = PoseNet.build_K(out['fs'], out['cs']).unflatten(0, sh)[0]  # first support frame only (trainer.py:259)
                 fwd['K'] = G.resize_K(K, x['imgs'].shape[-2:])
         fwd['_idxs'] = idxs
+        hook = getattr(self, 'bucket_hook', None)
+        if hook is not None and torch.is_grad_enabled(): register_bucket_hooks(self.nets, hook)
         return fwd
 
     # -- trainer.py:280-348 ------------------------------------------------------------------------------------------
-    def forward_postprocess(self, fwd: dict, x: dict, y: dict) -> dict:
-        size = x['imgs'].shape[-2:]
-        up = {s: G.upsample_to_depth(d, size, self.min_depth, self.max_depth) for s, d in fwd['disp'].items()}
-        fwd['disp_up'] = {s: v[0] for s, v in up.items()}
-        fwd['depth_up'] = {s: v[1] for s, v in up.items()}
+    def forward_postprocess(self, fwd: dict, x: dict, y: dict, want_up: bool = True) -> dict:
+        """`disp_up` / `depth_up` (trainer.py:316-321) are produced for the logging statistics and for callers of the reference's
+        handler signature; the loss kernel itself starts from the low-resolution disparities (the maps are tagged with their
+        source, `functional.disp_to_depth`), so nothing is differentiated through these up-sampled copies."""
+        if want_up:
+            size = x['imgs'].shape[-2:]
+            up = {s: G.upsample_to_depth(d, size, self.min_depth, self.max_depth) for s, d in fwd['disp'].items()}
+            fwd['disp_up'] = {s: v[0] for s, v in up.items()}
+            fwd['depth_up'] = {s: v[1] for s, v in up.items()}
         fwd['Ts'] = torch.stack([fwd[f'T_{i}'] for i in fwd['_idxs']])
         return fwd
 
@@ -96,8 +103,9 @@ class MonoDepthStep(nn.Module):
         loss, loss_dict = 0., {}
         for k, crit in self.losses.items():
             if k == 'img_recon':
-                l, ld = H.image_recon(crit, None, depths=fwd['depth_up'], masks=None, imgs=y['imgs'], supp_imgs=y['supp_imgs'],
-                                      Ts=fwd['Ts'], Ks=fwd.get('K', y['K']), want_warp=want_maps, noise=noise)
+                l, ld = H.image_recon(crit, None, depths=fwd.get('depth_up'), masks=None, imgs=y['imgs'], supp_imgs=y['supp_imgs'],
+                                      Ts=fwd['Ts'], Ks=fwd.get('K', y['K']), want_warp=want_maps, noise=noise,
+                                      disps=fwd['disp'], depth_range=(self.min_depth, self.max_depth))
             elif k == 'disp_smooth':
                 l, ld = H.disp_smooth(crit, fwd['disp'], y['imgs'], want_maps=want_maps)
             else:
@@ -108,13 +116,42 @@ class MonoDepthStep(nn.Module):
         return loss, loss_dict
 
     # -- trainer.py:115-190 ------------------------------------------------------------------------------------------
-    def step(self, batch, mode: str = 'train', want_maps: bool = False, noise: Tensor | None = None):
-        """`noise`: explicit auto-mask tie-break noise (S*b,1,H,W) replacing the per-step draw (parity tests)."""
+    def step(self, batch, mode: str = 'train', want_maps: bool = False, noise: Tensor | None = None, want_up: bool | None = None):
+        """`noise`: explicit auto-mask tie-break noise (S*b,1,H,W) replacing the per-step draw (parity tests).
+        `want_up`: also materialise the up-sampled `disp_up` / `depth_up` maps (logging statistics, `summarize`); by default only
+        outside plain training steps — the loss does not need them."""
         x, y, m = batch
         fwd = self.forward(x)
-        fwd = self.forward_postprocess(fwd, x, y)
+        fwd = self.forward_postprocess(fwd, x, y, want_up=(want_maps or mode != 'train') if want_up is None else want_up)
         loss, loss_dict = self.forward_loss(fwd, x, y, want_maps=want_maps or mode != 'train', noise=noise)
         return loss, loss_dict, fwd
+
+
+def gradient_buckets(nets) -> list[str]:
+    """Parameter-name prefixes of `nets` (a ModuleDict with 'depth' and optionally 'pose') in the order their gradients become
+    FINAL during backward: the pose network (built last in the forward, so autograd runs it first), the depth decoder, then the
+    depth encoder from its deepest stage to the stem. `FlatAdamW(nets, buckets=...)` lays the flat buffers out in this order."""
+    out = []
+    if 'pose' in nets: out.append('pose.')
+    out.append('depth.decoders.')
+    enc = nets['depth'].encoder
+    parts = [n for n, _ in enc.named_children() if n.startswith(('stages_', 'layer'))]
+    out += [f'depth.encoder.{n}.' for n in reversed(parts[1:])]   # the first stage completes with the stem: last (implicit) bucket
+    return out
+
+
+def register_bucket_hooks(nets, bucket_ready) -> None:
+    """After a forward pass: attach `bucket_ready(j)` to the autograd node whose completion makes bucket j of `gradient_buckets`
+    final (the first operation of the corresponding part, recorded by the networks as `marks` / `first_node`)."""
+    nodes = []
+    if 'pose' in nets: nodes.append(getattr(nets['pose'].encoder, 'marks', {}).get('stem'))
+    dec = nets['depth'].decoders['disp']
+    nodes.append(getattr(dec, 'first_node', None))
+    enc = nets['depth'].encoder
+    parts = [n for n, _ in enc.named_children() if n.startswith(('stages_', 'layer'))]
+    nodes += [getattr(enc, 'marks', {}).get(n) for n in reversed(parts[1:])]
+    for j, node in enumerate(nodes):
+        if node is not None: node.register_hook(lambda *a, j=j: bucket_ready(j))
 
 
 class StepSummary:
@@ -151,34 +188,76 @@ def summarize(fwd: dict) -> StepSummary:
 
 
 class GraphedTrainStep:
-    """One training step (zero_grad -> networks -> losses -> backward) captured ONCE as a CUDA graph and replayed every step.
+    """One training step (networks -> losses -> backward, + the overlapped gradient all-reduce when world > 1) captured ONCE as a
+    CUDA graph and replayed every step.
 
     The step is ~1 800 kernel launches from ~1 000 Python-level operations; enqueueing them from the host takes longer than the
     GPU needs to execute them, so the eager loop is launch-bound. Capturing is possible because nothing on the path synchronises
     or allocates outside torch's graph-private pool: libstv entry points only enqueue kernels / memsets on the stream they are
-    given (tensor maps are host-encoded kernel arguments), and the matrix inverses are libstv kernels, not ATen's batched LU.
-    The gradient all-reduce (world > 1) and the AdamW kernel (its bias correction is a host scalar) stay outside the graph.
+    given (tensor maps are host-encoded kernel arguments), the matrix inverses are libstv kernels, not ATen's batched LU, and
+    the auto-mask tie-break noise is seeded by a device-side counter that the loss kernel itself advances (fresh noise per replay,
+    like the reference's per-step randn_like, reconstruction.py:72).
 
-    The auto-mask tie-break noise seed (a host integer, advanced per call in eager mode) is frozen at capture time: the noise
-    PATTERN then repeats every step — it only decides exact ties between the warped and the static error."""
-    def __init__(self, model: MonoDepthStep, opt, example_batch, warmup: int = 3, pool=None):
-        self.model, self.opt = model, opt
+    Outside the graph: the gradient memset (so that `accumulate` > 1 micro-batches can add up before one optimiser step, Lightning's
+    accumulate_grad_batches, cfg/kbr/default.yaml:122) and the AdamW kernels (bias correction and learning rate are host scalars).
+    Data parallel (world > 1): with `opt` built on `gradient_buckets(model.nets)` each bucket's NCCL all-reduce is issued from an
+    autograd hook the moment backward has finalised it and is captured INSIDE the graph on NCCL's stream, so the exchange overlaps
+    with the rest of backward; if that capture is not possible the all-reduce runs after the replay (`overlap` tells which).
+
+    `model` needs `.step(batch) -> (loss, ...)` and `.nets`; the reference's own MonoDepthModule qualifies after `plugin.install()`.
+    The returned loss is a static tensor of the graph's pool: read (or copy) it before the next replay of ANY graph of the pool."""
+    def __init__(self, model, opt, example_batch, warmup: int = 3, pool=None, accumulate: int = 1, overlap: bool | None = None):
+        self.model, self.opt, self.accumulate, self._micro = model, opt, max(1, int(accumulate)), 0
         x, y, _ = example_batch
         clone = lambda d: {k: (v.clone() if torch.is_tensor(v) and v.is_cuda else v) for k, v in d.items()}
         self.static = (clone(x), clone(y), {})
+        # Warm-up replays must not leave traces in the training state: BatchNorm running statistics (momentum updates) and the
+        # tie-break noise counter are restored afterwards.
+        buffers = [b for b in model.nets.buffers() if b.is_cuda]
+        saved = [b.clone() for b in buffers]
+        losses = getattr(model, 'losses', None)   # a dict here, an nn.ModuleDict in the reference's module
+        crit = losses['img_recon'] if losses is not None and 'img_recon' in losses else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(max(warmup, 1)): self._fwd_bwd()   # lazy one-time initialisation must not happen under capture
+            for _ in range(max(warmup, 1)):   # lazy one-time initialisation must not happen under capture
+                self.opt.zero_grad()
+                self._fwd_bwd(False)
         torch.cuda.current_stream().wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, pool=pool):
-            self.loss = self._fwd_bwd()
-
-    def _fwd_bwd(self) -> Tensor:
+        step0 = crit.noise_step.clone() if crit is not None and getattr(crit, 'noise_step', None) is not None else None
+        want_overlap = (opt.world > 1 and len(opt.buckets) > 1) if overlap is None else (overlap and opt.world > 1)
+        self.overlap = False
+        self.graph = None
+        if want_overlap:
+            try:
+                self._capture(pool, True)
+                self.overlap = True
+            except Exception as e:   # e.g. an NCCL build that cannot be captured: fall back to the exchange after the replay
+                self.overlap_error = f'{type(e).__name__}: {str(e)[:200]}'
+                torch.cuda.synchronize()
+                self.graph = None
+        if self.graph is None: self._capture(pool, False)
         self.opt.zero_grad()
-        loss, _, _ = self.model.step(self.static)
-        loss.backward()
+        for b, v in zip(buffers, saved): b.copy_(v)
+        if step0 is not None: crit.noise_step.copy_(step0 - max(warmup, 1))
+
+    def _capture(self, pool, overlap: bool) -> None:
+        self.opt.zero_grad()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=pool):
+            self.loss = self._fwd_bwd(overlap)
+        self.graph = graph
+
+    def _fwd_bwd(self, overlap: bool) -> Tensor:
+        self.model.bucket_hook = self.opt.bucket_ready if overlap else None
+        try:
+            loss = self.model.step(self.static)[0]
+            loss.backward()
+            if overlap:
+                self.opt.all_reduce_async()    # the last (stem) bucket, and any whose hook did not fire
+                self.opt.wait_all_reduce()     # joins NCCL's stream back into the capturing stream
+        finally:
+            self.model.bucket_hook = None
         return loss.detach()
 
     def load(self, batch) -> None:
@@ -187,11 +266,26 @@ class GraphedTrainStep:
             for k, v in dst.items():
                 if torch.is_tensor(v) and v.is_cuda: v.copy_(src[k], non_blocking=True)
 
-    def run(self, batch=None) -> Tensor:
+    def replay(self, batch=None) -> Tensor:
+        """Load + replay only (no gradient memset, exchange or optimiser step): the building block of `run` and of runners that
+        own the accumulation themselves."""
         if batch is not None: self.load(batch)
         self.graph.replay()
-        self.opt.all_reduce_async()
-        self.opt.step()
+        return self.loss
+
+    def run(self, batch=None) -> Tensor:
+        """One micro-batch. Every `accumulate`-th call ends with the gradient exchange (if not overlapped inside the graph) and the
+        optimiser step on the mean of the accumulated gradients."""
+        if self._micro == 0: self.opt.zero_grad()
+        if batch is not None: self.load(batch)
+        boundary = self._micro + 1 == self.accumulate
+        if self.overlap and not boundary: raise RuntimeError('accumulate > 1 needs overlap=False (the captured exchange runs every replay).')
+        self.graph.replay()
+        self._micro += 1
+        if boundary:
+            if not self.overlap: self.opt.all_reduce_async()
+            self.opt.step(grad_scale=1.0/self.accumulate)
+            self._micro = 0
         return self.loss
 
     # -- pipelined input path: the next batch crosses PCIe on a side stream while the current step computes ---------------------
@@ -234,10 +328,11 @@ class ShapeCachedTrainStep:
     kernels are shape-agnostic (no per-shape compilation), so a new shape costs one eager warm-up + one capture.
 
     `max_graphs` bounds the cache (least recently used shape is dropped)."""
-    def __init__(self, model: MonoDepthStep, opt, warmup: int = 2, max_graphs: int = 64):
-        self.model, self.opt, self.warmup, self.max_graphs = model, opt, warmup, max_graphs
+    def __init__(self, model: MonoDepthStep, opt, warmup: int = 2, max_graphs: int = 64, accumulate: int = 1):
+        self.model, self.opt, self.warmup, self.max_graphs, self.accumulate = model, opt, warmup, max_graphs, accumulate
         self.steps: dict[tuple, GraphedTrainStep] = {}
         self.pool = None
+        self._micro = 0
 
     @staticmethod
     def key(batch) -> tuple:
@@ -249,7 +344,14 @@ class ShapeCachedTrainStep:
         step = self.steps.pop(k, None)
         if step is None:
             if len(self.steps) >= self.max_graphs: self.steps.pop(next(iter(self.steps)))
-            step = GraphedTrainStep(self.model, self.opt, batch, warmup=self.warmup, pool=self.pool)
+            step = GraphedTrainStep(self.model, self.opt, batch, warmup=self.warmup, pool=self.pool, accumulate=1, overlap=False)
             if self.pool is None: self.pool = step.graph.pool()
         self.steps[k] = step  # most recently used last
-        return step.run(batch)
+        if self._micro == 0: self.opt.zero_grad()
+        loss = step.replay(batch)
+        self._micro += 1
+        if self._micro == self.accumulate:   # micro-batches of different shapes accumulate into the same flat gradient buffer
+            self.opt.all_reduce_async()
+            self.opt.step(grad_scale=1.0/self.accumulate)
+            self._micro = 0
+        return loss

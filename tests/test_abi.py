@@ -46,11 +46,11 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     assert b'STV_MAX_SCALES' in lib.stv_last_error()
     cfg.S = 4
     assert lib.stv_photo_workspace_bytes(C.byref(cfg)) > 0
-    rc = lib.stv_photo_fwd(C.byref(cfg), None, None, None, None, None, None, None, None, None, None, None, None, None, 0, None)
+    rc = lib.stv_photo_fwd(C.byref(cfg), None, None, None, None, None, None, None, None, None, None, None, None, 0, None)
     assert rc == 1 and b'NULL' in lib.stv_last_error()
     with pytest.raises(ValueError): L.check(rc, 'stv_photo_fwd')
     cfg.H = 2
-    assert lib.stv_photo_fwd(C.byref(cfg), None, None, None, None, None, None, None, None, None, None, None, None, None, 0, None) == 1
+    assert lib.stv_photo_fwd(C.byref(cfg), None, None, None, None, None, None, None, None, None, None, None, None, 0, None) == 1
     assert lib.stv_adamw_step(None, None, None, None, 8, 0, 1e-3, .9, .999, 1e-8, 0., 1., 1, None) == 1
     assert lib.stv_disp_to_depth_fwd(1, 0, 4, 8, 8, 0.1, 100., None, None, None, None) == 1
 

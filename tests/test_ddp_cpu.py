@@ -30,19 +30,52 @@ def _train(model, opt, x, y, steps=3):
     return torch.cat([p.detach().reshape(-1) for p in model.parameters()])
 
 
-def _worker(rank, world, init_file, out_dir):
+def _train_bucketed(model, opt, x, y, steps=3, accumulate=1):
+    """The overlapped protocol: autograd hooks start a bucket's all-reduce as soon as backward has finalised it (the node of the
+    FIRST layer of the part that owns the bucket), the remaining bucket follows after backward; optional gradient accumulation."""
+    for _ in range(steps):
+        opt.zero_grad()
+        for m in range(accumulate):
+            h = model[2](model[1](model[0](x[m::accumulate])))
+            h.grad_fn.register_hook(lambda *a: opt.bucket_ready(0) if m == accumulate - 1 else None)   # layers 2.. are final here
+            ((model[4](model[3](h)) - y[m::accumulate])**2).mean().backward()
+        opt.all_reduce_async()
+        opt.step(grad_scale=1.0/accumulate)
+    return torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+
+
+def _worker(rank, world, init_file, out_dir, bucketed=False):
     from slowtv_monodepth_b200 import _lib
     from slowtv_monodepth_b200.optim import FlatAdamW
     _lib.host_test_mode(True)  # spawned process: opt in to the host reference arithmetic (the product path is CUDA-only)
     dist.init_process_group('gloo', init_method=f'file://{init_file}', rank=rank, world_size=world)
     try:
         model = _model()
-        opt = FlatAdamW(model, lr=1e-2, weight_decay=1e-2)
-        assert opt.world == world
+        if rank == 1:   # a rank that starts from different weights is brought in line by the constructor's broadcast
+            with torch.no_grad():
+                for p in model.parameters(): p.add_(1.0)
+        opt = FlatAdamW(model, lr=1e-2, weight_decay=1e-2, buckets=['4.', '2.'] if bucketed else None)
+        assert opt.world == world and len(opt.buckets) == (3 if bucketed else 1)
         x, y = _data(rank)
-        torch.save(_train(model, opt, x, y), os.path.join(out_dir, f'rank{rank}.pt'))
+        out = _train_bucketed(model, opt, x, y, accumulate=2) if bucketed else _train(model, opt, x, y)
+        torch.save(out, os.path.join(out_dir, f'rank{rank}.pt'))
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_bucketed_overlap_and_accumulation_match_single_process():
+    """Buckets in gradient-completion order, all-reduces started from autograd hooks, two accumulated micro-batches per step:
+    same parameters as plain single-process training on the whole batch."""
+    from slowtv_monodepth_b200.optim import FlatAdamW
+    with tempfile.TemporaryDirectory() as d:
+        init = os.path.join(d, 'init')
+        mp.spawn(_worker, args=(2, init, d, True), nprocs=2, join=True)
+        r0, r1 = torch.load(os.path.join(d, 'rank0.pt')), torch.load(os.path.join(d, 'rank1.pt'))
+    assert torch.equal(r0, r1), 'ranks diverged'
+    model = _model()
+    ref = _train(model, FlatAdamW(model, lr=1e-2, weight_decay=1e-2), *_data())
+    assert torch.allclose(r0, ref, atol=2e-6, rtol=1e-5), (r0 - ref).abs().max()
 
 
 @pytest.mark.timeout(120)

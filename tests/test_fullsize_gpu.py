@@ -2,10 +2,11 @@
 configs[2], [3] and [4] (batch 1-2: the oracle needs a few seconds per case) with the protocol of tests/test_loss_gpu.py;
 (b) at the full batch, size-independent properties of the loss stack.
 
-  * two independent implementations agree: the lean backward fed by the forward's coefficient planes vs. the self-contained
-    backward that re-warps and rebuilds the SSIM sums (different kernels, different tiling, different data flow);
+  * two independent implementations agree: the single-pass kernel (warp-per-strip sweep, in-kernel up-sampling, unit gradients)
+    vs. the two-pass kernels (tile-per-block forward, self-contained backward that re-warps and rebuilds the SSIM sums,
+    separate up-sampling kernels) — different kernels, different tiling, different data flow;
   * linearity of the backward in the incoming gradient; bit-identical repeat runs (fixed-order reductions, no float atomics);
-  * the decision bytes and the loss value do not depend on whether the coefficient planes are requested;
+  * the decision bytes and the loss value agree between the two formulations;
   * the resampling kernel against ATen's at the augmentation's real sizes.
 Shapes: configs[2] (b=8, n=2, S=4, 384x640), configs[3] (n=4), configs[4] (b=4, 512x1024), and two ragged sizes that force the
 non-texture / non-TMA code paths."""
@@ -15,8 +16,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 CASES = {'config3': (8, 2, 4, (384, 640)), 'config4_n4': (4, 4, 4, (384, 640)), 'config5_hr': (4, 2, 4, (512, 1024)),
-         # odd width: rows are not 16-byte granular, so the support frames cannot be bound as a texture and the coefficient tiles
-         # cannot travel by TMA — the plain-load variants of the forward and of both backward kernels run instead
+         # odd width: rows are not 32-byte granular, so the support frames cannot be bound as a texture — the plain-load variant
+         # of the single-pass kernel runs instead; sizes that are no multiple of the strip geometry (28 columns x 8..32 rows)
          'ragged_37x53': (3, 2, 2, (37, 53)), 'ragged_50x66_n3': (2, 3, 3, (50, 66))}
 
 
@@ -38,20 +39,23 @@ def test_loss_stack_matches_oracle_at_full_size(name):
     U.check_loss_stack(inp, cfg, got)
 
 
-def _run(d, coef: bool, scale: float = 1.0):
+def _run(d, fused: bool, scale: float = 1.0):
     from slowtv_monodepth_b200 import functional as F_, geometry as G
-    F_.PHOTO_COEF = coef
+    F_.PHOTO_FORCE_TWO_PASS = not fused
     try:
         disps = [x.clone().requires_grad_() for x in d['disps']]
         aa, t, K = (d[k].clone().requires_grad_() for k in ('aa', 't', 'K'))
         H, W = d['imgs'].shape[-2:]
-        depths = [G.upsample_to_depth(x, (H, W), 0.1, 100.)[1] for x in disps]
-        loss, sel, _ = F_.photo_loss(depths, d['imgs'], d['supp_imgs'], G.T_from_AAt(aa, t), K, noise_seed=7)
+        if fused: loss, sel, _ = F_.photo_loss(disps, d['imgs'], d['supp_imgs'], G.T_from_AAt(aa, t), K, noise_seed=7, disp_size=(H, W),
+                                               min_depth=0.1, max_depth=100.)
+        else:
+            depths = [G.upsample_to_depth(x, (H, W), 0.1, 100.)[1] for x in disps]
+            loss, sel, _ = F_.photo_loss(depths, d['imgs'], d['supp_imgs'], G.T_from_AAt(aa, t), K, noise_seed=7)
         (loss*scale).backward()
         torch.cuda.synchronize()
         return loss.detach(), sel, [x.grad for x in disps], aa.grad, t.grad, K.grad
     finally:
-        F_.PHOTO_COEF = True
+        F_.PHOTO_FORCE_TWO_PASS = False
 
 
 @pytest.mark.parametrize('name', CASES)
@@ -63,15 +67,21 @@ def test_photometric_pair_properties_at_full_size(name):
     rel = lambda a, r: ((a.double() - r.double()).norm()/r.double().norm().clamp(min=1e-30)).item()
 
     lean, full = _run(d, True), _run(d, False)
-    # same forward up to the last ulp of the SSIM quotient (the coefficient variant rounds num/den once more), same decisions
-    # except at exact near-ties
+    # same forward up to float32 rounding of the SSIM quotient (rcp + multiply vs. divide), same decisions except at near-ties
     assert torch.isfinite(lean[0]) and abs(lean[0].item() - full[0].item()) <= 1e-6*abs(full[0].item())
     flips = (lean[1] != full[1])
     assert flips.float().mean().item() < 1e-4, flips.float().mean().item()
+    # Per pixel: the two float32 evaluations round differently, so the handful of pixels within rounding of a discrete event
+    # (decision, L1 sign, texel cell — tests/test_loss_gpu.py) legitimately differ O(1) there; everywhere else they agree to 1e-4
+    # of the map's RMS. Requirement: > 99.5 % of the pixels of every scale agree (the oracle tests above hold the values).
     for s in range(S):
-        if flips[s].any(): continue   # a flipped decision legitimately changes the gradient around it (tests/test_loss_gpu.py protocol)
-        assert rel(lean[2][s], full[2][s]) < 1e-4, (s, rel(lean[2][s], full[2][s]))       # d/d disparity (the parity bar; measured 3e-5: rcp.approx vs. exact division in the SSIM coefficients)
-    for j, what in ((3, 'aa'), (4, 't'), (5, 'K')): assert rel(lean[j], full[j]) < 1e-4, (what, rel(lean[j], full[j]))
+        a, r = lean[2][s].double(), full[2][s].double()
+        rms = r.pow(2).mean().sqrt()
+        ok = ((a - r).abs() <= 1e-4*rms + 1e-4*r.abs()).double().mean().item()
+        assert ok > 0.995, (s, ok)
+    # pose / intrinsics gradients are sums over ALL pixels, including those few: 1e-3 here; against the float64 oracle they are held
+    # to 1e-4 / the reference's own float32 noise floor in test_loss_stack_matches_oracle_at_full_size
+    for j, what in ((3, 'aa'), (4, 't'), (5, 'K')): assert rel(lean[j], full[j]) < 1e-3, (what, rel(lean[j], full[j]))
 
     again = _run(d, True)
     for j in (3, 4, 5): assert torch.equal(lean[j], again[j])                                               # deterministic

@@ -18,6 +18,7 @@ def test_graphed_step_matches_eager():
     # replay on a NEW batch, then the same batch eagerly: the flat gradient buffers must agree
     crit = model.losses['img_recon']
     g.load(b1)
+    opt.zero_grad()             # the gradient memset lives outside the graph (micro-batches may accumulate)
     crit.noise_step.fill_(41)   # the tie-break noise is seeded by a DEVICE counter that every call (and replay) advances
     g.graph.replay()
     torch.cuda.synchronize()
@@ -59,6 +60,7 @@ def test_shape_cached_graphs_follow_the_aspect_ratio_augmentation():
     step = runner.steps[runner.key(b)]
     crit = model.losses['img_recon']
     crit.noise_step.fill_(7)
+    opt.zero_grad()   # the gradient memset lives outside the graph (micro-batches may accumulate)
     step.load(b); step.graph.replay(); torch.cuda.synchronize()
     loss_g, grad_g = step.loss.clone(), opt.grad.clone()
     opt.zero_grad()

@@ -32,16 +32,14 @@ pytestmark = pytest.mark.gpu
 TOL_LOSS, TOL_GRAD = 1e-5, 1e-4
 
 
-@pytest.mark.parametrize('coef', [True, False], ids=['coef-bwd', 'recompute-bwd'])
+@pytest.mark.parametrize('mode', ['fused-disp', 'fused-depth', 'two-pass'])
 @pytest.mark.parametrize('name', U.LOSS_CASES)
-def test_loss_stack_matches_oracle(name, coef, monkeypatch):
-    """Both backward kernels: the lean one fed by the forward's coefficient planes (min-reprojection) and the self-contained
-    one that re-warps and rebuilds the SSIM sums (always used for mean reduction)."""
-    from slowtv_monodepth_b200 import functional as F_
-    monkeypatch.setattr(F_, 'PHOTO_COEF', coef)
+def test_loss_stack_matches_oracle(name, mode):
+    """All three routes: the single-pass kernel fed with low-resolution disparities (the training step) or with up-sampled depth
+    maps (the reference's handler signature), and the two-pass kernels (always used for the mean reduction)."""
     inp, cfg, ref = U.load_golden(name)
-    if coef and not cfg.get('use_min', True): pytest.skip('coefficient planes need min-reprojection; covered by recompute-bwd')
-    got = U.run_cuda(inp, cfg)
+    if mode != 'two-pass' and not cfg.get('use_min', True): pytest.skip('the single-pass kernel needs min-reprojection; covered by two-pass')
+    got = U.run_cuda(inp, cfg, mode=mode)
     torch.cuda.synchronize()
     U.check_loss_stack(inp, cfg, got, TOL_LOSS, TOL_GRAD)
 

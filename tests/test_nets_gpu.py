@@ -151,7 +151,7 @@ def test_step_summary_has_the_reference_keys_and_values():
     torch.manual_seed(0)
     model = MonoDepthStep(default_cfg('resnet18', 'resnet18', learn_K=True)).cuda().train()
     batch = syn.make_batch(2, 2, (64, 96), seed=0, device='cuda')
-    with torch.no_grad(): _, _, fwd = model.step(batch)
+    with torch.no_grad(): _, _, fwd = model.step(batch, want_up=True)
     got = summarize(fwd).to_host()
     for s in range(4):
         for key in ('disp', 'depth'):

@@ -30,7 +30,7 @@ CFG = {
 }
 
 
-def _modules(install_kwargs, batch=None):
+def _modules(install_kwargs, batch=None, exact_geometry=False):
     """-> (reference module built from the reference's classes, reference module built after install(), plugin[, the pure
     reference's step result]) with shared weights. `install()` rebinds class-level names, so the pure reference step (when a
     batch is given) runs BEFORE it."""
@@ -48,6 +48,10 @@ def _modules(install_kwargs, batch=None):
     ref = ref.cuda().train()
     ref_out = None
     if batch is not None:
+        # MonoDepthModule.__init__ sets float32 matmuls to TF32 (trainer.py:30), which on a GPU also rounds the reference's own
+        # geometry (the K^-1 / T / K `bmm`s of ViewSynth, geometry.py:313,386,341) to 10 mantissa bits. `exact_geometry` restores
+        # float32 matmuls for the comparison that isolates the loss side.
+        if exact_geometry: torch.set_float32_matmul_precision('highest')
         torch.backends.cudnn.deterministic = True
         try: ref_out = _step(ref, batch)
         finally: torch.backends.cudnn.deterministic = False
@@ -77,7 +81,7 @@ def batch():
 
 
 def test_loss_side_drop_in_matches_the_reference_step(batch):
-    ref, ours, plugin, (l_ref, ld_ref, g_ref) = _modules(dict(nets=False, loss=True), batch)
+    ref, ours, plugin, (l_ref, ld_ref, g_ref) = _modules(dict(nets=False, loss=True), batch, exact_geometry=True)
     try:
         from slowtv_monodepth_b200 import losses
         assert isinstance(ours.losses['img_recon'], losses.ReconstructionLoss) and type(ours.nets['depth']) is type(ref.nets['depth'])
@@ -94,6 +98,7 @@ def test_loss_side_drop_in_matches_the_reference_step(batch):
         assert e < 3e-2, e   # float32 sub-gradient events (L1 sign / texel cell) differ between ANY two float32 evaluations
     finally:
         torch.backends.cudnn.deterministic = False
+        torch.set_float32_matmul_precision('high')
         plugin.uninstall()
 
 

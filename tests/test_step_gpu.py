@@ -10,7 +10,7 @@ numerics (`matmul: high`, cfg/default.yaml:171; cuDNN TF32). The yardstick is th
   ours = the product.
 All three get the same explicit tie-break noise and the product's per-pixel decisions (min-reprojection winner, auto-mask;
 `forced_sel`), so the comparison is between smooth functions and a per-tensor bound is meaningful:
-  loss:               |ours - ref| <= max(2 |lib - ref|, 1e-4 |ref|)
+  loss:               |ours - ref| <= max(2 |lib - ref|, 1e-3 |ref|)   (cuDNN picks float32 kernels at this tiny size: TF32 floor)
   every parameter p:  ||g_ours - g_ref|| <= 2 ||g_lib - g_ref|| + 2e-3 ||g_ref||_global-scale floor (see `bound` below).
 """
 import pytest
@@ -71,7 +71,7 @@ def test_training_step_matches_oracle(depth_enc, n, learn_K):
     e_loss, e_loss_lib = abs(lp.item() - lo.item())/abs(lo.item()), abs(ll.item() - lo.item())/abs(lo.item())
     print(f'{depth_enc} n={n} learn_K={learn_K}: loss {lp.item():.6f} (ref {lo.item():.6f}; rel err ours {e_loss:.2e}, lib {e_loss_lib:.2e}); '
           f'whole-gradient rel err ours {E_ours:.3e}, lib {E_lib:.3e}')
-    assert torch.isfinite(lp) and e_loss <= max(2*e_loss_lib, 1e-4), (lp.item(), lo.item(), ll.item())
+    assert torch.isfinite(lp) and e_loss <= max(2*e_loss_lib, 1e-3), (lp.item(), lo.item(), ll.item())
     assert E_ours <= max(2*E_lib, 2e-3), (E_ours, E_lib)
     # Per tensor: a tensor's error is bounded by twice the library's on the same tensor plus a floor of 2 x the library's
     # whole-gradient relative error applied to that tensor's own magnitude (tensors the library happens to get almost exactly

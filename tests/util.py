@@ -53,7 +53,7 @@ def run_oracle(inp: dict, cfg: dict, dtype=torch.float64, forced_sel=None, w_smo
     Ts = OL.T_from_AAt(aa, t)
     H, W = d['imgs'].shape[-2:]
     mn, mx = cfg.get('min_depth', 0.1), cfg.get('max_depth', 100.)
-    disps_up = [OL.resize_bilinear(x, (H, W)) for x in disps]
+    disps_up = [OL.resize_bilinear(x, (H, W))*1 for x in disps]   # (*1: a node of its own even when the resize is the identity)
     depths = [OL.disp_to_depth(x, mn, mx) for x in disps_up]
     l_rec, o = OL.image_recon(depths, d['imgs'], d['supp_imgs'], Ts, K, cfg.get('use_min', True), cfg.get('use_automask', True),
                               d['noise'], loss_name=cfg.get('loss_name', 'ssim'), forced_sel=forced_sel)
@@ -65,7 +65,7 @@ def run_oracle(inp: dict, cfg: dict, dtype=torch.float64, forced_sel=None, w_smo
                disp_grad=o2['disp_grad'].detach(), image_grad=o2['image_grad'].detach())
     for s, x in enumerate(disps): out[f'g_disp{s}'] = x.grad
     for s, x in enumerate(depths): out[f'g_depth{s}'] = x.grad
-    for s, x in enumerate(disps_up): out[f'g_dispup{s}'] = x.grad if x.grad is not None else disps[s].grad  # scale 0 is not resized
+    for s, x in enumerate(disps_up): out[f'g_dispup{s}'] = x.grad   # photometric term only (the smoothness acts on `disps`)
     if 'automask' in o: out['automask0'] = o['automask']
     return out
 
@@ -158,9 +158,13 @@ def rel_masked(a, b, good) -> float:
     return ((a - b).norm()/b.norm().clamp(min=1e-30)).item()
 
 
-def run_cuda(inp: dict, cfg: dict, w_smooth: float = 1e-3, device='cuda') -> dict:
-    """The product path: libstv kernels through the host-side mirror modules."""
-    from slowtv_monodepth_b200 import geometry as G, handlers as Hd
+def run_cuda(inp: dict, cfg: dict, w_smooth: float = 1e-3, device='cuda', mode: str = 'fused-disp') -> dict:
+    """The product path: libstv kernels through the host-side mirror modules.
+      mode 'fused-disp'   single-pass kernel fed with the low-resolution disparities (what the training step runs);
+      mode 'fused-depth'  single-pass kernel fed with up-sampled depth maps (stv_disp_to_depth_fwd/bwd around it: what a caller of
+                          the reference's handlers.image_recon signature gets);
+      mode 'two-pass'     stv_photo_fwd + stv_photo_bwd (always used for the mean reduction)."""
+    from slowtv_monodepth_b200 import functional as F_, geometry as G, handlers as Hd
     from slowtv_monodepth_b200.losses import ReconstructionLoss
     from slowtv_monodepth_b200.regularizers import SmoothReg
 
@@ -170,22 +174,32 @@ def run_cuda(inp: dict, cfg: dict, w_smooth: float = 1e-3, device='cuda') -> dic
     Ts = G.T_from_AAt(aa, t)
     H, W = d['imgs'].shape[-2:]
     mn, mx = cfg.get('min_depth', 0.1), cfg.get('max_depth', 100.)
-    depths = {s: G.upsample_to_depth(x, (H, W), mn, mx)[1] for s, x in enumerate(disps)}
-    for x in depths.values(): x.retain_grad()
-    crit = ReconstructionLoss(cfg.get('loss_name', 'ssim'), cfg.get('use_min', True), cfg.get('use_automask', True))
-    l_rec, ld, sel, warp0 = crit.fused(list(depths.values()), d['imgs'], d['supp_imgs'], Ts, K, noise=d['noise'], want_warp=True)
+    use_min = cfg.get('use_min', True)
+    crit = ReconstructionLoss(cfg.get('loss_name', 'ssim'), use_min, cfg.get('use_automask', True))
+    F_.PHOTO_FORCE_TWO_PASS, F_.KEEP_UNIT_GRADS = mode == 'two-pass', True
+    try:
+        if mode == 'fused-disp' and use_min:
+            l_rec, ld, sel, warp0 = crit.fused(disps, d['imgs'], d['supp_imgs'], Ts, K, noise=d['noise'], want_warp=True, from_disp=(mn, mx))
+            depths, kind = None, 'disp'
+        else:
+            depths = {s: G.upsample_to_depth(x, (H, W), mn, mx)[1] for s, x in enumerate(disps)}
+            for x in depths.values(): x.retain_grad()
+            l_rec, ld, sel, warp0 = crit.fused(list(depths.values()), d['imgs'], d['supp_imgs'], Ts, K, noise=d['noise'], want_warp=True)
+            kind = 'depth'
+        unit = F_.LAST_UNIT_GRADS
+    finally:
+        F_.PHOTO_FORCE_TWO_PASS, F_.KEEP_UNIT_GRADS, F_.LAST_UNIT_GRADS = False, False, None
     o = {'supp_imgs_warp': warp0, **{k: v[0] for k, v in ld.items()}}
     l_sm, o2 = Hd.disp_smooth(SmoothReg(use_edges=True), dict(enumerate(disps)), d['imgs'])
     (l_rec + w_smooth*l_sm).backward()
+    with torch.no_grad(): depth_up0 = G.upsample_to_depth(d['disps'][0], (H, W), mn, mx)[1]
     out = dict(loss_recon=l_rec.detach(), loss_smooth=l_sm.detach(), g_aa=aa.grad, g_t=t.grad, g_K=K.grad,
-               warp0=o['supp_imgs_warp'], depth_up0=depths[0].detach(), disp_grad=o2['disp_grad'], image_grad=o2['image_grad'],
-               sel=sel.flatten(0, 1).unsqueeze(1))
+               warp0=o['supp_imgs_warp'], depth_up0=depth_up0, disp_grad=o2['disp_grad'], image_grad=o2['image_grad'],
+               sel=sel.flatten(0, 1).unsqueeze(1), up_kind=kind)
     for s, x in enumerate(disps): out[f'g_disp{s}'] = x.grad
-    for s, x in depths.items(): out[f'g_up{s}'] = x.grad
-    out['up_kind'] = 'depth'
+    for s in range(len(disps)): out[f'g_up{s}'] = depths[s].grad if depths is not None else unit[s]  # dL/dloss_recon = 1 here
     if 'automask' in o: out['automask0'] = o['automask']
     return out
-
 
 def check_loss_stack(inp: dict, cfg: dict, got: dict, tol_loss: float = 1e-5, tol_grad: float = 1e-4) -> None:
     """The parity protocol of tests/test_loss_gpu.py (see its docstring) for one set of inputs and one CUDA result."""
@@ -215,8 +229,15 @@ def check_loss_stack(inp: dict, cfg: dict, got: dict, tol_loss: float = 1e-5, to
     assert bad.float().mean().item() < 0.05, f'{bad.float().mean().item():.2%} unstable pixels'
     assert rel(got['loss_recon'], want['loss_recon']) < tol_loss
     assert rel(got['loss_smooth'], want['loss_smooth']) < tol_loss
+    # Pose / intrinsics gradients are sums over ALL pixels, including those within float32 rounding of a sub-gradient event (whose
+    # per-pixel term legitimately differs O(1) between any two float32 evaluations). The bar is tol_grad, or — where the
+    # reference's OWN float32 arithmetic (the oracle run in float32 with the same decisions) is further than that from the
+    # float64 answer — twice that noise floor.
+    with eps32():
+        ref32 = run_oracle(inp, cfg, torch.float32, forced_sel=sel if use_min else None)
     for k in ('g_aa', 'g_t', 'g_K'):
-        assert rel(got[k], want[k]) < tol_grad, f'{k}: {rel(got[k], want[k]):.3e}'
+        floor = rel(ref32[k], want[k])
+        assert rel(got[k], want[k]) < max(tol_grad, 2*floor), f'{k}: {rel(got[k], want[k]):.3e} (float32 reference noise floor {floor:.3e})'
     check_pixel_gradients(inp, cfg, got, want, bad, tol_grad)
     for k in ('warp0', 'depth_up0', 'disp_grad', 'image_grad'):
         assert rel(got[k], want[k]) < 1e-5, f'{k}: {rel(got[k], want[k]):.3e}'

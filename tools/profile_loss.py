@@ -11,6 +11,7 @@ from slowtv_monodepth_b200.regularizers import SmoothReg
 
 ap = argparse.ArgumentParser()
 for k, v in dict(b=8, H=384, W=640, n=2, S=4, iters=5).items(): ap.add_argument(f'--{k}', type=int, default=v)
+ap.add_argument('--mode', default='disp', choices=['disp', 'depth', 'two-pass'])
 a = ap.parse_args()
 dev = 'cuda'
 d = syn.make_loss_inputs(a.b, a.n, a.S, (a.H, a.W), seed=0)
@@ -21,15 +22,24 @@ crit, sm = ReconstructionLoss('ssim', True, True), SmoothReg(use_edges=True)
 F_.enable_kernel_timing(True)
 for it in range(a.iters):
     Ts = G.T_from_AAt(aa, t)
-    depths = {s: G.upsample_to_depth(x, (a.H, a.W), 0.1, 100.)[1] for s, x in enumerate(disps)}
-    l1, _ = Hd.image_recon(crit, None, depths, None, d['imgs'], d['supp_imgs'], Ts, d['K'], want_warp=False)
+    F_.PHOTO_FORCE_TWO_PASS = a.mode == 'two-pass'
+    if a.mode == 'disp':
+        l1, _ = Hd.image_recon(crit, None, None, None, d['imgs'], d['supp_imgs'], Ts, d['K'], want_warp=False, disps=dict(enumerate(disps)),
+                               depth_range=(0.1, 100.))
+    else:
+        depths = {s: G.upsample_to_depth(x, (a.H, a.W), 0.1, 100.)[1] for s, x in enumerate(disps)}
+        for x in depths.values(): x._stv_src = None if a.mode == 'depth' else x._stv_src
+        l1 = crit.fused(list(depths.values()), d['imgs'], d['supp_imgs'], Ts, d['K'], want_warp=False)[0]
     l2, _ = Hd.disp_smooth(sm, dict(enumerate(disps)), d['imgs'], want_maps=False)
     (l1 + 1e-3*l2).backward()
 torch.cuda.synchronize()
 px = a.b*a.H*a.W
+tot = 0.
 for k, v in F_.kernel_timings().items():
     v = v[1:]
     ms = sum(v)/len(v)
-    by = {'stv_photo_fwd': (12 + 12*a.n + 12*a.n*a.S + 4*a.S)*px, 'stv_photo_bwd': (12 + 12*a.n + 12*a.n*a.S + 8*a.S)*px}.get(k)
-    print(f'{k:16s} {ms*1e3:9.1f} us' + (f'  {by/1e9/(ms/1e3):8.1f} GB/s algorithmic' if by else ''))
+    tot += ms if k.startswith('stv_photo') else 0.
+    print(f'{k:16s} {ms*1e3:9.1f} us')
+by = (12 + 12*a.n + 12*a.n*a.S + 4*a.S)*px + (12 + 12*a.n + 12*a.n*a.S + 8*a.S)*px   # forward + backward algorithmic bytes
+print(f'photometric pair ({a.mode}): {tot*1e3:.1f} us for {by/1e6:.0f} MB algorithmic = {by/1e9/(tot/1e3):.0f} GB/s')
 print('loss', l1.item(), l2.item())
