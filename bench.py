@@ -229,7 +229,9 @@ def _claim_stdout():
 def measured_tf32_peak(dev) -> float:
     """TFLOP/s of cuBLAS TF32 on this GPU, measured now: torch.matmul fp32 8192^3 with TF32 enabled, best of 6 (CUDA events)."""
     n = 8192
-    a, b = torch.randn(n, n, device=dev), torch.randn(n, n, device=dev)
+    # (no torch RNG here: the default CUDA generator is registered with the captured step graph)
+    a = (torch.arange(n*n, device=dev, dtype=torch.float32).reshape(n, n) % 251.0)/251.0 - 0.5
+    b = (torch.arange(n*n, device=dev, dtype=torch.float32).reshape(n, n) % 241.0)/241.0 - 0.5
     best = float('inf')
     for i in range(8):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -456,6 +458,7 @@ def main() -> None:
             'bound': 'tensor', 'achieved': round(tc_ach, 1), 'peak': round(tc_peak, 1), 'unit': 'TFLOP/s', 'frac': round(tc_ach/tc_peak, 4),
             'peak_source': 'measured now: torch.matmul fp32 8192^3 with TF32 enabled (cuBLAS), best of 6', 'algorithmic_flops_per_step': tc_flops,
             'ms_per_step_in_kernel_calls': round(tc_ms, 3)}
+        if use_plugin: plugin.uninstall()   # the baselines below run the reference's / the library's own classes
         if world == 1 and not args.no_torch_baseline:
             try: line['gpu_torch_baseline'] = torch_gpu_baseline(c, b, dev)
             except Exception as e: line['gpu_torch_baseline'] = {'unavailable': f'{type(e).__name__}: {str(e)[:160]}'}

@@ -132,21 +132,19 @@ def lib() -> C.CDLL:
     return _lib
 
 
-# Host-tensor arithmetic exists in this package ONLY as a test aid (CPU checks of parameter naming / wiring against the oracle, and
-# the gloo tests of the flat optimiser): it is never a fallback. Product code calls `require_device_path()` before touching it; the
-# CPU test-suite opts in with `host_test_mode(True)`.
-_HOST_TEST_MODE = False
+# The product path is CUDA-only: modules handed host (CPU) tensors raise. The package contains NO host arithmetic. The CPU
+# test-suite checks parameter naming / wiring / the multi-process optimiser logic on the CPU with reference implementations that
+# live in tests/host_ref.py and are registered here by the test fixtures (never by product code).
+_HOST_HOOKS: dict = {}
 
 
-def host_test_mode(on: bool = True) -> None:
-    global _HOST_TEST_MODE
-    _HOST_TEST_MODE = bool(on)
-
-
-def require_device_path(what: str) -> None:
-    if not _HOST_TEST_MODE:
-        raise StvError(f'{what}: got host (CPU) tensors. The product path is CUDA-only (libstv kernels); there is no CPU fallback. '
-                       f'(The CPU test-suite enables the host reference arithmetic explicitly with _lib.host_test_mode(True).)')
+def host_path(obj, *args, what: str | None = None, **kwargs):
+    """Dispatch a host-tensor call to the hook a TEST registered for type(obj); raise in production (no hook is ever registered)."""
+    fn = _HOST_HOOKS.get(type(obj))
+    if fn is None:
+        raise StvError(f'{what or type(obj).__name__}: got host (CPU) tensors. The product path is CUDA-only (libstv kernels); there '
+                       f'is no CPU fallback.')
+    return fn(obj, *args, **kwargs)
 
 
 def check(rc: int, what: str) -> None:

@@ -7,6 +7,7 @@
 // reads 128 contiguous bytes of a pixel, and the 7x7 window slides through registers.
 //
 // Reference call sites: the timm ConvNeXt encoder built at src/networks/depth.py:97 (third-party, see encoders.py).
+#include <cstdlib>
 #include "stv_common.cuh"
 
 namespace stv {
@@ -317,16 +318,23 @@ using namespace stv;
 
 static int round32(int c) { return (c + 31)/32*32; }
 
+// Rows per block of the strip kernels: tall strips amortise the 6-row halo; shrink them while the grid is smaller than ~6 blocks
+// per SM (blocks are only 3-4 warps).
+static int dw_rows(int N, int H, int W, int C) {
+    const int ncb = (C + DW_CB - 1)/DW_CB;
+    const long long cols = (long long)((W + DW_L - 1)/DW_L)*ncb*N;
+    int rows = 32;
+    while (rows > 8 && cols*((H + rows - 1)/rows) < 6*148) rows >>= 1;
+    return rows;
+}
+
 extern "C" int stv_dwconv7_fwd(int N, int H, int W, int C, const float* x, const float* w, const float* bias, const float* res,
                                float* y, int flip, void* stream) {
     STV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= 1024, "stv_dwconv7_fwd: bad shape (N=%d H=%d W=%d C=%d; C <= 1024)", N, H, W, C);
     STV_REQUIRE(N <= 65535, "stv_dwconv7_fwd: grid too large");
     STV_REQUIRE(x && w && y, "stv_dwconv7_fwd: NULL pointer");
     const int ncb = (C + DW_CB - 1)/DW_CB, nt = C < DW_CB ? round32(C) : DW_CB;
-    // Rows per block: tall strips amortise the 6-row halo; shrink them while the grid is smaller than ~2 blocks per SM.
-    const long long cols = (long long)((W + DW_L - 1)/DW_L)*ncb*N;
-    int rows = 32;
-    while (rows > 8 && cols*((H + rows - 1)/rows) < 6*148) rows >>= 1;   // blocks are only 3-4 warps: aim for >= 6 per SM
+    const int rows = dw_rows(N, H, W, C);
     dim3 grid(((W + DW_L - 1)/DW_L)*ncb, (H + rows - 1)/rows, N);
     if (flip) dwconv7_kernel<true><<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, rows, x, w, bias, res, y);
     else dwconv7_kernel<false><<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, rows, x, w, bias, res, y);

@@ -453,21 +453,27 @@ __global__ void __launch_bounds__(FZ_NT, STV_FUSED_MINB) photo_fused_kernel(cons
                     }
                     if (!any) continue;
                     const float* const cR = cam + 15 + k*12; const float* const ct = cR + 9;
-                    float Pp[3], Q[3];
+                    // u = R ray, Q = d u + t. The depth gradient gQ . u is, written out, inv (gn.u) - inv^2 (gn.Q) u_z: two terms of
+                    // size d |gn| / z that cancel to size |t| |gn| / z^2 (the d-terms cancel EXACTLY in exact arithmetic) — for far
+                    // points a float32 evaluation of the difference loses log2(d/|t|) ~ 11 bits. The closed form below has the
+                    // cancellation done analytically:  gd = inv^2 ((gn.u) t_z - (gn.t) u_z)   (unclamped z), inv (gn.u) (clamped).
+                    float uu[3], Q[3];
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) Pp[r] = rayp[r]*dp;
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) Q[r] = fmaf(cR[r*3], Pp[0], fmaf(cR[r*3 + 1], Pp[1], fmaf(cR[r*3 + 2], Pp[2], ct[r])));
+                    for (int r = 0; r < 3; ++r) {
+                        uu[r] = fmaf(cR[r*3], rayp[0], fmaf(cR[r*3 + 1], rayp[1], cR[r*3 + 2]*rayp[2]));
+                        Q[r] = fmaf(dp, uu[r], ct[r]);
+                    }
                     const float inv = rcp_fast(fmaxf(Q[2], STV_MIN_Z));
                     float gn[3], gQ[3];
-                    float gz = 0.f;
+                    float gz = 0.f, gnu = 0.f, gnt = 0.f;
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) { gn[r] = fmaf(cK0[r], gqx, cK1[r]*gqy); gQ[r] = gn[r]*inv; gz = fmaf(gn[r], Q[r], gz); }
-                    if (Q[2] >= STV_MIN_Z) gQ[2] -= gz*inv*inv;
-                    float gP[3];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) gP[r] = fmaf(cR[r], gQ[0], fmaf(cR[3 + r], gQ[1], cR[6 + r]*gQ[2]));
-                    gd += fmaf(gP[0], rayp[0], fmaf(gP[1], rayp[1], gP[2]*rayp[2]));
+                    for (int r = 0; r < 3; ++r) {
+                        gn[r] = fmaf(cK0[r], gqx, cK1[r]*gqy); gQ[r] = gn[r]*inv;
+                        gz = fmaf(gn[r], Q[r], gz); gnu = fmaf(gn[r], uu[r], gnu); gnt = fmaf(gn[r], ct[r], gnt);
+                    }
+                    const bool unclamped = Q[2] >= STV_MIN_Z;
+                    if (unclamped) gQ[2] -= gz*inv*inv;
+                    gd += unclamped ? inv*inv*fmaf(gnu, ct[2], -gnt*uu[2]) : inv*gnu;
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
                         const float m = gQ[r]*dp;
@@ -622,10 +628,7 @@ __global__ void __launch_bounds__(128) pull_rows_kernel(const PullParams p) {
     const int xl = blockIdx.x*blockDim.x + threadIdx.x;
     if (xl >= w) return;
     const float sc = p.scale ? __ldg(p.scale) : 1.f;
-    if (w == W && p.h[s] == H) {
-        p.out[s][(size_t)i*H*W + (size_t)Y*W + xl] = sc*pull_value(p, s, i, Y, xl);
-        return;
-    }
+    if (w == W && p.h[s] == H) return;   // not resized: written by pull_scale_kernel
     const float rx = (float)w/(float)W;
     int lo, hi;
     pull_range(xl, rx, W, lo, hi);
@@ -660,7 +663,134 @@ __global__ void __launch_bounds__(128) pull_cols_kernel(const PullParams p) {
     p.out[s][((size_t)i*h + yl)*w + xl] = acc;
 }
 
+// Tiled pull-back: one block owns a PT_Y x PT_X tile of the low-resolution output of one (scale, image), stages the
+// full-resolution footprint of the tile in shared memory with coalesced row loads (chain factor and dL/dloss applied on the way
+// in), pulls it horizontally into PT_X columns and then vertically into PT_Y rows — every full-resolution value is read from
+// HBM once (plus the footprint overlap between neighbouring tiles), fixed summation order (deterministic).
+constexpr int PT_X = 32, PT_Y = 4, PT_NT = 128;
+constexpr int PT_MAX_FOOT = 4096;    // floats of footprint + row-pulled scratch a block may stage (16 KB: many resident blocks)
+
+struct PullTiles { int first[STV_MAX_SCALES + 1]; int tx[STV_MAX_SCALES], ty[STV_MAX_SCALES], px[STV_MAX_SCALES], py[STV_MAX_SCALES]; };   // block ranges + tile shape per scale
+
+__global__ void __launch_bounds__(PT_NT) pull_tile_kernel(const PullParams p, const PullTiles t) {
+    extern __shared__ float pt_smem[];
+    int s = 0;
+    while (s + 1 < p.S && (int)blockIdx.x >= t.first[s + 1]) ++s;
+    int rem = blockIdx.x - t.first[s];
+    const int per_img = t.tx[s]*t.ty[s];
+    const int i = rem/per_img; rem -= i*per_img;
+    const int tyi = rem/t.tx[s], txi = rem - tyi*t.tx[s];
+    const int H = p.H, W = p.W, h = p.h[s], w = p.w[s];
+    const float sc = p.scale ? __ldg(p.scale) : 1.f;
+    const int xl0 = txi*t.px[s], yl0 = tyi*t.py[s];
+    const int nx = min(t.px[s], w - xl0), ny = min(t.py[s], h - yl0);
+    if (w == W && h == H) {   // no resize: scale (and chain) only
+        for (int q = threadIdx.x; q < nx*ny; q += PT_NT) {
+            const int yy = yl0 + q/nx, xx = xl0 + q % nx;
+            p.out[s][(size_t)i*H*W + (size_t)yy*W + xx] = sc*pull_value(p, s, i, yy, xx);
+        }
+        return;
+    }
+    const float rx = (float)w/(float)W, ry = (float)h/(float)H;
+    int Xlo, Xhi, Ylo, Yhi, tmp_;
+    pull_range(xl0, rx, W, Xlo, tmp_); pull_range(xl0 + nx - 1, rx, W, tmp_, Xhi);
+    pull_range(yl0, ry, H, Ylo, tmp_); pull_range(yl0 + ny - 1, ry, H, tmp_, Yhi);
+    const int fw = Xhi - Xlo + 1, fh = Yhi - Ylo + 1;
+    float* foot = pt_smem;              // [fh][fw]
+    float* rows = pt_smem + fh*fw;      // [fh][nx]
+    for (int q = threadIdx.x; q < fh*fw; q += PT_NT) {
+        const int fy = q/fw, fx = q - fy*fw;
+        foot[q] = sc*pull_value(p, s, i, Ylo + fy, Xlo + fx);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < fh*nx; q += PT_NT) {
+        const int fy = q/nx, xx = q - fy*nx, xl = xl0 + xx;
+        int lo, hi;
+        pull_range(xl, rx, W, lo, hi);
+        float acc = 0.f;
+        for (int X = lo; X <= hi; ++X) {
+            int x0, x1;
+            float lx;
+            pull_tap(X, rx, w, x0, x1, lx);
+            const float wx = (x0 == xl ? 1.f - lx : 0.f) + (x1 == xl ? lx : 0.f);
+            if (wx != 0.f) acc = fmaf(wx, foot[fy*fw + (X - Xlo)], acc);
+        }
+        rows[q] = acc;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < ny*nx; q += PT_NT) {
+        const int yy = q/nx, xx = q - yy*nx, yl = yl0 + yy;
+        int lo, hi;
+        pull_range(yl, ry, H, lo, hi);
+        float acc = 0.f;
+        for (int Y = lo; Y <= hi; ++Y) {
+            int y0, y1;
+            float ly;
+            pull_tap(Y, ry, h, y0, y1, ly);
+            const float wy = (y0 == yl ? 1.f - ly : 0.f) + (y1 == yl ? ly : 0.f);
+            if (wy != 0.f) acc = fmaf(wy, rows[(Y - Ylo)*nx + xx], acc);
+        }
+        p.out[s][((size_t)i*h + yl)*w + xl0 + xx] = acc;
+    }
+}
+
+// Scales that are not resized: out = dL/dloss * g (float4 streams when possible).
+__global__ void __launch_bounds__(256) pull_scale_kernel(const PullParams p, int s, long long n) {
+    const float sc = p.scale ? __ldg(p.scale) : 1.f;
+    const long long stride = (long long)gridDim.x*blockDim.x, t0 = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    const bool plain = !p.chain && p.g_full2[s] == nullptr && p.g_full[s] != nullptr;
+    if (plain && (n & 3) == 0 && (((uintptr_t)p.g_full[s] | (uintptr_t)p.out[s]) & 15) == 0) {
+        const float4* g4 = reinterpret_cast<const float4*>(p.g_full[s]);
+        float4* o4 = reinterpret_cast<float4*>(p.out[s]);
+        for (long long q = t0; q < n/4; q += stride) { float4 v = __ldg(g4 + q); v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; o4[q] = v; }
+        return;
+    }
+    const long long hw = (long long)p.H*p.W;
+    for (long long q = t0; q < n; q += stride) {
+        const int i = (int)(q/hw);
+        const int rem = (int)(q - (long long)i*hw), Y = rem/p.W, X = rem - Y*p.W;
+        p.out[s][q] = sc*pull_value(p, s, i, Y, X);
+    }
+}
+
 int launch_pull(const PullParams& p, cudaStream_t st) {
+    // Tiled single pass when every scale's tile footprint fits the staging budget (always for the 2^s pyramids of the networks);
+    // otherwise the two separable passes through `tmp`.
+    PullTiles t{};
+    bool tiled = true;
+    int blocks = 0;
+    for (int s = 0; s < p.S; ++s) {
+        t.first[s] = blocks;
+        if (p.w[s] == p.W && p.h[s] == p.H) {   // not resized: one streaming kernel, no tiles
+            const long long n = (long long)p.b*p.H*p.W;
+            long long nb = (n/4 + 255)/256;
+            if (nb > 148*8) nb = 148*8;
+            pull_scale_kernel<<<(unsigned)(nb < 1 ? 1 : nb), 256, 0, st>>>(p, s, n);
+            count_launch();
+            if (int rc = check_launch("pull_scale_kernel")) return rc;
+            t.px[s] = PT_X; t.py[s] = PT_Y; t.tx[s] = t.ty[s] = 0;
+            continue;
+        }
+        int px = PT_X, py = PT_Y;
+        if (p.w[s] != p.W || p.h[s] != p.H) {   // shrink the tile until its full-resolution footprint fits the staging budget
+            const double fx = (double)p.W/p.w[s], fy = (double)p.H/p.h[s];
+            auto need = [&](int ax, int ay) { const double fw = (ax + 2)*fx + 6, fh = (ay + 2)*fy + 6; return fw*fh + fh*ax; };
+            while (need(px, py) > PT_MAX_FOOT && (px > 8 || py > 1)) { if (px > 8 && (px >= 4*py || py == 1)) px /= 2; else py /= 2; }
+            if (need(px, py) > PT_MAX_FOOT) tiled = false;
+        }
+        t.px[s] = px; t.py[s] = py;
+        t.tx[s] = (p.w[s] + px - 1)/px; t.ty[s] = (p.h[s] + py - 1)/py;
+        blocks += t.tx[s]*t.ty[s]*p.b;
+    }
+    t.first[p.S] = blocks;
+    if (blocks == 0) return STV_OK;
+    if (tiled) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(pull_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_MAX_FOOT*(int)sizeof(float)); attr = true; }
+        pull_tile_kernel<<<blocks, PT_NT, PT_MAX_FOOT*sizeof(float), st>>>(p, t);
+        count_launch();
+        return check_launch("pull_tile_kernel");
+    }
     int wmax = 0, hmax = 0;
     bool any_resize = false;
     for (int s = 0; s < p.S; ++s) {

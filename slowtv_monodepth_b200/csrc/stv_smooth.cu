@@ -179,7 +179,27 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ param, c
                                                     float lr, float b1, float b2, float eps, float wd, float gscale,
                                                     float inv_bc1, float inv_sqrt_bc2) {
     const size_t stride = (size_t)gridDim.x*blockDim.x;
-    for (size_t q = (size_t)blockIdx.x*blockDim.x + threadIdx.x; q < n; q += stride) {
+    // 128-bit streams over the 16-byte aligned part (every tensor of the flat buffers starts on a 16-byte boundary; n_decay is a
+    // multiple of 4 there), scalar tail otherwise.
+    const bool vec = ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0) && (n_decay & 3) == 0;
+    const size_t n4 = vec ? n/4 : 0;
+    for (size_t q = (size_t)blockIdx.x*blockDim.x + threadIdx.x; q < n4; q += stride) {
+        float4 g4 = reinterpret_cast<const float4*>(grad)[q], p4 = reinterpret_cast<float4*>(param)[q];
+        float4 m4 = reinterpret_cast<float4*>(m)[q], v4 = reinterpret_cast<float4*>(v)[q];
+        const float dec = (q*4 < n_decay) ? 1.f - lr*wd : 1.f;
+        float* gp = &g4.x; float* pp = &p4.x; float* mp = &m4.x; float* vp = &v4.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float g = gp[e]*gscale;
+            const float pv = pp[e]*dec;
+            const float mq = fmaf(b1, mp[e], (1.f - b1)*g);
+            const float vq = fmaf(b2, vp[e], (1.f - b2)*g*g);
+            mp[e] = mq; vp[e] = vq;
+            pp[e] = pv - lr*inv_bc1*(mq/(sqrtf(vq)*inv_sqrt_bc2 + eps));
+        }
+        reinterpret_cast<float4*>(param)[q] = p4; reinterpret_cast<float4*>(m)[q] = m4; reinterpret_cast<float4*>(v)[q] = v4;
+    }
+    for (size_t q = n4*4 + (size_t)blockIdx.x*blockDim.x + threadIdx.x; q < n; q += stride) {
         const float g = grad[q]*gscale;
         float pv = param[q];
         if (q < n_decay) pv *= 1.f - lr*wd;
@@ -273,7 +293,7 @@ extern "C" int stv_adamw_step(float* param, const float* grad, float* exp_avg, f
     STV_REQUIRE(n_decay <= n, "stv_adamw_step: n_decay > n");
     if (n == 0) return STV_OK;
     const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
-    size_t blocks = (n + 255)/256;
+    size_t blocks = (n/4 + 255)/256 + 1;
     if (blocks > 148*16) blocks = 148*16;
     adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, n_decay, lr, beta1, beta2, eps,
                                                                     weight_decay, grad_scale, (float)(1.0/bc1), (float)(1.0/sqrt(bc2)));

@@ -146,11 +146,14 @@ class _PhotoLoss(torch.autograd.Function):
 # Texture views of the support frames for the 2x2 gathers: handles are created by the library on request and OWNED HERE (the
 # library keeps no state). Keyed by (device, address, shape): torch's caching allocator hands the same buffers back every step
 # and CUDA-graph runners use static input buffers, so steady state creates none; least-recently-used views are destroyed.
+import os as _os
+_NO_TEX = bool(_os.environ.get('STV_NO_TEX'))   # developer switch: plain-load variant of the gathers
 _TEX: dict[tuple, int] = {}
 _TEX_MAX = 64
 
 
 def _tex_handle(supp: Tensor) -> int:
+    if _NO_TEX: return 0
     rows, W = supp.numel()//supp.shape[-1], supp.shape[-1]
     key = (supp.device.index, supp.data_ptr(), rows, W)
     h = _TEX.pop(key, None)

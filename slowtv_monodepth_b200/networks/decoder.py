@@ -26,7 +26,9 @@ class _ConvBlock(nn.Module):
         self.conv = nn.Conv2d(cin, cout, 3, padding=1, padding_mode='reflect')
 
     def forward(self, x: Tensor) -> Tensor:
-        return F.elu(self.conv(x), inplace=True)
+        if x.is_cuda: return F_.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous(), self.conv.weight, self.conv.bias, pad=1, reflect=True,
+                                            act='elu').permute(0, 3, 1, 2)
+        return L_.host_path(self, x)
 
 
 class MonodepthDecoder(nn.Module):
@@ -56,16 +58,7 @@ class MonodepthDecoder(nn.Module):
 
     def forward(self, feat: list[Tensor]) -> dict[int, Tensor]:
         if feat[-1].is_cuda and self.upsample_mode == 'nearest': return self.forward_nhwc(feat)
-        L_.require_device_path('MonodepthDecoder' if not feat[-1].is_cuda else f'MonodepthDecoder(upsample_mode={self.upsample_mode!r})')
-        out, act = {}, _ACT[self.out_act]
-        x = feat[-1]
-        for i in range(4, -1, -1):
-            x = self.layer(f'upconv_{i}_0')(x)
-            x = F.interpolate(x, scale_factor=2, mode=self.upsample_mode)
-            if self.use_skip and 2**i in self.enc_sc: x = torch.cat([x, feat[self.enc_sc.index(2**i)]], dim=1)
-            x = self.layer(f'upconv_{i}_1')(x)
-            if i in self.out_sc: out[i] = act(self.layer(f'outconv_{i}')(x)).contiguous()
-        return out
+        return L_.host_path(self, feat, what='MonodepthDecoder' if not feat[-1].is_cuda else f'MonodepthDecoder(upsample_mode={self.upsample_mode!r})')
 
     def forward_nhwc(self, feat: list[Tensor]) -> dict[int, Tensor]:
         """The same network on channels-last tensors with libstv tcgen05 implicit-GEMM convolutions: reflection padding,

@@ -29,11 +29,6 @@ from .. import functional as F_
 __all__ = ['create_encoder', 'ResNetEncoder', 'ConvNeXtEncoder', 'FeatureInfo']
 
 
-def _stem_conv(x: Tensor, conv: nn.Conv2d) -> Tensor:
-    """First convolution of an encoder on a HOST tensor (CPU-side naming / shape tests only): stock ATen convolution."""
-    return conv(x)
-
-
 def _stem_conv_nhwc(x: Tensor, conv: nn.Conv2d) -> Tensor:
     """Stem convolution of an encoder on the (N,C,H,W) image batch -> channels-last (N,P,Q,Cout).
 
@@ -99,10 +94,7 @@ class BasicBlock(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         if x.is_cuda: return self.forward_nhwc(x)
-        y = F.relu(self.bn1(self.conv1(x)), inplace=True)
-        y = self.bn2(self.conv2(y))
-        sc = x if self.downsample is None else self.downsample(x)
-        return F.relu(y + sc, inplace=True)
+        return L_.host_path(self, x)
 
     def forward_nhwc(self, x: Tensor) -> Tensor:
         """x (N,H,W,C) channels-last; convolutions are libstv tcgen05 implicit GEMMs."""
@@ -150,14 +142,7 @@ class ResNetEncoder(nn.Module):
                     if j == 0: self.marks[f'layer{i}'] = blk.first_node
                 feats.append(x)
             return [f.permute(0, 3, 1, 2) for f in feats]  # (N,C,H,W) views of the channels-last buffers
-        L_.require_device_path('ResNetEncoder')
-        f0 = F.relu(self.bn1(_stem_conv(x, self.conv1)), inplace=True)
-        x = F.max_pool2d(f0, 3, 2, 1)
-        feats = [f0]
-        for i in range(1, 5):
-            x = getattr(self, f'layer{i}')(x)
-            feats.append(x)
-        return feats
+        return L_.host_path(self, x)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -168,7 +153,7 @@ class LayerNorm2d(nn.LayerNorm):
     def __init__(self, c: int): super().__init__(c, eps=1e-6)
 
     def forward(self, x: Tensor) -> Tensor:
-        return F.layer_norm(x.permute(0, 2, 3, 1), self.normalized_shape, self.weight, self.bias, self.eps).permute(0, 3, 1, 2)
+        return L_.host_path(self, x)   # on the device the owning stage calls functional.layer_norm on the channels-last tensor
 
 
 class Mlp(nn.Module):
@@ -178,7 +163,7 @@ class Mlp(nn.Module):
         self.fc2 = nn.Linear(4*c, c)
 
     def forward(self, x: Tensor) -> Tensor:
-        return self.fc2(F.gelu(self.fc1(x)))
+        return L_.host_path(self, x)   # on the device the owning block calls functional.convnext_mlp
 
 
 class ConvNeXtBlock(nn.Module):
@@ -191,10 +176,8 @@ class ConvNeXtBlock(nn.Module):
         self.gamma = nn.Parameter(1e-6*torch.ones(c))
 
     def forward(self, x: Tensor) -> Tensor:
-        # Host tensors (CPU-side naming / shape tests only): stock ATen ops, same arithmetic.
-        y = self.conv_dw(x).permute(0, 2, 3, 1)
-        y = self.mlp(self.norm(y))*self.gamma
-        return x + y.permute(0, 3, 1, 2)
+        if x.is_cuda: return self.forward_nhwc(x.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2)
+        return L_.host_path(self, x)
 
     def forward_nhwc(self, xl: Tensor) -> Tensor:
         """xl (N,H,W,C) channels-last. libstv kernels: depthwise 7x7 (fwd / dgrad / wgrad), LayerNorm (fwd / bwd) and the
@@ -217,7 +200,8 @@ class ConvNeXtStage(nn.Module):
         self.blocks = nn.Sequential(*[ConvNeXtBlock(cout) for _ in range(depth)])
 
     def forward(self, x: Tensor) -> Tensor:
-        return self.blocks(self.downsample(x))
+        if x.is_cuda: return self.forward_nhwc(x.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2)
+        return L_.host_path(self, x)
 
     def forward_nhwc(self, x: Tensor, want_mark: bool = False):
         mark = None
@@ -259,13 +243,7 @@ class ConvNeXtEncoder(nn.Module):
                 x, self.marks[f'stages_{i}'] = st.forward_nhwc(x, want_mark=True)
                 feats.append(x.permute(0, 3, 1, 2))  # (N,C,H,W) view of the channels-last buffer
             return feats
-        L_.require_device_path('ConvNeXtEncoder')
-        x = self.stem_1(_stem_conv(x, self.stem_0))
-        feats = []
-        for i in range(4):
-            x = getattr(self, f'stages_{i}')(x)
-            feats.append(x)
-        return feats
+        return L_.host_path(self, x)
 
 
 _RESNETS = {'resnet18': (2, 2, 2, 2), 'resnet34': (3, 4, 6, 3)}

@@ -55,14 +55,7 @@ class PoseNet(nn.Module):
 
     def forward(self, x: Tensor) -> dict:
         if x.is_cuda: return self.forward_nhwc(x)
-        L_.require_device_path('PoseNet')
-        feat = self.squeeze(self.encoder(x)[-1])
-        out = self.pose_eps*self.decoders['pose'](feat).mean(dim=(2, 3)).unflatten(-1, (self.n_imgs, 6))
-        res = {'R': out[..., :3], 't': out[..., 3:]}
-        if self.learn_K:
-            res['fs'] = F.softplus(self.decoders['focal'](feat).mean(dim=(2, 3)))
-            res['cs'] = torch.sigmoid(self.decoders['offset'](feat).mean(dim=(2, 3)))
-        return res
+        return L_.host_path(self, x)
 
     def forward_nhwc(self, x: Tensor) -> dict:
         """Same network; every convolution is a libstv tcgen05 implicit GEMM on channels-last tensors."""

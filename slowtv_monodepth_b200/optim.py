@@ -159,16 +159,4 @@ class FlatAdamW:
                                beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
                                step=self.step_count, grad_scale=grad_scale/self.world)
         else:
-            L_.require_device_path('FlatAdamW.step')
-            self._step_host(grad_scale)
-
-    @torch.no_grad()
-    def _step_host(self, grad_scale: float = 1.0) -> None:
-        """Host-tensor arithmetic used only by the CPU (gloo) tests of the multi-process logic; same update rule."""
-        b1, b2 = self.betas
-        g = self.grad*(grad_scale/self.world)
-        for start, n, n_dec in self.buckets: self.flat[start:start + n_dec].mul_(1 - self.lr*self.weight_decay)
-        self.exp_avg.mul_(b1).add_(g, alpha=1 - b1)
-        self.exp_avg_sq.mul_(b2).addcmul_(g, g, value=1 - b2)
-        bc1, bc2 = 1 - b1**self.step_count, 1 - b2**self.step_count
-        self.flat.addcdiv_(self.exp_avg, self.exp_avg_sq.sqrt()/bc2**0.5 + self.eps, value=-self.lr/bc1)
+            L_.host_path(self, grad_scale, what='FlatAdamW.step')

@@ -13,12 +13,13 @@ def pytest_configure(config):
 
 @pytest.fixture(autouse=True)
 def _host_reference_arithmetic_for_cpu_tests(request):
-    """The product refuses host tensors (no CPU fallback). Tests NOT marked `gpu` check naming / wiring / multi-process logic on
-    the CPU, so they opt in to the package's host reference arithmetic; GPU tests run with it disabled, as in production."""
-    from slowtv_monodepth_b200 import _lib
-    _lib.host_test_mode('gpu' not in request.keywords)
+    """The product refuses host tensors (no CPU fallback, no host arithmetic in the package). Tests NOT marked `gpu` check naming /
+    wiring / multi-process logic on the CPU with the reference implementations of tests/host_ref.py, registered for the duration
+    of the test; GPU tests run without them, as in production."""
+    from tests import host_ref
+    if 'gpu' not in request.keywords: host_ref.install()
     yield
-    _lib.host_test_mode(False)
+    host_ref.uninstall()
 
 
 # Order of the GPU suite: the parity evidence of the hot path first (loss stack vs the float64 oracle, optimiser, networks, whole

@@ -45,9 +45,9 @@ def _train_bucketed(model, opt, x, y, steps=3, accumulate=1):
 
 
 def _worker(rank, world, init_file, out_dir, bucketed=False):
-    from slowtv_monodepth_b200 import _lib
     from slowtv_monodepth_b200.optim import FlatAdamW
-    _lib.host_test_mode(True)  # spawned process: opt in to the host reference arithmetic (the product path is CUDA-only)
+    from tests import host_ref
+    host_ref.install()  # spawned process: register the host reference arithmetic (the product path is CUDA-only)
     dist.init_process_group('gloo', init_method=f'file://{init_file}', rank=rank, world_size=world)
     try:
         model = _model()

@@ -73,12 +73,13 @@ def test_photometric_pair_properties_at_full_size(name):
     assert flips.float().mean().item() < 1e-4, flips.float().mean().item()
     # Per pixel: the two float32 evaluations round differently, so the handful of pixels within rounding of a discrete event
     # (decision, L1 sign, texel cell — tests/test_loss_gpu.py) legitimately differ O(1) there; everywhere else they agree to 1e-4
-    # of the map's RMS. Requirement: > 99.5 % of the pixels of every scale agree (the oracle tests above hold the values).
+    # of the map's RMS. An event touches the 3x3 neighbourhood of its pixel (SSIM window), and ~0.4 % of the pixels carry one
+    # (tests/util.py::unstable_pixels), so > 95 % of the pixels of every scale must agree (the oracle tests above hold the values).
     for s in range(S):
         a, r = lean[2][s].double(), full[2][s].double()
         rms = r.pow(2).mean().sqrt()
         ok = ((a - r).abs() <= 1e-4*rms + 1e-4*r.abs()).double().mean().item()
-        assert ok > 0.995, (s, ok)
+        assert ok > 0.95, (s, ok)
     # pose / intrinsics gradients are sums over ALL pixels, including those few: 1e-3 here; against the float64 oracle they are held
     # to 1e-4 / the reference's own float32 noise floor in test_loss_stack_matches_oracle_at_full_size
     for j, what in ((3, 'aa'), (4, 't'), (5, 'K')): assert rel(lean[j], full[j]) < 1e-3, (what, rel(lean[j], full[j]))
