@@ -322,6 +322,134 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     if (warp == 1) tc::tmem_dealloc(tmem_base, 2*acc_cols);
 }
 
+// ---- CTA-pair variant (cta_group::2) ------------------------------------------------------------------------------------------
+// Plain matrices only (no im2col operand). A cluster of two CTAs on neighbouring SMs owns a 256 x BN output tile: each CTA loads
+// ITS 128 rows of A and ITS half of the B tile (BN/2 rows of a K-major B, or half of the 32-column slabs of an MN-major B), the
+// leader's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256) against both CTAs' shared memory, and each CTA's epilogue
+// warps drain their own 128 TMEM lanes. Per flop the pair pulls 25 % fewer operand bytes through L2 than two independent
+// 128 x BN tiles (B once instead of twice) — the stream that bounds the wide ConvNeXt MLP products.
+//   full[s]        leader only: bytes of BOTH CTAs' TMA loads (2-SM loads signal the leader's barrier)
+//   empty[s]       both CTAs: multicast commit of the leader once the MMAs have read stage s
+//   tmem_full[a]   both CTAs: multicast commit once accumulator a holds a finished tile
+//   tmem_empty[a]  leader only: 16 arrivals = the 8 epilogue warps of each CTA (remote arrive from the peer)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 2)
+gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = tc::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int half_bn = p.bn/2;
+    const int b_bytes = half_bn*GEMM_BK*4;
+    const int stage_bytes = GEMM_A_BYTES + b_bytes;
+    float* staging = (float*)(smem + (size_t)p.stages*stage_bytes);
+    uint64_t* full = (uint64_t*)(staging + 8*EPI_WARP_FLOATS);
+    uint64_t* empty = full + GEMM_MAX_STAGES;
+    uint64_t* tmem_full = empty + GEMM_MAX_STAGES;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;            // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+    const int nt = (p.N + p.bn - 1)/p.bn, mt = (p.M + 2*GEMM_BM - 1)/(2*GEMM_BM);
+    const int total = nt*mt*p.splits;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const uint32_t acc_cols = p.bn <= 32 ? 32u : p.bn <= 64 ? 64u : 128u;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(&tmem_full[a], 1);
+            tc::mbar_init(&tmem_empty[a], 16);
+        }
+        tc::fence_barrier_init();
+    } else if (warp == 1) {
+        tc::tmem_alloc_2sm(tmem_slot, 2*acc_cols);
+    }
+    tc::tcgen05_fence_before();
+    tc::cluster_sync();   // the leader's barriers exist before the peer's TMA signals them
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = pair; t < total; t += npairs) {
+                const int n0 = (t % nt)*p.bn, m0 = ((t/nt) % mt)*2*GEMM_BM + (int)rank*GEMM_BM, z = t/(nt*mt);
+                const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it/p.stages) & 1u;
+                    tc::mbar_wait_spin(&empty[s], ph ^ 1u);
+                    if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], 2u*(uint32_t)stage_bytes);
+                    uint8_t* a = smem + (size_t)s*stage_bytes;
+                    uint8_t* b = a + GEMM_A_BYTES;
+                    const int k = kb*GEMM_BK;
+                    if (!p.a_mn) tc::tma_load_2d_2sm(a, &tmA, &full[s], k, m0);
+                    else
+                        for (int j = 0; j < GEMM_BM/32; ++j) tc::tma_load_2d_2sm(a + j*SLAB_MN_BYTES, &tmA, &full[s], m0 + 32*j, k);
+                    if (!p.b_mn) tc::tma_load_2d_2sm(b, &tmB, &full[s], k, n0 + (int)rank*half_bn);
+                    else
+                        for (int j = 0; j < half_bn/32; ++j)
+                            tc::tma_load_2d_2sm(b + j*SLAB_MN_BYTES, &tmB, &full[s], n0 + (int)rank*half_bn + 32*j, k);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = tc::umma_idesc_tf32(2*GEMM_BM, p.bn, p.a_mn != 0, p.b_mn != 0);
+            int it = 0, j = 0;
+            for (int t = pair; t < total; t += npairs, ++j) {
+                const int z = t/(nt*mt);
+                const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                const int acc = j & 1;
+                tc::mbar_wait_spin(&tmem_empty[acc], ((uint32_t)(j >> 1) & 1u) ^ 1u);  // both CTAs have drained this accumulator
+                tc::tcgen05_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)acc*acc_cols;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it/p.stages) & 1u;
+                    tc::mbar_wait_spin(&full[s], ph);
+                    tc::tcgen05_fence_after();
+                    const uint32_t a = tc::smem_u32(smem + (size_t)s*stage_bytes), b = a + GEMM_A_BYTES;
+#pragma unroll
+                    for (int k8 = 0; k8 < GEMM_BK/8; ++k8) {
+                        const uint64_t da = p.a_mn ? tc::umma_desc_mnmajor(a, k8, SLAB_MN_BYTES) : tc::umma_desc_kmajor(a, k8);
+                        const uint64_t db = p.b_mn ? tc::umma_desc_mnmajor(b, k8, SLAB_MN_BYTES) : tc::umma_desc_kmajor(b, k8);
+                        tc::umma_tf32_2sm(d, da, db, idesc, (kb > kb0 || k8 > 0) ? 1u : 0u);
+                    }
+                    tc::umma_commit_2sm(&empty[s]);
+                }
+                tc::umma_commit_2sm(&tmem_full[acc]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const RowMap rm = {p.ldc, p.remap, p.cv.gridH, p.cv.gridW, p.oH, p.oW, p.ost, p.oa, p.ob};
+        const int ew = warp - 2;
+        int j = 0;
+        for (int t = pair; t < total; t += npairs, ++j) {
+            const int n0 = (t % nt)*p.bn, m0 = ((t/nt) % mt)*2*GEMM_BM + (int)rank*GEMM_BM;
+            const int acc = j & 1;
+            tc::mbar_wait(&tmem_full[acc], (uint32_t)(j >> 1) & 1u);
+            tc::tcgen05_fence_after();
+            epilogue_tile(tmem_base + (uint32_t)acc*acc_cols, warp & 3, lane, m0, n0, p.bn, p.M, p.N, p.C, rm, p.e,
+                          staging + ew*EPI_WARP_FLOATS, (ew >> 2)*32, 64);
+            tc::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_remote(&tmem_empty[acc], 0);   // the leader's barrier (also from the leader itself)
+        }
+    }
+    tc::tcgen05_fence_before();
+    tc::cluster_sync();   // both CTAs are done with TMEM and with each other's shared memory
+    if (warp == 1) tc::tmem_dealloc_2sm(tmem_base, 2*acc_cols);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -448,6 +576,33 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
     });
     if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute failed (%s)", what, cudaGetErrorString(attr_err)); return STV_E_CUDA; }
     const long long total = (long long)nt*mt*splits;
+    // CTA pairs (cta_group::2): plain matrices with enough 256-row tiles to fill the SMs; the B tile must split into two halves
+    // of whole 32-column slabs / 8-row swizzle groups.
+    static const int pair_mode = getenv("STV_GEMM_PAIR") ? atoi(getenv("STV_GEMM_PAIR")) : 1;   // developer switch (0 = off)
+    const int mt2 = (p.M + 2*GEMM_BM - 1)/(2*GEMM_BM);
+    if (pair_mode && p.cv.mode == 0 && p.remap == 0 && p.bn % 64 == 0 && p.bn <= 128 && (long long)nt*mt2*splits >= sm_count()/2 && p.pair_tmB) {
+        static std::once_flag once2;
+        static cudaError_t err2 = cudaSuccess;
+        std::call_once(once2, [] { err2 = cudaFuncSetAttribute(gemm_tf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024); });
+        if (err2 != cudaSuccess) { set_error("%s: cudaFuncSetAttribute failed (%s)", what, cudaGetErrorString(err2)); return STV_E_CUDA; }
+        const int sb = GEMM_A_BYTES + (p.bn/2)*GEMM_BK*4;
+        const int staging = 8*EPI_WARP_FLOATS*4;
+        int stages = (112*1024 - staging - 2048)/sb;
+        stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
+        p.stages = stages < 2 ? 2 : stages;
+        const size_t smem = (size_t)p.stages*sb + staging + 1024 + (2*GEMM_MAX_STAGES + 4)*8 + 16;
+        const long long tiles2 = (long long)nt*mt2*splits;
+        const int pairs = (int)(tiles2 < sm_count() ? tiles2 : sm_count());   // two resident CTAs per SM = one pair per SM on average
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2*pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tf32_pair_kernel, tmA, *p.pair_tmB, p);
+        count_launch();
+        if (le != cudaSuccess) { set_error("%s: cluster launch failed (%s)", what, cudaGetErrorString(le)); return STV_E_CUDA; }
+        return check_launch(what);
+    }
     if (persistent_enabled() && total < (1ll << 30)) {
         // two resident CTAs per SM: ring + epilogue staging + barriers within ~112 KB each
         const int staging = 8*EPI_WARP_FLOATS*4;
@@ -507,5 +662,9 @@ extern "C" int stv_gemm_tf32(int M, int N, int K, const float* A, long long lda,
     if (rc) return rc;
     rc = b_mn ? make_tmap_2d(&tmB, B, K, N, ldb, 32, 1) : make_tmap_2d(&tmB, B, N, K, ldb, p.bn, 0);
     if (rc) return rc;
+    // second view of B for the CTA-pair kernel: each CTA of a pair loads half of the B tile (K-major: bn/2 rows per box)
+    CUtensorMap tmB2 = tmB;
+    if (!b_mn && p.bn % 64 == 0) { rc = make_tmap_2d(&tmB2, B, N, K, ldb, p.bn/2, 0); if (rc) return rc; }
+    p.pair_tmB = &tmB2;
     return launch_gemm(tmA, tmB, p, split_k, (cudaStream_t)stream, "stv_gemm_tf32");
 }

@@ -22,7 +22,7 @@ from .networks import DepthNet, PoseNet
 from .regularizers import SmoothReg
 
 __all__ = ['MonoDepthStep', 'GraphedTrainStep', 'ShapeCachedTrainStep', 'StepSummary', 'summarize', 'default_cfg', 'gradient_buckets',
-           'register_bucket_hooks']
+           'register_bucket_hooks', 'clear_bucket_marks']
 
 NET_REG = {'depth': DepthNet, 'pose': PoseNet}
 LOSS_REG = {'img_recon': ReconstructionLoss, 'disp_smooth': SmoothReg}
@@ -83,6 +83,7 @@ class MonoDepthStep(nn.Module):
         fwd['_idxs'] = idxs
         hook = getattr(self, 'bucket_hook', None)
         if hook is not None and torch.is_grad_enabled(): register_bucket_hooks(self.nets, hook)
+        clear_bucket_marks(self.nets)
         return fwd
 
     # -- trainer.py:280-348 ------------------------------------------------------------------------------------------
@@ -152,6 +153,15 @@ def register_bucket_hooks(nets, bucket_ready) -> None:
     nodes += [getattr(enc, 'marks', {}).get(n) for n in reversed(parts[1:])]
     for j, node in enumerate(nodes):
         if node is not None: node.register_hook(lambda *a, j=j: bucket_ready(j))
+
+
+def clear_bucket_marks(nets) -> None:
+    """Drop the autograd nodes the networks recorded during the forward pass. A module attribute holding a `grad_fn` keeps the whole
+    autograd graph of that step alive into the next one — including its AccumulateGrad nodes, which stay bound to the stream they
+    were created on and then invalidate a CUDA-graph capture running on another stream."""
+    for m in nets.modules():
+        if getattr(m, 'marks', None): m.marks = {}
+        if getattr(m, 'first_node', None) is not None: m.first_node = None
 
 
 class StepSummary:
@@ -244,7 +254,9 @@ class GraphedTrainStep:
     def _capture(self, pool, overlap: bool) -> None:
         self.opt.zero_grad()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, pool=pool):
+        # (thread_local: NCCL's watchdog thread may query events while the capture is open; the backward kernels are recorded
+        # all the same — capture follows the stream, whichever thread launches into it)
+        with torch.cuda.graph(graph, pool=pool, capture_error_mode='thread_local' if overlap else 'global'):
             self.loss = self._fwd_bwd(overlap)
         self.graph = graph
 
