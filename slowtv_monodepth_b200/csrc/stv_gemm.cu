@@ -209,96 +209,115 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Producer and MMA issuer: the WHOLE warp runs the loop control (warp-uniform values: ring slot / phase counters instead of
+    // `it % stages`, incremental tap / pixel counters instead of per-k-block divisions, descriptors = template + address) and
+    // lane 0 issues — see the note in stv_tc.cuh: with everything inside `if (lane == 0)` the issuing thread needed ~150
+    // instructions per k-block and was the bottleneck of the kernel.
+    const uint32_t ring = tc::smem_u32(smem), full0 = tc::smem_u32(full), empty0 = tc::smem_u32(empty);
+    const int stages = p.stages;
     if (warp == 0) {
-        if (lane == 0) {
-            const ConvOperand& cv = p.cv;
-            int it = 0;  // k-blocks issued so far by this CTA (ring position carries over from tile to tile)
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int n0 = (t % nt)*p.bn, m0 = ((t/nt) % mt)*GEMM_BM, z = t/(nt*mt);
-                const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-                int bn_ = 0, bw = 0, bh = 0, tap = 0, cb = 0;
-                int slab_c[8], slab_rs[8];
-                if (cv.mode == 1) {
-                    const int hw = cv.gridH*cv.gridW;
-                    bn_ = m0/hw;
-                    const int rem = m0 - bn_*hw, py = rem/cv.gridW, px = rem - py*cv.gridW;
-                    bw = cv.lw + px*cv.stride; bh = cv.lh + py*cv.stride;
-                    tap = kb0/cv.cblocks; cb = kb0 - tap*cv.cblocks;
-                } else if (cv.mode == 2) {
+        const ConvOperand& cv = p.cv;
+        const int mode = cv.mode, nslab = p.bn >> 5;
+        int s = 0;
+        uint32_t ph = 0;   // ring slot and its phase carry over from tile to tile
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const int n0 = (t % nt)*p.bn, m0 = ((t/nt) % mt)*GEMM_BM, z = t/(nt*mt);
+            const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            int bn_ = 0, bw = 0, bh = 0, r = 0, sx = 0, cb = 0;   // mode 1: tile origin, current tap and channel block
+            int pn = 0, py = 0, px = 0;                           // mode 2: grid pixel of the k-block's first row
+            int slab_c[8], slab_rs[8];
+            if (mode == 1) {
+                const int hw = cv.gridH*cv.gridW;
+                bn_ = m0/hw;
+                const int rem = m0 - bn_*hw, qy = rem/cv.gridW, qx = rem - qy*cv.gridW;
+                bw = cv.lw + qx*cv.stride; bh = cv.lh + qy*cv.stride;
+                const int tap = kb0/cv.cblocks;
+                cb = kb0 - tap*cv.cblocks; r = tap/cv.S; sx = tap - r*cv.S;
+            } else if (mode == 2) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col = n0 + 32*j, tp = col/cv.C;
-                        const bool ok = j < p.bn/32 && tp < cv.R*cv.S;
-                        slab_c[j] = ok ? col - tp*cv.C : cv.C;
-                        const int r = ok ? tp/cv.S : 0, sx = ok ? tp - r*cv.S : 0;
-                        slab_rs[j] = (r << 8) | sx;
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const int col = n0 + 32*j, tp = col/cv.C;
+                    const bool ok = j < nslab && tp < cv.R*cv.S;
+                    slab_c[j] = ok ? col - tp*cv.C : cv.C;
+                    const int rr = ok ? tp/cv.S : 0, ss = ok ? tp - rr*cv.S : 0;
+                    slab_rs[j] = (rr << 8) | ss;
                 }
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it/p.stages) & 1u;
-                    tc::mbar_wait_spin(&empty[s], ph ^ 1u);
-                    tc::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
-                    uint8_t* a = smem + (size_t)s*stage_bytes;
-                    uint8_t* b = a + GEMM_A_BYTES;
+                const int hw = cv.gridH*cv.gridW, k = kb0*GEMM_BK;
+                pn = k/hw;
+                const int rem = k - pn*hw;
+                py = rem/cv.gridW; px = rem - py*cv.gridW;
+            }
+            for (int kb = kb0; kb < kb1; ++kb) {
+                tc::mbar_wait_spin_s(empty0 + 8*s, ph ^ 1u);
+                if (tc::elect_one()) {
+                    const uint32_t fb = full0 + 8*s, a = ring + (uint32_t)(s*stage_bytes), b = a + GEMM_A_BYTES;
+                    tc::mbar_arrive_expect_tx_s(fb, (uint32_t)stage_bytes);
                     const int k = kb*GEMM_BK;
-                    if (cv.mode == 1) {
-                        const int r = tap/cv.S, sx = tap - r*cv.S;
-                        tc::tma_load_im2col_4d(a, &tmA, &full[s], cb*GEMM_BK, bw, bh, bn_, (uint16_t)(cv.flip ? cv.S - 1 - sx : sx),
-                                               (uint16_t)(cv.flip ? cv.R - 1 - r : r));
-                        if (!p.b_mn) tc::tma_load_2d(b, &tmB, &full[s], k, n0);
-                        else
-                            for (int j = 0; j < p.bn/32; ++j)
-                                tc::tma_load_2d(b + j*SLAB_MN_BYTES, &tmB, &full[s],
-                                                ((cv.r0 + cv.tstep*r)*cv.Sfull + cv.s0 + cv.tstep*sx)*cv.b_tap_cols + n0 + 32*j, cb*GEMM_BK);
-                        if (++cb == cv.cblocks) { cb = 0; ++tap; }
-                        continue;
-                    }
-                    if (!p.a_mn) tc::tma_load_2d(a, &tmA, &full[s], k, m0);
-                    else
-                        for (int j = 0; j < GEMM_BM/32; ++j) tc::tma_load_2d(a + j*SLAB_MN_BYTES, &tmA, &full[s], m0 + 32*j, k);
-                    if (cv.mode == 2) {
-                        const int hw = cv.gridH*cv.gridW, n = k/hw, rem = k - n*hw, py = rem/cv.gridW, px = rem - py*cv.gridW;
-                        const int w = cv.lw + px*cv.stride, h = cv.lh + py*cv.stride;
+                    if (mode == 1) {
+                        tc::tma_load_im2col_4d_s(a, &tmA, fb, cb*GEMM_BK, bw, bh, bn_, (uint16_t)(cv.flip ? cv.S - 1 - sx : sx),
+                                                 (uint16_t)(cv.flip ? cv.R - 1 - r : r));
+                        if (!p.b_mn) tc::tma_load_2d_s(b, &tmB, fb, k, n0);
+                        else {
+                            const int col = ((cv.r0 + cv.tstep*r)*cv.Sfull + cv.s0 + cv.tstep*sx)*cv.b_tap_cols + n0;
+                            for (int j = 0; j < nslab; ++j) tc::tma_load_2d_s(b + j*SLAB_MN_BYTES, &tmB, fb, col + 32*j, cb*GEMM_BK);
+                        }
+                    } else {
+                        if (!p.a_mn) tc::tma_load_2d_s(a, &tmA, fb, k, m0);
+                        else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (j < p.bn/32)
-                                tc::tma_load_im2col_4d(b + j*SLAB_MN_BYTES, &tmB, &full[s], slab_c[j], w, h, n, (uint16_t)(slab_rs[j] & 255),
-                                                       (uint16_t)(slab_rs[j] >> 8));
-                    } else if (!p.b_mn) tc::tma_load_2d(b, &tmB, &full[s], k, n0);
-                    else
-                        for (int j = 0; j < p.bn/32; ++j) tc::tma_load_2d(b + j*SLAB_MN_BYTES, &tmB, &full[s], n0 + 32*j, k);
+                            for (int j = 0; j < GEMM_BM/32; ++j) tc::tma_load_2d_s(a + j*SLAB_MN_BYTES, &tmA, fb, m0 + 32*j, k);
+                        }
+                        if (mode == 2) {
+                            const int w = cv.lw + px*cv.stride, h = cv.lh + py*cv.stride;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (j < nslab)
+                                    tc::tma_load_im2col_4d_s(b + j*SLAB_MN_BYTES, &tmB, fb, slab_c[j], w, h, pn, (uint16_t)(slab_rs[j] & 255),
+                                                             (uint16_t)(slab_rs[j] >> 8));
+                        } else if (!p.b_mn) tc::tma_load_2d_s(b, &tmB, fb, k, n0);
+                        else
+                            for (int j = 0; j < nslab; ++j) tc::tma_load_2d_s(b + j*SLAB_MN_BYTES, &tmB, fb, n0 + 32*j, k);
+                    }
                 }
+                if (mode == 1) { if (++cb == cv.cblocks) { cb = 0; if (++sx == cv.S) { sx = 0; ++r; } } }
+                else if (mode == 2) {
+                    px += GEMM_BK;
+                    while (px >= cv.gridW) { px -= cv.gridW; if (++py == cv.gridH) { py = 0; ++pn; } }
+                }
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = tc::umma_idesc_tf32(GEMM_BM, p.bn, p.a_mn != 0, p.b_mn != 0);
-            int it = 0, j = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
-                const int z = t/(nt*mt);
-                const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-                const int acc = j & 1;
-                tc::mbar_wait_spin(&tmem_empty[acc], ((uint32_t)(j >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        const uint32_t idesc = tc::umma_idesc_tf32(GEMM_BM, p.bn, p.a_mn != 0, p.b_mn != 0);
+        const uint64_t da0 = tc::umma_desc_template(p.a_mn != 0, SLAB_MN_BYTES), db0 = tc::umma_desc_template(p.b_mn != 0, SLAB_MN_BYTES);
+        const uint32_t ka = tc::umma_desc_kstep(p.a_mn != 0), kbs = tc::umma_desc_kstep(p.b_mn != 0);
+        const uint32_t tmem_full0 = tc::smem_u32(tmem_full), tmem_empty0 = tc::smem_u32(tmem_empty);
+        int s = 0, j = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+            const int z = t/(nt*mt);
+            const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            const int acc = j & 1;
+            tc::mbar_wait_spin_s(tmem_empty0 + 8*acc, ((uint32_t)(j >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+            tc::tcgen05_fence_after();
+            const uint32_t d = tmem_base + (uint32_t)acc*acc_cols;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                tc::mbar_wait_spin_s(full0 + 8*s, ph);
                 tc::tcgen05_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)acc*acc_cols;
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it/p.stages) & 1u;
-                    tc::mbar_wait_spin(&full[s], ph);
-                    tc::tcgen05_fence_after();
-                    const uint32_t a = tc::smem_u32(smem + (size_t)s*stage_bytes), b = a + GEMM_A_BYTES;
+                if (tc::elect_one()) {
+                    const uint32_t a = (ring + (uint32_t)(s*stage_bytes)) >> 4;
+                    uint64_t da = da0 + a, db = db0 + (a + (GEMM_A_BYTES >> 4));
+                    tc::umma_tf32(d, da, db, idesc, kb > kb0 ? 1u : 0u);
 #pragma unroll
-                    for (int k8 = 0; k8 < GEMM_BK/8; ++k8) {
-                        const uint64_t da = p.a_mn ? tc::umma_desc_mnmajor(a, k8, SLAB_MN_BYTES) : tc::umma_desc_kmajor(a, k8);
-                        const uint64_t db = p.b_mn ? tc::umma_desc_mnmajor(b, k8, SLAB_MN_BYTES) : tc::umma_desc_kmajor(b, k8);
-                        tc::umma_tf32(d, da, db, idesc, (kb > kb0 || k8 > 0) ? 1u : 0u);
+                    for (int k8 = 1; k8 < GEMM_BK/8; ++k8) {
+                        da += ka; db += kbs;
+                        tc::umma_tf32(d, da, db, idesc, 1u);
                     }
-                    tc::umma_commit(&empty[s]);
+                    tc::umma_commit_s(empty0 + 8*s);   // frees the stage once these MMAs have read it
                 }
-                tc::umma_commit(&tmem_full[acc]);
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
+            if (tc::elect_one()) tc::umma_commit_s(tmem_full0 + 8*acc);
         }
         __syncwarp();
     } else {
@@ -323,16 +342,18 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 }
 
 // ---- CTA-pair variant (cta_group::2) ------------------------------------------------------------------------------------------
-// Plain matrices only (no im2col operand). A cluster of two CTAs on neighbouring SMs owns a 256 x BN output tile: each CTA loads
-// ITS 128 rows of A and ITS half of the B tile (BN/2 rows of a K-major B, or half of the 32-column slabs of an MN-major B), the
-// leader's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256) against both CTAs' shared memory, and each CTA's epilogue
-// warps drain their own 128 TMEM lanes. Per flop the pair pulls 25 % fewer operand bytes through L2 than two independent
-// 128 x BN tiles (B once instead of twice) — the stream that bounds the wide ConvNeXt MLP products.
+// Plain matrices only (no im2col operand). A cluster of two CTAs on neighbouring SMs owns a 256 x BN output tile (BN <= 256): each
+// CTA loads ITS 128 rows of A and ITS half of the B tile (BN/2 rows of a K-major B, or half of the 32-column slabs of an MN-major
+// B), the leader's elected thread issues tcgen05.mma.cta_group::2 (M = 256) against both CTAs' shared memory, and each CTA's
+// epilogue warps drain their own 128 TMEM lanes. Per flop a 256 x 256 pair tile moves HALF the operand bytes of 128 x 128 tiles
+// through L2 -> shared memory and reads half as much shared memory per MMA — TF32 operands are 4 bytes, so the 128 x 128 kernel
+// needs 118 B/clk of operand reads per SM at full tensor rate. One CTA per SM (the accumulators are double-buffered
+// over all 512 TMEM columns at BN = 256), 5-8 stage ring.
 //   full[s]        leader only: bytes of BOTH CTAs' TMA loads (2-SM loads signal the leader's barrier)
 //   empty[s]       both CTAs: multicast commit of the leader once the MMAs have read stage s
 //   tmem_full[a]   both CTAs: multicast commit once accumulator a holds a finished tile
 //   tmem_empty[a]  leader only: 16 arrivals = the 8 epilogue warps of each CTA (remote arrive from the peer)
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = tc::smem_u32(smem_raw);
@@ -343,7 +364,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int half_bn = p.bn/2;
     const int b_bytes = half_bn*GEMM_BK*4;
     const int stage_bytes = GEMM_A_BYTES + b_bytes;
-    float* staging = (float*)(smem + (size_t)p.stages*stage_bytes);
+    const int stages = p.stages;
+    float* staging = (float*)(smem + (size_t)stages*stage_bytes);
     uint64_t* full = (uint64_t*)(staging + 8*EPI_WARP_FLOATS);
     uint64_t* empty = full + GEMM_MAX_STAGES;
     uint64_t* tmem_full = empty + GEMM_MAX_STAGES;   // [2]
@@ -353,12 +375,12 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int nt = (p.N + p.bn - 1)/p.bn, mt = (p.M + 2*GEMM_BM - 1)/(2*GEMM_BM);
     const int total = nt*mt*p.splits;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const uint32_t acc_cols = p.bn <= 32 ? 32u : p.bn <= 64 ? 64u : 128u;
+    const uint32_t acc_cols = p.bn <= 64 ? 64u : p.bn <= 128 ? 128u : 256u;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA);
         tc::tma_prefetch_desc(&tmB);
-        for (int s = 0; s < p.stages; ++s) {
+        for (int s = 0; s < stages; ++s) {
             tc::mbar_init(&full[s], 1);
             tc::mbar_init(&empty[s], 1);
         }
@@ -374,58 +396,65 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tc::cluster_sync();   // the leader's barriers exist before the peer's TMA signals them
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t ring = tc::smem_u32(smem), full0 = tc::smem_u32(full), empty0 = tc::smem_u32(empty);
 
     if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;
-            for (int t = pair; t < total; t += npairs) {
-                const int n0 = (t % nt)*p.bn, m0 = ((t/nt) % mt)*2*GEMM_BM + (int)rank*GEMM_BM, z = t/(nt*mt);
-                const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it/p.stages) & 1u;
-                    tc::mbar_wait_spin(&empty[s], ph ^ 1u);
-                    if (rank == 0) tc::mbar_arrive_expect_tx(&full[s], 2u*(uint32_t)stage_bytes);
-                    uint8_t* a = smem + (size_t)s*stage_bytes;
-                    uint8_t* b = a + GEMM_A_BYTES;
+        const int nslab = half_bn >> 5;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = pair; t < total; t += npairs) {
+            const int n0 = (t % nt)*p.bn + (int)rank*half_bn, m0 = ((t/nt) % mt)*2*GEMM_BM + (int)rank*GEMM_BM, z = t/(nt*mt);
+            const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                tc::mbar_wait_spin_s(empty0 + 8*s, ph ^ 1u);
+                if (tc::elect_one()) {
+                    const uint32_t fb = full0 + 8*s, a = ring + (uint32_t)(s*stage_bytes), b = a + GEMM_A_BYTES;
+                    if (rank == 0) tc::mbar_arrive_expect_tx_s(fb, 2u*(uint32_t)stage_bytes);
                     const int k = kb*GEMM_BK;
-                    if (!p.a_mn) tc::tma_load_2d_2sm(a, &tmA, &full[s], k, m0);
+                    if (!p.a_mn) tc::tma_load_2d_2sm_s(a, &tmA, fb, k, m0);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < GEMM_BM/32; ++j) tc::tma_load_2d_2sm_s(a + j*SLAB_MN_BYTES, &tmA, fb, m0 + 32*j, k);
+                    }
+                    if (!p.b_mn) tc::tma_load_2d_2sm_s(b, &tmB, fb, k, n0);
                     else
-                        for (int j = 0; j < GEMM_BM/32; ++j) tc::tma_load_2d_2sm(a + j*SLAB_MN_BYTES, &tmA, &full[s], m0 + 32*j, k);
-                    if (!p.b_mn) tc::tma_load_2d_2sm(b, &tmB, &full[s], k, n0 + (int)rank*half_bn);
-                    else
-                        for (int j = 0; j < half_bn/32; ++j)
-                            tc::tma_load_2d_2sm(b + j*SLAB_MN_BYTES, &tmB, &full[s], n0 + (int)rank*half_bn + 32*j, k);
+                        for (int j = 0; j < nslab; ++j) tc::tma_load_2d_2sm_s(b + j*SLAB_MN_BYTES, &tmB, fb, n0 + 32*j, k);
                 }
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             const uint32_t idesc = tc::umma_idesc_tf32(2*GEMM_BM, p.bn, p.a_mn != 0, p.b_mn != 0);
-            int it = 0, j = 0;
+            const uint64_t da0 = tc::umma_desc_template(p.a_mn != 0, SLAB_MN_BYTES), db0 = tc::umma_desc_template(p.b_mn != 0, SLAB_MN_BYTES);
+            const uint32_t ka = tc::umma_desc_kstep(p.a_mn != 0), kbs = tc::umma_desc_kstep(p.b_mn != 0);
+            const uint32_t tmem_full0 = tc::smem_u32(tmem_full), tmem_empty0 = tc::smem_u32(tmem_empty);
+            int s = 0, j = 0;
+            uint32_t ph = 0;
             for (int t = pair; t < total; t += npairs, ++j) {
                 const int z = t/(nt*mt);
                 const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
                 const int acc = j & 1;
-                tc::mbar_wait_spin(&tmem_empty[acc], ((uint32_t)(j >> 1) & 1u) ^ 1u);  // both CTAs have drained this accumulator
+                tc::mbar_wait_spin_s(tmem_empty0 + 8*acc, ((uint32_t)(j >> 1) & 1u) ^ 1u);  // both CTAs have drained this accumulator
                 tc::tcgen05_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)acc*acc_cols;
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it/p.stages) & 1u;
-                    tc::mbar_wait_spin(&full[s], ph);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    tc::mbar_wait_spin_s(full0 + 8*s, ph);
                     tc::tcgen05_fence_after();
-                    const uint32_t a = tc::smem_u32(smem + (size_t)s*stage_bytes), b = a + GEMM_A_BYTES;
+                    if (tc::elect_one()) {
+                        const uint32_t a = (ring + (uint32_t)(s*stage_bytes)) >> 4;
+                        uint64_t da = da0 + a, db = db0 + (a + (GEMM_A_BYTES >> 4));
+                        tc::umma_tf32_2sm(d, da, db, idesc, kb > kb0 ? 1u : 0u);
 #pragma unroll
-                    for (int k8 = 0; k8 < GEMM_BK/8; ++k8) {
-                        const uint64_t da = p.a_mn ? tc::umma_desc_mnmajor(a, k8, SLAB_MN_BYTES) : tc::umma_desc_kmajor(a, k8);
-                        const uint64_t db = p.b_mn ? tc::umma_desc_mnmajor(b, k8, SLAB_MN_BYTES) : tc::umma_desc_kmajor(b, k8);
-                        tc::umma_tf32_2sm(d, da, db, idesc, (kb > kb0 || k8 > 0) ? 1u : 0u);
+                        for (int k8 = 1; k8 < GEMM_BK/8; ++k8) {
+                            da += ka; db += kbs;
+                            tc::umma_tf32_2sm(d, da, db, idesc, 1u);
+                        }
+                        tc::umma_commit_2sm_s(empty0 + 8*s);
                     }
-                    tc::umma_commit_2sm(&empty[s]);
+                    if (++s == stages) { s = 0; ph ^= 1u; }
                 }
-                tc::umma_commit_2sm(&tmem_full[acc]);
+                if (tc::elect_one()) tc::umma_commit_2sm_s(tmem_full0 + 8*acc);
             }
         }
         __syncwarp();
@@ -576,42 +605,60 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
     });
     if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute failed (%s)", what, cudaGetErrorString(attr_err)); return STV_E_CUDA; }
     const long long total = (long long)nt*mt*splits;
-    // CTA pairs (cta_group::2): plain matrices with enough 256-row tiles to fill the SMs; the B tile must split into two halves
-    // of whole 32-column slabs / 8-row swizzle groups.
-    static const int pair_mode = getenv("STV_GEMM_PAIR") ? atoi(getenv("STV_GEMM_PAIR")) : 1;   // developer switch (0 = off)
-    const int mt2 = (p.M + 2*GEMM_BM - 1)/(2*GEMM_BM);
-    if (pair_mode && p.cv.mode == 0 && p.remap == 0 && p.bn % 64 == 0 && p.bn <= 128 && (long long)nt*mt2*splits >= sm_count()/2 && p.pair_tmB) {
-        static std::once_flag once2;
-        static cudaError_t err2 = cudaSuccess;
-        std::call_once(once2, [] { err2 = cudaFuncSetAttribute(gemm_tf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024); });
-        if (err2 != cudaSuccess) { set_error("%s: cudaFuncSetAttribute failed (%s)", what, cudaGetErrorString(err2)); return STV_E_CUDA; }
-        const int sb = GEMM_A_BYTES + (p.bn/2)*GEMM_BK*4;
-        const int staging = 8*EPI_WARP_FLOATS*4;
-        int stages = (112*1024 - staging - 2048)/sb;
-        stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
-        p.stages = stages < 2 ? 2 : stages;
-        const size_t smem = (size_t)p.stages*sb + staging + 1024 + (2*GEMM_MAX_STAGES + 4)*8 + 16;
-        const long long tiles2 = (long long)nt*mt2*splits;
-        const int pairs = (int)(tiles2 < sm_count() ? tiles2 : sm_count());   // two resident CTAs per SM = one pair per SM on average
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2*pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        const cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tf32_pair_kernel, tmA, *p.pair_tmB, p);
-        count_launch();
-        if (le != cudaSuccess) { set_error("%s: cluster launch failed (%s)", what, cudaGetErrorString(le)); return STV_E_CUDA; }
-        return check_launch(what);
+    // CTA pairs (cta_group::2): plain matrices whose 256 x bn2 pair tiles keep most of the 74 SM pairs busy. bn2 = the multiple of 64
+    // (<= 256) that wastes the fewest columns (ties -> wider): each CTA's half of the B tile is whole 32-column slabs.
+    static const int pair_mode = getenv("STV_GEMM_PAIR") ? atoi(getenv("STV_GEMM_PAIR")) : 1;   // developer switch: 0 off, 1 heuristic, 2 whenever legal
+    if (pair_mode && p.cv.mode == 0 && p.remap == 0 && p.pair_B != nullptr && p.M > GEMM_BM && p.N >= 64) {
+        int bn2 = 64, best_cost = 1 << 30;
+        for (int bn = 256; bn >= 64; bn -= 64) {
+            const int cost = ((p.N + bn - 1)/bn)*bn;
+            if (cost < best_cost) { bn2 = bn; best_cost = cost; }
+        }
+        const int mt2 = (p.M + 2*GEMM_BM - 1)/(2*GEMM_BM);
+        const int npairs_max = sm_count()/2;
+        while (bn2 > 64 && bn2 % 128 == 0 && (long long)mt2*((p.N + bn2 - 1)/bn2)*splits < npairs_max) bn2 /= 2;   // few tiles: narrower, more of them
+        const int nt2 = (p.N + bn2 - 1)/bn2;
+        const long long tiles2 = (long long)nt2*mt2*splits;
+        const bool waste_ok = (long long)nt2*bn2*4 <= (long long)p.N*5;   // <= 25 % padded columns
+        if (pair_mode == 2 || (tiles2 >= npairs_max/2 && waste_ok)) {
+            static std::once_flag once2;
+            static cudaError_t err2 = cudaSuccess;
+            std::call_once(once2, [] { err2 = cudaFuncSetAttribute(gemm_tf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024); });
+            if (err2 != cudaSuccess) { set_error("%s: cudaFuncSetAttribute failed (%s)", what, cudaGetErrorString(err2)); return STV_E_CUDA; }
+            CUtensorMap tmB2 = tmB;
+            if (!p.b_mn) { if (int rc = make_tmap_2d(&tmB2, p.pair_B, p.N, p.K, p.pair_ldb, bn2/2, 0)) return rc; }
+            GemmParams q = p;
+            q.bn = bn2;
+            const int sb = GEMM_A_BYTES + (bn2/2)*GEMM_BK*4;
+            const int staging = 8*EPI_WARP_FLOATS*4;
+            int stages = (226*1024 - staging - 2048)/sb;
+            stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
+            q.stages = stages;
+            const size_t smem = (size_t)stages*sb + staging + 1024 + (2*GEMM_MAX_STAGES + 4)*8 + 16;
+            const int pairs = (int)(tiles2 < npairs_max ? tiles2 : npairs_max);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2*pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            const cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tf32_pair_kernel, tmA, tmB2, q);
+            count_launch();
+            if (le != cudaSuccess) { set_error("%s: cluster launch failed (%s)", what, cudaGetErrorString(le)); return STV_E_CUDA; }
+            return check_launch(what);
+        }
     }
     if (persistent_enabled() && total < (1ll << 30)) {
-        // two resident CTAs per SM: ring + epilogue staging + barriers within ~112 KB each
+        // Two resident CTAs per SM (ring + epilogue staging + barriers within ~112 KB each: one CTA's epilogue overlaps the other's
+        // main loop), or ONE with the whole shared memory as a deeper ring (developer switch STV_GEMM_RESIDENT=1).
+        static const int res_cfg = getenv("STV_GEMM_RESIDENT") ? atoi(getenv("STV_GEMM_RESIDENT")) : 2;
+        const int per_sm = res_cfg == 1 ? 1 : 2;
         const int staging = 8*EPI_WARP_FLOATS*4;
-        int stages = (112*1024 - staging - 2048)/stage_bytes;
+        int stages = ((per_sm == 1 ? 226 : 112)*1024 - staging - 2048)/stage_bytes;
         stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
         stages = stages < 2 ? 2 : stages;
         p.stages = stages;
         const size_t smem = (size_t)stages*stage_bytes + staging + 1024 /*alignment slack*/ + (2*GEMM_MAX_STAGES + 4)*8 + 16;
-        const int resident = 2*sm_count();
+        const int resident = per_sm*sm_count();
         const int grid = (int)(total < resident ? total : resident);
         gemm_tf32_persistent_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
         count_launch();
@@ -662,9 +709,6 @@ extern "C" int stv_gemm_tf32(int M, int N, int K, const float* A, long long lda,
     if (rc) return rc;
     rc = b_mn ? make_tmap_2d(&tmB, B, K, N, ldb, 32, 1) : make_tmap_2d(&tmB, B, N, K, ldb, p.bn, 0);
     if (rc) return rc;
-    // second view of B for the CTA-pair kernel: each CTA of a pair loads half of the B tile (K-major: bn/2 rows per box)
-    CUtensorMap tmB2 = tmB;
-    if (!b_mn && p.bn % 64 == 0) { rc = make_tmap_2d(&tmB2, B, N, K, ldb, p.bn/2, 0); if (rc) return rc; }
-    p.pair_tmB = &tmB2;
+    p.pair_B = B; p.pair_ldb = ldb;   // the CTA-pair kernel re-encodes B with half-tile boxes
     return launch_gemm(tmA, tmB, p, split_k, (cudaStream_t)stream, "stv_gemm_tf32");
 }

@@ -32,7 +32,8 @@ struct GemmParams {
     stv_gemm_epi e;
     ConvOperand cv;
     int remap, oH, oW, ost, oa, ob;  // RowMap of the output (stv_epi.cuh); rows enumerate (n, cv.gridH, cv.gridW) when remap != 0
-    const CUtensorMap* pair_tmB;     // host only: B viewed with half-tile boxes for the CTA-pair kernel (NULL: pairs not possible)
+    const float* pair_B;             // host only: B of a plain GEMM (the CTA-pair kernel re-encodes it with half-tile boxes), or NULL
+    long long pair_ldb;
 };
 
 int make_tmap_2d(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows, int mn_major);

@@ -663,14 +663,32 @@ __global__ void __launch_bounds__(128) pull_cols_kernel(const PullParams p) {
     p.out[s][((size_t)i*h + yl)*w + xl] = acc;
 }
 
-// Tiled pull-back: one block owns a PT_Y x PT_X tile of the low-resolution output of one (scale, image), stages the
+// Tiled pull-back: one block owns a px x py tile of the low-resolution output of one (scale, image), stages the
 // full-resolution footprint of the tile in shared memory with coalesced row loads (chain factor and dL/dloss applied on the way
-// in), pulls it horizontally into PT_X columns and then vertically into PT_Y rows — every full-resolution value is read from
+// in), pulls it horizontally into px columns and then vertically into py rows — every full-resolution value is read from
 // HBM once (plus the footprint overlap between neighbouring tiles), fixed summation order (deterministic).
-constexpr int PT_X = 32, PT_Y = 4, PT_NT = 128;
-constexpr int PT_MAX_FOOT = 4096;    // floats of footprint + row-pulled scratch a block may stage (16 KB: many resident blocks)
+// The bilinear tap weights of the tile's columns / rows are tabulated once per block (the same float arithmetic as the forward
+// up-sampling, pull_tap), so the two accumulation loops are one shared-memory weight, one shared-memory value and one FMA per tap.
+constexpr int PT_X = 32, PT_Y = 16, PT_NT = 128;
+constexpr int PT_MAX_FOOT = 9216;    // floats of footprint + row-pulled scratch + tap tables a block may stage (36 KB: 6 blocks per SM)
 
-struct PullTiles { int first[STV_MAX_SCALES + 1]; int tx[STV_MAX_SCALES], ty[STV_MAX_SCALES], px[STV_MAX_SCALES], py[STV_MAX_SCALES]; };   // block ranges + tile shape per scale
+struct PullTiles {   // block ranges + tile shape + taps per output (table pitch) per scale
+    int first[STV_MAX_SCALES + 1];
+    int tx[STV_MAX_SCALES], ty[STV_MAX_SCALES], px[STV_MAX_SCALES], py[STV_MAX_SCALES], kw[STV_MAX_SCALES], kh[STV_MAX_SCALES];
+};
+
+// Taps of output index `il` along one axis: inputs [lo, lo + cnt) with weights wt[0..cnt) (zero where an input does not touch il).
+__device__ __forceinline__ void pull_taps(int il, float r, int n_in_lowres, int n_out, int pitch, int& lo, int& cnt, float* wt) {
+    int hi;
+    pull_range(il, r, n_out, lo, hi);
+    cnt = min(hi - lo + 1, pitch);
+    for (int j = 0; j < cnt; ++j) {
+        int i0, i1;
+        float lam;
+        pull_tap(lo + j, r, n_in_lowres, i0, i1, lam);
+        wt[j] = (i0 == il ? 1.f - lam : 0.f) + (i1 == il ? lam : 0.f);
+    }
+}
 
 __global__ void __launch_bounds__(PT_NT) pull_tile_kernel(const PullParams p, const PullTiles t) {
     extern __shared__ float pt_smem[];
@@ -692,45 +710,51 @@ __global__ void __launch_bounds__(PT_NT) pull_tile_kernel(const PullParams p, co
         return;
     }
     const float rx = (float)w/(float)W, ry = (float)h/(float)H;
+    const int KW = t.kw[s], KH = t.kh[s];
     int Xlo, Xhi, Ylo, Yhi, tmp_;
     pull_range(xl0, rx, W, Xlo, tmp_); pull_range(xl0 + nx - 1, rx, W, tmp_, Xhi);
     pull_range(yl0, ry, H, Ylo, tmp_); pull_range(yl0 + ny - 1, ry, H, tmp_, Yhi);
     const int fw = Xhi - Xlo + 1, fh = Yhi - Ylo + 1;
-    float* foot = pt_smem;              // [fh][fw]
-    float* rows = pt_smem + fh*fw;      // [fh][nx]
-    for (int q = threadIdx.x; q < fh*fw; q += PT_NT) {
-        const int fy = q/fw, fx = q - fy*fw;
-        foot[q] = sc*pull_value(p, s, i, Ylo + fy, Xlo + fx);
+    float* foot = pt_smem;                  // [fh][fw]
+    float* rows = foot + fh*fw;             // [fh][nx]
+    float* wxt = rows + fh*nx;              // [nx][KW]
+    float* wyt = wxt + nx*KW;               // [ny][KH]
+    int* xlo = (int*)(wyt + ny*KH);         // [nx] first footprint column, [nx] taps
+    int* xcn = xlo + nx;
+    int* ylo = xcn + nx;                    // [ny] first footprint row, [ny] taps
+    int* ycn = ylo + ny;
+    for (int q = threadIdx.x; q < nx + ny; q += PT_NT) {
+        int lo, cnt;
+        if (q < nx) { pull_taps(xl0 + q, rx, w, W, KW, lo, cnt, wxt + q*KW); xlo[q] = lo - Xlo; xcn[q] = cnt; }
+        else { const int yy = q - nx; pull_taps(yl0 + yy, ry, h, H, KH, lo, cnt, wyt + yy*KH); ylo[yy] = lo - Ylo; ycn[yy] = cnt; }
+    }
+    {   // footprint rows, coalesced; the plain case (no chain, no second map) is a bare scaled copy
+        const bool plain = !p.chain && p.g_full2[s] == nullptr && p.g_full[s] != nullptr;
+        const float* __restrict__ g = p.g_full[s] + (size_t)i*H*W + (size_t)Ylo*W + Xlo;
+        for (int fy = threadIdx.x/32; fy < fh; fy += PT_NT/32) {
+            for (int fx = threadIdx.x & 31; fx < fw; fx += 32)
+                foot[fy*fw + fx] = plain ? sc*__ldg(g + (size_t)fy*W + fx) : sc*pull_value(p, s, i, Ylo + fy, Xlo + fx);
+        }
     }
     __syncthreads();
     for (int q = threadIdx.x; q < fh*nx; q += PT_NT) {
-        const int fy = q/nx, xx = q - fy*nx, xl = xl0 + xx;
-        int lo, hi;
-        pull_range(xl, rx, W, lo, hi);
+        const int fy = q/nx, xx = q - fy*nx;
+        const float* __restrict__ f = foot + fy*fw + xlo[xx];
+        const float* __restrict__ wt = wxt + xx*KW;
+        const int cnt = xcn[xx];
         float acc = 0.f;
-        for (int X = lo; X <= hi; ++X) {
-            int x0, x1;
-            float lx;
-            pull_tap(X, rx, w, x0, x1, lx);
-            const float wx = (x0 == xl ? 1.f - lx : 0.f) + (x1 == xl ? lx : 0.f);
-            if (wx != 0.f) acc = fmaf(wx, foot[fy*fw + (X - Xlo)], acc);
-        }
+        for (int j = 0; j < cnt; ++j) acc = fmaf(wt[j], f[j], acc);
         rows[q] = acc;
     }
     __syncthreads();
     for (int q = threadIdx.x; q < ny*nx; q += PT_NT) {
-        const int yy = q/nx, xx = q - yy*nx, yl = yl0 + yy;
-        int lo, hi;
-        pull_range(yl, ry, H, lo, hi);
+        const int yy = q/nx, xx = q - yy*nx;
+        const float* __restrict__ f = rows + ylo[yy]*nx + xx;
+        const float* __restrict__ wt = wyt + yy*KH;
+        const int cnt = ycn[yy];
         float acc = 0.f;
-        for (int Y = lo; Y <= hi; ++Y) {
-            int y0, y1;
-            float ly;
-            pull_tap(Y, ry, h, y0, y1, ly);
-            const float wy = (y0 == yl ? 1.f - ly : 0.f) + (y1 == yl ? ly : 0.f);
-            if (wy != 0.f) acc = fmaf(wy, rows[(Y - Ylo)*nx + xx], acc);
-        }
-        p.out[s][((size_t)i*h + yl)*w + xl0 + xx] = acc;
+        for (int j = 0; j < cnt; ++j) acc = fmaf(wt[j], f[j*nx], acc);
+        p.out[s][((size_t)i*h + yl0 + yy)*w + xl0 + xx] = acc;
     }
 }
 
@@ -772,10 +796,14 @@ int launch_pull(const PullParams& p, cudaStream_t st) {
             continue;
         }
         int px = PT_X, py = PT_Y;
-        if (p.w[s] != p.W || p.h[s] != p.H) {   // shrink the tile until its full-resolution footprint fits the staging budget
+        {   // shrink the tile until its full-resolution footprint + scratch + tap tables fit the staging budget
             const double fx = (double)p.W/p.w[s], fy = (double)p.H/p.h[s];
-            auto need = [&](int ax, int ay) { const double fw = (ax + 2)*fx + 6, fh = (ay + 2)*fy + 6; return fw*fh + fh*ax; };
-            while (need(px, py) > PT_MAX_FOOT && (px > 8 || py > 1)) { if (px > 8 && (px >= 4*py || py == 1)) px /= 2; else py /= 2; }
+            t.kw[s] = (int)(2*fx) + 6; t.kh[s] = (int)(2*fy) + 6;   // pull_range spans at most 2f + 5 inputs
+            auto need = [&](int ax, int ay) {
+                const double fw = (ax + 2)*fx + 6, fh = (ay + 2)*fy + 6;
+                return fw*fh + fh*ax + ax*t.kw[s] + ay*t.kh[s] + 2*(ax + ay) + 8;
+            };
+            while (need(px, py) > PT_MAX_FOOT && (px > 8 || py > 1)) { if (py > 1 && (py >= 4 || px <= 8)) py /= 2; else px /= 2; }
             if (need(px, py) > PT_MAX_FOOT) tiled = false;
         }
         t.px[s] = px; t.py[s] = py;

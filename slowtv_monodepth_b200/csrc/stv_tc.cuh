@@ -211,6 +211,64 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// One lane of a converged warp (PTX elect.sync): the compiler knows exactly one thread is active under this predicate, so values
+// it feeds to uniform-register operands (UTMALDG / UTCHMMA descriptors) need no per-value election loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// ---- lean single-issuer loops ----------------------------------------------------------------------------------------
+// The producer and MMA-issuer loops run on ONE thread each and sit on the critical path of every k-block (4 MMAs = ~280 tensor
+// cycles at M = N = 128): ~150 scalar instructions per k-block (runtime `%`, descriptor assembly, per-operand election loops that
+// move divergent-code values into uniform registers) made the issuing thread, not the tensor pipe or L2, the bottleneck
+// (profiles/r2_gemm_issue_bound.txt). These variants take 32-bit shared-memory addresses, so that the whole warp can run the loop
+// control with warp-uniform values and one lane issues.
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin_s(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_s(bar, parity)) return;
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (!mbar_try_wait_s(bar, parity)) {
+        if ((++spins & 0xFFFFu) == 0) {   // watchdog: a pipeline bug must trap, never hang the GPU
+            const uint64_t now = globaltimer();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_s(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_s(uint32_t dst, const CUtensorMap* m, uint32_t bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(m), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_s(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h, int n,
+                                                     uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(dst), "l"(m), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+__device__ __forceinline__ void umma_commit_s(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Descriptor of a slab at shared-memory address 0 (the caller adds address >> 4 into the low 14 bits: the ring lies below 256 KB)
+// and the increment, in descriptor units, from one K = 8 MMA to the next.
+__device__ __forceinline__ uint64_t umma_desc_template(bool mn_major, uint32_t slab_bytes) {
+    return mn_major ? umma_desc(0, slab_bytes, 512, 1) : umma_desc(0, 16, 1024, 2);
+}
+__device__ __forceinline__ uint32_t umma_desc_kstep(bool mn_major) { return mn_major ? (1024u >> 4) : (32u >> 4); }
+
 // ---- cta_group::2 (CTA pair = one 256-row MMA; tools/probe/cta2_gemm_probe.cu established the protocol on a B200) --------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync() {
@@ -244,6 +302,14 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, 
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)0b11) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm_s(uint32_t dst, const CUtensorMap* m, uint32_t bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(m), "r"(bar & 0xFEFFFFFFu), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_s(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)0b11) : "memory");
 }
 // Arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {

@@ -88,10 +88,12 @@ def oracle_pull_to_disp(inp: dict, cfg: dict, g_full: list, kind: str = 'depth',
     return [x.grad for x in disps]
 
 
-def unstable_pixels(inp: dict, cfg: dict, tol_val: float = 4e-6, tol_pos: float = 5e-4):
+def unstable_pixels(inp: dict, cfg: dict, tol_val: float = 4e-6, tol_pos: float = 5e-4, pos_err: float = 2e-4):
     """Pixels whose float32 result may legitimately differ O(1) from the exact one because a *discrete* event sits within
     float32 rounding of flipping (computed from the float64 oracle):
-      - |warp - target| < tol_val on some channel (sign of the L1 sub-gradient),
+      - |warp - target| < tol_val + pos_err * (|d warp/d ix| + |d warp/d iy|) on some channel (sign of the L1 sub-gradient): a
+        float32 sample position up to 1024 is only known to ~1e-4 px (ulp(512..1024) = 6e-5, a few roundings in the projection
+        chain), so ANY float32 evaluation of the warped value is off by that times the local image gradient,
       - sample position within tol_pos of a texel boundary or of the image border (bilinear gradient is discontinuous),
       - projected depth within tol_val of the 0.1 clamp.
     -> (bad (S*b,1,H,W) bool, candidate errors (S*b, n[+1], H, W) for decision margins)."""
@@ -109,9 +111,13 @@ def unstable_pixels(inp: dict, cfg: dict, tol_val: float = 4e-6, tol_pos: float 
     for k in range(n):
         Tk, Kk = Ts[k].repeat(S, 1, 1), d['K'].repeat(S, 1, 1)
         ix, iy, z, _ = OL.warp_coords(dep, Tk, Kk)
-        w = OL.sample_bilinear_border(d['supp_imgs'][k].repeat(S, 1, 1, 1), ix, iy)
+        src = d['supp_imgs'][k].repeat(S, 1, 1, 1)
+        w = OL.sample_bilinear_border(src, ix, iy)
         errs.append(fn(w, tgt))
-        bad |= ((w - tgt).abs() < tol_val).any(1, keepdim=True)
+        h = 1e-3   # finite differences of the (piecewise linear) sampler: the steeper side of each axis
+        slope = sum(torch.maximum((OL.sample_bilinear_border(src, ix + dx, iy + dy) - w).abs(),
+                                  (OL.sample_bilinear_border(src, ix - dx, iy - dy) - w).abs())/h for dx, dy in ((h, 0.), (0., h)))
+        bad |= ((w - tgt).abs() < tol_val + pos_err*slope).any(1, keepdim=True)
         for c, size in ((ix, W), (iy, H)):
             cc = c.clamp(0, size - 1)
             bad |= (((cc - cc.round()).abs() < tol_pos) & (c > -tol_pos) & (c < size - 1 + tol_pos)).unsqueeze(1)
