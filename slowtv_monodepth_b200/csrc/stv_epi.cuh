@@ -144,32 +144,37 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int q, int lan
     const int rsub = lane >> 3, cq = (lane & 7)*4;
     for (int c = c_first; c < bn; c += c_step) {
         if (n0 + c >= N) break;  // warp-uniform
-        uint32_t v[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(q*32) << 16) + (uint32_t)c, v);
-        tc::tmem_ld_wait();
         if (vec) {
-            float4* stage = (float4*)(xs + lane*EPI_LD);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                stage[j] = make_float4(__uint_as_float(v[4*j]), __uint_as_float(v[4*j + 1]), __uint_as_float(v[4*j + 2]), __uint_as_float(v[4*j + 3]));
-            __syncwarp();
+            // The chunk's own global reads (bias, layer scale, residual OR activation-derivative source) are requested BEFORE the
+            // accumulator is read back: with one or two resident warps per scheduler nothing else hides their latency, and they
+            // then overlap with the TMEM read + the transposition through shared memory instead of following them.
             const int n = n0 + c + cq;
-            if (n < N) {
-                const float4 bb = e.bias ? __ldg((const float4*)(e.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 gg = e.gamma ? __ldg((const float4*)(e.gamma + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
-                const int row0 = m0 + q*32 + rsub;
-                size_t roffs[8];
+            const bool col_ok = n < N;
+            const int row0 = m0 + q*32 + rsub;
+            size_t roffs[8];
+            float4 pre[8];
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), gg = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (col_ok) {
+                if (e.bias) bb = __ldg((const float4*)(e.bias + n));
+                if (e.gamma) gg = __ldg((const float4*)(e.gamma + n));
 #pragma unroll
                 for (int i = 0; i < 8; ++i) roffs[i] = row0 + 4*i < M ? rm.off(row0 + 4*i) : 0;
-                // The epilogue's own global reads (residual OR activation-derivative source) are issued for the whole chunk
-                // up front: with one resident warp per scheduler a load placed next to its use costs a full memory latency.
                 const float* __restrict__ pre_src = e.res ? e.res : e.dact_src;
-                float4 pre[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int row = row0 + 4*i;
                     pre[i] = (pre_src && row < M) ? __ldg((const float4*)(pre_src + roffs[i] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+            }
+            uint32_t v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(q*32) << 16) + (uint32_t)c, v);
+            tc::tmem_ld_wait();
+            float4* stage = (float4*)(xs + lane*EPI_LD);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                stage[j] = make_float4(__uint_as_float(v[4*j]), __uint_as_float(v[4*j + 1]), __uint_as_float(v[4*j + 2]), __uint_as_float(v[4*j + 3]));
+            __syncwarp();
+            if (col_ok) {
                 // Descriptor fields are kernel-uniform: dispatch once per chunk to a loop specialised on the combinations the networks
                 // use (fc1, fc2, GELU' dgrad, plain store, split-K accumulate, conv + ELU / ReLU); anything else takes the generic loop.
                 float4 cs;
@@ -203,6 +208,9 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int q, int lan
             }
             __syncwarp();
         } else {  // narrow outputs (e.g. the 1-channel disparity heads): one row per thread, scalar columns
+            uint32_t v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(q*32) << 16) + (uint32_t)c, v);
+            tc::tmem_ld_wait();
             const int row = m0 + q*32 + lane;
             if (row >= M) continue;
             const size_t roff = rm.off(row);

@@ -28,6 +28,18 @@
 
 namespace stv {
 
+// Developer instrumentation (-DSTV_GEMM_TRACE, tools/gemm_trace.py; never in the shipped build): clock64 stamps of CTA 0's roles.
+//   [0] entry  [1] set-up done  [2] last commit  [3] epilogue sees the accumulator  [4] epilogue done  [5] exit
+//   [16 + i] producer passes the EMPTY wait of its i-th k-block   [528 + i] MMA thread passes the FULL wait of its i-th k-block
+#ifdef STV_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[1040];
+#define STV_TRACE(slot) do { if (blockIdx.x == 0) g_gemm_trace[(slot)] = (unsigned long long)clock64(); } while (0)
+#define STV_TRACE_KB(base, i) do { if (blockIdx.x == 0 && (i) < 512) g_gemm_trace[(base) + (i)] = (unsigned long long)clock64(); } while (0)
+#else
+#define STV_TRACE(slot) do {} while (0)
+#define STV_TRACE_KB(base, i) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -169,7 +181,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // overlap the epilogue of tile j. The epilogue stages its transposed chunks in a dedicated region (the ring stays busy).
 //   tmem_full[a]  : MMA warp -> epilogue ("accumulator a holds a finished tile"), one tcgen05.commit per tile
 //   tmem_empty[a] : epilogue -> MMA warp ("accumulator a has been read out"), one arrival per epilogue warp
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __launch_bounds__(GEMM_THREADS_WIDE, 1)
 gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = tc::smem_u32(smem_raw);
@@ -178,8 +190,9 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b_bytes = p.bn*GEMM_BK*4;
     const int stage_bytes = GEMM_A_BYTES + b_bytes;
+    const int nepi = (int)(blockDim.x >> 5) - 2;     // epilogue warps: 8 (two CTAs per SM) or 16 (one)
     float* staging = (float*)(smem + (size_t)p.stages*stage_bytes);
-    uint64_t* full = (uint64_t*)(staging + 8*EPI_WARP_FLOATS);
+    uint64_t* full = (uint64_t*)(staging + nepi*EPI_WARP_FLOATS);
     uint64_t* empty = full + GEMM_MAX_STAGES;
     uint64_t* tmem_full = empty + GEMM_MAX_STAGES;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;            // [2]
@@ -188,6 +201,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const int nt = (p.N + p.bn - 1)/p.bn, mt = (p.M + GEMM_BM - 1)/GEMM_BM;
     const int total = nt*mt*p.splits;
     const uint32_t acc_cols = p.bn <= 32 ? 32u : p.bn <= 64 ? 64u : 128u;
+    if (threadIdx.x == 0) STV_TRACE(0);
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA);
@@ -198,7 +212,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(&tmem_full[a], 1);
-            tc::mbar_init(&tmem_empty[a], 8);
+            tc::mbar_init(&tmem_empty[a], (uint32_t)nepi);
         }
         tc::fence_barrier_init();
     } else if (warp == 1) {
@@ -208,6 +222,8 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     __syncthreads();
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) STV_TRACE(1);
+    [[maybe_unused]] int trace_i = 0;
 
     // Producer and MMA issuer: the WHOLE warp runs the loop control (warp-uniform values: ring slot / phase counters instead of
     // `it % stages`, incremental tap / pixel counters instead of per-k-block divisions, descriptors = template + address) and
@@ -249,6 +265,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             }
             for (int kb = kb0; kb < kb1; ++kb) {
                 tc::mbar_wait_spin_s(empty0 + 8*s, ph ^ 1u);
+                if (lane == 0) { STV_TRACE_KB(16, trace_i); ++trace_i; }
                 if (tc::elect_one()) {
                     const uint32_t fb = full0 + 8*s, a = ring + (uint32_t)(s*stage_bytes), b = a + GEMM_A_BYTES;
                     tc::mbar_arrive_expect_tx_s(fb, (uint32_t)stage_bytes);
@@ -303,6 +320,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             const uint32_t d = tmem_base + (uint32_t)acc*acc_cols;
             for (int kb = kb0; kb < kb1; ++kb) {
                 tc::mbar_wait_spin_s(full0 + 8*s, ph);
+                if (lane == 0) { STV_TRACE_KB(528, trace_i); ++trace_i; }
                 tc::tcgen05_fence_after();
                 if (tc::elect_one()) {
                     const uint32_t a = (ring + (uint32_t)(s*stage_bytes)) >> 4;
@@ -318,6 +336,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                 if (++s == stages) { s = 0; ph ^= 1u; }
             }
             if (tc::elect_one()) tc::umma_commit_s(tmem_full0 + 8*acc);
+            if (lane == 0 && j == 0) STV_TRACE(2);
         }
         __syncwarp();
     } else {
@@ -329,8 +348,10 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             const int acc = j & 1;
             tc::mbar_wait(&tmem_full[acc], (uint32_t)(j >> 1) & 1u);
             tc::tcgen05_fence_after();
+            if (warp == 2 && lane == 0 && j == 0) STV_TRACE(3);
             epilogue_tile(tmem_base + (uint32_t)acc*acc_cols, warp & 3, lane, m0, n0, p.bn, p.M, p.N, p.C, rm, p.e,
-                          staging + ew*EPI_WARP_FLOATS, (ew >> 2)*32, 64);
+                          staging + ew*EPI_WARP_FLOATS, (ew >> 2)*32, 8*nepi);
+            if (warp == 2 && lane == 0 && j == 0) STV_TRACE(4);
             tc::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
@@ -338,6 +359,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
     tc::tcgen05_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) STV_TRACE(5);
     if (warp == 1) tc::tmem_dealloc(tmem_base, 2*acc_cols);
 }
 
@@ -353,7 +375,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 //   empty[s]       both CTAs: multicast commit of the leader once the MMAs have read stage s
 //   tmem_full[a]   both CTAs: multicast commit once accumulator a holds a finished tile
 //   tmem_empty[a]  leader only: 16 arrivals = the 8 epilogue warps of each CTA (remote arrive from the peer)
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS_WIDE, 1)
 gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = tc::smem_u32(smem_raw);
@@ -365,8 +387,9 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int b_bytes = half_bn*GEMM_BK*4;
     const int stage_bytes = GEMM_A_BYTES + b_bytes;
     const int stages = p.stages;
+    const int nepi = (int)(blockDim.x >> 5) - 2;
     float* staging = (float*)(smem + (size_t)stages*stage_bytes);
-    uint64_t* full = (uint64_t*)(staging + 8*EPI_WARP_FLOATS);
+    uint64_t* full = (uint64_t*)(staging + nepi*EPI_WARP_FLOATS);
     uint64_t* empty = full + GEMM_MAX_STAGES;
     uint64_t* tmem_full = empty + GEMM_MAX_STAGES;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;            // [2]
@@ -376,6 +399,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int total = nt*mt*p.splits;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const uint32_t acc_cols = p.bn <= 64 ? 64u : p.bn <= 128 ? 128u : 256u;
+    if (threadIdx.x == 0) STV_TRACE(0);
+    [[maybe_unused]] int trace_i = 0;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA);
@@ -386,7 +411,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(&tmem_full[a], 1);
-            tc::mbar_init(&tmem_empty[a], 16);
+            tc::mbar_init(&tmem_empty[a], (uint32_t)(2*nepi));
         }
         tc::fence_barrier_init();
     } else if (warp == 1) {
@@ -397,6 +422,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tc::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t ring = tc::smem_u32(smem), full0 = tc::smem_u32(full), empty0 = tc::smem_u32(empty);
+    if (threadIdx.x == 0) STV_TRACE(1);
 
     if (warp == 0) {
         const int nslab = half_bn >> 5;
@@ -407,6 +433,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
             for (int kb = kb0; kb < kb1; ++kb) {
                 tc::mbar_wait_spin_s(empty0 + 8*s, ph ^ 1u);
+                if (lane == 0) { STV_TRACE_KB(16, trace_i); ++trace_i; }
                 if (tc::elect_one()) {
                     const uint32_t fb = full0 + 8*s, a = ring + (uint32_t)(s*stage_bytes), b = a + GEMM_A_BYTES;
                     if (rank == 0) tc::mbar_arrive_expect_tx_s(fb, 2u*(uint32_t)stage_bytes);
@@ -440,6 +467,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const uint32_t d = tmem_base + (uint32_t)acc*acc_cols;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     tc::mbar_wait_spin_s(full0 + 8*s, ph);
+                    if (lane == 0) { STV_TRACE_KB(528, trace_i); ++trace_i; }
                     tc::tcgen05_fence_after();
                     if (tc::elect_one()) {
                         const uint32_t a = (ring + (uint32_t)(s*stage_bytes)) >> 4;
@@ -455,6 +483,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
                 if (tc::elect_one()) tc::umma_commit_2sm_s(tmem_full0 + 8*acc);
+                if (lane == 0 && j == 0) STV_TRACE(2);
             }
         }
         __syncwarp();
@@ -467,8 +496,10 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int acc = j & 1;
             tc::mbar_wait(&tmem_full[acc], (uint32_t)(j >> 1) & 1u);
             tc::tcgen05_fence_after();
+            if (warp == 2 && lane == 0 && j == 0) STV_TRACE(3);
             epilogue_tile(tmem_base + (uint32_t)acc*acc_cols, warp & 3, lane, m0, n0, p.bn, p.M, p.N, p.C, rm, p.e,
-                          staging + ew*EPI_WARP_FLOATS, (ew >> 2)*32, 64);
+                          staging + ew*EPI_WARP_FLOATS, (ew >> 2)*32, 8*nepi);
+            if (warp == 2 && lane == 0 && j == 0) STV_TRACE(4);
             tc::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_remote(&tmem_empty[acc], 0);   // the leader's barrier (also from the leader itself)
@@ -476,6 +507,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     tc::tcgen05_fence_before();
     tc::cluster_sync();   // both CTAs are done with TMEM and with each other's shared memory
+    if (threadIdx.x == 0) STV_TRACE(5);
     if (warp == 1) tc::tmem_dealloc_2sm(tmem_base, 2*acc_cols);
 }
 
@@ -609,18 +641,21 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
     // (<= 256) that wastes the fewest columns (ties -> wider): each CTA's half of the B tile is whole 32-column slabs.
     static const int pair_mode = getenv("STV_GEMM_PAIR") ? atoi(getenv("STV_GEMM_PAIR")) : 1;   // developer switch: 0 off, 1 heuristic, 2 whenever legal
     if (pair_mode && p.cv.mode == 0 && p.remap == 0 && p.pair_B != nullptr && p.M > GEMM_BM && p.N >= 64) {
-        int bn2 = 64, best_cost = 1 << 30;
-        for (int bn = 256; bn >= 64; bn -= 64) {
+        int bn2 = 128, best_cost = 1 << 30;
+        for (int bn = 256; bn >= 128; bn -= 64) {
             const int cost = ((p.N + bn - 1)/bn)*bn;
             if (cost < best_cost) { bn2 = bn; best_cost = cost; }
         }
         const int mt2 = (p.M + 2*GEMM_BM - 1)/(2*GEMM_BM);
         const int npairs_max = sm_count()/2;
-        while (bn2 > 64 && bn2 % 128 == 0 && (long long)mt2*((p.N + bn2 - 1)/bn2)*splits < npairs_max) bn2 /= 2;   // few tiles: narrower, more of them
         const int nt2 = (p.N + bn2 - 1)/bn2;
         const long long tiles2 = (long long)nt2*mt2*splits;
         const bool waste_ok = (long long)nt2*bn2*4 <= (long long)p.N*5;   // <= 25 % padded columns
-        if (pair_mode == 2 || (tiles2 >= npairs_max/2 && waste_ok)) {
+        // Measured (profiles/r2_gemm_pair_vs_single.txt): the pair kernel wins 20-30 % on the plain / bias / residual / split-K
+        // products once ~80 % of the 74 SM pairs have a tile; it loses on the GELU / GELU' epilogues, which are issue-bound and
+        // want the 16 epilogue warps per SM of the two-CTA kernel.
+        const bool heavy_epi = p.e.act == STV_ACT_GELU || (p.e.dact_src != nullptr && p.e.dact == STV_ACT_GELU);
+        if (pair_mode == 2 || (tiles2 >= (npairs_max*4)/5 && waste_ok && !heavy_epi)) {
             static std::once_flag once2;
             static cudaError_t err2 = cudaSuccess;
             std::call_once(once2, [] { err2 = cudaFuncSetAttribute(gemm_tf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024); });
@@ -630,14 +665,15 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
             GemmParams q = p;
             q.bn = bn2;
             const int sb = GEMM_A_BYTES + (bn2/2)*GEMM_BK*4;
-            const int staging = 8*EPI_WARP_FLOATS*4;
+            static const int pair_threads = (getenv("STV_GEMM_PAIR_EPI") && atoi(getenv("STV_GEMM_PAIR_EPI")) == 8) ? GEMM_THREADS : GEMM_THREADS_WIDE;
+            const int staging = (pair_threads/32 - 2)*EPI_WARP_FLOATS*4;
             int stages = (226*1024 - staging - 2048)/sb;
             stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
             q.stages = stages;
             const size_t smem = (size_t)stages*sb + staging + 1024 + (2*GEMM_MAX_STAGES + 4)*8 + 16;
             const int pairs = (int)(tiles2 < npairs_max ? tiles2 : npairs_max);
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(2*pairs); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+            cfg.gridDim = dim3(2*pairs); cfg.blockDim = dim3(pair_threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
@@ -652,7 +688,8 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
         // main loop), or ONE with the whole shared memory as a deeper ring (developer switch STV_GEMM_RESIDENT=1).
         static const int res_cfg = getenv("STV_GEMM_RESIDENT") ? atoi(getenv("STV_GEMM_RESIDENT")) : 2;
         const int per_sm = res_cfg == 1 ? 1 : 2;
-        const int staging = 8*EPI_WARP_FLOATS*4;
+        const int threads = per_sm == 1 ? GEMM_THREADS_WIDE : GEMM_THREADS;
+        const int staging = (threads/32 - 2)*EPI_WARP_FLOATS*4;
         int stages = ((per_sm == 1 ? 226 : 112)*1024 - staging - 2048)/stage_bytes;
         stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
         stages = stages < 2 ? 2 : stages;
@@ -660,7 +697,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
         const size_t smem = (size_t)stages*stage_bytes + staging + 1024 /*alignment slack*/ + (2*GEMM_MAX_STAGES + 4)*8 + 16;
         const int resident = per_sm*sm_count();
         const int grid = (int)(total < resident ? total : resident);
-        gemm_tf32_persistent_kernel<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
+        gemm_tf32_persistent_kernel<<<grid, threads, smem, stream>>>(tmA, tmB, p);
         count_launch();
         return check_launch(what);
     }
@@ -678,6 +715,13 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
 }  // namespace stv
 
 using namespace stv;
+
+#ifdef STV_GEMM_TRACE
+extern "C" int stv_debug_gemm_trace(unsigned long long* out, int n) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(unsigned long long)*(size_t)(n < 1040 ? n : 1040));
+}
+#endif
 
 extern "C" int stv_gemm_tf32(int M, int N, int K, const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn,
                              float* C, long long ldc, const stv_gemm_epi* epi, int split_k, void* stream) {

@@ -6,6 +6,7 @@
 namespace stv {
 
 constexpr int GEMM_BM = 128, GEMM_BK = 32, GEMM_THREADS = 320, GEMM_MAX_STAGES = 8;  // warps: TMA, MMA, 8 x epilogue
+constexpr int GEMM_THREADS_WIDE = 576;            // one CTA per SM: TMA, MMA, 16 x epilogue (the persistent kernels take either)
 constexpr int GEMM_A_BYTES = GEMM_BM*GEMM_BK*4;  // 16 KB per stage
 constexpr int SLAB_MN_BYTES = 32*128;            // MN-major slab: 32 k-rows x 128 B
 

@@ -75,6 +75,58 @@ def _sink(p: Tensor | None, phys=None) -> Tensor | None:
     return g if g.is_contiguous() else None
 
 
+# Weight-gradient side stream. In backward, a layer's weight gradient is off the critical path (nothing downstream reads it
+# before the optimiser) while its data gradient feeds the next layer. With the gradient sink on, the weight-gradient kernels have
+# no autograd output at all, so they are enqueued on a second stream that forks from the backward stream at the layer and joins
+# it once, when backward ends (autograd engine callback): the GPU co-schedules their CTAs with the data-gradient kernels of the
+# following layers, filling the partial waves and the prologue / epilogue bubbles of these ~10 GFLOP products. Captured CUDA
+# graphs record the fork / join as graph edges. Tensors read on the side stream are `record_stream`ed (the caching allocator then
+# defers their reuse; during capture until the capture ends).
+import os as _os0
+WGRAD_STREAM = not bool(_os0.environ.get('STV_WGRAD_STREAM_OFF'))   # developer switch for A/B runs
+_SIDE_STREAMS: dict[int, 'torch.cuda.Stream'] = {}
+_SIDE_PENDING: dict[int, bool] = {}
+
+
+def join_side_stream(device=None) -> None:
+    """Make the current stream wait for the weight-gradient side stream (no host synchronisation)."""
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if _SIDE_PENDING.pop(dev, False): torch.cuda.current_stream(dev).wait_stream(_SIDE_STREAMS[dev])
+
+
+class _side_stream:
+    """`with _side_stream(t1, t2, ...):` — enqueue the enclosed libstv calls on the weight-gradient stream (no-op when disabled or
+    outside a backward pass). t_i: tensors the enclosed kernels read or write."""
+    def __init__(self, *tensors): self.tensors, self.cm = tensors, None
+
+    def __enter__(self):
+        if not WGRAD_STREAM or not GRAD_SINK: return self
+        t0 = next((t for t in self.tensors if t is not None), None)
+        if t0 is None or not t0.is_cuda: return self
+        dev = t0.device.index
+        cur = torch.cuda.current_stream(dev)
+        side = _SIDE_STREAMS.get(dev)
+        if side is None: side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+        if not _SIDE_PENDING.get(dev, False):
+            try: torch.autograd.Variable._execution_engine.queue_callback(lambda dev=dev, cur=cur: _join_on(dev, cur))
+            except RuntimeError: return self   # not inside a backward pass: stay on the current stream
+            _SIDE_PENDING[dev] = True
+        side.wait_stream(cur)
+        for t in self.tensors:
+            if t is not None: t.record_stream(side)
+        self.cm = torch.cuda.stream(side)
+        self.cm.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.cm is not None: self.cm.__exit__(*a)
+        return False
+
+
+def _join_on(dev: int, stream) -> None:
+    if _SIDE_PENDING.pop(dev, False): stream.wait_stream(_SIDE_STREAMS[dev])
+
+
 def _f32c(t: Tensor | None) -> Tensor | None:
     if t is None: return None
     if t.dtype != torch.float32: raise ValueError(f'Expected float32, got {t.dtype}.')
@@ -541,8 +593,9 @@ class _DwConv7(torch.autograd.Function):
                 gw = ctx.w_sink if sink else torch.empty_like(w)
                 gb = (ctx.b_sink if sink else torch.empty(Cc, dtype=torch.float32, device=dev)) if ctx.has_bias else None
                 ws = _ws(lib.stv_dwconv7_wgrad_workspace_bytes(N, H, W, Cc), dev)
-                L.check(lib.stv_dwconv7_wgrad(N, H, W, Cc, L.ptr(x), L.ptr(gy), L.ptr(gw), L.ptr(gb), int(sink), L.ptr(ws), ws.numel(),
-                                              L.stream()), 'stv_dwconv7_wgrad')
+                with (_side_stream(x, gy, ws) if sink else _side_stream()):
+                    L.check(lib.stv_dwconv7_wgrad(N, H, W, Cc, L.ptr(x), L.ptr(gy), L.ptr(gw), L.ptr(gb), int(sink), L.ptr(ws), ws.numel(),
+                                                  L.stream()), 'stv_dwconv7_wgrad')
                 if sink: gw = gb = None  # accumulated in place into weight.grad / bias.grad
         return gx, gw, gb, None
 
@@ -737,7 +790,7 @@ class _Conv2dNHWC(torch.autograd.Function):
             dw = None
             if ctx.needs_input_grad[2]:
                 dw = ctx.w_sink if ctx.w_sink is not None else torch.zeros_like(wq)
-                with _timed('stv_conv_wgrad', g):
+                with (_side_stream(src1, src2, dZ) if ctx.w_sink is not None else _side_stream()), _timed('stv_conv_wgrad', g):
                     L.check(lib.stv_conv_wgrad(C.byref(g), L.ptr(src1), L.ptr(src2), L.ptr(dZ), L.ptr(dw), 0, L.stream()), 'stv_conv_wgrad')
                 dw = None if ctx.w_sink is not None else dw[:Cout, :, :, :ctx.cin].permute(0, 3, 1, 2)
             d1 = d2 = None
@@ -956,20 +1009,22 @@ class _ConvNeXtMlp(torch.autograd.Function):
         db1 = ctx.b1_sink if ctx.b1_sink is not None else torch.zeros(Hd, dtype=torch.float32, device=g.device)
         dz = gemm_tf32(g, w2g, b_mn=True, dact='gelu', dact_src=z, colsum=db1)  # (M, 4C) = (g W2g) * GELU'(z); db1 = its column sums
         dx = gemm_tf32(dz, w1, b_mn=True) if ctx.needs_input_grad[0] else None
-        dw1 = ctx.w1_sink if ctx.w1_sink is not None else torch.zeros_like(w1)
-        gemm_tf32(dz, x, a_mn=True, b_mn=True, out=dw1, accumulate=True, split_k=_split_k(Hd, Cc, M))
-        if ctx.w1_sink is not None: dw1 = None
-        if ctx.b1_sink is not None: db1 = None
-        G = torch.zeros_like(w2)                                             # g^T h, before the layer-scale
-        gemm_tf32(g, h, a_mn=True, b_mn=True, out=G, accumulate=True, split_k=_split_k(Cc, Hd, M))
-        gs = colsum(g)
         w2s, b2s, gas = ctx.tail_sinks
         sunk = w2s is not None and b2s is not None and gas is not None
-        if sunk: dw2, db2, dga = w2s, b2s, gas                               # accumulate straight into the flat gradient buffer
-        else: dw2, db2, dga = torch.zeros_like(w2), torch.zeros_like(b2), torch.zeros_like(gamma)
-        with torch.cuda.device(g.device):
-            L.check(lib.stv_ls_tail(Cc, Hd, L.ptr(G), L.ptr(w2), L.ptr(b2), L.ptr(gamma), L.ptr(gs), L.ptr(dw2), L.ptr(db2), L.ptr(dga),
-                                    L.stream()), 'stv_ls_tail')
+        # Both weight-gradient products and the layer-scale tail are off the critical path: side stream when every result is sunk.
+        with (_side_stream(dz, x, g, h) if (sunk and ctx.w1_sink is not None and ctx.b1_sink is not None) else _side_stream()):
+            dw1 = ctx.w1_sink if ctx.w1_sink is not None else torch.zeros_like(w1)
+            gemm_tf32(dz, x, a_mn=True, b_mn=True, out=dw1, accumulate=True, split_k=_split_k(Hd, Cc, M))
+            if ctx.w1_sink is not None: dw1 = None
+            if ctx.b1_sink is not None: db1 = None
+            G = torch.zeros_like(w2)                                             # g^T h, before the layer-scale
+            gemm_tf32(g, h, a_mn=True, b_mn=True, out=G, accumulate=True, split_k=_split_k(Cc, Hd, M))
+            gs = colsum(g)
+            if sunk: dw2, db2, dga = w2s, b2s, gas                               # accumulate straight into the flat gradient buffer
+            else: dw2, db2, dga = torch.zeros_like(w2), torch.zeros_like(b2), torch.zeros_like(gamma)
+            with torch.cuda.device(g.device):
+                L.check(lib.stv_ls_tail(Cc, Hd, L.ptr(G), L.ptr(w2), L.ptr(b2), L.ptr(gamma), L.ptr(gs), L.ptr(dw2), L.ptr(db2), L.ptr(dga),
+                                        L.stream()), 'stv_ls_tail')
         g_res = g if ctx.needs_input_grad[1] else None
         if g_res is not None and ctx.link is not None:  # handed to the block's depthwise data-gradient kernel (see _DwConv7.backward)
             ctx.link['g_res'] = g_res

@@ -136,6 +136,7 @@ class FlatAdamW:
         if self.world <= 1 or j in self._reduced or j >= len(self.buckets): return
         start, n, _ = self.buckets[j]
         self._reduced.add(j)
+        if self.grad.is_cuda: F_.join_side_stream(self.grad.device)   # weight gradients enqueued on the side stream so far
         self._works.append(dist.all_reduce(self.grad[start:start + n], op=dist.ReduceOp.SUM, async_op=True))
 
     def all_reduce_async(self):

@@ -28,14 +28,22 @@ SHAPES = [('upconv_4_0', 12, 20, 768, 0, False, 256, 3, 1, 1, True),
           ('res_conv1', 384, 640, 8, 0, False, 64, 7, 2, 3, False)]
 
 
-def timeit(fn, n=5):
-    for _ in range(2): fn()
+def timeit(fn, n=10):
+    """GPU time per call: n calls captured in ONE CUDA graph and replayed, so that the host's launch path (ctypes + tensor-map
+    encoding, ~20-30 us per call — longer than most of these kernels) is not in the measurement. Operands are re-used by the n
+    calls, i.e. L2-warm where they fit: the in-step numbers (tools/step_profile.py) are the cold-cache counterpart."""
+    for _ in range(3): fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n): fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1)/n
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n): fn()
+    g.replay(); torch.cuda.synchronize()
+    best = float('inf')
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1)/n)
+    return best
 
 
 print(f'{"layer":12s} {"GF(fwd)":>8s} | ours fwd  bwd (ms) TF/s(fwd) | cudnn fwd  bwd (ms)')

@@ -12,6 +12,7 @@ from slowtv_monodepth_b200.regularizers import SmoothReg
 ap = argparse.ArgumentParser()
 for k, v in dict(b=8, H=384, W=640, n=2, S=4, iters=5).items(): ap.add_argument(f'--{k}', type=int, default=v)
 ap.add_argument('--mode', default='disp', choices=['disp', 'depth', 'two-pass'])
+ap.add_argument('--kernels', action='store_true', help='also print the CUPTI duration of every kernel of one iteration (torch.profiler)')
 a = ap.parse_args()
 dev = 'cuda'
 d = syn.make_loss_inputs(a.b, a.n, a.S, (a.H, a.W), seed=0)
@@ -20,7 +21,12 @@ disps = [x.requires_grad_() for x in d['disps']]
 aa, t = d['aa'].requires_grad_(), d['t'].requires_grad_()
 crit, sm = ReconstructionLoss('ssim', True, True), SmoothReg(use_edges=True)
 F_.enable_kernel_timing(True)
-for it in range(a.iters):
+prof = None
+for it in range(a.iters + (1 if a.kernels else 0)):
+    if a.kernels and it == a.iters:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        prof = profile(activities=[ProfilerActivity.CUDA]); prof.__enter__()
     Ts = G.T_from_AAt(aa, t)
     F_.PHOTO_FORCE_TWO_PASS = a.mode == 'two-pass'
     if a.mode == 'disp':
@@ -33,6 +39,10 @@ for it in range(a.iters):
     l2, _ = Hd.disp_smooth(sm, dict(enumerate(disps)), d['imgs'], want_maps=False)
     (l1 + 1e-3*l2).backward()
 torch.cuda.synchronize()
+if prof is not None:
+    prof.__exit__(None, None, None)
+    for e in sorted(prof.events(), key=lambda e: e.time_range.start):
+        if str(e.device_type).endswith('CUDA'): print(f'   {e.device_time_total:9.1f} us  {e.name[:110]}')
 px = a.b*a.H*a.W
 tot = 0.
 for k, v in F_.kernel_timings().items():
