@@ -30,7 +30,7 @@ constexpr int FZ_NT = FZ_WARPS*32;
 constexpr int FZ_NPART_K = 6;    // d/dK rows 0-1 accumulators (shared by the support frames)
 
 template <int N> struct FzLayout {
-    static constexpr int CAM = 9 + 3 + 3 + N*12;       // Kinv3x3, K row 0, K row 1, then per frame R (9) + t (3)
+    static constexpr int CAM = 12 + 4 + 4 + N*12;      // float4 rows: Kinv rows 0-2 (w = 0), K row 0, K row 1, then per frame (R[r][0..2], t[r]), r = 0..2
     static constexpr int CAM_PAD = (CAM + 31)/32*32;
     static constexpr int RV = 5 + 9*N;                 // ring values per lane: depth, target RGB, d depth/d src, per frame w[3], gx[3], gy[3]
     static constexpr int PER_WARP = CAM_PAD + 3*RV*32; // floats
@@ -123,19 +123,18 @@ __global__ void __launch_bounds__(FZ_NT, STV_FUSED_MINB) photo_fused_kernel(cons
         const float* __restrict__ Ki = p.Kinv + (size_t)i*16;
         for (int q = lane; q < LY::CAM; q += 32) {
             float v;
-            if (q < 9) v = __ldg(Ki + (q/3)*4 + q % 3);
-            else if (q < 12) v = __ldg(Km + (q - 9));
-            else if (q < 15) v = __ldg(Km + 4 + (q - 12));
+            if (q < 12) v = (q & 3) < 3 ? __ldg(Ki + q) : 0.f;       // rows 0-2 of the 4x4 inverse intrinsics
+            else if (q < 20) v = __ldg(Km + (q - 12));               // rows 0-1 of the intrinsics
             else {
-                const int k = (q - 15)/12, e = (q - 15) % 12;
-                const float* __restrict__ Tm = p.T + ((size_t)k*p.b + i)*16;
-                v = e < 9 ? __ldg(Tm + (e/3)*4 + e % 3) : __ldg(Tm + (e - 9)*4 + 3);
+                const int k = (q - 20)/12, e = (q - 20) % 12;        // rows 0-2 of T_k: (R | t)
+                v = __ldg(p.T + ((size_t)k*p.b + i)*16 + e);
             }
             cam[q] = v;
         }
     }
     __syncwarp();
-    const float* const cKi = cam; const float* const cK0 = cam + 9; const float* const cK1 = cam + 12;
+    // read back as 128-bit broadcasts (one LDS per matrix row instead of one per element: the constants do not fit in registers)
+    const float4* const cam4 = reinterpret_cast<const float4*>(cam);
 
     // low-resolution taps of this lane's column (mode 1)
     const int hs = p.h[s], ws = p.w[s];
@@ -244,7 +243,7 @@ __global__ void __launch_bounds__(FZ_NT, STV_FUSED_MINB) photo_fused_kernel(cons
         if (it + 1 < n_it) request(it + 1, cur);   // next row's loads fly while this row is processed
         float ray[3], P[3];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) { ray[r] = fmaf(cKi[r*3], u, fmaf(cKi[r*3 + 1], v, cKi[r*3 + 2])); P[r] = ray[r]*d; }
+        for (int r = 0; r < 3; ++r) { const float4 ki = cam4[r]; ray[r] = fmaf(ki.x, u, fmaf(ki.y, v, ki.z)); P[r] = ray[r]*d; }
         rw[0] = d;
 #pragma unroll
         for (int c = 0; c < 3; ++c) rw[(1 + c)*32] = tv[c];
@@ -253,14 +252,14 @@ __global__ void __launch_bounds__(FZ_NT, STV_FUSED_MINB) photo_fused_kernel(cons
         float wv[N][3];
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-            const float* const cR = cam + 15 + k*12; const float* const ct = cR + 9;
             float Q[3];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) Q[r] = fmaf(cR[r*3], P[0], fmaf(cR[r*3 + 1], P[1], fmaf(cR[r*3 + 2], P[2], ct[r])));
+            for (int r = 0; r < 3; ++r) { const float4 rt = cam4[5 + k*3 + r]; Q[r] = fmaf(rt.x, P[0], fmaf(rt.y, P[1], fmaf(rt.z, P[2], rt.w))); }
             const float inv = rcp_fast(fmaxf(Q[2], STV_MIN_Z));  // max(max(z, eps), 0.1) == max(z, 0.1)
             const float nx = Q[0]*inv, ny = Q[1]*inv, nz = Q[2]*inv;
-            float ix = fmaf(fmaf(cK0[0], nx, fmaf(cK0[1], ny, cK0[2]*nz)), sx, -0.5f);
-            float iy = fmaf(fmaf(cK1[0], nx, fmaf(cK1[1], ny, cK1[2]*nz)), sy, -0.5f);
+            const float4 k0 = cam4[3], k1 = cam4[4];
+            float ix = fmaf(fmaf(k0.x, nx, fmaf(k0.y, ny, k0.z*nz)), sx, -0.5f);
+            float iy = fmaf(fmaf(k1.x, nx, fmaf(k1.y, ny, k1.z*nz)), sy, -0.5f);
             const float mxc = (float)(W - 1), myc = (float)(H - 1);
             const float bx = (ix > 0.f && ix < mxc) ? sx : 0.f, by = (iy > 0.f && iy < myc) ? sy : 0.f;  // d(clamped)/d(raw) * d ix/d qx
             ix = fminf(fmaxf(ix, 0.f), mxc);
@@ -433,7 +432,9 @@ __global__ void __launch_bounds__(FZ_NT, STV_FUSED_MINB) photo_fused_kernel(cons
                 const float vp = (float)ypa;
                 float rayp[3];
 #pragma unroll
-                for (int r = 0; r < 3; ++r) rayp[r] = fmaf(cKi[r*3], u, fmaf(cKi[r*3 + 1], vp, cKi[r*3 + 2]));
+                for (int r = 0; r < 3; ++r) { const float4 ki = cam4[r]; rayp[r] = fmaf(ki.x, u, fmaf(ki.y, vp, ki.z)); }
+                const float4 k0p = cam4[3], k1p = cam4[4];
+                const float cK0[3] = {k0p.x, k0p.y, k0p.z}, cK1[3] = {k1p.x, k1p.y, k1p.z};
                 float gd = 0.f;
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
@@ -452,15 +453,16 @@ __global__ void __launch_bounds__(FZ_NT, STV_FUSED_MINB) photo_fused_kernel(cons
                         gqy = fmaf(gw, rp[(5 + k*9 + 6 + c)*32], gqy);
                     }
                     if (!any) continue;
-                    const float* const cR = cam + 15 + k*12; const float* const ct = cR + 9;
                     // u = R ray, Q = d u + t. The depth gradient gQ . u is, written out, inv (gn.u) - inv^2 (gn.Q) u_z: two terms of
                     // size d |gn| / z that cancel to size |t| |gn| / z^2 (the d-terms cancel EXACTLY in exact arithmetic) — for far
                     // points a float32 evaluation of the difference loses log2(d/|t|) ~ 11 bits. The closed form below has the
                     // cancellation done analytically:  gd = inv^2 ((gn.u) t_z - (gn.t) u_z)   (unclamped z), inv (gn.u) (clamped).
-                    float uu[3], Q[3];
+                    float uu[3], Q[3], ct[3];
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
-                        uu[r] = fmaf(cR[r*3], rayp[0], fmaf(cR[r*3 + 1], rayp[1], cR[r*3 + 2]*rayp[2]));
+                        const float4 rt = cam4[5 + k*3 + r];
+                        uu[r] = fmaf(rt.x, rayp[0], fmaf(rt.y, rayp[1], rt.z*rayp[2]));
+                        ct[r] = rt.w;
                         Q[r] = fmaf(dp, uu[r], ct[r]);
                     }
                     const float inv = rcp_fast(fmaxf(Q[2], STV_MIN_Z));

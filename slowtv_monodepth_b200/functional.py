@@ -75,45 +75,67 @@ def _sink(p: Tensor | None, phys=None) -> Tensor | None:
     return g if g.is_contiguous() else None
 
 
-# Weight-gradient side stream. In backward, a layer's weight gradient is off the critical path (nothing downstream reads it
-# before the optimiser) while its data gradient feeds the next layer. With the gradient sink on, the weight-gradient kernels have
-# no autograd output at all, so they are enqueued on a second stream that forks from the backward stream at the layer and joins
-# it once, when backward ends (autograd engine callback): the GPU co-schedules their CTAs with the data-gradient kernels of the
-# following layers, filling the partial waves and the prologue / epilogue bubbles of these ~10 GFLOP products. Captured CUDA
-# graphs record the fork / join as graph edges. Tensors read on the side stream are `record_stream`ed (the caching allocator then
-# defers their reuse; during capture until the capture ends).
+# Auxiliary streams. (1) Weight-gradient side streams: in backward, a layer's weight gradient is off the critical path (nothing
+# downstream reads it before the optimiser) while its data gradient feeds the next layer. With the gradient sink on, the
+# weight-gradient kernels have no autograd output at all, so they are enqueued on a second stream that forks from the stream of
+# the backward node and joins the caller's stream once, when backward ends (autograd engine callback): the GPU co-schedules their
+# CTAs with the data-gradient kernels of the following layers, filling the partial waves and the prologue / epilogue bubbles of
+# these ~10 GFLOP products. (2) Branch streams (`branch_stream`): the pose network runs beside the depth network, forward AND
+# backward (autograd replays every node on the stream of its forward). Captured CUDA graphs record the forks / joins as graph
+# edges. Tensors read across streams are `record_stream`ed (the caching allocator then defers their reuse; during capture until
+# the capture ends).
 import os as _os0
-WGRAD_STREAM = not bool(_os0.environ.get('STV_WGRAD_STREAM_OFF'))   # developer switch for A/B runs
-_SIDE_STREAMS: dict[int, 'torch.cuda.Stream'] = {}
-_SIDE_PENDING: dict[int, bool] = {}
+WGRAD_STREAM = not bool(_os0.environ.get('STV_WGRAD_STREAM_OFF'))     # developer switches for A/B runs
+BRANCH_STREAMS = not bool(_os0.environ.get('STV_BRANCH_STREAM_OFF'))
+_SIDE_STREAMS: dict[tuple, 'torch.cuda.Stream'] = {}    # (device, origin stream handle) -> weight-gradient stream
+_BRANCH_STREAMS: dict[tuple, 'torch.cuda.Stream'] = {}  # (device, name) -> branch stream
+_DIRTY: set = set()                                     # streams with work not yet joined into the caller's stream
+_JOIN_QUEUED = [False]
+
+
+def _join_all() -> None:
+    """The CURRENT stream waits for every auxiliary stream that has un-joined work (no host synchronisation)."""
+    _JOIN_QUEUED[0] = False
+    cur = torch.cuda.current_stream()
+    for st in list(_DIRTY):
+        if st.device == cur.device and st != cur:   # (a branch stream joining others stays pending itself)
+            cur.wait_stream(st)
+            _DIRTY.discard(st)
 
 
 def join_side_stream(device=None) -> None:
-    """Make the current stream wait for the weight-gradient side stream (no host synchronisation)."""
-    dev = torch.cuda.current_device() if device is None else torch.device(device).index
-    if _SIDE_PENDING.pop(dev, False): torch.cuda.current_stream(dev).wait_stream(_SIDE_STREAMS[dev])
+    """Make the current stream wait for the auxiliary streams (weight gradients, branches): call before reading gradients from a
+    stream-ordered consumer outside autograd's own end-of-backward join (the optimiser and the all-reduce do)."""
+    if _DIRTY: _join_all()
+
+
+def _queue_join() -> bool:
+    """Ask the autograd engine to join the auxiliary streams into the caller's stream when the running backward pass ends."""
+    if _JOIN_QUEUED[0]: return True
+    try: torch.autograd.Variable._execution_engine.queue_callback(_join_all)
+    except RuntimeError: return False   # not inside a backward pass
+    _JOIN_QUEUED[0] = True
+    return True
 
 
 class _side_stream:
-    """`with _side_stream(t1, t2, ...):` — enqueue the enclosed libstv calls on the weight-gradient stream (no-op when disabled or
-    outside a backward pass). t_i: tensors the enclosed kernels read or write."""
+    """`with _side_stream(t1, t2, ...):` — enqueue the enclosed libstv calls on the weight-gradient stream of the current stream
+    (no-op when disabled or outside a backward pass). t_i: tensors the enclosed kernels read or write."""
     def __init__(self, *tensors): self.tensors, self.cm = tensors, None
 
     def __enter__(self):
         if not WGRAD_STREAM or not GRAD_SINK: return self
         t0 = next((t for t in self.tensors if t is not None), None)
-        if t0 is None or not t0.is_cuda: return self
+        if t0 is None or not t0.is_cuda or not _queue_join(): return self
         dev = t0.device.index
         cur = torch.cuda.current_stream(dev)
-        side = _SIDE_STREAMS.get(dev)
-        if side is None: side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
-        if not _SIDE_PENDING.get(dev, False):
-            try: torch.autograd.Variable._execution_engine.queue_callback(lambda dev=dev, cur=cur: _join_on(dev, cur))
-            except RuntimeError: return self   # not inside a backward pass: stay on the current stream
-            _SIDE_PENDING[dev] = True
+        key = (dev, cur.cuda_stream)
+        side = _SIDE_STREAMS.get(key)
+        if side is None: side = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
         for t in self.tensors:
             if t is not None: t.record_stream(side)
+        _DIRTY.add(side)
         self.cm = torch.cuda.stream(side)
         self.cm.__enter__()
         return self
@@ -123,8 +145,44 @@ class _side_stream:
         return False
 
 
-def _join_on(dev: int, stream) -> None:
-    if _SIDE_PENDING.pop(dev, False): stream.wait_stream(_SIDE_STREAMS[dev])
+class branch_stream:
+    """`with branch_stream('pose', inputs) as br: ...; br.outputs(tensors)` — run an independent branch of the forward pass on its
+    own stream, forked from the current one; `join()` (called by the user after the concurrent work has been enqueued) makes the
+    current stream wait for it. Backward replays the branch on the same stream; its tail is joined when backward ends."""
+    def __init__(self, name: str, inputs=()):
+        self.name, self.inputs, self.cm, self.st, self.cur = name, [t for t in inputs if torch.is_tensor(t) and t.is_cuda], None, None, None
+
+    def __enter__(self):
+        if not BRANCH_STREAMS or not self.inputs: return self
+        dev = self.inputs[0].device.index
+        self.cur = torch.cuda.current_stream(dev)
+        key = (dev, self.name)
+        st = _BRANCH_STREAMS.get(key)
+        if st is None: st = _BRANCH_STREAMS[key] = torch.cuda.Stream(device=dev)
+        st.wait_stream(self.cur)
+        for t in self.inputs: t.record_stream(st)
+        self.st = st
+        self.cm = torch.cuda.stream(st)
+        self.cm.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.cm is not None: self.cm.__exit__(*a)
+        return False
+
+    def join(self, outputs=()) -> None:
+        """The forking stream waits for the branch; `outputs` (tensors produced on the branch, consumed on the forking stream) are
+        recorded there, and the first one that takes part in autograd arms the end-of-backward join of the branch stream."""
+        if self.st is None: return
+        self.cur.wait_stream(self.st)
+        armed = False
+        for t in outputs:
+            if not (torch.is_tensor(t) and t.is_cuda): continue
+            t.record_stream(self.cur)
+            if t.requires_grad and not armed:
+                st = self.st
+                t.register_hook(lambda g, st=st: (_DIRTY.add(st), _queue_join(), g)[2])
+                armed = True
 
 
 def _f32c(t: Tensor | None) -> Tensor | None:

@@ -66,20 +66,26 @@ class MonoDepthStep(nn.Module):
     def forward(self, x: dict) -> dict:
         fwd = {}
         idxs = [int(i) for i in x['supp_idxs']]  # host ints: no device sync
-        fwd |= self.nets['depth'](x['imgs'])
+        # The pose network is independent of the depth network: it runs on its own stream, forward and backward, beside it
+        # (functional.branch_stream); everything it produces is joined before the loss reads it.
+        br = None
         if 'pose' in self.nets:
             inv = lambda i: self.always_fwd_pose and i < 0
-            pairs = torch.stack([torch.cat([s, x['imgs']] if inv(i) else [x['imgs'], s], dim=1)
-                                 for i, s in zip(idxs, x['supp_imgs']) if i != 0])  # (n, b, 6, h, w)
-            sh = pairs.shape[:2]
-            out = self.nets['pose'](pairs.flatten(0, 1))
-            Ts = G.T_from_AAt(aa=out['R'][:, 0], t=out['t'][:, 0]).unflatten(0, sh)
-            for i, T in zip([i for i in idxs if i != 0], Ts):
-                fwd[f'T_{i}'] = F_.inv4x4(T) if inv(i) else T
-            if 'fs' in out:
-                fwd['fs'], fwd['cs'] = out['fs'].unflatten(0, sh), out['cs'].unflatten(0, sh)
-                K = PoseNet.build_K(out['fs'], out['cs']).unflatten(0, sh)[0]  # first support frame only (trainer.py:259)
-                fwd['K'] = G.resize_K(K, x['imgs'].shape[-2:])
+            with F_.branch_stream('pose', [x['imgs'], x['supp_imgs']]) as br:
+                pairs = torch.stack([torch.cat([s, x['imgs']] if inv(i) else [x['imgs'], s], dim=1)
+                                     for i, s in zip(idxs, x['supp_imgs']) if i != 0])  # (n, b, 6, h, w)
+                sh = pairs.shape[:2]
+                out = self.nets['pose'](pairs.flatten(0, 1))
+                Ts = G.T_from_AAt(aa=out['R'][:, 0], t=out['t'][:, 0]).unflatten(0, sh)
+                for i, T in zip([i for i in idxs if i != 0], Ts):
+                    fwd[f'T_{i}'] = F_.inv4x4(T) if inv(i) else T
+                if 'fs' in out:
+                    fwd['fs'], fwd['cs'] = out['fs'].unflatten(0, sh), out['cs'].unflatten(0, sh)
+                    K = PoseNet.build_K(out['fs'], out['cs']).unflatten(0, sh)[0]  # first support frame only (trainer.py:259)
+                    fwd['K'] = G.resize_K(K, x['imgs'].shape[-2:])
+            pose_out = [v for v in fwd.values() if torch.is_tensor(v)]
+        fwd |= self.nets['depth'](x['imgs'])
+        if br is not None: br.join(pose_out)
         fwd['_idxs'] = idxs
         hook = getattr(self, 'bucket_hook', None)
         if hook is not None and torch.is_grad_enabled(): register_bucket_hooks(self.nets, hook)
