@@ -437,6 +437,7 @@ static int fprop_tma(const stv_conv_geom* g, int P, int Q, const float* x, const
     CUtensorMap tmA, tmB;
     if (int rc = make_tmap_im2col(&tmA, x, g->N, g->H, g->W, g->C1, -g->pad, -g->pad, g->pad - (g->S - 1), g->pad - (g->R - 1), g->stride, GEMM_BM, 0)) return rc;
     if (int rc = make_tmap_2d(&tmB, w, g->Cout, Ktot, Ktot, p.bn, 0)) return rc;
+    p.pair_B = w; p.pair_ldb = Ktot;   // the CTA-pair kernel re-encodes the filters with half-tile boxes
     return launch_gemm(tmA, tmB, p, 1, st, "stv_conv_fprop(tma)");
 }
 
@@ -456,6 +457,7 @@ static int dgrad_tma(const stv_conv_geom* g, int P, int Q, const float* dy, cons
     CUtensorMap tmA, tmB;
     if (int rc = make_tmap_im2col(&tmA, dy, g->N, P, Q, g->Cout, cv.lw, cv.lh, cv.lw + (g->W - Q), cv.lh + (g->H - P), 1, GEMM_BM, 0)) return rc;
     if (int rc = make_tmap_2d(&tmB, w, g->Cout, (long long)g->R*g->S*Cin, (long long)g->R*g->S*Cin, 32, 1)) return rc;
+    p.pair_B = w;   // MN-major filters: the 32-column slab boxes serve the CTA-pair kernel as they are
     return launch_gemm(tmA, tmB, p, 1, st, "stv_conv_dgrad(tma)");
 }
 
@@ -488,6 +490,7 @@ static int dgrad_tma_strided(const stv_conv_geom* g, int P, int Q, const float* 
             if (epi) p.e = *epi;
             CUtensorMap tmA;
             if (int rc = make_tmap_im2col(&tmA, dy, g->N, P, Q, g->Cout, cv.lw, cv.lh, cv.lw + (Ws - Q), cv.lh + (Hs - P), 1, GEMM_BM, 0)) return rc;
+            p.pair_B = w;
             if (int rc = launch_gemm(tmA, tmB, p, 1, st, "stv_conv_dgrad(tma, strided)")) return rc;
         }
     return STV_OK;

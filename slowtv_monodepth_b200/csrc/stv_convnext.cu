@@ -50,6 +50,13 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_kernel(int H, int W, int C, int
     for (int sl = 0; sl < 7; ++sl)
 #pragma unroll
         for (int j = 0; j < DW_L; ++j) acc[sl][j] = b;
+    // The residual (`res`, the data-gradient variant) is folded into the accumulator's initial value: it is requested when the
+    // row's slot is recycled, one input row before the row's first product, instead of as a dependent load at the store.
+    if (res != nullptr) {
+        const size_t rowoff = img + (size_t)y0*W*C + c;
+#pragma unroll
+        for (int j = 0; j < DW_L; ++j) if (coff[j + 3] >= 0) acc[0][j] = b + __ldg(res + rowoff + coff[j + 3]);
+    }
     // input row i (image row y0 - 3 + i) feeds output rows o = i - ky (ky = 0..6), kept in slot o mod 7
     for (int g = 0; g*7 < nrows + 6; ++g) {
 #pragma unroll
@@ -76,15 +83,19 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_kernel(int H, int W, int C, int
             if (o >= 0 && o < nrows) {
                 const size_t rowoff = img + (size_t)(y0 + o)*W*C + c;
 #pragma unroll
-                for (int j = 0; j < DW_L; ++j) {
-                    if (coff[j + 3] >= 0) {
-                        const float r = acc[(jr + 1) % 7][j];
-                        y[rowoff + coff[j + 3]] = res ? r + __ldg(res + rowoff + coff[j + 3]) : r;
-                    }
-                }
+                for (int j = 0; j < DW_L; ++j)
+                    if (coff[j + 3] >= 0) y[rowoff + coff[j + 3]] = acc[(jr + 1) % 7][j];
             }
+            // the slot of row o is reused by row o + 7 = i + 1
+            const int on = i + 1;
+            if (res != nullptr && on < nrows) {
+                const size_t rowoff = img + (size_t)(y0 + on)*W*C + c;
 #pragma unroll
-            for (int j = 0; j < DW_L; ++j) acc[(jr + 1) % 7][j] = b;  // slot of row o is reused by row o + 7
+                for (int j = 0; j < DW_L; ++j) acc[(jr + 1) % 7][j] = coff[j + 3] >= 0 ? b + __ldg(res + rowoff + coff[j + 3]) : b;
+            } else {
+#pragma unroll
+                for (int j = 0; j < DW_L; ++j) acc[(jr + 1) % 7][j] = b;
+            }
         }
     }
 }

@@ -425,12 +425,22 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (threadIdx.x == 0) STV_TRACE(1);
 
     if (warp == 0) {
-        const int nslab = half_bn >> 5;
+        const ConvOperand& cv = p.cv;
+        const int mode = cv.mode, nslab = half_bn >> 5;
         int s = 0;
         uint32_t ph = 0;
         for (int t = pair; t < total; t += npairs) {
             const int n0 = (t % nt)*p.bn + (int)rank*half_bn, m0 = ((t/nt) % mt)*2*GEMM_BM + (int)rank*GEMM_BM, z = t/(nt*mt);
             const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            int bn_ = 0, bw = 0, bh = 0, r = 0, sx = 0, cb = 0;   // mode 1 (A = im2col rows): this CTA's tile origin, current tap and channel block
+            if (mode == 1) {
+                const int hw = cv.gridH*cv.gridW;
+                bn_ = m0/hw;
+                const int rem = m0 - bn_*hw, qy = rem/cv.gridW, qx = rem - qy*cv.gridW;
+                bw = cv.lw + qx*cv.stride; bh = cv.lh + qy*cv.stride;
+                const int tap = kb0/cv.cblocks;
+                cb = kb0 - tap*cv.cblocks; r = tap/cv.S; sx = tap - r*cv.S;
+            }
             for (int kb = kb0; kb < kb1; ++kb) {
                 tc::mbar_wait_spin_s(empty0 + 8*s, ph ^ 1u);
                 if (lane == 0) { STV_TRACE_KB(16, trace_i); ++trace_i; }
@@ -438,15 +448,26 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     const uint32_t fb = full0 + 8*s, a = ring + (uint32_t)(s*stage_bytes), b = a + GEMM_A_BYTES;
                     if (rank == 0) tc::mbar_arrive_expect_tx_s(fb, 2u*(uint32_t)stage_bytes);
                     const int k = kb*GEMM_BK;
-                    if (!p.a_mn) tc::tma_load_2d_2sm_s(a, &tmA, fb, k, m0);
-                    else {
+                    if (mode == 1) {
+                        tc::tma_load_im2col_4d_2sm_s(a, &tmA, fb, cb*GEMM_BK, bw, bh, bn_, (uint16_t)(cv.flip ? cv.S - 1 - sx : sx),
+                                                     (uint16_t)(cv.flip ? cv.R - 1 - r : r));
+                        if (!p.b_mn) tc::tma_load_2d_2sm_s(b, &tmB, fb, k, n0);
+                        else {
+                            const int col = ((cv.r0 + cv.tstep*r)*cv.Sfull + cv.s0 + cv.tstep*sx)*cv.b_tap_cols + n0;
+                            for (int j = 0; j < nslab; ++j) tc::tma_load_2d_2sm_s(b + j*SLAB_MN_BYTES, &tmB, fb, col + 32*j, cb*GEMM_BK);
+                        }
+                    } else {
+                        if (!p.a_mn) tc::tma_load_2d_2sm_s(a, &tmA, fb, k, m0);
+                        else {
 #pragma unroll
-                        for (int j = 0; j < GEMM_BM/32; ++j) tc::tma_load_2d_2sm_s(a + j*SLAB_MN_BYTES, &tmA, fb, m0 + 32*j, k);
+                            for (int j = 0; j < GEMM_BM/32; ++j) tc::tma_load_2d_2sm_s(a + j*SLAB_MN_BYTES, &tmA, fb, m0 + 32*j, k);
+                        }
+                        if (!p.b_mn) tc::tma_load_2d_2sm_s(b, &tmB, fb, k, n0);
+                        else
+                            for (int j = 0; j < nslab; ++j) tc::tma_load_2d_2sm_s(b + j*SLAB_MN_BYTES, &tmB, fb, n0 + 32*j, k);
                     }
-                    if (!p.b_mn) tc::tma_load_2d_2sm_s(b, &tmB, fb, k, n0);
-                    else
-                        for (int j = 0; j < nslab; ++j) tc::tma_load_2d_2sm_s(b + j*SLAB_MN_BYTES, &tmB, fb, n0 + 32*j, k);
                 }
+                if (mode == 1) { if (++cb == cv.cblocks) { cb = 0; if (++sx == cv.S) { sx = 0; ++r; } } }
                 if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
@@ -637,12 +658,13 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
     });
     if (attr_err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute failed (%s)", what, cudaGetErrorString(attr_err)); return STV_E_CUDA; }
     const long long total = (long long)nt*mt*splits;
-    // CTA pairs (cta_group::2): plain matrices whose 256 x bn2 pair tiles keep most of the 74 SM pairs busy. bn2 = the multiple of 64
+    // CTA pairs (cta_group::2): plain matrices and im2col-A convolutions (forward / data gradient) whose 256 x bn2 pair tiles keep most of the 74 SM pairs busy. bn2 = the multiple of 64
     // (<= 256) that wastes the fewest columns (ties -> wider): each CTA's half of the B tile is whole 32-column slabs.
     static const int pair_mode = getenv("STV_GEMM_PAIR") ? atoi(getenv("STV_GEMM_PAIR")) : 1;   // developer switch: 0 off, 1 heuristic, 2 whenever legal
-    if (pair_mode && p.cv.mode == 0 && p.remap == 0 && p.pair_B != nullptr && p.M > GEMM_BM && p.N >= 64) {
+    static const int pair_conv = getenv("STV_GEMM_PAIR_CONV") ? atoi(getenv("STV_GEMM_PAIR_CONV")) : 0;   // im2col-A pairs: measured slower on the step
+    if (pair_mode && (p.cv.mode == 0 || (p.cv.mode == 1 && (pair_conv || pair_mode == 2))) && p.pair_B != nullptr && p.M > GEMM_BM && p.N >= 64) {
         int bn2 = 128, best_cost = 1 << 30;
-        for (int bn = 256; bn >= 128; bn -= 64) {
+        for (int bn = 256; bn >= 64; bn -= 64) {
             const int cost = ((p.N + bn - 1)/bn)*bn;
             if (cost < best_cost) { bn2 = bn; best_cost = cost; }
         }

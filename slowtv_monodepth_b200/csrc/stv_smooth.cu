@@ -117,14 +117,20 @@ __global__ void __launch_bounds__(SM_NT) smooth_fwd_kernel(SmoothParams p) {
 }
 
 __global__ void smooth_finalize_kernel(SmoothParams p, float* __restrict__ loss) {
-    // One thread per (s, i) computes the stats; thread 0 then combines (tiny: S*b <= a few hundred).
-    for (int e = threadIdx.x; e < p.S*p.b; e += blockDim.x) {
+    // One WARP per (s, i) sums that image's block partials (lanes stride over them, fixed-order shuffle tree in double: the result
+    // does not depend on the launch) and computes the stats; thread 0 then combines (tiny: S*b <= a few hundred).
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int e = wid; e < p.S*p.b; e += nw) {
         const int s = e/p.b;
         const int nb = p.blk_off[s + 1] - p.blk_off[s];
         double a = 0.0;
-        for (int q = 0; q < nb; ++q) a += (double)p.loss_part[(size_t)e*p.max_blk + q];
-        p.stats[e*2 + 0] = mean_from_parts(p.sum_part + (size_t)e*NCHUNK, p.h[s]*p.w[s]);
-        p.stats[e*2 + 1] = (float)a;
+        for (int q = lane; q < nb; q += 32) a += (double)p.loss_part[(size_t)e*p.max_blk + q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) {
+            p.stats[e*2 + 0] = mean_from_parts(p.sum_part + (size_t)e*NCHUNK, p.h[s]*p.w[s]);
+            p.stats[e*2 + 1] = (float)a;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -265,7 +271,7 @@ extern "C" int stv_smooth_fwd(const stv_smooth_cfg* c, const float* const* disp,
     smooth_fwd_kernel<<<dim3(p.blk_off[c->S], c->b), SM_NT, 0, st>>>(p);
     count_launch();
     if (int rc = check_launch("smooth_fwd_kernel")) return rc;
-    smooth_finalize_kernel<<<1, 128, 0, st>>>(p, loss);
+    smooth_finalize_kernel<<<1, 1024, 0, st>>>(p, loss);
     count_launch();
     return check_launch("smooth_finalize_kernel");
 }

@@ -307,6 +307,12 @@ __device__ __forceinline__ void tma_load_2d_2sm_s(uint32_t dst, const CUtensorMa
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(m), "r"(bar & 0xFEFFFFFFu), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void tma_load_im2col_4d_2sm_s(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h, int n,
+                                                         uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(dst), "l"(m), "r"(bar & 0xFEFFFFFFu), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
 __device__ __forceinline__ void umma_commit_2sm_s(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"((uint16_t)0b11) : "memory");

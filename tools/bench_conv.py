@@ -10,6 +10,7 @@ from slowtv_monodepth_b200 import functional as F_
 ap = argparse.ArgumentParser(); ap.add_argument('--b', type=int, default=8); ap.add_argument('--only', default=''); a = ap.parse_args()
 torch.backends.cudnn.benchmark = True; torch.backends.cudnn.allow_tf32 = True
 dev = 'cuda'
+torch.cuda.set_stream(torch.cuda.Stream())
 #         name            H    W    C1   C2  up1   Cout R st pad reflect
 SHAPES = [('upconv_4_0', 12, 20, 768, 0, False, 256, 3, 1, 1, True),
           ('upconv_4_1', 24, 40, 256, 384, True, 256, 3, 1, 1, True),
@@ -32,10 +33,11 @@ def timeit(fn, n=10):
     """GPU time per call: n calls captured in ONE CUDA graph and replayed, so that the host's launch path (ctypes + tensor-map
     encoding, ~20-30 us per call — longer than most of these kernels) is not in the measurement. Operands are re-used by the n
     calls, i.e. L2-warm where they fit: the in-step numbers (tools/step_profile.py) are the cold-cache counterpart."""
-    for _ in range(3): fn()
+    st = torch.cuda.current_stream()   # the script runs on ONE non-default stream (set below): tensors, warm-up and capture alike —
+    for _ in range(3): fn()            # autograd's AccumulateGrad nodes stay bound to the stream their tensor was created on
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    with torch.cuda.graph(g, stream=st):
         for _ in range(n): fn()
     g.replay(); torch.cuda.synchronize()
     best = float('inf')

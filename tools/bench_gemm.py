@@ -9,16 +9,18 @@ from slowtv_monodepth_b200 import functional as F_
 ap = argparse.ArgumentParser(); ap.add_argument('--b', type=int, default=8); ap.add_argument('--only', default=''); ap.add_argument('--once', action='store_true', help='run every case once, ours only (ncu captures)'); a = ap.parse_args()
 torch.backends.cuda.matmul.allow_tf32 = True
 dev = 'cuda'
+torch.cuda.set_stream(torch.cuda.Stream())
 
 
 def timeit(fn, n=10):
     """GPU time per call: n calls captured in ONE CUDA graph and replayed, so that the host's launch path (ctypes + tensor-map
     encoding, ~20-30 us per call — longer than most of these kernels) is not in the measurement. Operands are re-used by the n
     calls, i.e. L2-warm where they fit: the in-step numbers (tools/step_profile.py) are the cold-cache counterpart."""
-    for _ in range(3): fn()
+    st = torch.cuda.current_stream()   # the script runs on ONE non-default stream (set below): tensors, warm-up and capture alike —
+    for _ in range(3): fn()            # autograd's AccumulateGrad nodes stay bound to the stream their tensor was created on
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    with torch.cuda.graph(g, stream=st):
         for _ in range(n): fn()
     g.replay(); torch.cuda.synchronize()
     best = float('inf')
