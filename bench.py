@@ -473,7 +473,19 @@ def main() -> None:
             r = cpu_reference(c, steps=5, warmup=2, budget_s=60.0)
             line['cpu_baseline'] = {'value': round(r['value'], 4), 'unit': 'images/s', 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']}
         print(json.dumps(line), file=out, flush=True)
-    if world > 1: dist.destroy_process_group()
+    if world > 1:
+        # The step graph holds captured NCCL collectives: release it before the communicator goes away, and never let a
+        # shutdown problem hang the job after the result line is out (bounded wait, then a hard exit on every rank).
+        import gc
+        sync_all()
+        graphed = train_step = None
+        gc.collect()
+        torch.cuda.synchronize()
+        th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        th.start()
+        th.join(20.0)
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':
