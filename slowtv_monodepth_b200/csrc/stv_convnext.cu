@@ -24,38 +24,38 @@ constexpr int DW_CB = 128;  // channels (= threads) per block; blockIdx.x = x_ti
 // 7 output rows it contributes to, held in a 7-slot ring of register accumulators; when the last contributing input row of
 // an output row has been consumed the row is written out. Global loads per output drop from 12.25 (7 input rows re-read per
 // output row) to (DW_L+6)/DW_L * (rows+6)/rows ~ 2.4; the slot indices are compile-time constants (rows processed in groups of 7).
-template <bool FLIP>
+template <bool FLIP, int L>
 __global__ void __launch_bounds__(DW_CB) dwconv7_kernel(int H, int W, int C, int ncb, int rows, const float* __restrict__ x,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         const float* __restrict__ res, float* __restrict__ y) {
     const int c = (blockIdx.x % ncb)*DW_CB + threadIdx.x;
     if (c >= C) return;
-    const int x0 = (blockIdx.x/ncb)*DW_L, y0 = blockIdx.y*rows, n = blockIdx.z;
+    const int x0 = (blockIdx.x/ncb)*L, y0 = blockIdx.y*rows, n = blockIdx.z;
     const int nrows = min(rows, H - y0);  // output rows of this block
     float wr[49];
 #pragma unroll
     for (int t = 0; t < 49; ++t) wr[t] = __ldg(w + (size_t)c*49 + (FLIP ? 48 - t : t));
     const float b = bias ? __ldg(bias + c) : 0.f;
     const size_t img = (size_t)n*H*W*C;
-    // Column offsets (in elements, relative to the start of an image row of this channel) of the DW_L + 6 input columns,
+    // Column offsets (in elements, relative to the start of an image row of this channel) of the L + 6 input columns,
     // computed once: -1 marks a column outside the image. Every load / store below is then base + 32-bit offset.
-    int coff[DW_L + 6];
+    int coff[L + 6];
 #pragma unroll
-    for (int q = 0; q < DW_L + 6; ++q) {
+    for (int q = 0; q < L + 6; ++q) {
         const int xx = x0 + q - 3;
         coff[q] = (xx >= 0 && xx < W) ? xx*C : -1;
     }
-    float acc[7][DW_L];
+    float acc[7][L];
 #pragma unroll
     for (int sl = 0; sl < 7; ++sl)
 #pragma unroll
-        for (int j = 0; j < DW_L; ++j) acc[sl][j] = b;
+        for (int j = 0; j < L; ++j) acc[sl][j] = b;
     // The residual (`res`, the data-gradient variant) is folded into the accumulator's initial value: it is requested when the
     // row's slot is recycled, one input row before the row's first product, instead of as a dependent load at the store.
     if (res != nullptr) {
         const size_t rowoff = img + (size_t)y0*W*C + c;
 #pragma unroll
-        for (int j = 0; j < DW_L; ++j) if (coff[j + 3] >= 0) acc[0][j] = b + __ldg(res + rowoff + coff[j + 3]);
+        for (int j = 0; j < L; ++j) if (coff[j + 3] >= 0) acc[0][j] = b + __ldg(res + rowoff + coff[j + 3]);
     }
     // input row i (image row y0 - 3 + i) feeds output rows o = i - ky (ky = 0..6), kept in slot o mod 7
     for (int g = 0; g*7 < nrows + 6; ++g) {
@@ -66,9 +66,9 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_kernel(int H, int W, int C, int
             const int yin = y0 - 3 + i;
             if (yin >= 0 && yin < H) {
                 const float* row = x + img + (size_t)yin*W*C + c;
-                float v[DW_L + 6];
+                float v[L + 6];
 #pragma unroll
-                for (int q = 0; q < DW_L + 6; ++q) v[q] = coff[q] >= 0 ? __ldg(row + coff[q]) : 0.f;
+                for (int q = 0; q < L + 6; ++q) v[q] = coff[q] >= 0 ? __ldg(row + coff[q]) : 0.f;
 #pragma unroll
                 for (int ky = 0; ky < 7; ++ky) {
                     const int o = i - ky;
@@ -76,14 +76,14 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_kernel(int H, int W, int C, int
 #pragma unroll
                     for (int kx = 0; kx < 7; ++kx)
 #pragma unroll
-                        for (int j = 0; j < DW_L; ++j) acc[(jr - ky + 7) % 7][j] = fmaf(wr[ky*7 + kx], v[j + kx], acc[(jr - ky + 7) % 7][j]);
+                        for (int j = 0; j < L; ++j) acc[(jr - ky + 7) % 7][j] = fmaf(wr[ky*7 + kx], v[j + kx], acc[(jr - ky + 7) % 7][j]);
                 }
             }
             const int o = i - 6;  // complete: its last input row (ky = 6) was row i
             if (o >= 0 && o < nrows) {
                 const size_t rowoff = img + (size_t)(y0 + o)*W*C + c;
 #pragma unroll
-                for (int j = 0; j < DW_L; ++j)
+                for (int j = 0; j < L; ++j)
                     if (coff[j + 3] >= 0) y[rowoff + coff[j + 3]] = acc[(jr + 1) % 7][j];
             }
             // the slot of row o is reused by row o + 7 = i + 1
@@ -91,10 +91,10 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_kernel(int H, int W, int C, int
             if (res != nullptr && on < nrows) {
                 const size_t rowoff = img + (size_t)(y0 + on)*W*C + c;
 #pragma unroll
-                for (int j = 0; j < DW_L; ++j) acc[(jr + 1) % 7][j] = coff[j + 3] >= 0 ? b + __ldg(res + rowoff + coff[j + 3]) : b;
+                for (int j = 0; j < L; ++j) acc[(jr + 1) % 7][j] = coff[j + 3] >= 0 ? b + __ldg(res + rowoff + coff[j + 3]) : b;
             } else {
 #pragma unroll
-                for (int j = 0; j < DW_L; ++j) acc[(jr + 1) % 7][j] = b;
+                for (int j = 0; j < L; ++j) acc[(jr + 1) % 7][j] = b;
             }
         }
     }
@@ -331,12 +331,17 @@ static int round32(int c) { return (c + 31)/32*32; }
 
 // Rows per block of the strip kernels: tall strips amortise the 6-row halo; shrink them while the grid is smaller than ~6 blocks
 // per SM (blocks are only 3-4 warps).
-static int dw_rows(int N, int H, int W, int C) {
+// Columns per thread (8, or 4 for the small deep-stage maps, where 8 leaves the 148 SMs with a few hundred blocks of latency-bound
+// threads) and rows per block: tall strips amortise the 6 warm-up rows; enough blocks for ~6 per SM.
+static void dw_shape(int N, int H, int W, int C, int& L, int& rows) {
     const int ncb = (C + DW_CB - 1)/DW_CB;
-    const long long cols = (long long)((W + DW_L - 1)/DW_L)*ncb*N;
-    int rows = 32;
-    while (rows > 8 && cols*((H + rows - 1)/rows) < 6*148) rows >>= 1;
-    return rows;
+    auto blocks = [&](int l, int r) { return (long long)((W + l - 1)/l)*ncb*N*((H + r - 1)/r); };
+    L = DW_L; rows = 32;
+    while (rows > 8 && blocks(L, rows) < 6*148) rows >>= 1;
+    if (blocks(L, rows) < 4*148) {
+        L = 4;
+        while (rows > 4 && blocks(L, rows) < 6*148) rows >>= 1;
+    }
 }
 
 extern "C" int stv_dwconv7_fwd(int N, int H, int W, int C, const float* x, const float* w, const float* bias, const float* res,
@@ -345,10 +350,17 @@ extern "C" int stv_dwconv7_fwd(int N, int H, int W, int C, const float* x, const
     STV_REQUIRE(N <= 65535, "stv_dwconv7_fwd: grid too large");
     STV_REQUIRE(x && w && y, "stv_dwconv7_fwd: NULL pointer");
     const int ncb = (C + DW_CB - 1)/DW_CB, nt = C < DW_CB ? round32(C) : DW_CB;
-    const int rows = dw_rows(N, H, W, C);
-    dim3 grid(((W + DW_L - 1)/DW_L)*ncb, (H + rows - 1)/rows, N);
-    if (flip) dwconv7_kernel<true><<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, rows, x, w, bias, res, y);
-    else dwconv7_kernel<false><<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, rows, x, w, bias, res, y);
+    int L, rows;
+    dw_shape(N, H, W, C, L, rows);
+    dim3 grid(((W + L - 1)/L)*ncb, (H + rows - 1)/rows, N);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (L == 8) {
+        if (flip) dwconv7_kernel<true, 8><<<grid, nt, 0, st>>>(H, W, C, ncb, rows, x, w, bias, res, y);
+        else dwconv7_kernel<false, 8><<<grid, nt, 0, st>>>(H, W, C, ncb, rows, x, w, bias, res, y);
+    } else {
+        if (flip) dwconv7_kernel<true, 4><<<grid, nt, 0, st>>>(H, W, C, ncb, rows, x, w, bias, res, y);
+        else dwconv7_kernel<false, 4><<<grid, nt, 0, st>>>(H, W, C, ncb, rows, x, w, bias, res, y);
+    }
     count_launch();
     return check_launch("dwconv7_kernel");
 }

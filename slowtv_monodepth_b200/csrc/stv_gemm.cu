@@ -233,13 +233,14 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const int stages = p.stages;
     if (warp == 0) {
         const ConvOperand& cv = p.cv;
-        const int mode = cv.mode, nslab = p.bn >> 5;
+        const int mode = cv.mode, nslab = p.bn >> 5, pf = p.pf;
         int s = 0;
         uint32_t ph = 0;   // ring slot and its phase carry over from tile to tile
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int n0 = (t % nt)*p.bn, m0 = ((t/nt) % mt)*GEMM_BM, z = t/(nt*mt);
             const int kb0 = z*p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
             int bn_ = 0, bw = 0, bh = 0, r = 0, sx = 0, cb = 0;   // mode 1: tile origin, current tap and channel block
+            int pr = 0, psx = 0, pcb = 0;                         // mode 1: the same counters `pf` k-blocks ahead (L2 prefetch)
             int pn = 0, py = 0, px = 0;                           // mode 2: grid pixel of the k-block's first row
             int slab_c[8], slab_rs[8];
             if (mode == 1) {
@@ -249,6 +250,8 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                 bw = cv.lw + qx*cv.stride; bh = cv.lh + qy*cv.stride;
                 const int tap = kb0/cv.cblocks;
                 cb = kb0 - tap*cv.cblocks; r = tap/cv.S; sx = tap - r*cv.S;
+                const int ptap = (kb0 + pf)/cv.cblocks;
+                pcb = kb0 + pf - ptap*cv.cblocks; pr = ptap/cv.S; psx = ptap - pr*cv.S;
             } else if (mode == 2) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -295,8 +298,25 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                         else
                             for (int j = 0; j < nslab; ++j) tc::tma_load_2d_s(b + j*SLAB_MN_BYTES, &tmB, fb, n0 + 32*j, k);
                     }
+                    // L2 prefetch of the STREAMED operand(s) `pf` k-blocks ahead (activations / gradients come from HBM; filters and
+                    // weights are L2-resident and are not prefetched)
+                    if (pf > 0 && kb + pf < kb1) {
+                        const int kp = (kb + pf)*GEMM_BK;
+                        if (mode == 1) tc::tma_prefetch_im2col_4d(&tmA, pcb*GEMM_BK, bw, bh, bn_, (uint16_t)(cv.flip ? cv.S - 1 - psx : psx),
+                                                                  (uint16_t)(cv.flip ? cv.R - 1 - pr : pr));
+                        else if (!p.a_mn) tc::tma_prefetch_2d(&tmA, kp, m0);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < GEMM_BM/32; ++j) tc::tma_prefetch_2d(&tmA, m0 + 32*j, kp);
+                            if (mode == 0 && p.b_mn)
+                                for (int j = 0; j < nslab; ++j) tc::tma_prefetch_2d(&tmB, n0 + 32*j, kp);
+                        }
+                    }
                 }
-                if (mode == 1) { if (++cb == cv.cblocks) { cb = 0; if (++sx == cv.S) { sx = 0; ++r; } } }
+                if (mode == 1) {
+                    if (++cb == cv.cblocks) { cb = 0; if (++sx == cv.S) { sx = 0; ++r; } }
+                    if (++pcb == cv.cblocks) { pcb = 0; if (++psx == cv.S) { psx = 0; ++pr; } }
+                }
                 else if (mode == 2) {
                     px += GEMM_BK;
                     while (px >= cv.gridW) { px -= cv.gridW; if (++py == cv.gridH) { py = 0; ++pn; } }
@@ -716,6 +736,8 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
         stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
         stages = stages < 2 ? 2 : stages;
         p.stages = stages;
+        static const int pf_cfg = getenv("STV_GEMM_PF") ? atoi(getenv("STV_GEMM_PF")) : 4;   // developer switch: L2 prefetch distance (0 = off)
+        p.pf = pf_cfg;
         const size_t smem = (size_t)stages*stage_bytes + staging + 1024 /*alignment slack*/ + (2*GEMM_MAX_STAGES + 4)*8 + 16;
         const int resident = per_sm*sm_count();
         const int grid = (int)(total < resident ? total : resident);

@@ -27,6 +27,7 @@ struct ConvOperand {
 struct GemmParams {
     int M, N, K;
     int bn, stages, a_mn, b_mn;
+    int pf;                          // L2 prefetch distance in k-blocks (0 = off), set by launch_gemm
     int kb_total, kb_per_split, splits;
     float* C;
     long long ldc;

@@ -259,6 +259,15 @@ __device__ __forceinline__ void tma_load_im2col_4d_s(uint32_t dst, const CUtenso
         "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
         ::"r"(dst), "l"(m), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
 }
+// L2 prefetch of a box a few k-blocks ahead of its load: the load then finds its lines in L2 (the 2-CTA/SM kernel has room for a
+// 2-3 stage ring only, so its k-block period is the load latency over the ring depth — profiles/r2_gemm_timeline.txt).
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(m), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_im2col_4d(const CUtensorMap* m, int c, int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.im2col [%0, {%1, %2, %3, %4}], {%5, %6};"
+                 ::"l"(m), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
 __device__ __forceinline__ void umma_commit_s(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
