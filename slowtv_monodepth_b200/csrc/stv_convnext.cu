@@ -331,17 +331,15 @@ static int round32(int c) { return (c + 31)/32*32; }
 
 // Rows per block of the strip kernels: tall strips amortise the 6-row halo; shrink them while the grid is smaller than ~6 blocks
 // per SM (blocks are only 3-4 warps).
-// Columns per thread (8, or 4 for the small deep-stage maps, where 8 leaves the 148 SMs with a few hundred blocks of latency-bound
-// threads) and rows per block: tall strips amortise the 6 warm-up rows; enough blocks for ~6 per SM.
-static void dw_shape(int N, int H, int W, int C, int& L, int& rows) {
+// Rows per block: tall strips amortise the 6 warm-up rows; enough blocks for ~6 per SM. (Measured and rejected, gpurun_out/r2w:
+// 4 instead of 8 columns per thread for the small deep-stage maps — four times the blocks, but 0.39 vs 0.26 ms for the twelve
+// stage-2/3 data gradients: the halo loads per output grow from 1.75x to 2.5x and the 49 weights are re-read by twice the threads.)
+static int dw_rows(int N, int H, int W, int C) {
     const int ncb = (C + DW_CB - 1)/DW_CB;
-    auto blocks = [&](int l, int r) { return (long long)((W + l - 1)/l)*ncb*N*((H + r - 1)/r); };
-    L = DW_L; rows = 32;
-    while (rows > 8 && blocks(L, rows) < 6*148) rows >>= 1;
-    if (blocks(L, rows) < 4*148) {
-        L = 4;
-        while (rows > 4 && blocks(L, rows) < 6*148) rows >>= 1;
-    }
+    const long long cols = (long long)((W + DW_L - 1)/DW_L)*ncb*N;
+    int rows = 32;
+    while (rows > 8 && cols*((H + rows - 1)/rows) < 6*148) rows >>= 1;
+    return rows;
 }
 
 extern "C" int stv_dwconv7_fwd(int N, int H, int W, int C, const float* x, const float* w, const float* bias, const float* res,
@@ -350,17 +348,10 @@ extern "C" int stv_dwconv7_fwd(int N, int H, int W, int C, const float* x, const
     STV_REQUIRE(N <= 65535, "stv_dwconv7_fwd: grid too large");
     STV_REQUIRE(x && w && y, "stv_dwconv7_fwd: NULL pointer");
     const int ncb = (C + DW_CB - 1)/DW_CB, nt = C < DW_CB ? round32(C) : DW_CB;
-    int L, rows;
-    dw_shape(N, H, W, C, L, rows);
-    dim3 grid(((W + L - 1)/L)*ncb, (H + rows - 1)/rows, N);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (L == 8) {
-        if (flip) dwconv7_kernel<true, 8><<<grid, nt, 0, st>>>(H, W, C, ncb, rows, x, w, bias, res, y);
-        else dwconv7_kernel<false, 8><<<grid, nt, 0, st>>>(H, W, C, ncb, rows, x, w, bias, res, y);
-    } else {
-        if (flip) dwconv7_kernel<true, 4><<<grid, nt, 0, st>>>(H, W, C, ncb, rows, x, w, bias, res, y);
-        else dwconv7_kernel<false, 4><<<grid, nt, 0, st>>>(H, W, C, ncb, rows, x, w, bias, res, y);
-    }
+    const int rows = dw_rows(N, H, W, C);
+    dim3 grid(((W + DW_L - 1)/DW_L)*ncb, (H + rows - 1)/rows, N);
+    if (flip) dwconv7_kernel<true, DW_L><<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, rows, x, w, bias, res, y);
+    else dwconv7_kernel<false, DW_L><<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, rows, x, w, bias, res, y);
     count_launch();
     return check_launch("dwconv7_kernel");
 }
