@@ -426,6 +426,9 @@ static bool tma_eligible(const stv_conv_geom* g) {
 static int fprop_tma(const stv_conv_geom* g, int P, int Q, const float* x, const float* w, float* y, const stv_gemm_epi* epi, cudaStream_t st) {
     GemmParams p = {};
     const int Ktot = g->R*g->S*g->C1;
+    if (conv3_eligible(g->N, P, Q, g->C1, g->Cout, g->R, g->S, g->stride))
+        return conv3_launch(x, g->N, g->H, g->W, g->C1, P, Q, -g->pad, -g->pad, g->R, g->S, w, g->Cout, 0, 0, 0, g->Cout, Ktot, y, g->Cout, epi, st,
+                            "stv_conv_fprop(row segments)");
     p.M = g->N*P*Q; p.N = g->Cout; p.K = Ktot;
     p.bn = pick_bn(p.N, (p.M + GEMM_BM - 1)/GEMM_BM);
     p.kb_total = Ktot/GEMM_BK; p.kb_per_split = p.kb_total;
@@ -444,6 +447,9 @@ static int fprop_tma(const stv_conv_geom* g, int P, int Q, const float* x, const
 static int dgrad_tma(const stv_conv_geom* g, int P, int Q, const float* dy, const float* w, float* dx, const stv_gemm_epi* epi, cudaStream_t st) {
     GemmParams p = {};
     const int Cin = g->C1 + g->C2;
+    if (conv3_eligible(g->N, g->H, g->W, g->Cout, Cin, g->R, g->S, 1))
+        return conv3_launch(dy, g->N, P, Q, g->Cout, g->H, g->W, g->pad - (g->S - 1), g->pad - (g->R - 1), g->R, g->S, w, Cin, 1, 1, Cin, g->Cout,
+                            (long long)g->R*g->S*Cin, dx, Cin, epi, st, "stv_conv_dgrad(row segments)");
     p.M = g->N*g->H*g->W; p.N = Cin; p.K = g->R*g->S*g->Cout;
     p.bn = pick_bn(p.N, (p.M + GEMM_BM - 1)/GEMM_BM);
     p.b_mn = 1;

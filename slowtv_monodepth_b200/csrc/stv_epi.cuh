@@ -88,13 +88,27 @@ __device__ __forceinline__ void mul_gelu_grad4(float4& x, const float4 s) {
 
 // Output row -> element offset. Plain GEMM / convolution outputs are row-major (row*ldc). A stride-s data gradient is computed
 // as s*s stride-1 sub-problems, one per output parity (a, b): row (n, y', x') of a sub-problem lands at pixel (n, s*y'+a, s*x'+b).
+// remap == 2 (row-segment convolution, stv_conv3.cu): GEMM rows enumerate (image row n*H + y, segment, 128 pixels); pixels past
+// the end of the image row do not exist (`ROW_NONE`).
+constexpr size_t ROW_NONE = ~(size_t)0;
 struct RowMap {
     long long ldc;
     int remap, gH, gW, oH, oW, ost, oa, ob;
     __device__ __forceinline__ size_t off(int row) const {
         if (!remap) return (size_t)row*ldc;
+        if (remap == 2) {   // gW = segments per image row, oW = pixels per image row
+            const int tile = row >> 7, i = row & 127, line = tile/gW, x = (tile - line*gW)*128 + i;
+            return x < oW ? ((size_t)line*oW + x)*ldc : ROW_NONE;
+        }
         const int hw = gH*gW, n = row/hw, rem = row - n*hw, y = rem/gW, x = rem - y*gW;
         return ((size_t)(n*oH + y*ost + oa)*oW + (x*ost + ob))*ldc;
+    }
+    // every one of the 128 rows starting at m0 exists
+    __device__ __forceinline__ bool tile_full(int m0, int M) const {
+        if (m0 + 128 > M) return false;
+        if (remap != 2) return true;
+        const int tile = m0 >> 7, line = tile/gW;
+        return (tile - line*gW)*128 + 128 <= oW;
     }
 };
 
@@ -116,7 +130,7 @@ __device__ __forceinline__ float4 epilogue_rows(const stv_gemm_epi& e, float* __
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        if (!FULL && row0 + 4*i >= M) break;
+        if (!FULL && roffs[i] == ROW_NONE) continue;
         const size_t o = roffs[i] + n;
         float4 x = *(const float4*)(xs + (4*i + rsub)*EPI_LD + cq);
         x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
@@ -158,12 +172,11 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int q, int lan
                 if (e.bias) bb = __ldg((const float4*)(e.bias + n));
                 if (e.gamma) gg = __ldg((const float4*)(e.gamma + n));
 #pragma unroll
-                for (int i = 0; i < 8; ++i) roffs[i] = row0 + 4*i < M ? rm.off(row0 + 4*i) : 0;
+                for (int i = 0; i < 8; ++i) roffs[i] = row0 + 4*i < M ? rm.off(row0 + 4*i) : ROW_NONE;
                 const float* __restrict__ pre_src = e.res ? e.res : e.dact_src;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int row = row0 + 4*i;
-                    pre[i] = (pre_src && row < M) ? __ldg((const float4*)(pre_src + roffs[i] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    pre[i] = (pre_src && roffs[i] != ROW_NONE) ? __ldg((const float4*)(pre_src + roffs[i] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             uint32_t v[32];
@@ -178,7 +191,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int q, int lan
                 // Descriptor fields are kernel-uniform: dispatch once per chunk to a loop specialised on the combinations the networks
                 // use (fc1, fc2, GELU' dgrad, plain store, split-K accumulate, conv + ELU / ReLU); anything else takes the generic loop.
                 float4 cs;
-                const bool full = m0 + 128 <= M;
+                const bool full = rm.tile_full(m0, M);
                 const bool plain = !e.aux && !e.gamma && !e.res && !e.dact_src && !e.accumulate && !e.colsum;
 #define STV_EPI_ROWS(...) cs = full ? epilogue_rows<__VA_ARGS__, true>(e, C, xs, roffs, pre, bb, gg, row0, M, n, rsub, cq) \
                                : epilogue_rows<__VA_ARGS__, false>(e, C, xs, roffs, pre, bb, gg, row0, M, n, rsub, cq)
@@ -214,6 +227,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int q, int lan
             const int row = m0 + q*32 + lane;
             if (row >= M) continue;
             const size_t roff = rm.off(row);
+            if (roff == ROW_NONE) continue;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int n = n0 + c + j;

@@ -28,18 +28,6 @@
 
 namespace stv {
 
-// Developer instrumentation (-DSTV_GEMM_TRACE, tools/gemm_trace.py; never in the shipped build): clock64 stamps of CTA 0's roles.
-//   [0] entry  [1] set-up done  [2] last commit  [3] epilogue sees the accumulator  [4] epilogue done  [5] exit
-//   [16 + i] producer passes the EMPTY wait of its i-th k-block   [528 + i] MMA thread passes the FULL wait of its i-th k-block
-#ifdef STV_GEMM_TRACE
-__device__ unsigned long long g_gemm_trace[1040];
-#define STV_TRACE(slot) do { if (blockIdx.x == 0) g_gemm_trace[(slot)] = (unsigned long long)clock64(); } while (0)
-#define STV_TRACE_KB(base, i) do { if (blockIdx.x == 0 && (i) < 512) g_gemm_trace[(base) + (i)] = (unsigned long long)clock64(); } while (0)
-#else
-#define STV_TRACE(slot) do {} while (0)
-#define STV_TRACE_KB(base, i) do {} while (0)
-#endif
-
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];

@@ -49,4 +49,22 @@ int pick_bn(int N, long long row_tiles);
 // Fills p.stages, launches grid (ceil(M/128), ceil(N/bn), splits). p.bn, p.kb_total, p.kb_per_split must be set.
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int splits, cudaStream_t stream, const char* what);
 
+// Developer instrumentation (-DSTV_GEMM_TRACE, tools/gemm_trace.py; never in the shipped build): clock64 stamps of CTA 0's roles.
+//   [0] entry  [1] set-up done  [2] last commit  [3] epilogue sees the accumulator  [4] epilogue done  [5] exit
+//   [16 + i] producer passes the EMPTY wait of its i-th k-block   [528 + i] MMA thread passes the FULL wait of its i-th k-block
+#ifdef STV_GEMM_TRACE
+static __device__ unsigned long long g_gemm_trace[1040];   // one buffer per translation unit (no relocatable device code)
+#define STV_TRACE(slot) do { if (blockIdx.x == 0) g_gemm_trace[(slot)] = (unsigned long long)clock64(); } while (0)
+#define STV_TRACE_KB(base, i) do { if (blockIdx.x == 0 && (i) < 512) g_gemm_trace[(base) + (i)] = (unsigned long long)clock64(); } while (0)
+#else
+#define STV_TRACE(slot) do {} while (0)
+#define STV_TRACE_KB(base, i) do {} while (0)
+#endif
+
+// Row-segment convolution (stv_conv3.cu): the taps of a filter row share one staged input slab (row-shifted UMMA descriptors).
+bool conv3_eligible(int N, int oH, int oW, int Cin, int Cout, int R, int S, int stride);
+int conv3_launch(const float* x, int N, int iH, int iW, int Cin, int oH, int oW, int lw, int lh, int R, int S, const float* w, int Cout,
+                 int flip, int b_mn, int b_tap_cols, long long b_rows, long long b_cols, float* y, long long ldc, const stv_gemm_epi* epi,
+                 cudaStream_t st, const char* what);
+
 }  // namespace stv

@@ -32,7 +32,29 @@ CASES = {
     'pose_head_1x1':  (3, 6, 10, 256, 0, False, 12, 1, 1, 0, False),
     'tall_batch':     (5, 7, 33, 64, 0, False, 64, 3, 1, 1, False),
     'reflect_cout16': (2, 16, 24, 32, 0, False, 16, 3, 1, 1, True),
+    # full-size rows (also re-run through the row-segment kernel below): full segments, and a partly empty last segment behind a
+    # materialised reflection pad
+    'rowseg_256':     (2, 200, 256, 32, 0, False, 32, 3, 1, 1, False),
+    'rowseg_reflect': (1, 260, 386, 32, 0, False, 16, 3, 1, 1, True),
 }
+
+# Cases re-run with the row-segment kernel forced wherever its geometry allows (3 taps along x, stride 1, 32-channel blocks).
+ROWSEG_FORCED = ['zero3x3', 'up_cat_reflect', 'reflect3x3_c16', 'tall_batch', 'reflect_cout16', 'odd_sizes', 'zero3x3_c16', 'rowseg_256', 'rowseg_reflect']
+ROWSEG_EXTRA = {
+    'seg_300':       (2, 6, 300, 32, 0, False, 64, 3, 1, 1, False),    # 128 + 128 + 44 pixels
+    'seg_reflect':   (1, 5, 162, 32, 0, False, 32, 3, 1, 1, True),     # padded rows of 164
+    'seg_cout96':    (1, 4, 140, 64, 0, False, 96, 3, 1, 1, False),
+    'seg_cin64':     (2, 7, 130, 64, 0, False, 64, 3, 1, 1, False),    # two channel blocks, two column tiles, partial row block (7 = 4 + 3)
+    'seg_tall':      (1, 21, 40, 32, 0, False, 16, 3, 1, 1, True),     # many row blocks per CTA: accumulator double-buffering wraps
+}
+CASES_ALL = {**CASES, **ROWSEG_EXTRA}
+
+
+@pytest.fixture
+def force_rowseg(monkeypatch):
+    monkeypatch.setenv('STV_CONV_ROWSEG', '2')
+    yield
+
 
 
 def _ints(shape, gen, lo=-2, hi=3):
@@ -40,7 +62,7 @@ def _ints(shape, gen, lo=-2, hi=3):
 
 
 def _make(case, gen, scale=1.0):
-    N, H, W, C1, C2, up1, Cout, R, st, pad, refl = CASES[case]
+    N, H, W, C1, C2, up1, Cout, R, st, pad, refl = CASES_ALL[case]
     s1 = _ints((N, H//2, W//2, C1) if up1 else (N, H, W, C1), gen)*scale
     s2 = _ints((N, H, W, C2), gen)*scale if C2 else None
     w = (_ints((Cout, C1 + C2, R, R), gen)*scale).contiguous(memory_format=torch.channels_last)
@@ -84,6 +106,13 @@ def test_backward_exact(case):
         if g is None: continue
         assert g.grad is not None, name
         assert torch.equal(g.grad, r.grad.float()), f'{name}: max |diff| = {(g.grad - r.grad.float()).abs().max().item()}'
+
+
+@pytest.mark.parametrize('case', ROWSEG_FORCED + list(ROWSEG_EXTRA))
+def test_rowseg_kernel_exact(case, force_rowseg):
+    """Forward and backward through the row-segment kernel (forced): bit-exact like the im2col path."""
+    test_fprop_exact(case)
+    test_backward_exact(case)
 
 
 @pytest.mark.parametrize('act', ['relu', 'elu', 'sigmoid'])
