@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(FZ_NT, STV_FUSED_MINB) photo_fused_kernel(cons
     // vertical 3-row running sums: q1 = previous row, q2 = previous two rows
     f2 hS1[NP][3][2], hS2[NP][3][2], hS3[NP][3][2];   // per frame pair, channel: horizontal sums of w, w^2, w*t
     float hT1[3][2], hT2[3][2];                       // target
-    float vc[N][9][2];                                // masked coefficient sums per frame
+    f2 vc[NP][9][2];                                  // masked coefficient sums, two frames per packed pair
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         hT1[c][0] = hT1[c][1] = hT2[c][0] = hT2[c][1] = 0.f;
@@ -173,9 +173,9 @@ __global__ void __launch_bounds__(FZ_NT, STV_FUSED_MINB) photo_fused_kernel(cons
         }
     }
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
+    for (int q = 0; q < NP; ++q) {
 #pragma unroll
-        for (int j = 0; j < 9; ++j) vc[k][j][0] = vc[k][j][1] = 0.f;
+        for (int j = 0; j < 9; ++j) vc[q][j][0] = vc[q][j][1] = splat2(0.f);
     }
     float accA[N][3], accB[N][3], accC[N][3], accK[FZ_NPART_K];
 #pragma unroll
@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(FZ_NT, STV_FUSED_MINB) photo_fused_kernel(cons
             const float fx = ix - x0f, fy = iy - y0f;
             const int plane0 = (k*p.b + i)*3;
             float ta[3], tb[3], tc[3], td[3];  // taps (x0,y0) (x1,y0) (x0,y1) (x1,y1)
-            {   // the next sweep row gathers (approximately) one image row further down: warm L1 with it while this row is processed
+            {   // (measured: 843-852 us with, 855-870 us without this prefetch for the forward entry point at config 3)
+                // the next sweep row gathers (approximately) one image row further down: warm L1 with it while this row is processed
                 const int xi0 = (int)x0f, yi2 = min((int)y0f + 2, H - 1);
                 const float* __restrict__ q = p.supp + (size_t)plane0*HW + yi2*W + xi0;
 #pragma unroll
@@ -408,18 +409,27 @@ __global__ void __launch_bounds__(FZ_NT, STV_FUSED_MINB) photo_fused_kernel(cons
             const int yp = y - 2;
             const float myd = (yp == H - 2) ? 2.f : 1.f, myu_next = (yp == 0) ? 2.f : 1.f;
             float cs[N][9];
-            float ml[N], mm[N], mr[N];
+            f2 ml[NP], mm[NP], mr[NP];   // per-frame masks of the left / own / right window, frames (2q, 2q+1) packed
 #pragma unroll
-            for (int k = 0; k < N; ++k) { ml[k] = kl == k ? mxl : 0.f; mm[k] = kcode == k ? 1.f : 0.f; mr[k] = kr == k ? mxr : 0.f; }
+            for (int q = 0; q < NP; ++q) {
+                const int k0 = 2*q, k1 = 2*q + 1;   // (k1 == N for an odd frame count: kcode is never N, the lane stays zero)
+                ml[q] = mk2(kl == k0 ? mxl : 0.f, kl == k1 ? mxl : 0.f);
+                mm[q] = mk2(kcode == k0 ? 1.f : 0.f, kcode == k1 ? 1.f : 0.f);
+                mr[q] = mk2(kr == k0 ? mxr : 0.f, kr == k1 ? mxr : 0.f);
+            }
+            const f2 myd2 = splat2(myd), myu2 = splat2(myu_next);
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
                 const float cl = __shfl_up_sync(0xffffffffu, csel[j], 1), cr = __shfl_down_sync(0xffffffffu, csel[j], 1);
+                const f2 cl2 = splat2(cl), cr2 = splat2(cr), cm2 = splat2(csel[j]);
 #pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    const float hk = fmaf(ml[k], cl, fmaf(mr[k], cr, mm[k]*csel[j]));
-                    cs[k][j] = fmaf(myd, hk, vc[k][j][1]);
-                    vc[k][j][1] = fmaf(myu_next, vc[k][j][0], hk);
-                    vc[k][j][0] = hk;
+                for (int q = 0; q < NP; ++q) {
+                    const f2 hk = fma2(ml[q], cl2, fma2(mr[q], cr2, mm[q]*cm2));
+                    const f2 c2 = fma2(myd2, hk, vc[q][j][1]);
+                    vc[q][j][1] = fma2(myu2, vc[q][j][0], hk);
+                    vc[q][j][0] = hk;
+                    cs[2*q][j] = lo2(c2);
+                    if (2*q + 1 < N) cs[2*q + 1][j] = hi2(c2);
                 }
             }
             // ---------------- stage C: pixel row yp = y-2 ----------------
@@ -446,7 +456,7 @@ __global__ void __launch_bounds__(FZ_NT, STV_FUSED_MINB) photo_fused_kernel(cons
                         float gw = gs*fmaf(2.f*w, cs[k][c*3 + 1], fmaf(tp[c], cs[k][c*3 + 2], cs[k][c*3 + 0]));
                         if (kcode_prev == k) {
                             const float df = w - tp[c];
-                            gw += df > 0.f ? gl : (df < 0.f ? -gl : 0.f);
+                            gw += df != 0.f ? copysignf(gl, df) : 0.f;
                         }
                         any = any || gw != 0.f;
                         gqx = fmaf(gw, rp[(5 + k*9 + 3 + c)*32], gqx);
