@@ -331,7 +331,7 @@ static int round32(int c) { return (c + 31)/32*32; }
 
 // Rows per block of the strip kernels: tall strips amortise the 6-row halo; shrink them while the grid is smaller than ~6 blocks
 // per SM (blocks are only 3-4 warps).
-// Rows per block: tall strips amortise the 6 warm-up rows; enough blocks for ~6 per SM. (Measured and rejected, gpurun_out/r2w:
+// Rows per block: tall strips amortise the 6 warm-up rows; enough blocks for ~6 per SM. (Measured and rejected, profiles/r2_rejected_variants.txt:
 // 4 instead of 8 columns per thread for the small deep-stage maps — four times the blocks, but 0.39 vs 0.26 ms for the twelve
 // stage-2/3 data gradients: the halo loads per output grow from 1.75x to 2.5x and the 49 weights are re-read by twice the threads.)
 static int dw_rows(int N, int H, int W, int C) {

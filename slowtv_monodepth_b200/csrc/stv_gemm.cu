@@ -724,7 +724,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
         stages = stages > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : stages;
         stages = stages < 2 ? 2 : stages;
         p.stages = stages;
-        // L2 prefetch distance of the streamed operand in k-blocks. Measured (gpurun_out/r2v): 2 / 4 / 8 are all SLOWER than none on the
+        // L2 prefetch distance of the streamed operand in k-blocks. Measured (profiles/r2_rejected_variants.txt): 2 / 4 / 8 are all SLOWER than none on the
         // step (431 -> 415 images/s) — the load latency of the 2-stage ring is not DRAM-miss time — so it stays a developer switch.
         static const int pf_cfg = getenv("STV_GEMM_PF") ? atoi(getenv("STV_GEMM_PF")) : 0;
         p.pf = pf_cfg;
