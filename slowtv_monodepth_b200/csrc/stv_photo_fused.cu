@@ -525,6 +525,536 @@ __global__ void __launch_bounds__(FZ_NT, STV_FUSED_MINB) photo_fused_kernel(cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Three-warp variant of the sweep (gradients on). The monolithic kernel above needs 255 registers: 8 resident warps per SM, each
+// a chain of dependent instructions (~5 cycles per instruction), issue slots half idle with nothing to switch to. Here a strip
+// is owned by THREE warps of a 96-thread block, one per stage, each carrying only its own state across rows:
+//   warp G  stage A: loads, up-sampling, projection, gathers, bilinear warp            (state: the taps in flight)
+//   warp S  stage B: window sums, SSIM + L1, min-reprojection, auto-mask, decision      (state: 3-row sums of w, w^2, w t)
+//   warp C  masked coefficient window sums and stage C (the chain rule)                 (state: coefficient sums, pose moments)
+// Rows travel G -> S -> C through shared memory: the lane-private value ring of the monolithic kernel, FZ_R slots deep, plus a
+// decision ring (selected coefficients + decision code) S -> C. Hand-over is a producer / consumer ring on shared-memory
+// mbarriers (named barriers would do, but 3 x FZ_R of them per block cap the resident blocks: an SM has 32-64 barrier slots):
+// FULL_A[slot] G -> S, FULL_B[slot] S -> C, EMPTY[slot] C -> G and S once C no longer reads what they are about to overwrite
+// (C is the last reader of everything). G may run FZ_R - 3 rows ahead of C.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int FZ_R = 5;          // ring depth
+constexpr int FZ_RB = 10;        // decision-ring values per lane: 9 selected coefficients + the decision code
+constexpr int FZ_SPLIT_MAX_N = 2;
+constexpr int FZ_SPLIT_NT = 96;
+constexpr unsigned FZ_WAIT_HINT_NS = 2000;   // the hardware parks a waiting warp for up to this long instead of spinning on issue slots
+
+template <int N> struct FzSplitLayout {
+    using LY = FzLayout<N>;
+    static constexpr int RING_A = FZ_R*LY::RV*32;
+    static constexpr int RING_B = (FZ_R - 2)*FZ_RB*32;   // produced and consumed in the same iteration number
+    static constexpr int BARS = 6*FZ_R;                  // 3 x FZ_R mbarriers (8 bytes each)
+    static constexpr int PER_BLOCK = LY::CAM_PAD + RING_A + RING_B + BARS;   // floats
+};
+
+// One arrival per warp: __syncwarp orders the other lanes' shared-memory writes before lane 0's releasing arrive.
+__device__ __forceinline__ void fz_signal(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fz_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(FZ_WAIT_HINT_NS) : "memory");
+    } while (!done);
+}
+
+template <int N, bool TEX, int MINB>
+__global__ void __launch_bounds__(FZ_SPLIT_NT, MINB) photo_fused_split_kernel(const FusedParams p) {
+    using LY = FzLayout<N>;
+    using SL = FzSplitLayout<N>;
+    constexpr int NP = (N + 1)/2;
+    extern __shared__ __align__(16) float fz_smem[];
+    const int lane = threadIdx.x & 31;
+    const int role = threadIdx.x >> 5;   // 0: G, 1: S, 2: C
+    float* const cam = fz_smem;
+    float* const ring = cam + LY::CAM_PAD + lane;
+    float* const ringb = cam + LY::CAM_PAD + SL::RING_A + lane;
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(cam + LY::CAM_PAD + SL::RING_A + SL::RING_B);
+    const uint32_t bar_fa = bars, bar_fb = bars + 8*FZ_R, bar_e = bars + 16*FZ_R;   // FULL_A, FULL_B, EMPTY
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 3*FZ_R; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bars + 8*q));
+    }
+
+    const long long strip = blockIdx.x;
+    int t = (int)(strip % ((long long)p.nsx*p.nsy*p.S));
+    const int i = (int)(strip/((long long)p.nsx*p.nsy*p.S));
+    const int sxi = t % p.nsx; t /= p.nsx;
+    const int syi = t % p.nsy;
+    const int s = t/p.nsy;
+
+    const int H = p.H, W = p.W, HW = H*W;
+    const int x0 = sxi*FZ_COLS, y0 = syi*p.rows;
+    const int x = x0 - 2 + lane;
+    const int xa = fz_clampi(reflect_idx(x, W), 0, W - 1);
+    const bool col_centre = lane >= 1 && lane <= 30 && x >= 0 && x < W;
+    const bool col_inner = lane >= 2 && lane <= 29 && x < W;
+    const float u = (float)xa;
+
+    if (role == 0) {
+        const float* __restrict__ Km = p.K + (size_t)i*16;
+        const float* __restrict__ Ki = p.Kinv + (size_t)i*16;
+        for (int q = lane; q < LY::CAM; q += 32) {
+            float v;
+            if (q < 12) v = (q & 3) < 3 ? __ldg(Ki + q) : 0.f;
+            else if (q < 20) v = __ldg(Km + (q - 12));
+            else {
+                const int k = (q - 20)/12, e = (q - 20) % 12;
+                v = __ldg(p.T + ((size_t)k*p.b + i)*16 + e);
+            }
+            cam[q] = v;
+        }
+    }
+    __syncthreads();
+    const float4* const cam4 = reinterpret_cast<const float4*>(cam);
+
+    const int rows_here = min(p.rows, H - y0);
+    const int n_it = rows_here + 4;
+    const float inv_cnt = 1.f/((float)p.S*(float)p.b*(float)HW);
+    const float ws3 = p.w_ssim*(1.f/3.f), wl3 = p.w_l1*(1.f/3.f);
+
+    if (role == 0) {
+        // =============================== warp G: stage A ===============================
+        const float sx = (float)W/(float)(W - 1), sy = (float)H/(float)(H - 1);
+        const int hs = p.h[s], ws = p.w[s];
+        const bool resize = p.mode == 1 && (hs != H || ws != W);
+        int lx0 = 0, lx1 = 0;
+        float llx = 0.f;
+        const float ry = (float)hs/(float)H;
+        if (resize) {
+            const float src = fmaxf(((float)ws/(float)W)*((float)xa + 0.5f) - 0.5f, 0.f);
+            lx0 = min((int)src, ws - 1);
+            lx1 = lx0 + (lx0 < ws - 1 ? 1 : 0);
+            llx = src - (float)lx0;
+        }
+        const float* __restrict__ srcp = p.src[s] + (size_t)i*(p.mode == 1 ? hs*ws : HW);
+        const float* __restrict__ tg = p.tgt + (size_t)i*3*HW;
+        const bool want_warp = p.warp0 != nullptr && s == 0;
+
+        struct RowLoads { float t[3], a00, a01, a10, a11, lly; };
+        auto request = [&](int it_n, RowLoads& L) {
+            const int yn = y0 - 2 + it_n;
+            const int yan = fz_clampi(reflect_idx(yn, H), 0, H - 1);
+            const int on = yan*W + xa;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) L.t[c] = __ldg(tg + c*HW + on);
+            if (resize) {
+                const float src = fmaxf(ry*((float)yan + 0.5f) - 0.5f, 0.f);
+                const int ly0 = min((int)src, hs - 1), ly1 = ly0 + (ly0 < hs - 1 ? 1 : 0);
+                L.lly = src - (float)ly0;
+                const float* r0 = srcp + ly0*ws; const float* r1 = srcp + ly1*ws;
+                L.a00 = __ldg(r0 + lx0); L.a01 = __ldg(r0 + lx1); L.a10 = __ldg(r1 + lx0); L.a11 = __ldg(r1 + lx1);
+            } else { L.a00 = __ldg(srcp + on); L.a01 = L.a10 = L.a11 = 0.f; L.lly = 0.f; }
+        };
+        // Software pipeline: iteration `it` finishes row `it` from the taps requested one iteration earlier, then computes the
+        // sample positions of row it+1 and issues its gathers, then requests the plain loads of row it+2.
+        struct Taps { float ta[3], tb[3], tc[3], td[3], fx, fy, bx, by; };
+        struct RowA { float d, dchain, tv[3]; Taps tp[N]; };
+        auto gather = [&](int it_r, const RowLoads& L, RowA& A) {
+            const int yr = y0 - 2 + it_r;
+            const float v = (float)fz_clampi(reflect_idx(yr, H), 0, H - 1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) A.tv[c] = L.t[c];
+            A.dchain = 1.f;
+            {
+                const float sv = resize ? (1.f - L.lly)*((1.f - llx)*L.a00 + llx*L.a01) + L.lly*((1.f - llx)*L.a10 + llx*L.a11) : L.a00;
+                if (p.mode == 1) {
+                    const float dp = p.scaled ? __fadd_rn(__fmul_rn(p.d_mul, sv), p.d_add) : sv;
+                    A.d = dp > 0.f ? 1.0f/fmaxf(dp, STV_EPS32) : 0.f;
+                    A.dchain = (dp > 0.f && dp >= STV_EPS32) ? -(A.d*A.d)*(p.scaled ? p.d_mul : 1.f) : 0.f;
+                } else A.d = sv;
+            }
+            float P[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { const float4 ki = cam4[r]; P[r] = fmaf(ki.x, u, fmaf(ki.y, v, ki.z))*A.d; }
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                Taps& tp = A.tp[k];
+                float Q[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { const float4 rt = cam4[5 + k*3 + r]; Q[r] = fmaf(rt.x, P[0], fmaf(rt.y, P[1], fmaf(rt.z, P[2], rt.w))); }
+                const float inv = rcp_fast(fmaxf(Q[2], STV_MIN_Z));  // max(max(z, eps), 0.1) == max(z, 0.1)
+                const float nx = Q[0]*inv, ny = Q[1]*inv, nz = Q[2]*inv;
+                const float4 k0 = cam4[3], k1 = cam4[4];
+                float ix = fmaf(fmaf(k0.x, nx, fmaf(k0.y, ny, k0.z*nz)), sx, -0.5f);
+                float iy = fmaf(fmaf(k1.x, nx, fmaf(k1.y, ny, k1.z*nz)), sy, -0.5f);
+                const float mxc = (float)(W - 1), myc = (float)(H - 1);
+                tp.bx = (ix > 0.f && ix < mxc) ? sx : 0.f; tp.by = (iy > 0.f && iy < myc) ? sy : 0.f;
+                ix = fminf(fmaxf(ix, 0.f), mxc);
+                iy = fminf(fmaxf(iy, 0.f), myc);
+                const float x0f = floorf(ix), y0f = floorf(iy);
+                tp.fx = ix - x0f; tp.fy = iy - y0f;
+                const int plane0 = (k*p.b + i)*3;
+                if (TEX) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float4 t4 = tex2Dgather<float4>((cudaTextureObject_t)p.tex, x0f + 1.f, y0f + 1.f + (float)((plane0 + c)*H), 0);
+                        tp.ta[c] = t4.w; tp.tb[c] = t4.z; tp.tc[c] = t4.x; tp.td[c] = t4.y;
+                    }
+                } else {
+                    const int xi0 = (int)x0f, yi0 = (int)y0f, xi1 = min(xi0 + 1, W - 1), yi1 = min(yi0 + 1, H - 1);
+                    const float* __restrict__ sp = p.supp + (size_t)plane0*HW;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float* q = sp + c*HW;
+                        tp.ta[c] = __ldg(q + yi0*W + xi0); tp.tb[c] = __ldg(q + yi0*W + xi1);
+                        tp.tc[c] = __ldg(q + yi1*W + xi0); tp.td[c] = __ldg(q + yi1*W + xi1);
+                    }
+                }
+            }
+        };
+        RowLoads ld;
+        RowA cur;
+        request(0, ld);
+        gather(0, ld, cur);
+        if (n_it > 1) request(1, ld);
+        int slot_w = 0, slot_e = 0;
+        uint32_t par_e = 0;
+#pragma unroll 2
+        for (int it = 0; it < n_it; ++it) {
+            // the slot about to be overwritten held row it - FZ_R, last read by warp C in its iteration it - FZ_R + 2
+            if (it >= FZ_R - 2) {
+                fz_wait(bar_e + 8*slot_e, par_e);
+                if (++slot_e == FZ_R) { slot_e = 0; par_e ^= 1u; }
+            }
+            float* const rw = ring + slot_w*LY::RV*32;
+            rw[0] = cur.d;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) rw[(1 + c)*32] = cur.tv[c];
+            rw[4*32] = cur.dchain;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                const Taps& tp = cur.tp[k];
+                float wv[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float top = fmaf(tp.fx, tp.tb[c] - tp.ta[c], tp.ta[c]), bot = fmaf(tp.fx, tp.td[c] - tp.tc[c], tp.tc[c]);
+                    const float w = fmaf(tp.fy, bot - top, top);
+                    wv[c] = w;
+                    rw[(5 + k*9 + c)*32] = w;
+                    rw[(5 + k*9 + 3 + c)*32] = fmaf(tp.fy, (tp.td[c] - tp.tc[c]) - (tp.tb[c] - tp.ta[c]), tp.tb[c] - tp.ta[c])*tp.bx;
+                    rw[(5 + k*9 + 6 + c)*32] = (bot - top)*tp.by;
+                }
+                if (want_warp && col_inner && it >= 2 && it < rows_here + 2) {
+                    const int plane0 = (k*p.b + i)*3;
+                    const int ya = fz_clampi(reflect_idx(y0 - 2 + it, H), 0, H - 1);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) p.warp0[((size_t)plane0 + c)*HW + ya*W + xa] = wv[c];
+                }
+            }
+            fz_signal(bar_fa + 8*slot_w, lane);            // FULL_A[slot]: row y is in the value ring
+            if (it + 1 < n_it) {
+                gather(it + 1, ld, cur);                   // row it+1: sample positions + gathers
+                if (it + 2 < n_it) request(it + 2, ld);    // row it+2: target, source-map taps
+            }
+            slot_w = slot_w == FZ_R - 1 ? 0 : slot_w + 1;
+        }
+    } else if (role == 1) {
+        // =============================== warp S: window sums and stage B ===============================
+        uint8_t* __restrict__ selp = p.sel + ((size_t)s*p.b + i)*HW;
+        const float* __restrict__ e0p = p.e0 + (size_t)i*HW;
+        const uint64_t seed = p.seed ? p.seed + (p.step ? *p.step : 0ull) : 0ull;
+        f2 hS1[NP][3][2], hS2[NP][3][2], hS3[NP][3][2];
+        float hT1[3][2], hT2[3][2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            hT1[c][0] = hT1[c][1] = hT2[c][0] = hT2[c][1] = 0.f;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                hS1[q][c][0] = hS1[q][c][1] = hS2[q][c][0] = hS2[q][c][1] = hS3[q][c][0] = hS3[q][c][1] = splat2(0.f);
+            }
+        }
+        float loss_acc = 0.f;
+        // identity error (and explicit tie-break noise) of the centre row an iteration decides: requested one iteration ahead
+        auto request_e0 = [&](int it_n, float& e0, float& nz) {
+            const int ycn = y0 - 3 + it_n;
+            const bool ok = p.use_automask && col_centre && ycn >= 0 && ycn < H;
+            e0 = ok ? __ldg(e0p + (size_t)ycn*W + x) : 0.f;
+            nz = (ok && p.noise) ? __ldg(p.noise + ((size_t)s*p.b + i)*HW + (size_t)ycn*W + x) : 0.f;
+        };
+        float e0_next, nz_next;
+        request_e0(0, e0_next, nz_next);
+        int slot_w = 0, slot_c = FZ_R - 1, slot_b = 0, slot_e = 0;
+        uint32_t par_f = 0, par_e = 0;
+#pragma unroll 1
+        for (int it = 0; it < n_it; ++it) {
+            const int y = y0 - 2 + it;
+            const float e0_row = e0_next, nz_row = nz_next;
+            if (it + 1 < n_it) request_e0(it + 1, e0_next, nz_next);
+            fz_wait(bar_fa + 8*slot_w, par_f);
+            const float* const rw = ring + slot_w*LY::RV*32;
+            const float* const rc = ring + slot_c*LY::RV*32;
+            float tv[3], wv[N][3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tv[c] = rw[(1 + c)*32];
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) wv[k][c] = rw[(5 + k*9 + c)*32];
+            }
+
+            float T1[3], T2[3];
+            f2 S1[NP][3], S2[NP][3], S3[NP][3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float tl = __shfl_up_sync(0xffffffffu, tv[c], 1), tr = __shfl_down_sync(0xffffffffu, tv[c], 1);
+                const float h1 = tl + tv[c] + tr;
+                const float h2 = fmaf(tl, tl, fmaf(tv[c], tv[c], tr*tr));
+                T1[c] = hT1[c][1] + h1; T2[c] = hT2[c][1] + h2;
+                hT1[c][1] = hT1[c][0] + h1; hT1[c][0] = h1;
+                hT2[c][1] = hT2[c][0] + h2; hT2[c][0] = h2;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const int k0 = 2*q, k1 = (2*q + 1 < N) ? 2*q + 1 : 2*q;
+                    const float a0 = wv[k0][c], a1 = wv[k1][c];
+                    const float l0 = __shfl_up_sync(0xffffffffu, a0, 1), r0 = __shfl_down_sync(0xffffffffu, a0, 1);
+                    const float l1 = (k1 != k0) ? __shfl_up_sync(0xffffffffu, a1, 1) : l0;
+                    const float r1 = (k1 != k0) ? __shfl_down_sync(0xffffffffu, a1, 1) : r0;
+                    const f2 wl = mk2(l0, l1), wc = mk2(a0, a1), wr = mk2(r0, r1);
+                    const f2 g1 = wl + wc + wr;
+                    const f2 g2 = fma2(wl, wl, fma2(wc, wc, wr*wr));
+                    const f2 g3 = fma2(wl, splat2(tl), fma2(wc, splat2(tv[c]), wr*splat2(tr)));
+                    S1[q][c] = hS1[q][c][1] + g1; S2[q][c] = hS2[q][c][1] + g2; S3[q][c] = hS3[q][c][1] + g3;
+                    hS1[q][c][1] = hS1[q][c][0] + g1; hS1[q][c][0] = g1;
+                    hS2[q][c][1] = hS2[q][c][0] + g2; hS2[q][c][0] = g2;
+                    hS3[q][c][1] = hS3[q][c][0] + g3; hS3[q][c][0] = g3;
+                }
+            }
+
+            // ---------------- stage B: centre row yc = y-1 ----------------
+            int kcode = 255;
+            float csel[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) csel[j] = 0.f;
+            if (it >= 2) {
+                const int yc = y - 1;
+                const bool centre = col_centre && yc >= 0 && yc < H;
+                float e[N];
+                f2 ca[NP][3], cb[NP][3], cc[NP][3];
+#pragma unroll
+                for (int k = 0; k < N; ++k) e[k] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float tcv = rc[(1 + c)*32];
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        const int k0 = 2*q, k1 = (2*q + 1 < N) ? 2*q + 1 : 2*q;
+                        if (p.w_ssim > 0.f) {
+                            f2 eq;
+                            fz_ssim2(S1[q][c], S2[q][c], S3[q][c], T1[c], T2[c], eq, ca[q][c], cb[q][c], cc[q][c]);
+                            e[k0] = fmaf(ws3, lo2(eq), e[k0]);
+                            if (k1 != k0) e[k1] = fmaf(ws3, hi2(eq), e[k1]);
+                        } else ca[q][c] = cb[q][c] = cc[q][c] = splat2(0.f);
+                        if (p.w_l1 > 0.f) {
+                            e[k0] = fmaf(wl3, fabsf(rc[(5 + k0*9 + c)*32] - tcv), e[k0]);
+                            if (k1 != k0) e[k1] = fmaf(wl3, fabsf(rc[(5 + k1*9 + c)*32] - tcv), e[k1]);
+                        }
+                    }
+                }
+                float emin = e[0];
+                int ks = 0;
+#pragma unroll
+                for (int k = 1; k < N; ++k) if (e[k] < emin) { emin = e[k]; ks = k; }  // first index wins ties (torch.min)
+                bool is_static = false;
+                if (p.use_automask && centre) {
+                    const size_t nidx = ((size_t)s*p.b + i)*HW + (size_t)yc*W + x;
+                    float e0v = e0_row;
+                    if (p.noise) e0v = fmaf(STV_EPS32, nz_row, e0v);
+                    else if (seed) e0v = fmaf(STV_EPS32, hash_normal(seed, nidx), e0v);
+                    if (!(emin <= e0v)) { emin = e0v; is_static = true; }  // torch.min(cat(err, static)): index 0 wins ties
+                }
+                if (centre && !is_static) kcode = ks;
+                if (centre && col_inner && yc >= y0 && yc < y0 + rows_here) {   // this strip owns the pixel
+                    selp[(size_t)yc*W + x] = (uint8_t)(is_static ? STV_SEL_STATIC : ks);
+                    loss_acc += emin;
+                }
+                if (p.w_ssim > 0.f) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                        for (int k = 0; k < N; ++k) {
+                            const f2 a2 = ca[k/2][c], b2 = cb[k/2][c], c2 = cc[k/2][c];
+                            if (kcode == k) {
+                                csel[c*3 + 0] = (k & 1) ? hi2(a2) : lo2(a2);
+                                csel[c*3 + 1] = (k & 1) ? hi2(b2) : lo2(b2);
+                                csel[c*3 + 2] = (k & 1) ? hi2(c2) : lo2(c2);
+                            }
+                        }
+                    }
+                }
+            }
+            // the decision-ring slot held iteration it - (FZ_R - 2): wait until warp C has consumed it
+            if (it >= FZ_R - 2) {
+                fz_wait(bar_e + 8*slot_e, par_e);
+                if (++slot_e == FZ_R) { slot_e = 0; par_e ^= 1u; }
+            }
+            float* const rb = ringb + slot_b*FZ_RB*32;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) rb[j*32] = csel[j];
+            rb[9*32] = __int_as_float(kcode);
+            fz_signal(bar_fb + 8*slot_w, lane);   // FULL_B[slot]: the decision of row y-1 is in shared memory
+            slot_c = slot_w;
+            slot_b = slot_b == FZ_R - 3 ? 0 : slot_b + 1;
+            if (++slot_w == FZ_R) { slot_w = 0; par_f ^= 1u; }
+        }
+        loss_acc = warp_sum(loss_acc);
+        if (lane == 0) p.loss_partial[strip] = loss_acc;
+    } else {
+        // =============================== warp C: coefficient window sums and stage C ===============================
+        const float mxl = (x == 1) ? 2.f : 1.f, mxr = (x == W - 2) ? 2.f : 1.f;
+        const float gs = ws3*inv_cnt, gl = wl3*inv_cnt;
+        float* __restrict__ gup = p.g_unit[s] + (size_t)i*HW;
+        f2 vc[NP][9][2];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) vc[q][j][0] = vc[q][j][1] = splat2(0.f);
+        }
+        float accA[N][3], accB[N][3], accC[N][3], accK[FZ_NPART_K];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) accA[k][r] = accB[k][r] = accC[k][r] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < FZ_NPART_K; ++q) accK[q] = 0.f;
+        int kcode_prev = 255;
+        int slot_w = 0, slot_p = FZ_R - 2;   // slot of iteration `it`, of row y-2
+        int slot_b = 0;
+        uint32_t par_f = 0;
+#pragma unroll 1
+        for (int it = 0; it < n_it; ++it) {
+            const int y = y0 - 2 + it;
+            fz_wait(bar_fb + 8*slot_w, par_f);
+            const float* const rp = ring + slot_p*LY::RV*32;
+            const float* const rb = ringb + slot_b*FZ_RB*32;
+            const int kcode = __float_as_int(rb[9*32]);
+            float csel[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) csel[j] = rb[j*32];
+
+            const int kl = __shfl_up_sync(0xffffffffu, kcode, 1), kr = __shfl_down_sync(0xffffffffu, kcode, 1);
+            // Window of pixel row yp = y-2: myu(yp) c[yp-1] + c[yp] + myd(yp) c[yp+1] (see the monolithic kernel)
+            const int yp = y - 2;
+            const float myd = (yp == H - 2) ? 2.f : 1.f, myu_next = (yp == 0) ? 2.f : 1.f;
+            float cs[N][9];
+            f2 ml[NP], mm[NP], mr[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int k0 = 2*q, k1 = 2*q + 1;
+                ml[q] = mk2(kl == k0 ? mxl : 0.f, kl == k1 ? mxl : 0.f);
+                mm[q] = mk2(kcode == k0 ? 1.f : 0.f, kcode == k1 ? 1.f : 0.f);
+                mr[q] = mk2(kr == k0 ? mxr : 0.f, kr == k1 ? mxr : 0.f);
+            }
+            const f2 myd2 = splat2(myd), myu2 = splat2(myu_next);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const float cl = __shfl_up_sync(0xffffffffu, csel[j], 1), cr = __shfl_down_sync(0xffffffffu, csel[j], 1);
+                const f2 cl2 = splat2(cl), cr2 = splat2(cr), cm2 = splat2(csel[j]);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const f2 hk = fma2(ml[q], cl2, fma2(mr[q], cr2, mm[q]*cm2));
+                    const f2 c2 = fma2(myd2, hk, vc[q][j][1]);
+                    vc[q][j][1] = fma2(myu2, vc[q][j][0], hk);
+                    vc[q][j][0] = hk;
+                    cs[2*q][j] = lo2(c2);
+                    if (2*q + 1 < N) cs[2*q + 1][j] = hi2(c2);
+                }
+            }
+            // ---------------- stage C: pixel row yp = y-2 ----------------
+            if (it >= 4 && col_inner) {
+                const float dp = rp[0];
+                float tp[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) tp[c] = rp[(1 + c)*32];
+                const float vp = (float)yp;   // inside the image by construction (y0 <= yp < y0 + rows_here <= H)
+                float rayp[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { const float4 ki = cam4[r]; rayp[r] = fmaf(ki.x, u, fmaf(ki.y, vp, ki.z)); }
+                const float4 k0p = cam4[3], k1p = cam4[4];
+                const float cK0[3] = {k0p.x, k0p.y, k0p.z}, cK1[3] = {k1p.x, k1p.y, k1p.z};
+                float gd = 0.f;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    float gqx = 0.f, gqy = 0.f;
+                    bool any = false;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float w = rp[(5 + k*9 + c)*32];
+                        float gw = gs*fmaf(2.f*w, cs[k][c*3 + 1], fmaf(tp[c], cs[k][c*3 + 2], cs[k][c*3 + 0]));
+                        if (kcode_prev == k) {
+                            const float df = w - tp[c];
+                            gw += df != 0.f ? copysignf(gl, df) : 0.f;
+                        }
+                        any = any || gw != 0.f;
+                        gqx = fmaf(gw, rp[(5 + k*9 + 3 + c)*32], gqx);
+                        gqy = fmaf(gw, rp[(5 + k*9 + 6 + c)*32], gqy);
+                    }
+                    if (!any) continue;
+                    float uu[3], Q[3], ct[3];   // closed-form depth gradient: see the monolithic kernel
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const float4 rt = cam4[5 + k*3 + r];
+                        uu[r] = fmaf(rt.x, rayp[0], fmaf(rt.y, rayp[1], rt.z*rayp[2]));
+                        ct[r] = rt.w;
+                        Q[r] = fmaf(dp, uu[r], ct[r]);
+                    }
+                    const float inv = rcp_fast(fmaxf(Q[2], STV_MIN_Z));
+                    float gn[3], gQ[3];
+                    float gz = 0.f, gnu = 0.f, gnt = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        gn[r] = fmaf(cK0[r], gqx, cK1[r]*gqy); gQ[r] = gn[r]*inv;
+                        gz = fmaf(gn[r], Q[r], gz); gnu = fmaf(gn[r], uu[r], gnu); gnt = fmaf(gn[r], ct[r], gnt);
+                    }
+                    const bool unclamped = Q[2] >= STV_MIN_Z;
+                    if (unclamped) gQ[2] -= gz*inv*inv;
+                    gd += unclamped ? inv*inv*fmaf(gnu, ct[2], -gnt*uu[2]) : inv*gnu;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const float m = gQ[r]*dp;
+                        accA[k][r] += m;
+                        accB[k][r] = fmaf(m, vp, accB[k][r]);
+                        accC[k][r] += gQ[r];
+                        const float nr = Q[r]*inv;
+                        accK[r] = fmaf(gqx, nr, accK[r]);
+                        accK[3 + r] = fmaf(gqy, nr, accK[3 + r]);
+                    }
+                }
+                gup[(size_t)yp*W + x] = gd*rp[4*32];
+            }
+            kcode_prev = kcode;
+            // EMPTY[slot]: this iteration's decision record and row y-2 are consumed
+            fz_signal(bar_e + 8*slot_w, lane);
+            slot_p = slot_p == FZ_R - 1 ? 0 : slot_p + 1;
+            slot_b = slot_b == FZ_R - 3 ? 0 : slot_b + 1;
+            if (++slot_w == FZ_R) { slot_w = 0; par_f ^= 1u; }
+        }
+        float* __restrict__ gp = p.gpart + (size_t)strip*LY::NPART;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float m0 = warp_sum(accA[k][r]*u), m1 = warp_sum(accB[k][r]), m2 = warp_sum(accA[k][r]), m3 = warp_sum(accC[k][r]);
+                if (lane == 0) { gp[k*12 + r*4 + 0] = m0; gp[k*12 + r*4 + 1] = m1; gp[k*12 + r*4 + 2] = m2; gp[k*12 + r*4 + 3] = m3; }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < FZ_NPART_K; ++q) {
+            const float m = warp_sum(accK[q]);
+            if (lane == 0) gp[N*12 + q] = m;
+        }
+    }
+}
+
 }  // namespace stv
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -950,8 +1480,34 @@ extern "C" int stv_tex_destroy(unsigned long long handle) {
     return STV_OK;
 }
 
+// Three-warp variant (gradients on, n <= 2): STV_FUSED_SPLIT=0 falls back to the monolithic sweep (developer A/B switch).
+// Blocks per SM are chosen so that no role spills (ptxas: 128 registers at 5 blocks for n = 2; forcing 6-8 blocks spills and is
+// 20-70 % slower; n = 3, 4 need more state per warp than 15 resident warps leave and stay on the monolithic kernel:
+// profiles/r2_photo_split.txt).
+static bool fz_use_split(int n) {
+    static const int env = getenv("STV_FUSED_SPLIT") ? atoi(getenv("STV_FUSED_SPLIT")) : 1;
+    return env != 0 && n <= FZ_SPLIT_MAX_N;
+}
+
+template <int N>
+static int fz_launch_split(const FusedParams& p, long long strips, cudaStream_t st) {
+    const size_t smem = (size_t)FzSplitLayout<N>::PER_BLOCK*sizeof(float);
+    constexpr int MB = 5;
+#define FZ_GO(TEX)                                                                                                           \
+    do {                                                                                                                     \
+        static bool attr = false;                                                                                            \
+        if (!attr) { cudaFuncSetAttribute(photo_fused_split_kernel<N, TEX, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; } \
+        photo_fused_split_kernel<N, TEX, MB><<<(unsigned)strips, FZ_SPLIT_NT, smem, st>>>(p);                                 \
+    } while (0)
+    if (p.tex) FZ_GO(true); else FZ_GO(false);
+#undef FZ_GO
+    count_launch();
+    return check_launch("photo_fused_split_kernel");
+}
+
 template <int N>
 static int fz_launch(const FusedParams& p, long long strips, bool grad, cudaStream_t st) {
+    if (N <= FZ_SPLIT_MAX_N && grad && fz_use_split(N)) return fz_launch_split<(N <= FZ_SPLIT_MAX_N ? N : 1)>(p, strips, st);
     const size_t smem = (size_t)FZ_WARPS*FzLayout<N>::PER_WARP*sizeof(float);
     const unsigned blocks = (unsigned)((strips + FZ_WARPS - 1)/FZ_WARPS);
 #define FZ_GO(TEX, GRAD)                                                                                                     \
