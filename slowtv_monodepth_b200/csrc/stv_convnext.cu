@@ -163,6 +163,71 @@ __global__ void __launch_bounds__(DW_CB) dwconv7_wgrad_kernel(int H, int W, int 
     out[(size_t)49*C + c] = gsum;
 }
 
+// Strip variant (round 2): the forward kernel's vertical sweep applied to the weight gradient. A block owns DW_L columns x `rows`
+// gradient rows of one image; the thread's 49 partial sums stay in registers for the whole strip. Input row i (image row
+// y0 - 3 + i) is loaded ONCE (DW_L + 6 values) and multiplied with the 7 gradient rows o = i - ky it pairs with, which wait in a
+// 7-slot register ring (each gradient row is loaded once, too): 2 DW_L + 6 loads per 49 DW_L FMAs instead of 8 per 49 in the
+// window kernel above, and one partial record per 8 x rows pixels instead of one per 4 x 32.
+template <int L>
+__global__ void __launch_bounds__(DW_CB) dwconv7_wgrad_strip_kernel(int H, int W, int C, int ncb, int rows, const float* __restrict__ x,
+                                                                    const float* __restrict__ gy, float* __restrict__ partial) {
+    const int c = (blockIdx.x % ncb)*DW_CB + threadIdx.x;
+    if (c >= C) return;
+    const int x0 = (blockIdx.x/ncb)*L, y0 = blockIdx.y*rows, n = blockIdx.z;
+    const int nrows = min(rows, H - y0);
+    const size_t img = (size_t)n*H*W*C;
+    int coff[L + 6];
+#pragma unroll
+    for (int q = 0; q < L + 6; ++q) {
+        const int xx = x0 + q - 3;
+        coff[q] = (xx >= 0 && xx < W) ? xx*C : -1;
+    }
+    float acc[49], gsum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 49; ++t) acc[t] = 0.f;
+    float g[7][L];
+#pragma unroll
+    for (int sl = 0; sl < 7; ++sl)
+#pragma unroll
+        for (int j = 0; j < L; ++j) g[sl][j] = 0.f;
+    for (int gi = 0; gi*7 < nrows + 6; ++gi) {
+#pragma unroll
+        for (int jr = 0; jr < 7; ++jr) {
+            const int i = gi*7 + jr;
+            if (i >= nrows + 6) break;
+            // gradient row i enters slot i mod 7 (the row it replaces, i - 7, met its last input row one step ago)
+            if (i < nrows) {
+                const float* grow = gy + img + (size_t)(y0 + i)*W*C + c;
+#pragma unroll
+                for (int j = 0; j < L; ++j) { g[jr][j] = coff[j + 3] >= 0 ? __ldg(grow + coff[j + 3]) : 0.f; gsum += g[jr][j]; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < L; ++j) g[jr][j] = 0.f;
+            }
+            const int yin = y0 - 3 + i;
+            if (yin < 0 || yin >= H) continue;
+            const float* row = x + img + (size_t)yin*W*C + c;
+            float v[L + 6];
+#pragma unroll
+            for (int q = 0; q < L + 6; ++q) v[q] = coff[q] >= 0 ? __ldg(row + coff[q]) : 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 7; ++ky) {
+                const int o = i - ky;   // gradient row paired with this input row through filter row ky
+                if (o < 0 || o >= nrows) continue;
+#pragma unroll
+                for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+                    for (int j = 0; j < L; ++j) acc[ky*7 + kx] = fmaf(g[(jr - ky + 7) % 7][j], v[j + kx], acc[ky*7 + kx]);
+            }
+        }
+    }
+    const size_t blk = ((size_t)blockIdx.z*gridDim.y + blockIdx.y)*(gridDim.x/ncb) + blockIdx.x/ncb;
+    float* out = partial + blk*50*C;
+#pragma unroll
+    for (int t = 0; t < 49; ++t) out[(size_t)t*C + c] = acc[t];
+    out[(size_t)49*C + c] = gsum;
+}
+
 // out[c*49 + t] = sum_blk partial[blk][t][c];  gb[c] = sum_blk partial[blk][49][c]. A block owns 32 consecutive entries (t, c);
 // its 8 warps stride over the partial blocks (8 independent, coalesced load streams) and are combined in a fixed order.
 __global__ void __launch_bounds__(256) dwconv7_wgrad_reduce_kernel(int C, int nblk, const float* __restrict__ partial,
@@ -358,7 +423,15 @@ extern "C" int stv_dwconv7_fwd(int N, int H, int W, int C, const float* x, const
 
 extern "C" size_t stv_dwconv7_wgrad_workspace_bytes(int N, int H, int W, int C) {
     if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return 0;
-    return (size_t)N*((H + WG_RY - 1)/WG_RY)*((W + WG_XW - 1)/WG_XW)*50*C*sizeof(float);
+    const size_t window = (size_t)N*((H + WG_RY - 1)/WG_RY)*((W + WG_XW - 1)/WG_XW);
+    const size_t strip = (size_t)N*((H + 7)/8)*((W + DW_L - 1)/DW_L);   // strips are at least 8 rows tall
+    return (window > strip ? window : strip)*50*C*sizeof(float);
+}
+
+// Weight-gradient variant: STV_DW_WGRAD=window selects the round-1 window kernel (developer A/B switch).
+static bool dw_wgrad_strip() {
+    static const bool v = !(getenv("STV_DW_WGRAD") && getenv("STV_DW_WGRAD")[0] == 'w');
+    return v;
 }
 
 extern "C" int stv_dwconv7_wgrad(int N, int H, int W, int C, const float* x, const float* gy, float* gw, float* gb, int accumulate,
@@ -370,7 +443,11 @@ extern "C" int stv_dwconv7_wgrad(int N, int H, int W, int C, const float* x, con
     if (!ws || ws_bytes < need) { set_error("stv_dwconv7_wgrad: workspace too small (%zu < %zu bytes)", ws_bytes, need); return STV_E_WORKSPACE; }
     const int ncb = (C + DW_CB - 1)/DW_CB, nt = C < DW_CB ? round32(C) : DW_CB;
     dim3 grid(((W + WG_XW - 1)/WG_XW)*ncb, (H + WG_RY - 1)/WG_RY, N);
-    dwconv7_wgrad_kernel<<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, x, gy, (float*)ws);
+    if (dw_wgrad_strip()) {
+        const int rows = dw_rows(N, H, W, C);
+        grid = dim3(((W + DW_L - 1)/DW_L)*ncb, (H + rows - 1)/rows, N);
+        dwconv7_wgrad_strip_kernel<DW_L><<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, rows, x, gy, (float*)ws);
+    } else dwconv7_wgrad_kernel<<<grid, nt, 0, (cudaStream_t)stream>>>(H, W, C, ncb, x, gy, (float*)ws);
     count_launch();
     if (int rc = check_launch("dwconv7_wgrad_kernel")) return rc;
     const int nblk = (grid.x/ncb)*grid.y*grid.z;
