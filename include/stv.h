@@ -141,6 +141,33 @@ int stv_recon_fwd(const stv_photo_cfg* cfg, const float* pred, const float* tgt,
 int stv_recon_bwd(const stv_photo_cfg* cfg, const float* pred, const float* tgt, const uint8_t* sel, const float* grad_loss,
                   float* g_pred, void* stream);
 
+/* The whole registered `img_recon` / `feat_recon` / `autoenc_recon` class on ALREADY WARPED frames (SURVEY 8f rank 4;
+ * src/losses/reconstruction.py:13-126): any channel count C (feat_recon hands encoder features, src/core/handlers.py:70-119),
+ * loss_name ssim | l1 | l2 (src/losses/photometric.py:12-23, 54-88), explainability / uncertainty weighting masks
+ * (reconstruction.py:46-57), min / mean reduction, automask. pred, source (n,b,C,H,W); tgt (b,C,H,W); mask (b,n,H,W).
+ * sel (b,H,W) u8: k = warped frame k carries the pixel, 0x40 = mean of the frames; bit 7 set = the static error won (low bits:
+ * the static frame that was the minimum). err (b,H,W) nullable: the reduced error map (compute_photo / apply_automask).
+ * stv_recon_ex_bwd: g_pred (n,b,C,H,W) and / or g_mask (b,n,H,W) (either may be NULL). */
+#define STV_RECON_SSIM 0
+#define STV_RECON_L1 1
+#define STV_RECON_L2 2
+#define STV_RECON_MASK_NONE 0
+#define STV_RECON_MASK_EXPLAIN 1
+#define STV_RECON_MASK_UNCERT 2
+typedef struct {
+    int b, n, C, H, W;
+    int loss;                      /* STV_RECON_* */
+    int use_min, use_automask;
+    int mask_mode;                 /* STV_RECON_MASK_* */
+    unsigned long long noise_seed; /* as stv_photo_cfg.noise_seed */
+} stv_recon_cfg;
+size_t stv_recon_ex_workspace_bytes(const stv_recon_cfg* cfg);
+int stv_recon_ex_fwd(const stv_recon_cfg* cfg, const float* pred, const float* tgt, const float* source, const float* mask,
+                     const float* noise, unsigned long long* noise_step, float* loss, uint8_t* sel, float* err, void* ws,
+                     size_t ws_bytes, void* stream);
+int stv_recon_ex_bwd(const stv_recon_cfg* cfg, const float* pred, const float* tgt, const float* source, const float* mask,
+                     const uint8_t* sel, const float* grad_loss, float* g_pred, float* g_mask, void* stream);
+
 /* ViewSynth.forward (src/tools/geometry.py:366-391) on its own: input (B,C,H,W), depth (B,1,H,W), T,K,Kinv (B,4,4) ->
  * warp (B,C,H,W), depth_warp (B,1,H,W), mask_valid (B,1,H,W) u8. Any C; used by the stand-alone ViewSynth module. */
 int stv_view_synth_fwd(int B, int C, int H, int W, const float* input, const float* depth, const float* T,
@@ -209,6 +236,17 @@ size_t stv_layernorm_bwd_workspace_bytes(long long P, int C);
 int stv_layernorm_bwd(long long P, int C, const float* dy, const float* x, const float* mean, const float* rstd,
                       const float* gamma, float* dx, float* dgamma, float* dbeta, int accumulate /* dgamma, dbeta += */, void* ws,
                       size_t ws_bytes, void* stream);
+
+/* SmoothReg.forward with every constructor flag (src/regularizers/smooth.py:12-97): use_laplacian = second-order
+ * absolute gradients (compute_laplacian, :33-48), use_blur = 3x3 sigma-1 Gaussian pre-blur of every differentiated map
+ * (kornia.filters.gaussian_blur2d, reflect border), use_edges = exp(-|image gradient|) weights. Single scale: disp (b,1,H,W),
+ * img (b,C,H,W) at the same resolution. loss (); disp_grad / image_grad (b,1,H,W) nullable logging maps (:88-92).
+ * The backward needs the workspace the forward filled (>= stv_smooth_ex_workspace_bytes). */
+size_t stv_smooth_ex_workspace_bytes(int b, int C, int H, int W);
+int stv_smooth_ex_fwd(int b, int C, int H, int W, int use_edges, int use_laplacian, int use_blur, const float* disp,
+                      const float* img, float* loss, float* disp_grad, float* image_grad, void* ws, size_t ws_bytes, void* stream);
+int stv_smooth_ex_bwd(int b, int C, int H, int W, int use_edges, int use_laplacian, int use_blur, const float* disp,
+                      const float* grad_loss, float* g_disp, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Tensor-core products of the network layers (tcgen05.mma kind::tf32 + TMA + TMEM; fp32 storage, TF32 multiply, fp32

@@ -262,6 +262,60 @@ def reconstruction_loss(pred: Tensor, target: Tensor, source: Tensor | None, use
     return err.mean(), automask, err, sel.to(torch.uint8)
 
 
+def dense_error(pred: Tensor, target: Tensor, loss_name: str = 'ssim') -> Tensor:
+    """(b,c,h,w) x2 -> (b,1,h,w): PhotoError(0.85) | DenseL1Error | DenseL2Error (src/losses/photometric.py:12-23, 54-88)."""
+    if loss_name == 'ssim': return photo_error(pred, target)
+    if loss_name == 'l1': return (pred - target).abs().mean(1, keepdim=True)
+    if loss_name == 'l2': return (pred - target).pow(2).sum(1, keepdim=True).clamp(min=_eps(pred)).sqrt()
+    raise KeyError(loss_name)
+
+
+def apply_mask(err: Tensor, mask: Tensor | None, mask_name: str | None) -> Tensor:
+    """src/losses/reconstruction.py:46-57. err, mask (b,n,h,w)."""
+    if mask_name and mask is None: raise ValueError("Must provide a 'mask' when masking...")
+    if mask_name == 'explainability': return err*mask
+    if mask_name == 'uncertainty': return err*(-mask).exp() + mask
+    return err
+
+
+def reconstruction_loss_ex(pred: Tensor, target: Tensor, source: Tensor | None = None, mask: Tensor | None = None,
+                           loss_name: str = 'ssim', use_min: bool = False, use_automask: bool = False, mask_name: str | None = None,
+                           noise: Tensor | None = None):
+    """The whole registered class (src/losses/reconstruction.py:13-126) on pre-warped frames: pred, source (n,b,c,h,w), target
+    (b,c,h,w), mask (b,n,h,w) -> (loss, automask|None, err (b,1,h,w), sel (b,1,h,w) uint8 in the encoding of stv_recon_ex_fwd:
+    k | 0x40 (mean); bit 7 = automasked, low bits = the static frame that was the minimum)."""
+    def photo(frames):
+        e = torch.stack([dense_error(f, target, loss_name)[:, 0] for f in frames], 1)   # (b, n, h, w)
+        e = apply_mask(e, mask, mask_name)
+        if use_min:
+            v, k = e.min(1, keepdim=True)   # first index wins ties
+            return v, k
+        return e.mean(1, keepdim=True), torch.full_like(e[:, :1], 0x40, dtype=torch.long)
+    err, sel = photo(pred)
+    automask = None
+    if use_automask:
+        if source is None: raise ValueError("Must provide the original 'source' images when automasking...")
+        es, ksel = photo(source)
+        if noise is not None: es = es + _eps(es)*noise
+        both = torch.cat([err, es], 1)
+        err, idx = both.min(1, keepdim=True)
+        automask = idx == 0
+        sel = torch.where(automask, sel, ksel | 0x80)
+    return err.mean(), automask, err, sel.to(torch.uint8)
+
+
+def feat_recon(depth0: Tensor, feats: Tensor, supp_feats: Tensor, Ts: Tensor, Ks: Tensor, loss_name: str = 'l2', use_min: bool = False,
+               use_automask: bool = False, mask0: Tensor | None = None, mask_name: str | None = None, noise: Tensor | None = None):
+    """src/core/handlers.py:70-119: feats (b,c,h4,w4), supp_feats (n,b,c,h4,w4) at 1/4 resolution, depth0 (b,1,H,W).
+    -> (loss, warped features (n,b,c,H,W))."""
+    size = depth0.shape[-2:]
+    f = resize_bilinear(feats.detach(), size)
+    sf = torch.stack([resize_bilinear(x.detach(), size) for x in supp_feats])
+    warp = torch.stack([view_synth(sf[k], depth0, Ts[k], Ks)[0] for k in range(sf.shape[0])])
+    loss = reconstruction_loss_ex(warp, f, sf, mask0, loss_name, use_min, use_automask, mask_name, noise)[0]
+    return loss, warp
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Row 8: handlers.image_recon  (src/core/handlers.py:14-67)
 # ---------------------------------------------------------------------------------------------------------------------
@@ -298,6 +352,44 @@ def _abs_grad(x: Tensor, ch_mean: bool = False):
     dy = torch.cat([(x[..., :-1, :] - x[..., 1:, :]).abs(), torch.zeros_like(x[..., :1, :])], -2)
     if ch_mean: dx, dy = dx.mean(1, keepdim=True), dy.mean(1, keepdim=True)
     return dx, dy
+
+
+def gaussian_blur3(x: Tensor) -> Tensor:
+    """kornia.filters.gaussian_blur2d(x, (3, 3), (1, 1)) (kornia 0.6.10, third-party, absent here — PARITY UNPINNED): separable
+    normalised Gaussian taps exp(-d^2/2), d in {-1, 0, 1}, border_type='reflect' (no edge repeat)."""
+    g = torch.tensor([-1., 0., 1.], dtype=x.dtype, device=x.device).pow(2).mul(-0.5).exp()
+    g = g/g.sum()
+    xp = _reflect_pad1(x)
+    h = g[0]*xp[..., :, :-2] + g[1]*xp[..., :, 1:-1] + g[2]*xp[..., :, 2:]
+    return g[0]*h[..., :-2, :] + g[1]*h[..., 1:-1, :] + g[2]*h[..., 2:, :]
+
+
+def _abs_grad_ex(x: Tensor, use_blur: bool = False, ch_mean: bool = False):
+    """compute_grad (src/regularizers/smooth.py:12-30)."""
+    if use_blur: x = gaussian_blur3(x)
+    return _abs_grad(x, ch_mean)
+
+
+def _abs_laplacian(x: Tensor, use_blur: bool = False, ch_mean: bool = False):
+    """compute_laplacian (src/regularizers/smooth.py:33-48) -> (dxx, dyy, dxy, dyx)."""
+    dx, dy = _abs_grad_ex(x, use_blur)
+    dxx, dxy = _abs_grad_ex(dx, use_blur)
+    dyx, dyy = _abs_grad_ex(dy, use_blur)
+    if ch_mean: dxx, dxy, dyx, dyy = (v.mean(1, keepdim=True) for v in (dxx, dxy, dyx, dyy))
+    return dxx, dyy, dxy, dyx
+
+
+def smooth_reg_ex(disp: Tensor, img: Tensor, use_edges: bool = False, use_laplacian: bool = False, use_blur: bool = False):
+    """SmoothReg.forward with every constructor flag (src/regularizers/smooth.py:51-97) -> (loss, disp_grad, image_grad)."""
+    eps = _eps(disp)
+    fn = _abs_laplacian if use_laplacian else _abs_grad_ex
+    d = disp/disp.mean((2, 3), keepdim=True).clamp(min=eps)
+    ddx, ddy = fn(d, use_blur)[:2]
+    disp_grad = (ddx**2 + ddy**2).clamp(min=eps).sqrt()
+    idx, idy = fn(img, use_blur, True)[:2]
+    img_grad = (idx**2 + idy**2).clamp(min=eps).sqrt()
+    if use_edges: ddx, ddy = ddx*(-idx).exp(), ddy*(-idy).exp()
+    return ddx.mean() + ddy.mean(), disp_grad, img_grad
 
 
 def smooth_reg(disp: Tensor, img: Tensor, use_edges: bool = True):

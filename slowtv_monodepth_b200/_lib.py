@@ -29,6 +29,15 @@ class PhotoCfg(C.Structure):
                 ('noise_seed', C.c_uint64), ('depth_stride_s', C.c_int64)]
 
 
+class ReconCfg(C.Structure):
+    _fields_ = [('b', C.c_int), ('n', C.c_int), ('C', C.c_int), ('H', C.c_int), ('W', C.c_int), ('loss', C.c_int),
+                ('use_min', C.c_int), ('use_automask', C.c_int), ('mask_mode', C.c_int), ('noise_seed', C.c_uint64)]
+
+
+RECON_LOSS = {'ssim': 0, 'l1': 1, 'l2': 2}
+RECON_MASK = {None: 0, 'explainability': 1, 'uncertainty': 2}
+
+
 class PhotoSrc(C.Structure):
     _fields_ = [('mode', C.c_int), ('h', C.c_int*MAX_SCALES), ('w', C.c_int*MAX_SCALES), ('min_depth', C.c_float), ('max_depth', C.c_float)]
 
@@ -70,6 +79,12 @@ _SIGNATURES = {
     'stv_recon_workspace_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
     'stv_recon_fwd': (C.c_int, [C.POINTER(PhotoCfg)] + [_P]*9 + [C.c_size_t, _P]),
     'stv_recon_bwd': (C.c_int, [C.POINTER(PhotoCfg)] + [_P]*6),
+    'stv_smooth_ex_workspace_bytes': (C.c_size_t, [C.c_int]*4),
+    'stv_smooth_ex_fwd': (C.c_int, [C.c_int]*7 + [_P]*6 + [C.c_size_t, _P]),
+    'stv_smooth_ex_bwd': (C.c_int, [C.c_int]*7 + [_P]*4 + [C.c_size_t, _P]),
+    'stv_recon_ex_workspace_bytes': (C.c_size_t, [C.POINTER(ReconCfg)]),
+    'stv_recon_ex_fwd': (C.c_int, [C.POINTER(ReconCfg)] + [_P]*10 + [C.c_size_t, _P]),
+    'stv_recon_ex_bwd': (C.c_int, [C.POINTER(ReconCfg)] + [_P]*9),
     'stv_view_synth_fwd': (C.c_int, [C.c_int]*4 + [_P]*9),
     'stv_view_synth_workspace_bytes': (C.c_size_t, [C.c_int]*4),
     'stv_view_synth_bwd': (C.c_int, [C.c_int]*4 + [_P]*13 + [C.c_size_t, _P]),

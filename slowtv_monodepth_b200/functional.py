@@ -446,6 +446,82 @@ def recon_loss(pred: Tensor, target: Tensor, source: Tensor | None = None, *, lo
                             _f32c(noise), noise_step)
 
 
+class _ReconLossEx(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg: L.ReconCfg, pred, tgt, source, mask, noise, noise_step):
+        L.require_cuda(pred, tgt, source, mask, noise, noise_step, what='recon_loss_ex')
+        lib, dev = L.lib(), pred.device
+        with torch.cuda.device(dev):
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            sel = torch.empty((cfg.b, cfg.H, cfg.W), dtype=torch.uint8, device=dev)
+            ws = _ws(lib.stv_recon_ex_workspace_bytes(C.byref(cfg)), dev)
+            L.check(lib.stv_recon_ex_fwd(C.byref(cfg), L.ptr(pred), L.ptr(tgt), L.ptr(source), L.ptr(mask), L.ptr(noise), L.ptr(noise_step),
+                                         L.ptr(loss), L.ptr(sel), None, L.ptr(ws), ws.numel(), L.stream()), 'stv_recon_ex_fwd')
+        ctx.cfg = cfg
+        ctx.save_for_backward(pred, tgt, source, mask, sel)
+        ctx.mark_non_differentiable(sel)
+        return loss, sel
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_sel):
+        pred, tgt, source, mask, sel = ctx.saved_tensors
+        want_pred, want_mask = ctx.needs_input_grad[1], mask is not None and ctx.needs_input_grad[4]
+        if not (want_pred or want_mask): return (None,)*7
+        with torch.cuda.device(pred.device):
+            g_pred = torch.empty_like(pred) if want_pred else None
+            g_mask = torch.empty_like(mask) if want_mask else None
+            L.check(L.lib().stv_recon_ex_bwd(C.byref(ctx.cfg), L.ptr(pred), L.ptr(tgt), L.ptr(source), L.ptr(mask), L.ptr(sel),
+                                             L.ptr(g_loss.to(torch.float32).contiguous()), L.ptr(g_pred), L.ptr(g_mask), L.stream()),
+                    'stv_recon_ex_bwd')
+        return None, g_pred, None, None, g_mask, None, None
+
+
+def _recon_ex_args(pred, target, source, mask, loss_name, use_min, use_automask, mask_name, noise_seed):
+    if loss_name not in L.RECON_LOSS: raise KeyError(f'loss_name="{loss_name}" (ssim | l1 | l2)')
+    if mask_name not in L.RECON_MASK: raise ValueError(f'Invalid mask type: {mask_name}')
+    if pred.ndim == 4: pred = pred[None]
+    if source is not None and source.ndim == 4: source = source[None]
+    n, b, c, H, W = pred.shape
+    if target.shape != (b, c, H, W): raise ValueError(f'Invalid shapes. ({tuple(pred.shape)} vs. {tuple(target.shape)})')
+    if use_automask and source is None: raise ValueError("Must provide the original 'source' images when automasking...")
+    if source is not None and source.shape != pred.shape: raise ValueError(f'Invalid source shape. ({tuple(source.shape)} vs. {tuple(pred.shape)})')
+    if mask_name and mask is None: raise ValueError("Must provide a 'mask' when masking...")
+    if mask is not None and not mask_name: mask = None   # apply_mask ignores the tensor without a mask_name (reconstruction.py:55-56)
+    if mask is not None and mask.shape == (b, 1, H, W) and n > 1: mask = mask.expand(b, n, H, W)   # broadcasts like err*mask
+    if mask is not None and mask.shape != (b, n, H, W): raise ValueError(f'Invalid mask shape. ({tuple(mask.shape)} vs. {(b, n, H, W)})')
+    cfg = L.ReconCfg(b=b, n=n, C=c, H=H, W=W, loss=L.RECON_LOSS[loss_name], use_min=int(use_min), use_automask=int(use_automask),
+                     mask_mode=L.RECON_MASK[mask_name if mask is not None else None], noise_seed=int(noise_seed))
+    return cfg, pred, source, mask
+
+
+def recon_loss_ex(pred: Tensor, target: Tensor, source: Tensor | None = None, mask: Tensor | None = None, *, loss_name: str = 'ssim',
+                  use_min: bool = False, use_automask: bool = False, mask_name: str | None = None, noise: Tensor | None = None,
+                  noise_seed: int = 0, noise_step: Tensor | None = None):
+    """The full `ReconstructionLoss.forward` contract (src/losses/reconstruction.py:98-126): any channel count, loss_name
+    ssim | l1 | l2, explainability / uncertainty masks; differentiable in `pred` and `mask`.
+    pred (n,b,C,H,W) | (b,C,H,W); target (b,C,H,W); source like pred; mask (b,n,H,W) -> loss (), sel (b,H,W) uint8 (bit 7: automasked)."""
+    cfg, pred, source, mask = _recon_ex_args(pred, target, source, mask, loss_name, use_min, use_automask, mask_name, noise_seed)
+    return _ReconLossEx.apply(cfg, _f32c(pred), _f32c(target.detach()), _f32c(None if source is None else source.detach()), _f32c(mask),
+                              _f32c(noise), noise_step)
+
+
+def photo_error_ex(pred: Tensor, target: Tensor, mask: Tensor | None = None, *, loss_name: str = 'ssim', use_min: bool = True,
+                   mask_name: str | None = None) -> Tensor:
+    """`ReconstructionLoss.compute_photo` (reconstruction.py:79-96) for any channel count / loss / mask; forward only -> (b,1,H,W)."""
+    cfg, pred, _, mask = _recon_ex_args(pred, target, None, mask, loss_name, use_min, False, mask_name, 0)
+    L.require_cuda(pred, target, mask, what='photo_error_ex')
+    pred, target, mask = _f32c(pred.detach()), _f32c(target.detach()), _f32c(None if mask is None else mask.detach())
+    lib, dev = L.lib(), pred.device
+    with torch.cuda.device(dev):
+        err = torch.empty((cfg.b, 1, cfg.H, cfg.W), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        sel = torch.empty((cfg.b, cfg.H, cfg.W), dtype=torch.uint8, device=dev)
+        ws = _ws(lib.stv_recon_ex_workspace_bytes(C.byref(cfg)), dev)
+        L.check(lib.stv_recon_ex_fwd(C.byref(cfg), L.ptr(pred), L.ptr(target), None, L.ptr(mask), None, None, L.ptr(loss), L.ptr(sel),
+                                     L.ptr(err), L.ptr(ws), ws.numel(), L.stream()), 'stv_recon_ex_fwd')
+    return err
+
+
 class _Inv4x4(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A):
@@ -1096,6 +1172,43 @@ def convnext_mlp(x: Tensor, res: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2:
     if x.ndim != 2 or res.shape != x.shape or w1.shape[1] != x.shape[1] or w2.shape != w1.shape[::-1]:
         raise ValueError(f'convnext_mlp: bad shapes {tuple(x.shape)}, {tuple(res.shape)}, {tuple(w1.shape)}, {tuple(w2.shape)}')
     return _ConvNeXtMlp.apply(_f32c(x), _f32c(res), _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2), _f32c(gamma), link)
+
+
+class _SmoothLossEx(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, img, use_edges: bool, use_laplacian: bool, use_blur: bool):
+        L.require_cuda(disp, img, what='smooth_loss_ex')
+        b, _, H, W = disp.shape
+        Cc = img.shape[1]
+        lib, dev = L.lib(), disp.device
+        flags = (int(use_edges), int(use_laplacian), int(use_blur))
+        with torch.cuda.device(dev):
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            dg, ig = torch.empty_like(disp), torch.empty_like(disp)
+            ws = _ws(lib.stv_smooth_ex_workspace_bytes(b, Cc, H, W), dev)
+            L.check(lib.stv_smooth_ex_fwd(b, Cc, H, W, *flags, L.ptr(disp), L.ptr(img), L.ptr(loss), L.ptr(dg), L.ptr(ig), L.ptr(ws),
+                                          ws.numel(), L.stream()), 'stv_smooth_ex_fwd')
+        ctx.flags, ctx.shape = flags, (b, Cc, H, W)
+        ctx.save_for_backward(disp, ws)
+        ctx.mark_non_differentiable(dg, ig)
+        return loss, dg, ig
+
+    @staticmethod
+    def backward(ctx, g_loss, _g1, _g2):
+        disp, ws = ctx.saved_tensors
+        with torch.cuda.device(disp.device):
+            g = torch.empty_like(disp)
+            L.check(L.lib().stv_smooth_ex_bwd(*ctx.shape, *ctx.flags, L.ptr(disp), L.ptr(g_loss.to(torch.float32).contiguous()), L.ptr(g),
+                                              L.ptr(ws), ws.numel(), L.stream()), 'stv_smooth_ex_bwd')
+        return g, None, None, None, None
+
+
+def smooth_loss_ex(disp: Tensor, img: Tensor, *, use_edges: bool = False, use_laplacian: bool = False, use_blur: bool = False):
+    """`SmoothReg.forward` with every constructor flag (src/regularizers/smooth.py:51-97), single scale: disp (b,1,H,W), img (b,C,H,W)
+    -> (loss, disp_grad (b,1,H,W), image_grad (b,1,H,W)); differentiable in `disp`."""
+    if disp.ndim != 4 or disp.shape[1] != 1 or img.ndim != 4 or img.shape[0] != disp.shape[0] or img.shape[-2:] != disp.shape[-2:]:
+        raise ValueError(f'Non-matching shapes. ({tuple(disp.shape)} vs. {tuple(img.shape)})')
+    return _SmoothLossEx.apply(_f32c(disp), _f32c(img.detach()), bool(use_edges), bool(use_laplacian), bool(use_blur))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

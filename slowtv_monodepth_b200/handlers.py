@@ -7,7 +7,7 @@ from torch import Tensor
 from .losses import ReconstructionLoss
 from .regularizers import SmoothReg
 
-__all__ = ['image_recon', 'disp_smooth']
+__all__ = ['image_recon', 'feat_recon', 'disp_smooth']
 
 
 def _disparity_sources(depths: dict[int, Tensor], size) -> tuple | None:
@@ -34,7 +34,8 @@ def image_recon(crit: ReconstructionLoss, synth, depths: dict[int, Tensor], mask
     tagged outputs of `functional.disp_to_depth` (what the installed `forward_postprocess` produces) the same shortcut is taken
     automatically, so the reference's own `forward_loss` call site (trainer.py:389-393) gets it unchanged.
     """
-    if masks is not None: raise ValueError('Predicted photometric masks are not supported by the B200 loss kernels.')
+    if masks is not None or not crit.fusable or imgs.shape[1] != 3:
+        return _image_recon_general(crit, depths, masks, imgs, supp_imgs, Ts, Ks, noise=noise)
     if disps is None and crit.use_min and depths is not None:
         found = _disparity_sources(depths, imgs.shape[-2:])
         if found is not None: disps, depth_range = dict(zip(depths, found[0])), found[1]
@@ -47,6 +48,47 @@ def image_recon(crit: ReconstructionLoss, synth, depths: dict[int, Tensor], mask
     out = {k: v[0] for k, v in ld.items()}  # Only scale 0 (handlers.py:64-65).
     if want_warp: out['supp_imgs_warp'] = warp0
     return loss, out
+
+
+def _image_recon_general(crit: ReconstructionLoss, depths: dict[int, Tensor], masks, imgs: Tensor, supp_imgs: Tensor, Ts: Tensor,
+                         Ks: Tensor, *, noise: Tensor | None = None):
+    """The reference's own formulation (handlers.py:43-66) for what the single-pass kernel does not cover — predicted weighting
+    masks, loss_name 'l2', C-channel feature maps: one stand-alone warp of the (n, S, b)-expanded batch (stv_view_synth, any
+    channel count) followed by the general loss kernels (`ReconstructionLoss.forward`)."""
+    from . import functional as F_
+    n, S = supp_imgs.shape[0], len(depths)
+    b, c, H, W = imgs.shape
+    depth = torch.stack(list(depths.values()))                                            # (S, b, 1, H, W)
+    depth = depth[None].expand(n, *depth.shape).reshape(n*S*b, 1, H, W)
+    inp = supp_imgs[:, None].expand(n, S, b, c, H, W)
+    T = Ts[:, None].expand(n, S, b, 4, 4).reshape(n*S*b, 4, 4)
+    K = Ks[None, None].expand(n, S, b, 4, 4).reshape(n*S*b, 4, 4)
+    warp = F_.view_synth(inp.reshape(n*S*b, c, H, W).contiguous(), depth.contiguous(), T.contiguous(), K.contiguous())[0]
+    warp = warp.view(n, S*b, c, H, W)
+    tgt = imgs[None].expand(S, b, c, H, W).reshape(S*b, c, H, W)
+    src = inp.reshape(n, S*b, c, H, W)
+    m = None
+    if masks is not None: m = torch.stack(list(masks.values())).flatten(0, 1)            # (S*b, n, H, W)
+    if noise is not None: noise = noise.reshape(S*b, 1, H, W)
+    loss, ld = crit(warp, tgt.contiguous(), source=src.contiguous(), mask=m, noise=noise)
+    out = {k: v.unflatten(0, (S, b))[0] for k, v in ld.items()}                          # Only scale 0 (handlers.py:63-64).
+    out['supp_imgs_warp'] = warp.view(n, S, b, c, H, W)[:, 0]
+    return loss, out
+
+
+def feat_recon(crit: ReconstructionLoss, synth, depths: dict[int, Tensor], masks, feats, supp_feats, Ts: Tensor, Ks: Tensor):
+    """Reference: src/core/handlers.py:70-119 — feature-space reconstruction at the highest-resolution depth map with the x4
+    down-sampled encoder features, no gradient into the features. -> (loss, {'supp_feats_warp': (n,b,c,H,W)})."""
+    from . import functional as F_
+    if isinstance(feats, list): feats, supp_feats = feats[-4], supp_feats[-4]               # [*2, 4, 8, 16, 32] -> 4
+    feats, supp_feats = feats.detach(), supp_feats.detach()
+    size = tuple(depths[0].shape[-2:])
+    with torch.no_grad():                                                                  # ops.interpolate_like(mode='bilinear')
+        feats = F_.resample_bilinear(feats.contiguous(), size, mode='interp')
+        supp_feats = F_.resample_bilinear(supp_feats.contiguous(), size, mode='interp')
+    masks = {0: masks[0]} if masks is not None else None
+    loss, ld = image_recon(crit, synth, {0: depths[0]}, masks, feats, supp_feats, Ts, Ks)
+    return loss, {'supp_feats_warp': ld.pop('supp_imgs_warp')}
 
 
 def disp_smooth(crit: SmoothReg, disps: dict[int, Tensor], imgs: Tensor, *, want_maps: bool = True):

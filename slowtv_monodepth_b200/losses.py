@@ -19,18 +19,19 @@ __all__ = ['ReconstructionLoss']
 class ReconstructionLoss(nn.Module):
     """Reference: src/losses/reconstruction.py:13-126.
 
-    :param loss_name: 'ssim' (0.85 SSIM + 0.15 L1) or 'l1'. ('l2' is only used by `feat_recon`, out of scope.)
+    :param loss_name: 'ssim' (0.85 SSIM + 0.15 L1), 'l1' or 'l2' (the feature-space distance of `feat_recon`).
     :param use_min: minimum reprojection over the support frames instead of the mean.
     :param use_automask: mask pixels whose un-warped support frame already explains the target better.
-    :param mask_name: explainability / uncertainty weighting (not part of the KBR configuration) — rejected loudly.
+    :param mask_name: None | 'explainability' | 'uncertainty' weighting of the per-frame errors (reconstruction.py:46-57).
+
+    The single-pass fused kernel (`fused`) covers the KBR hot path: 3-channel frames, ssim | l1, no weighting mask. Everything
+    else the class is registered for ('l2', masks, C-channel features) runs on the general kernels behind `forward`
+    (stv_recon_ex_fwd / stv_recon_ex_bwd) after a stand-alone warp (`handlers.image_recon` picks the route).
     """
     def __init__(self, loss_name: str = 'ssim', use_min: bool = False, use_automask: bool = False, mask_name: str | None = None):
         super().__init__()
         if mask_name not in {'explainability', 'uncertainty', None}: raise ValueError(f'Invalid mask type: {mask_name}')
-        if mask_name is not None:
-            raise NotImplementedError(f'mask_name="{mask_name}" is outside the B200 hot path (SURVEY 8a row 14); use the reference class.')
-        if loss_name not in {'ssim', 'l1'}:
-            raise KeyError(f'loss_name="{loss_name}" is not provided by the B200 photometric kernels (ssim | l1).')
+        if loss_name not in {'ssim', 'l1', 'l2'}: raise KeyError(loss_name)  # the reference indexes a dict (reconstruction.py:37-41)
         self.loss_name, self.use_min, self.use_automask, self.mask_name = loss_name, use_min, use_automask, mask_name
         self.noise_seed = 0x5107  # Base seed of the in-kernel tie-break noise (reconstruction.py:72 draws randn_like per call).
         # Device-side call counter added to the seed: the kernels advance it themselves, so eager calls AND replays of a captured
@@ -38,10 +39,16 @@ class ReconstructionLoss(nn.Module):
         # runners warm up eagerly first). Tests set it (`noise_step.fill_(k)`) to reproduce a particular draw.
         self.noise_step: Tensor | None = None
 
+    @property
+    def fusable(self) -> bool:
+        """The single-pass warp + loss kernel serves this configuration (given 3-channel frames and no mask tensor)."""
+        return self.loss_name in {'ssim', 'l1'} and self.mask_name is None
+
     def compute_photo(self, pred: Tensor, target: Tensor, mask: Tensor | None = None) -> Tensor:
-        """pred (*n,b,3,h,w), target (b,3,h,w) -> (b,1,h,w). Forward only (used for automasks and `depth_regr`)."""
-        if mask is not None: raise ValueError('Weighting masks are not supported by the B200 photometric kernels.')
-        return F_.photo_error(pred, target, loss_name=self.loss_name, use_min=self.use_min)
+        """pred (*n,b,c,h,w), target (b,c,h,w), mask (b,n,h,w) -> (b,1,h,w). Forward only (used for automasks and `depth_regr`)."""
+        if self.mask_name and mask is None: raise ValueError("Must provide a 'mask' when masking...")
+        if self.fusable and target.shape[1] == 3: return F_.photo_error(pred, target, loss_name=self.loss_name, use_min=self.use_min)
+        return F_.photo_error_ex(pred, target, mask, loss_name=self.loss_name, use_min=self.use_min, mask_name=self.mask_name)
 
     def fused(self, depths: list[Tensor], target: Tensor, source: Tensor, T: Tensor, K: Tensor, K_inv: Tensor | None = None,
               noise: Tensor | None = None, want_warp: bool = False, from_disp: tuple | None = None):
@@ -66,14 +73,18 @@ class ReconstructionLoss(nn.Module):
 
     def forward(self, pred: Tensor, target: Tensor, source: Tensor | None = None, mask: Tensor | None = None, *,
                 noise: Tensor | None = None):
-        """Reference contract (reconstruction.py:98-126) on ALREADY WARPED frames: pred (*n,b,3,h,w), target (b,3,h,w),
-        source (*n,b,3,h,w) -> (loss, {'automask': (b,1,h,w) bool}); differentiable in `pred` (stv_recon_fwd / stv_recon_bwd).
+        """Reference contract (reconstruction.py:98-126) on ALREADY WARPED frames: pred (*n,b,c,h,w), target (b,c,h,w),
+        source (*n,b,c,h,w), mask (b,n,h,w) -> (loss, {'automask': (b,1,h,w) bool}); differentiable in `pred` and `mask`.
         The training hot path does not come through here — `handlers.image_recon` fuses the warp into the loss kernel — but
-        everything else that calls the registered `img_recon` class directly does (e.g. the virtual-stereo branch,
-        src/core/trainer.py:394-399)."""
-        if mask is not None: raise ValueError('Weighting masks are not supported by the B200 photometric kernels.')
+        everything else that calls the registered class directly does (the virtual-stereo branch, src/core/trainer.py:394-399;
+        `feat_recon` / masked configurations via `handlers.image_recon`'s general route)."""
         if self.use_automask and source is None: raise ValueError("Must provide the original 'source' images when automasking...")
         draw = self.use_automask and noise is None
+        if not (self.fusable and target.shape[1] == 3):
+            loss, sel = F_.recon_loss_ex(pred, target, source if self.use_automask else None, mask, loss_name=self.loss_name,
+                                         use_min=self.use_min, use_automask=self.use_automask, mask_name=self.mask_name, noise=noise,
+                                         noise_seed=self.noise_seed if draw else 0, noise_step=self._step_counter(target) if draw else None)
+            return loss, ({'automask': (sel < 128).unsqueeze(1)} if self.use_automask else {})
         loss, sel = F_.recon_loss(pred, target, source if self.use_automask else None, loss_name=self.loss_name, use_min=self.use_min,
                                   use_automask=self.use_automask, noise=noise, noise_seed=self.noise_seed if draw else 0,
                                   noise_step=self._step_counter(target) if draw else None)

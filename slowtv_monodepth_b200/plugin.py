@@ -6,7 +6,7 @@
 
 `install()` (a) triggers the reference's lazy registrations so the originals exist, (b) re-registers the B200 classes under
 the same keys with `overwrite=True` (registry.py:131-132), and (c) rebinds the names the trainer resolves at call time:
-`src.core.handlers.image_recon / disp_smooth` (trainer.py:389,437), `src.core.trainer.ViewSynth` (trainer.py:168) and
+`src.core.handlers.image_recon / feat_recon / disp_smooth` (trainer.py:389,402,437), `src.core.trainer.ViewSynth` (trainer.py:168) and
 `src.core.trainer.aspect_ratio_aug` (trainer.py:12,54-60; the GPU augmentation of SURVEY 8f).
 With `fast_step=True` (default) it also removes the host synchronisations of the reference's own `MonoDepthModule.step`, which
 otherwise cap the drop-in's speed whatever the kernels do: `forward` (trainer.py:192-278; ATen's host-synchronising
@@ -28,7 +28,9 @@ __all__ = ['install', 'uninstall', 'graphed_step', 'REPLACED']
 REPLACED = {
     'net': {'depth': networks.DepthNet, 'pose': networks.PoseNet},
     'dec': {'monodepth': networks.MonodepthDecoder},
-    'loss': {'img_recon': losses.ReconstructionLoss, 'disp_smooth': regularizers.SmoothReg},
+    # the reference registers ONE class under three keys (src/losses/reconstruction.py:12)
+    'loss': {'img_recon': losses.ReconstructionLoss, 'feat_recon': losses.ReconstructionLoss, 'autoenc_recon': losses.ReconstructionLoss,
+             'disp_smooth': regularizers.SmoothReg},
 }
 _saved: dict = {}
 
@@ -77,9 +79,11 @@ def install(nets: bool = True, loss: bool = True, fast_step: bool = True) -> Non
         for key, cls in REPLACED['loss'].items(): put('loss', key, cls)
         _saved.setdefault(('attr', 'image_recon'), ref_handlers.image_recon)
         _saved.setdefault(('attr', 'disp_smooth'), ref_handlers.disp_smooth)
+        _saved.setdefault(('attr', 'feat_recon'), ref_handlers.feat_recon)
         _saved.setdefault(('attr', 'ViewSynth'), ref_trainer.ViewSynth)
         ref_handlers.image_recon = handlers.image_recon
         ref_handlers.disp_smooth = handlers.disp_smooth
+        ref_handlers.feat_recon = handlers.feat_recon
         ref_trainer.ViewSynth = geometry.ViewSynth
     # MonoDepthModule.__init__ binds `aspect_ratio_aug` by name from src.core.trainer (trainer.py:12,54-60)
     _saved.setdefault(('attr', 'aspect_ratio_aug'), ref_trainer.aspect_ratio_aug)
@@ -113,6 +117,6 @@ def uninstall() -> None:
             if val is None: reg._REG[key[1]].pop(key[2], None)
             else: reg._REG[key[1]][key[2]] = val
         elif key[0] == 'method': setattr(ref_trainer.MonoDepthModule, key[1], val)
-        elif key[1] in ('image_recon', 'disp_smooth'): setattr(ref_handlers, key[1], val)
+        elif key[1] in ('image_recon', 'disp_smooth', 'feat_recon'): setattr(ref_handlers, key[1], val)
         else: setattr(ref_trainer, key[1], val)
     _saved.clear()

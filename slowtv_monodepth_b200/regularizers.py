@@ -10,21 +10,34 @@ __all__ = ['SmoothReg']
 
 
 class SmoothReg(nn.Module):
-    """Reference: src/regularizers/smooth.py:51-97 (first-order variant; Laplacian / blur are ablation-only, rejected)."""
+    """Reference: src/regularizers/smooth.py:51-97. The first-order variant (the KBR configuration) runs on the multi-scale hot-path
+    kernels (stv_smooth_fwd/bwd); `use_laplacian` / `use_blur` run scale by scale on the general ones (stv_smooth_ex_fwd/bwd)."""
     def __init__(self, use_edges: bool = False, use_laplacian: bool = False, use_blur: bool = False):
         super().__init__()
-        if use_laplacian or use_blur:
-            raise NotImplementedError('use_laplacian / use_blur are outside the B200 hot path (SURVEY 8a row 16).')
         self.use_edges, self.use_laplacian, self.use_blur = use_edges, use_laplacian, use_blur
+
+    @property
+    def general(self) -> bool:
+        return self.use_laplacian or self.use_blur
 
     def forward(self, disp: Tensor, img: Tensor):
         """disp (b,1,h,w), img (b,3,h,w) at the same resolution -> (loss, {'disp_grad', 'image_grad'})."""
         if disp.shape[-2:] != img.shape[-2:]: raise ValueError(f'Non-matching shapes. ({tuple(disp.shape)} vs. {tuple(img.shape)})')
+        if self.general:
+            loss, dg, ig = F_.smooth_loss_ex(disp, img, use_edges=self.use_edges, use_laplacian=self.use_laplacian, use_blur=self.use_blur)
+            return loss, {'disp_grad': dg, 'image_grad': ig}
         loss, dg, ig = F_.smooth_loss([disp], img, scales=[0], use_edges=self.use_edges, want_maps=True)
         return loss, {'disp_grad': dg, 'image_grad': ig}
 
     def multi_scale(self, disps: dict[int, Tensor], imgs: Tensor, want_maps: bool = True):
         """All scales in one launch set: mean_s(loss_s / 2**s) with the image resized in-kernel (handlers.py:278-279)."""
         keys = list(disps)
+        if self.general:   # handlers.py:276-280 verbatim: per scale, image resized to the disparity, loss_s / 2**s averaged
+            ls, maps = [], {}
+            for k in keys:
+                img_k = imgs if disps[k].shape[-2:] == imgs.shape[-2:] else F_.resample_bilinear(imgs, tuple(disps[k].shape[-2:]), mode='interp')
+                l, maps[k] = self.forward(disps[k], img_k)
+                ls.append(l/2**k)
+            return sum(ls)/len(ls), (maps.get(0, maps[keys[0]]) if want_maps else {})   # loss dict of the first scale (handlers.py:280)
         loss, dg, ig = F_.smooth_loss([disps[k] for k in keys], imgs, scales=keys, use_edges=self.use_edges, want_maps=want_maps)
         return loss, ({'disp_grad': dg, 'image_grad': ig} if want_maps else {})

@@ -37,7 +37,7 @@ def test_install_rebinds_the_reference_hooks_and_uninstall_restores_them():
         assert reg.NET_REG['depth'] is networks.DepthNet and reg.NET_REG['pose'] is networks.PoseNet
         assert reg.DEC_REG['monodepth'] is networks.MonodepthDecoder
         assert reg.LOSS_REG['img_recon'] is losses.ReconstructionLoss and reg.LOSS_REG['disp_smooth'] is regularizers.SmoothReg
-        assert reg.LOSS_REG['feat_recon'] is before['img_recon']          # aliases keep the reference class
+        assert reg.LOSS_REG['feat_recon'] is losses.ReconstructionLoss and reg.LOSS_REG['autoenc_recon'] is losses.ReconstructionLoss  # one class, three keys
         assert rt.ViewSynth is geometry.ViewSynth and rt.aspect_ratio_aug is aspect_ratio.aspect_ratio_aug
         assert rh.image_recon is handlers.image_recon and rh.disp_smooth is handlers.disp_smooth
 
