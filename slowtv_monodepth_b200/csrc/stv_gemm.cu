@@ -634,7 +634,12 @@ int pick_bn(int N, long long row_tiles) {
         const int tiles = (N + bn - 1)/bn, cost = tiles*bn;
         if (cost < best_cost) { best = bn; best_cost = cost; }
     }
-    while (best > 64 && best % 64 == 0 && row_tiles*((N + best - 1)/best) < 148) best /= 2;
+    // Measured and rejected (profiles/r2_rejected_variants.txt): narrowing only while every tile still gets an SM of its own
+    // (STV_GEMM_NARROW=0). The deep, narrow layers this changes (stage-3 ConvNeXt products: 90 full-width tiles instead of 180
+    // half-width ones) are bound by the L2 -> SM operand stream (276 MB in 50 us = 5.5 TB/s), not by the MMA rate: no gain.
+    static const int narrow_always = getenv("STV_GEMM_NARROW") ? atoi(getenv("STV_GEMM_NARROW")) : 1;
+    while (best > 64 && best % 64 == 0 && row_tiles*((N + best - 1)/best) < 148 &&
+           (narrow_always || row_tiles*((N + best/2 - 1)/(best/2)) <= 148)) best /= 2;
     return best;
 }
 
@@ -716,8 +721,11 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
     if (persistent_enabled() && total < (1ll << 30)) {
         // Two resident CTAs per SM (ring + epilogue staging + barriers within ~112 KB each: one CTA's epilogue overlaps the other's
         // main loop), or ONE with the whole shared memory as a deeper ring (developer switch STV_GEMM_RESIDENT=1).
-        static const int res_cfg = getenv("STV_GEMM_RESIDENT") ? atoi(getenv("STV_GEMM_RESIDENT")) : 2;
-        const int per_sm = res_cfg == 1 ? 1 : 2;
+        // STV_GEMM_RESIDENT: 1 = always one CTA per SM (deep ring), 2 = one CTA per SM for launches of at most one tile per SM,
+        // 3 = always two (default). Measured (profiles/r2_rejected_variants.txt): mode 2 changes nothing on the single-wave stage-3
+        // products (0.050 vs 0.047 ms for dx = dz.W1) — they are L2-stream-bound, the deeper ring has nothing to hide.
+        static const int res_cfg = getenv("STV_GEMM_RESIDENT") ? atoi(getenv("STV_GEMM_RESIDENT")) : 3;
+        const int per_sm = (res_cfg == 1 || (res_cfg == 2 && total <= sm_count() && p.kb_per_split >= 16)) ? 1 : 2;
         const int threads = per_sm == 1 ? GEMM_THREADS_WIDE : GEMM_THREADS;
         const int staging = (threads/32 - 2)*EPI_WARP_FLOATS*4;
         int stages = ((per_sm == 1 ? 226 : 112)*1024 - staging - 2048)/stage_bytes;
