@@ -450,7 +450,7 @@ def main() -> None:
             'e2e': {'value': round(b*world*args.steps/(ms_e2e/1e3), 3), 'unit': 'images/s', 'ms_per_step': round(ms_e2e/args.steps, 3),
                     'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'last_loss': last.get('loss'), 'api': api},
             'gpu_launches': launches,
-            'roofline': {'kernel': 'fused photometric loss: stv_photo_fused_fwd (loss + unit gradients in one sweep) + stv_photo_fused_bwd',
+            'roofline': {'kernel': 'fused photometric loss: stv_photo_fused_fwd (loss + unit gradients in one sweep, three warps per strip) + stv_photo_fused_bwd',
                          'bound': 'hbm', 'achieved': round(ach, 1),
                          'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(ach/peak, 4),
                          'traffic': traffic, 'traffic_source': traffic_src,
