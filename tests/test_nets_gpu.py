@@ -10,7 +10,7 @@ from tests import util as U
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('shape', [(2, 24, 40, 96), (1, 7, 9, 33), (2, 12, 20, 192), (1, 6, 10, 160)])
+@pytest.mark.parametrize('shape', [(2, 24, 40, 96), (1, 7, 9, 33), (2, 12, 20, 192), (1, 6, 10, 160), (1, 45, 21, 40), (3, 3, 3, 8)])
 def test_dwconv7_matches_oracle(shape):
     from slowtv_monodepth_b200 import functional as F_
     N, H, W, C = shape
