@@ -629,10 +629,20 @@ int pick_bn(int N, long long row_tiles) {
     // <= 128 columns: a 128 x 128 tile keeps the operand ring at 32 KB per stage, so two CTAs (20 warps) stay resident per SM and
     // one CTA's epilogue overlaps the other's main loop; wider tiles halve the residency and left the epilogue-heavy layers
     // (GELU / GELU' over 4C columns with only 3-12 k-blocks) latency-bound.
+    // Fewest column tiles first, then the narrowest width that still gives that count: a kind::tf32 MMA costs the same ~80 clocks
+    // for every N <= 128 (profiles/r2_conv3_timeline.txt), so the MMA count — not the padded columns — is what a tile width buys.
+    // (N = 160: two 96-wide tiles instead of five 32-wide ones; N = 576: five 128-wide instead of six 96-wide.)
+    // STV_GEMM_BN_RULE=0 restores the round-1 rule (fewest padded columns) for A/B runs.
+    static const int rule = getenv("STV_GEMM_BN_RULE") ? atoi(getenv("STV_GEMM_BN_RULE")) : 1;
     int best = 32, best_cost = 1 << 30;
-    for (int bn = 128; bn >= 32; bn -= 32) {
-        const int tiles = (N + bn - 1)/bn, cost = tiles*bn;
-        if (cost < best_cost) { best = bn; best_cost = cost; }
+    if (rule == 0) {
+        for (int bn = 128; bn >= 32; bn -= 32) {
+            const int tiles = (N + bn - 1)/bn, cost = tiles*bn;
+            if (cost < best_cost) { best = bn; best_cost = cost; }
+        }
+    } else {
+        const int tiles = (N + 127)/128;
+        best = ((N + tiles - 1)/tiles + 31)/32*32;
     }
     // Measured and rejected (profiles/r2_rejected_variants.txt): narrowing only while every tile still gets an SM of its own
     // (STV_GEMM_NARROW=0). The deep, narrow layers this changes (stage-3 ConvNeXt products: 90 full-width tiles instead of 180
