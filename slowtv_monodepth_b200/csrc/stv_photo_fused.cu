@@ -553,10 +553,10 @@ template <int N> struct FzSplitLayout {
     static constexpr int PER_BLOCK = LY::CAM_PAD + RING_A + RING_B + BARS;   // floats
 };
 
-// One arrival per warp: __syncwarp orders the other lanes' shared-memory writes before lane 0's releasing arrive.
-__device__ __forceinline__ void fz_signal(uint32_t bar, int lane) {
-    __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+// Every lane arrives for itself (barriers count 32): each lane's ring accesses are ordered by its OWN releasing arrive, with no
+// reliance on __syncwarp + one elected arrival being transitive (which compute-sanitizer's racecheck also cannot follow).
+__device__ __forceinline__ void fz_signal(uint32_t bar, int) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fz_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(FZ_SPLIT_NT, MINB) photo_fused_split_kernel(co
     const uint32_t bar_fa = bars, bar_fb = bars + 8*FZ_R, bar_e = bars + 16*FZ_R;   // FULL_A, FULL_B, EMPTY
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int q = 0; q < 3*FZ_R; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bars + 8*q));
+        for (int q = 0; q < 3*FZ_R; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" :: "r"(bars + 8*q));
     }
 
     const long long strip = blockIdx.x;

@@ -46,7 +46,7 @@ if prof is not None:
 px = a.b*a.H*a.W
 tot = 0.
 for k, v in F_.kernel_timings().items():
-    v = v[1:]
+    v = v[1:] if len(v) > 1 else v
     ms = sum(v)/len(v)
     tot += ms if k.startswith('stv_photo') else 0.
     print(f'{k:16s} {ms*1e3:9.1f} us')
