@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(FZ_SPLIT_NT, MINB) photo_fused_split_kernel(co
         if (n_it > 1) request(1, ld);
         int slot_w = 0, slot_e = 0;
         uint32_t par_e = 0;
-#pragma unroll 2
+#pragma unroll 1   // (unrolling any of the three loops is slower: 83 KB of SASS run concurrently by the three roles)
         for (int it = 0; it < n_it; ++it) {
             // the slot about to be overwritten held row it - FZ_R, last read by warp C in its iteration it - FZ_R + 2
             if (it >= FZ_R - 2) {
