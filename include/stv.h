@@ -237,6 +237,20 @@ int stv_layernorm_bwd(long long P, int C, const float* dy, const float* x, const
                       const float* gamma, float* dx, float* dgamma, float* dbeta, int accumulate /* dgamma, dbeta += */, void* ws,
                       size_t ws_bytes, void* stream);
 
+/* RegressionLoss (src/losses/regression.py:11-75), the class registered as `stereo_const` and `depth_regr`
+ * (src/core/handlers.py:151-259): loss = sum(mask e)/sum(mask), e = |p - t| (STV_REGR_L1), log(1 + |p - t|) (LOG_L1) or berHu with
+ * the dynamic threshold 0.2 max|p - t| (BERHU); invert: p, t = to_inv(pred), to_inv(target). pred, target, mask (nullable: ones),
+ * err (nullable: the masked error map `err_regr`), g_pred, g_target (either nullable): n contiguous floats. Deterministic
+ * (per-block partials, fixed order). The backward needs the workspace the forward filled (stv_regr_workspace_bytes()). */
+#define STV_REGR_L1 0
+#define STV_REGR_LOG_L1 1
+#define STV_REGR_BERHU 2
+size_t stv_regr_workspace_bytes(void);
+int stv_regr_fwd(long long n, int loss, int invert, const float* pred, const float* target, const float* mask, float* loss_out,
+                 float* err, void* ws, size_t ws_bytes, void* stream);
+int stv_regr_bwd(long long n, int loss, int invert, const float* pred, const float* target, const float* mask,
+                 const float* grad_loss, float* g_pred, float* g_target, void* ws, size_t ws_bytes, void* stream);
+
 /* SmoothReg.forward with every constructor flag (src/regularizers/smooth.py:12-97): use_laplacian = second-order
  * absolute gradients (compute_laplacian, :33-48), use_blur = 3x3 sigma-1 Gaussian pre-blur of every differentiated map
  * (kornia.filters.gaussian_blur2d, reflect border), use_edges = exp(-|image gradient|) weights. Single scale: disp (b,1,H,W),

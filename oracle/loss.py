@@ -316,6 +316,46 @@ def feat_recon(depth0: Tensor, feats: Tensor, supp_feats: Tensor, Ts: Tensor, Ks
     return loss, warp
 
 
+def regression_loss(pred: Tensor, target: Tensor, mask: Tensor | None = None, loss_name: str = 'berhu', invert: bool = False):
+    """RegressionLoss.forward (src/losses/regression.py:11-38, 67-75) -> (loss, masked error map)."""
+    if invert: pred, target = to_inv(pred), to_inv(target)
+    if mask is None: mask = torch.ones_like(target)
+    diff = (pred - target).abs()
+    if loss_name == 'l1': e = diff
+    elif loss_name == 'log_l1': e = (1 + diff).log()
+    elif loss_name == 'berhu':
+        delta = 0.2*diff.max()
+        e = torch.where(diff <= delta, diff, (diff.pow(2) + delta.pow(2))/(2*delta + _eps(pred)))
+    else: raise KeyError(loss_name)
+    err = mask*e
+    return err.sum()/mask.sum(), err
+
+
+def stereo_const(disps: list[Tensor], depths: list[Tensor], disps_stereo: list[Tensor], depths_stereo: list[Tensor], T_stereo: Tensor,
+                 K: Tensor, loss_name: str = 'l1'):
+    """src/core/handlers.py:151-198 -> (loss, warped disparities (2*S*b,1,h,w): virtual-stereo half first)."""
+    S = len(disps)
+    d, z, ds, zs = (torch.cat(v) for v in (disps, depths, disps_stereo, depths_stereo))   # (S*b, 1, h, w), scale-major
+    T = torch.cat([T_stereo]*S)
+    all_disps = torch.cat((ds, d))
+    warp = view_synth(all_disps, torch.cat((z, zs)), torch.cat((T, torch.linalg.inv(T))), torch.cat([K]*(2*S)))[0]
+    return regression_loss(all_disps, warp, None, loss_name)[0], warp
+
+
+def depth_regr(depths: list[Tensor], targets: Tensor, imgs: Tensor, supp_imgs: Tensor, Ts: Tensor, Ks: Tensor, loss_name: str = 'log_l1',
+               invert: bool = False, use_automask: bool = True, photo_name: str = 'ssim', photo_min: bool = True):
+    """src/core/handlers.py:201-259 -> (loss, mask (S*b,1,h,w) bool)."""
+    S, n = len(depths), supp_imgs.shape[0]
+    z, tg, im = torch.cat(depths), torch.cat([targets]*S), torch.cat([imgs]*S)
+    masks = tg > 0
+    if use_automask:
+        def warp_all(dep):
+            return torch.stack([view_synth(torch.cat([supp_imgs[k]]*S), dep, torch.cat([Ts[k]]*S), torch.cat([Ks]*S))[0] for k in range(n)])
+        automask = compute_photo(warp_all(z), im, photo_min, photo_name) > compute_photo(warp_all(tg), im, photo_min, photo_name)
+        masks = masks & automask
+    return regression_loss(z, tg, masks.to(z.dtype), loss_name, invert)[0], masks
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Row 8: handlers.image_recon  (src/core/handlers.py:14-67)
 # ---------------------------------------------------------------------------------------------------------------------

@@ -37,6 +37,15 @@ SMOOTH = {
     'smooth_lap_plain': dict(use_edges=False, use_laplacian=True, b=1, H=9, W=12, seed=22),
     'smooth_grad_plain': dict(use_edges=False, use_laplacian=False, b=2, H=8, W=10, seed=23),
 }
+REGR = {
+    'regr_berhu_mask': dict(loss_name='berhu', invert=False, masked=True, n=(2, 1, 9, 13), seed=61),
+    'regr_logl1_invert': dict(loss_name='log_l1', invert=True, masked=True, n=(2, 1, 8, 10), seed=62),
+    'regr_l1_plain': dict(loss_name='l1', invert=False, masked=False, n=(1, 1, 7, 9), seed=63),
+    'regr_berhu_invert_plain': dict(loss_name='berhu', invert=True, masked=False, n=(1, 1, 6, 11), seed=64),
+}
+STEREO = {'stereo_l1': dict(loss_name='l1', b=2, S=2, H=12, W=20, seed=71)}
+HINTS = {'hints_logl1_auto': dict(loss_name='log_l1', invert=False, use_automask=True, b=2, S=2, n=2, H=16, W=24, seed=81),
+         'hints_berhu_invert': dict(loss_name='berhu', invert=True, use_automask=False, b=1, S=1, n=2, H=12, W=16, seed=82)}
 FEAT = {
     'feat_l2_mean': dict(loss_name='l2', use_min=False, use_automask=False, b=2, n=2, C=6, H=16, W=24, seed=31),
     'feat_l2_min_auto': dict(loss_name='l2', use_min=True, use_automask=True, b=1, n=2, C=4, H=16, W=20, seed=32),
@@ -72,6 +81,40 @@ def feat_inputs(c: dict, dtype=torch.float64) -> dict:
     K = torch.tensor([[.58*W, 0, .5*W, 0], [0, 1.92*H, .5*H, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=dtype).expand(c['b'], 4, 4).clone()
     noise = torch.from_numpy(rs.standard_normal((c['b'], 1, H, W)).astype(np.float32)).to(dtype)
     return dict(feats=feats, supp=supp, depth=depth, aa=aa, t=t, K=K, noise=noise)
+
+
+def regr_inputs(c: dict, dtype=torch.float64) -> dict:
+    rs = np.random.RandomState(c['seed'])
+    f = lambda: torch.from_numpy(rs.random_sample(c['n']).astype(np.float32)).to(dtype)
+    pred, tgt = 0.2 + 3*f(), 0.2 + 3*f()
+    mask = (f() > 0.3).to(dtype)
+    return dict(pred=pred, tgt=tgt, mask=mask)
+
+
+def stereo_inputs(c: dict, dtype=torch.float64) -> dict:
+    rs = np.random.RandomState(c['seed'])
+    H, W, b = c['H'], c['W'], c['b']
+    f = lambda *s: torch.from_numpy(rs.random_sample(s).astype(np.float32)).to(dtype)
+    disps = [0.05 + 0.9*f(b, 1, H, W) for _ in range(c['S'])]
+    disps_st = [0.05 + 0.9*f(b, 1, H, W) for _ in range(c['S'])]
+    T = torch.eye(4, dtype=dtype).repeat(b, 1, 1); T[:, 0, 3] = -0.1
+    K = torch.tensor([[.58*W, 0, .5*W, 0], [0, 1.92*H, .5*H, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=dtype).expand(b, 4, 4).clone()
+    return dict(disps=disps, disps_st=disps_st, T=T, K=K)
+
+
+def hints_inputs(c: dict, dtype=torch.float64) -> dict:
+    rs = np.random.RandomState(c['seed'])
+    H, W, b, n = c['H'], c['W'], c['b'], c['n']
+    f = lambda *s: torch.from_numpy(rs.random_sample(s).astype(np.float32)).to(dtype)
+    depths = [1.0 + 4.0*f(b, 1, H, W) for _ in range(c['S'])]
+    hints = 1.0 + 4.0*f(b, 1, H, W)
+    hints[:, :, :2] = 0        # invalid hints (masked out by `targets > 0`)
+    imgs = f(b, 3, H, W)
+    supp = (imgs[None] + 0.2*(f(n, b, 3, H, W) - 0.5)).clamp(0, 1)
+    aa = torch.from_numpy((0.01*rs.standard_normal((n, b, 3))).astype(np.float32)).to(dtype)
+    t = torch.from_numpy((0.05*rs.standard_normal((n, b, 3))).astype(np.float32)).to(dtype)
+    K = torch.tensor([[.58*W, 0, .5*W, 0], [0, 1.92*H, .5*H, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=dtype).expand(b, 4, 4).clone()
+    return dict(depths=depths, hints=hints, imgs=imgs, supp=supp, aa=aa, t=t, K=K)
 
 
 def main() -> None:
@@ -114,6 +157,40 @@ def main() -> None:
         out[f'{name}/loss'] = loss.detach().numpy(); out[f'{name}/g_depth'] = depth.grad.numpy()
         out[f'{name}/warp'] = ld['supp_feats_warp'].detach().numpy().astype(np.float32)
         print(name, float(loss))
+    from src.tools import to_scaled
+    for name, c in REGR.items():
+        d = regr_inputs(c)
+        pred, tgt = d['pred'].clone().requires_grad_(), d['tgt'].clone().requires_grad_()
+        loss, ld = losses.RegressionLoss(c['loss_name'], invert=c['invert'])(pred, tgt, d['mask'] if c['masked'] else None)
+        loss.backward()
+        out[f'{name}/loss'] = loss.detach().numpy(); out[f'{name}/g_pred'] = pred.grad.numpy(); out[f'{name}/g_tgt'] = tgt.grad.numpy()
+        out[f'{name}/err'] = ld['err_regr'].detach().numpy()
+        print(name, float(loss))
+    for name, c in STEREO.items():
+        d = stereo_inputs(c)
+        disps = {s: x.clone().requires_grad_() for s, x in enumerate(d['disps'])}
+        disps_st = {s: x.clone().requires_grad_() for s, x in enumerate(d['disps_st'])}
+        depths = {s: to_scaled(x, 0.1, 100.)[1] for s, x in disps.items()}
+        depths_st = {s: to_scaled(x, 0.1, 100.)[1] for s, x in disps_st.items()}
+        loss, ld = handlers.stereo_const(losses.RegressionLoss(c['loss_name']), ViewSynth((c['H'], c['W'])).to(torch.float64), disps, depths,
+                                         disps_st, depths_st, d['T'], d['K'])
+        loss.backward()
+        out[f'{name}/loss'] = loss.detach().numpy()
+        for s in disps: out[f'{name}/g_disp{s}'] = disps[s].grad.numpy(); out[f'{name}/g_disp_st{s}'] = disps_st[s].grad.numpy()
+        out[f'{name}/disps_warp'] = ld['disps_warp'].detach().numpy().astype(np.float32)
+        print(name, float(loss))
+    for name, c in HINTS.items():
+        d = hints_inputs(c)
+        depths = {s: x.clone().requires_grad_() for s, x in enumerate(d['depths'])}
+        photo = losses.ReconstructionLoss('ssim', use_min=True).compute_photo
+        crit = losses.RegressionLoss(c['loss_name'], invert=c['invert'], use_automask=c['use_automask'])
+        loss, ld = handlers.depth_regr(crit, ViewSynth((c['H'], c['W'])).to(torch.float64), photo, depths, d['hints'], d['imgs'], d['supp'],
+                                       T_from_AAt(d['aa'], d['t']), d['K'])
+        loss.backward()
+        out[f'{name}/loss'] = loss.detach().numpy()
+        for s in depths: out[f'{name}/g_depth{s}'] = depths[s].grad.numpy()
+        out[f'{name}/mask'] = ld['mask_regr'].numpy().astype(np.uint8)
+        print(name, float(loss), float(ld['mask_regr'].float().mean()))
     np.savez_compressed(GOLDEN/'ext_cases.npz', **out)
     print('->', GOLDEN/'ext_cases.npz', (GOLDEN/'ext_cases.npz').stat().st_size//1024, 'KiB')
 

@@ -36,6 +36,7 @@ class ReconCfg(C.Structure):
 
 RECON_LOSS = {'ssim': 0, 'l1': 1, 'l2': 2}
 RECON_MASK = {None: 0, 'explainability': 1, 'uncertainty': 2}
+REGR_LOSS = {'l1': 0, 'log_l1': 1, 'berhu': 2}
 
 
 class PhotoSrc(C.Structure):
@@ -79,6 +80,9 @@ _SIGNATURES = {
     'stv_recon_workspace_bytes': (C.c_size_t, [C.POINTER(PhotoCfg)]),
     'stv_recon_fwd': (C.c_int, [C.POINTER(PhotoCfg)] + [_P]*9 + [C.c_size_t, _P]),
     'stv_recon_bwd': (C.c_int, [C.POINTER(PhotoCfg)] + [_P]*6),
+    'stv_regr_workspace_bytes': (C.c_size_t, []),
+    'stv_regr_fwd': (C.c_int, [C.c_longlong, C.c_int, C.c_int] + [_P]*6 + [C.c_size_t, _P]),
+    'stv_regr_bwd': (C.c_int, [C.c_longlong, C.c_int, C.c_int] + [_P]*7 + [C.c_size_t, _P]),
     'stv_smooth_ex_workspace_bytes': (C.c_size_t, [C.c_int]*4),
     'stv_smooth_ex_fwd': (C.c_int, [C.c_int]*7 + [_P]*6 + [C.c_size_t, _P]),
     'stv_smooth_ex_bwd': (C.c_int, [C.c_int]*7 + [_P]*4 + [C.c_size_t, _P]),

@@ -522,6 +522,46 @@ def photo_error_ex(pred: Tensor, target: Tensor, mask: Tensor | None = None, *, 
     return err
 
 
+class _RegrLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, mask, loss_code: int, invert: bool):
+        L.require_cuda(pred, target, mask, what='regr_loss')
+        lib, dev, n = L.lib(), pred.device, pred.numel()
+        with torch.cuda.device(dev):
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            err = torch.empty_like(pred)
+            ws = _ws(lib.stv_regr_workspace_bytes(), dev)
+            L.check(lib.stv_regr_fwd(n, loss_code, int(invert), L.ptr(pred), L.ptr(target), L.ptr(mask), L.ptr(loss), L.ptr(err), L.ptr(ws),
+                                     ws.numel(), L.stream()), 'stv_regr_fwd')
+        ctx.args = (n, loss_code, int(invert))
+        ctx.save_for_backward(pred, target, mask, ws)
+        ctx.mark_non_differentiable(err)
+        return loss, err
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_err):
+        pred, target, mask, ws = ctx.saved_tensors
+        want_p, want_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (want_p or want_t): return (None,)*5
+        with torch.cuda.device(pred.device):
+            gp = torch.empty_like(pred) if want_p else None
+            gt = torch.empty_like(target) if want_t else None
+            L.check(L.lib().stv_regr_bwd(*ctx.args, L.ptr(pred), L.ptr(target), L.ptr(mask), L.ptr(g_loss.to(torch.float32).contiguous()),
+                                         L.ptr(gp), L.ptr(gt), L.ptr(ws), ws.numel(), L.stream()), 'stv_regr_bwd')
+        return gp, gt, None, None, None
+
+
+def regr_loss(pred: Tensor, target: Tensor, mask: Tensor | None = None, *, loss_name: str = 'berhu', invert: bool = False):
+    """`RegressionLoss.forward` (src/losses/regression.py:67-75): sum(mask e)/sum(mask) with e = l1 | log_l1 | berhu of (pred, target),
+    optionally on to_inv of both; differentiable in `pred` and `target`. -> (loss (), err_regr like pred)."""
+    if loss_name not in L.REGR_LOSS: raise KeyError(loss_name)
+    if pred.shape != target.shape: raise ValueError(f'Non-matching shapes. ({tuple(pred.shape)} vs. {tuple(target.shape)})')
+    if mask is not None:
+        if mask.dtype != torch.float32: mask = mask.to(torch.float32)
+        if mask.shape != pred.shape: mask = mask.expand_as(pred)
+    return _RegrLoss.apply(_f32c(pred), _f32c(target), _f32c(None if mask is None else mask.detach()), L.REGR_LOSS[loss_name], bool(invert))
+
+
 class _Inv4x4(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A):

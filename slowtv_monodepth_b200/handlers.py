@@ -4,10 +4,10 @@ from __future__ import annotations
 import torch
 from torch import Tensor
 
-from .losses import ReconstructionLoss
+from .losses import ReconstructionLoss, RegressionLoss
 from .regularizers import SmoothReg
 
-__all__ = ['image_recon', 'feat_recon', 'disp_smooth']
+__all__ = ['image_recon', 'feat_recon', 'stereo_const', 'depth_regr', 'disp_smooth']
 
 
 def _disparity_sources(depths: dict[int, Tensor], size) -> tuple | None:
@@ -89,6 +89,54 @@ def feat_recon(crit: ReconstructionLoss, synth, depths: dict[int, Tensor], masks
     masks = {0: masks[0]} if masks is not None else None
     loss, ld = image_recon(crit, synth, {0: depths[0]}, masks, feats, supp_feats, Ts, Ks)
     return loss, {'supp_feats_warp': ld.pop('supp_imgs_warp')}
+
+
+def stereo_const(crit: RegressionLoss, synth, disps: dict[int, Tensor], depths: dict[int, Tensor], disps_stereo: dict[int, Tensor],
+                 depths_stereo: dict[int, Tensor], T_stereo: Tensor, K: Tensor):
+    """Reference: src/core/handlers.py:151-198 — virtual stereo consistency: each view's disparities warped into the other view
+    (stv_view_synth on the 1-channel maps) and regressed onto that view's own prediction (stv_regr_fwd/bwd; gradients reach both).
+    -> (loss, {'disps_warp', 'stereo_disps_warp'} of the first scale)."""
+    from . import functional as F_
+    S = len(disps)
+    st = lambda d: torch.stack(list(d.values())).flatten(0, 1)                             # (S*b, 1, H, W)
+    d, z, ds, zs = st(disps), st(depths), st(disps_stereo), st(depths_stereo)
+    b = d.shape[0]//S
+    T = T_stereo[None].expand(S, b, 4, 4).reshape(S*b, 4, 4)
+    Kx = K[None, None].expand(2, S, b, 4, 4).reshape(2*S*b, 4, 4)
+    all_disps = torch.cat((ds, d))
+    warp = F_.view_synth(all_disps.contiguous(), torch.cat((z, zs)).contiguous(), torch.cat((T, F_.inv4x4(T.contiguous()))).contiguous(),
+                         Kx.contiguous())[0]
+    loss, _ = crit(all_disps, warp)
+    stereo_warp, disp_warp = warp.chunk(2)
+    return loss, {'disps_warp': disp_warp.unflatten(0, (S, b))[0], 'stereo_disps_warp': stereo_warp.unflatten(0, (S, b))[0]}
+
+
+def depth_regr(crit: RegressionLoss, synth, photo, depths: dict[int, Tensor], targets: Tensor, imgs: Tensor, supp_imgs: Tensor,
+               Ts: Tensor, Ks: Tensor):
+    """Reference: src/core/handlers.py:201-259 — proxy depth regression with the DepthHints automask (the hint must explain the
+    target better than the prediction: photo(warp by depth) > photo(warp by hint)). `photo` = `ReconstructionLoss.compute_photo`.
+    -> (loss, {'mask_regr'} of the first scale) — the reference rebinds its dict on the last line (handlers.py:257-258), so the
+    `automask_hints` entry it builds never leaves the function; neither does it here."""
+    from . import functional as F_
+    S = len(depths)
+    b, c, H, W = imgs.shape
+    im = imgs[None].expand(S, b, c, H, W).reshape(S*b, c, H, W).contiguous()
+    z = torch.stack(list(depths.values())).flatten(0, 1)                                  # (S*b, 1, H, W)
+    tg = targets[None].expand(S, *targets.shape).reshape(S*b, 1, H, W).contiguous()
+    masks = tg > 0
+    if crit.use_automask:
+        n = supp_imgs.shape[0]
+        sup = supp_imgs[:, None].expand(n, S, b, c, H, W).reshape(n*S*b, c, H, W).contiguous()
+        T = Ts[:, None].expand(n, S, b, 4, 4).reshape(n*S*b, 4, 4).contiguous()
+        Kx = Ks[None, None].expand(n, S, b, 4, 4).reshape(n*S*b, 4, 4).contiguous()
+        with torch.no_grad():   # the comparison is a boolean mask: no gradient leaves it
+            rep = lambda x: x[None].expand(n, *x.shape).reshape(n*S*b, 1, H, W).contiguous()
+            hints_warp = F_.view_synth(sup, rep(tg), T, Kx)[0].view(n, S*b, c, H, W)
+            imgs_warp = F_.view_synth(sup, rep(z.detach()), T, Kx)[0].view(n, S*b, c, H, W)
+            automask = photo(imgs_warp, im) > photo(hints_warp, im)
+        masks = masks & automask
+    loss, out = crit(z, tg, masks)
+    return loss, {'mask_regr': out['mask_regr'].unflatten(0, (S, b))[0]}
 
 
 def disp_smooth(crit: SmoothReg, disps: dict[int, Tensor], imgs: Tensor, *, want_maps: bool = True):

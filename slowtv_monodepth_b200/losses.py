@@ -13,7 +13,7 @@ from torch import Tensor
 
 from . import functional as F_
 
-__all__ = ['ReconstructionLoss']
+__all__ = ['ReconstructionLoss', 'RegressionLoss']
 
 
 class ReconstructionLoss(nn.Module):
@@ -89,3 +89,22 @@ class ReconstructionLoss(nn.Module):
                                   use_automask=self.use_automask, noise=noise, noise_seed=self.noise_seed if draw else 0,
                                   noise_step=self._step_counter(target) if draw else None)
         return loss, ({'automask': (sel != 255).unsqueeze(1)} if self.use_automask else {})
+
+
+class RegressionLoss(nn.Module):
+    """Reference: src/losses/regression.py:41-75 — the class registered as `depth_regr` and `stereo_const`.
+
+    :param loss_name: 'l1' | 'log_l1' | 'berhu' (dynamic threshold 0.2 max|pred - target|).
+    :param invert: convert both inputs with `to_inv` first (depths -> disparities).
+    :param use_automask: read by `handlers.depth_regr` (the DepthHints automask is computed there, as in the reference).
+    """
+    def __init__(self, loss_name: str = 'berhu', invert: bool = False, use_automask: bool = False):
+        super().__init__()
+        if loss_name not in {'l1', 'log_l1', 'berhu'}: raise KeyError(loss_name)
+        self.loss_name, self.invert, self.use_automask = loss_name, invert, use_automask
+
+    def forward(self, pred: Tensor, target: Tensor, mask: Tensor | None = None):
+        """-> (loss, {'err_regr': mask*err, 'mask_regr': mask}); differentiable in `pred` and `target` (stv_regr_fwd / stv_regr_bwd)."""
+        if mask is None: mask = torch.ones_like(target)
+        loss, err = F_.regr_loss(pred, target, mask, loss_name=self.loss_name, invert=self.invert)
+        return loss, {'err_regr': err, 'mask_regr': mask}

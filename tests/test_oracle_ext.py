@@ -55,3 +55,42 @@ def test_blur_is_a_normalised_reflecting_gaussian():
     assert torch.allclose(O.gaussian_blur3(torch.ones_like(x)), torch.ones_like(x), atol=1e-15)
     assert torch.allclose(O.gaussian_blur3(x.flip(-1)).flip(-1), O.gaussian_blur3(x), atol=1e-15)
     assert O.gaussian_blur3(x).shape == x.shape
+
+
+@pytest.mark.parametrize('name', list(G.REGR))
+def test_regression_loss_matches_reference(name):
+    c, d = G.REGR[name], G.regr_inputs(G.REGR[name])
+    pred, tgt = d['pred'].clone().requires_grad_(), d['tgt'].clone().requires_grad_()
+    loss, err = O.regression_loss(pred, tgt, d['mask'] if c['masked'] else None, c['loss_name'], c['invert'])
+    loss.backward()
+    assert abs(loss.item() - EXT[f'{name}/loss'].item()) <= 1e-12*abs(EXT[f'{name}/loss'].item())
+    assert U.rel(pred.grad, torch.from_numpy(EXT[f'{name}/g_pred'])) < 1e-10 and U.rel(tgt.grad, torch.from_numpy(EXT[f'{name}/g_tgt'])) < 1e-10
+    assert U.rel(err, torch.from_numpy(EXT[f'{name}/err'])) < 1e-12
+
+
+@pytest.mark.parametrize('name', list(G.STEREO))
+def test_stereo_const_matches_reference(name):
+    c, d = G.STEREO[name], G.stereo_inputs(G.STEREO[name])
+    disps = [x.clone().requires_grad_() for x in d['disps']]
+    disps_st = [x.clone().requires_grad_() for x in d['disps_st']]
+    loss, warp = O.stereo_const(disps, [O.disp_to_depth(x, 0.1, 100.) for x in disps], disps_st, [O.disp_to_depth(x, 0.1, 100.) for x in disps_st],
+                                d['T'], d['K'], c['loss_name'])
+    loss.backward()
+    assert abs(loss.item() - EXT[f'{name}/loss'].item()) <= 1e-10*abs(EXT[f'{name}/loss'].item())
+    for s in range(c['S']):
+        assert U.rel(disps[s].grad, torch.from_numpy(EXT[f'{name}/g_disp{s}'])) < 1e-8
+        assert U.rel(disps_st[s].grad, torch.from_numpy(EXT[f'{name}/g_disp_st{s}'])) < 1e-8
+    first = warp.chunk(2)[1][:c['b']]   # `disps_warp` of the first scale
+    assert U.rel(first, torch.from_numpy(EXT[f'{name}/disps_warp']).double()) < 1e-6
+
+
+@pytest.mark.parametrize('name', list(G.HINTS))
+def test_depth_regr_matches_reference(name):
+    c, d = G.HINTS[name], G.hints_inputs(G.HINTS[name])
+    depths = [x.clone().requires_grad_() for x in d['depths']]
+    loss, masks = O.depth_regr(depths, d['hints'], d['imgs'], d['supp'], O.T_from_AAt(d['aa'], d['t']), d['K'], c['loss_name'], c['invert'],
+                               c['use_automask'])
+    loss.backward()
+    assert abs(loss.item() - EXT[f'{name}/loss'].item()) <= 1e-10*abs(EXT[f'{name}/loss'].item())
+    for s in range(c['S']): assert U.rel(depths[s].grad, torch.from_numpy(EXT[f'{name}/g_depth{s}'])) < 1e-8
+    assert np.array_equal(masks[:c['b']].numpy().astype(np.uint8), EXT[f'{name}/mask'])
