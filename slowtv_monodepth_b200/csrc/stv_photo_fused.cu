@@ -1404,11 +1404,20 @@ using namespace stv;
 
 static size_t fz_align(size_t v) { return (v + 255) & ~(size_t)255; }
 
-static int fz_rows(const stv_photo_cfg* c) {
+static bool fz_use_split(int n);
+
+// `split`: the launch goes to the three-warp kernel (the forward and the backward entry points must agree on it).
+static int fz_rows(const stv_photo_cfg* c, bool split) {
     // Strip height: tall strips amortise the 4 warm-up rows; enough strips to fill 148 SMs x ~12 resident warps several times.
     static const int env = getenv("STV_FUSED_ROWS") ? atoi(getenv("STV_FUSED_ROWS")) : 0;  // developer sweep
     if (env > 0) return env < 8 ? 8 : env;   // the workspace / partial buffers are sized for >= 8 rows per strip
     const long long per_row_strips = (long long)c->b*c->S*((c->W + FZ_COLS - 1)/FZ_COLS);
+    if (split) {
+        // The three-warp kernel also pays a G -> S -> C pipeline fill per strip: it wants taller strips, as long as ~3 waves of the
+        // 148 x 5 resident blocks remain (config 3: 96 rows, 0.69 -> 0.65 ms; 192 / 384 rows: no further gain; profiles/r2_photo_split.txt).
+        for (int rows : {96, 64, 48})
+            if (per_row_strips*((c->H + rows - 1)/rows) >= 2200) return rows;
+    }
     int rows = 32;
     while (rows > 8 && per_row_strips*((c->H + rows - 1)/rows) < 148*12*3) rows /= 2;
     return rows;
@@ -1555,7 +1564,7 @@ extern "C" int stv_photo_fused_fwd(const stv_photo_cfg* c, const stv_photo_src* 
         const float i_max = 1.f/src->min_depth, i_min = src->max_depth > 0.f ? 1.f/src->max_depth : 0.f;
         p.d_mul = i_max - i_min; p.d_add = i_min;
     }
-    p.rows = fz_rows(c);
+    p.rows = fz_rows(c, grad && c->n <= FZ_SPLIT_MAX_N && fz_use_split(c->n));
     p.nsx = (c->W + FZ_COLS - 1)/FZ_COLS; p.nsy = (c->H + p.rows - 1)/p.rows;
     p.tgt = tgt; p.supp = supp; p.T = T; p.K = K; p.Kinv = Kinv; p.noise = noise;
     float* e0 = (float*)ws;
@@ -1595,7 +1604,7 @@ extern "C" int stv_photo_fused_bwd(const stv_photo_cfg* c, const stv_photo_src* 
     STV_REQUIRE(grad_loss && g_unit && gpart && T && Kinv, "stv_photo_fused_bwd: NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (gT != nullptr) {
-        const int rows = fz_rows(c);
+        const int rows = fz_rows(c, c->n <= FZ_SPLIT_MAX_N && fz_use_split(c->n));   // the forward ran with gradients on
         const int spi = (int)(fz_strips(c, rows)/c->b);
         fused_finalize_kernel<<<c->b, 256, 0, st>>>(gpart, spi, c->n, c->b, T, Kinv, grad_loss, gT, gK, gKinv);
         count_launch();
