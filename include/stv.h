@@ -262,6 +262,13 @@ int stv_smooth_ex_fwd(int b, int C, int H, int W, int use_edges, int use_laplaci
 int stv_smooth_ex_bwd(int b, int C, int H, int W, int use_edges, int use_laplacian, int use_blur, const float* disp,
                       const float* grad_loss, float* g_disp, void* ws, size_t ws_bytes, void* stream);
 
+/* Reproducible mode. With STV_DETERMINISTIC=1 in the environment (read once per process) every floating-point accumulation of the
+ * library has one contributor per address per launch: stv_gemm_tf32 / stv_conv_wgrad ignore split_k (and stv_gemm_tf32 refuses the
+ * fused `colsum`), the column reductions behind stv_colsum / stv_act_bwd / stv_bn_* run on one row block, stv_head3x3_bwd accumulates
+ * its weight gradient one x-tile per launch. Two runs of the same step then give bit-identical gradients (tests/test_determinism_gpu.py);
+ * the step is several times slower. Without it the weight / bias gradients and the BatchNorm sums are accumulated with atomics whose
+ * order varies from run to run (differences at rounding level). */
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Tensor-core products of the network layers (tcgen05.mma kind::tf32 + TMA + TMEM; fp32 storage, TF32 multiply, fp32
  * accumulate = the reference's `torch.set_float32_matmul_precision('high')`, src/core/trainer.py:30).

@@ -10,6 +10,16 @@
 #define STV_C1 1e-4f                       // SSIM eps1 = 0.01**2 (src/losses/photometric.py:30)
 #define STV_C2 9e-4f                       // SSIM eps2 = 0.03**2 (src/losses/photometric.py:31)
 
+#include <cstdlib>
+
+// Reproducible mode (STV_DETERMINISTIC=1, read once per process): every floating-point accumulation has ONE contributor per address
+// per launch — no split-K, column reductions on a single row block, the head weight gradient one x-tile at a time — so that two runs
+// of the same step give bit-identical gradients. Several times slower; a debugging aid like cuDNN's deterministic switch.
+inline bool stv_deterministic() {
+    static const bool on = std::getenv("STV_DETERMINISTIC") && std::getenv("STV_DETERMINISTIC")[0] == '1';
+    return on;
+}
+
 namespace stv {
 
 // ---- host-side error plumbing ---------------------------------------------------------------------------------------

@@ -510,6 +510,7 @@ static int wgrad_tma(const stv_conv_geom* g, int P, int Q, const float* x, const
     p.bn = pick_bn(p.N, 1 << 20);
     p.a_mn = 1; p.b_mn = 1;
     p.kb_total = (int)((npix + GEMM_BK - 1)/GEMM_BK);
+    if (stv_deterministic()) split_k = 1;
     if (split_k <= 0) {  // at most two full waves of CTAs, at least 8 k-blocks each
         const int tiles = ((p.M + GEMM_BM - 1)/GEMM_BM)*((p.N + p.bn - 1)/p.bn);
         split_k = (2*148)/tiles;
@@ -656,6 +657,7 @@ extern "C" int stv_conv_wgrad(const stv_conv_geom* g, const float* src1, const f
     p.M = g->Cout; p.N = p.g.Ktot; p.gridH = P; p.gridW = Q;
     p.bn = pick_bn(p.N, 1 << 20); p.b_mn = 1; p.taps_kb = 1;
     p.kb_total = (int)((p.npix + CV_BK - 1)/CV_BK);
+    if (stv_deterministic()) split_k = 1;
     if (split_k <= 0) {  // ~2 waves of CTAs, at least 8 k-blocks each
         const int tiles = ((p.M + CV_BM - 1)/CV_BM)*((p.N + p.bn - 1)/p.bn);
         split_k = (2*148)/tiles;  // floor: at most two full waves of CTAs

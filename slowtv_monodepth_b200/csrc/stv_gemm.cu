@@ -786,6 +786,10 @@ extern "C" int stv_gemm_tf32(int M, int N, int K, const float* A, long long lda,
     stv_gemm_epi e = {};
     if (epi) e = *epi;
     STV_REQUIRE(split_k >= 1, "stv_gemm_tf32: split_k must be >= 1");
+    if (stv_deterministic()) {   // one contributor per output element; the fused column sums have one per row tile, so they are refused
+        split_k = 1;
+        STV_REQUIRE(e.colsum == nullptr, "stv_gemm_tf32: the fused column sums are not reproducible (STV_DETERMINISTIC=1): use stv_colsum");
+    }
     STV_REQUIRE(split_k == 1 || e.accumulate, "stv_gemm_tf32: split_k > 1 needs an accumulating epilogue");
     STV_REQUIRE(!(e.accumulate && (e.aux || e.act || e.res)), "stv_gemm_tf32: accumulate cannot be combined with aux/act/res");
     if (e.bias) STV_REQUIRE(((uintptr_t)e.bias & 15) == 0, "stv_gemm_tf32: bias must be 16-byte aligned");

@@ -138,11 +138,11 @@ __global__ void __launch_bounds__(HD_THREADS) head3x3_dgrad_kernel(int H, int W,
 // a block walks rows blockIdx.x, blockIdx.x + gridDim.x, ... so that it ends with ONE set of 9*C atomics.
 __global__ void __launch_bounds__(HD_THREADS) head3x3_wgrad_kernel(int NH, int H, int W, int C, const float* __restrict__ x,
                                                                    const float* __restrict__ dz, float* __restrict__ dw,
-                                                                   float* __restrict__ db) {
+                                                                   float* __restrict__ db, int ytile0) {
     __shared__ __align__(16) float red[HD_THREADS/32][9*128 + 4];  // per-warp partial (9 taps x up to 128 channels) + bias term
     const int lp = C >> 2, rpb = HD_THREADS/lp;
     const int run = threadIdx.x/lp, c = (threadIdx.x % lp)*4;
-    const int x0 = (blockIdx.y*rpb + run)*HD_RUN;
+    const int x0 = ((ytile0 + blockIdx.y)*rpb + run)*HD_RUN;
     float4 acc[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -239,8 +239,12 @@ extern "C" int stv_head3x3_bwd(int N, int H, int W, int C, const float* x, const
         // few, long-running blocks: every block ends with 9*C atomics
         int rows = (148*4 + xt - 1)/xt;
         rows = rows < N*H ? rows : N*H;
-        head3x3_wgrad_kernel<<<dim3(rows, xt), HD_THREADS, 0, st>>>(N*H, H, W, C, x, dz_ws, dw, db);
-        count_launch();
+        if (stv_deterministic()) {   // one block per launch, x-tile after x-tile: one contributor per weight at a time
+            for (int t = 0; t < xt; ++t) { head3x3_wgrad_kernel<<<dim3(1, 1), HD_THREADS, 0, st>>>(N*H, H, W, C, x, dz_ws, dw, db, t); count_launch(); }
+        } else {
+            head3x3_wgrad_kernel<<<dim3(rows, xt), HD_THREADS, 0, st>>>(N*H, H, W, C, x, dz_ws, dw, db, 0);
+            count_launch();
+        }
     }
     return check_launch("stv_head3x3_bwd");
 }

@@ -217,6 +217,7 @@ static void colred4_grid(long long M, int C, dim3& grid, int& rpb) {
     rpb = (int)((M + want - 1)/want);
     const int min_rows = G >= 32 ? 64 : 64*(32/G);
     if (rpb < min_rows) rpb = min_rows;
+    if (stv_deterministic()) rpb = (int)(M < 0x7fffffffll ? M : 0x7fffffffll);   // one row block: one contributor per column
     grid = dim3(colb, (unsigned)((M + rpb - 1)/rpb));
 }
 
@@ -489,6 +490,7 @@ static int rows_per_block(long long M, int C) {
     long long want = (4ll*148*8 + col_blocks - 1)/col_blocks;
     long long rpb = (M + want - 1)/want;
     if (rpb < 64) rpb = 64;
+    if (stv_deterministic()) rpb = M < 0x7fffffffll ? M : 0x7fffffffll;   // one row block: one contributor per column
     return (int)rpb;
 }
 

@@ -201,6 +201,8 @@ def _ws(nbytes: int, device) -> Tensor:
 # Developer switches (parity / property tests): route min-reprojection through the two-pass kernels as well; keep a reference to
 # the single-pass kernel's full-resolution unit-gradient maps of the most recent call.
 PHOTO_FORCE_TWO_PASS = False
+# Reproducible mode (STV_DETERMINISTIC=1, read by libstv too: include/stv.h): bit-identical gradients from run to run, several times slower.
+DETERMINISTIC = _os0.environ.get('STV_DETERMINISTIC', '') == '1'
 KEEP_UNIT_GRADS = False
 LAST_UNIT_GRADS = None
 
@@ -1181,7 +1183,10 @@ class _ConvNeXtMlp(torch.autograd.Function):
             w2g = torch.empty_like(w2)                                       # (C, 4C): layer-scale folded into fc2
             L.check(lib.stv_rowscale(Cc, Hd, L.ptr(w2), L.ptr(gamma), L.ptr(w2g), L.stream()), 'stv_rowscale')
         db1 = ctx.b1_sink if ctx.b1_sink is not None else torch.zeros(Hd, dtype=torch.float32, device=g.device)
-        dz = gemm_tf32(g, w2g, b_mn=True, dact='gelu', dact_src=z, colsum=db1)  # (M, 4C) = (g W2g) * GELU'(z); db1 = its column sums
+        if DETERMINISTIC:   # the fused column sums take one atomic per row tile: not reproducible
+            dz = gemm_tf32(g, w2g, b_mn=True, dact='gelu', dact_src=z)
+            L.check(L.lib().stv_colsum(dz.shape[0], dz.shape[1], dz.shape[1], L.ptr(dz), L.ptr(db1), L.stream()), 'stv_colsum')
+        else: dz = gemm_tf32(g, w2g, b_mn=True, dact='gelu', dact_src=z, colsum=db1)  # (M, 4C) = (g W2g) * GELU'(z); db1 = its column sums
         dx = gemm_tf32(dz, w1, b_mn=True) if ctx.needs_input_grad[0] else None
         w2s, b2s, gas = ctx.tail_sinks
         sunk = w2s is not None and b2s is not None and gas is not None
