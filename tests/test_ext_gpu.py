@@ -229,3 +229,56 @@ def test_depth_regr_matches_the_reference_handler(name):
     want = EXT[f'{name}/loss'].item()
     assert abs(loss.item() - want) <= 2e-5*abs(want)
     for s in depths: assert U.rel(depths[s].grad.cpu().double(), torch.from_numpy(EXT[f'{name}/g_depth{s}'])) < TOL_GRAD
+
+
+@pytest.mark.parametrize('shape', [(1, 1, 3, 3, 3), (2, 1, 4, 3, 5), (1, 3, 2, 5, 4)])   # (b, n, C, H, W): minimum sizes, single frame, odd shapes
+@pytest.mark.parametrize('loss_name,mask_name', [('ssim', 'uncertainty'), ('l2', None), ('l1', 'explainability')])
+def test_recon_ex_edge_shapes_match_oracle(shape, loss_name, mask_name):
+    """Smallest legal maps (3 x 3: every pixel is a reflected border), one frame handed as a 4-D tensor, ragged sizes."""
+    b, n, C, H, W = shape
+    d = _cuda(G.recon_inputs(dict(b=b, n=n, C=C, H=H, W=W, seed=90 + H*W), torch.float32))
+    pred = (d['pred'][0] if n == 1 else d['pred']).contiguous().requires_grad_()
+    src = (d['src'][0] if n == 1 else d['src']).contiguous()
+    mask = d['mask'].requires_grad_()
+    crit = ReconstructionLoss(loss_name, True, True, mask_name)
+    loss, ld = crit(pred, d['tgt'], source=src, mask=mask if mask_name else None, noise=d['noise'])
+    loss.backward()
+    rp, rm = d['pred'].detach().double().cpu().requires_grad_(), d['mask'].detach().double().cpu().requires_grad_()
+    want, automask, _, _ = O.reconstruction_loss_ex(rp, d['tgt'].double().cpu(), d['src'].double().cpu(), rm if mask_name else None, loss_name, True, True,
+                                                    mask_name, d['noise'].double().cpu())
+    want.backward()
+    if not torch.equal(ld['automask'].cpu(), automask): pytest.skip('a decision flipped at a float32 near-tie')
+    assert abs(loss.item() - want.item()) <= TOL_LOSS*abs(want.item())
+    assert U.rel(pred.grad.cpu().double().reshape(rp.shape), rp.grad) < TOL_GRAD
+    if mask_name: assert U.rel(mask.grad.cpu().double(), rm.grad) < TOL_GRAD
+
+
+@pytest.mark.parametrize('flags', [(True, True, True), (False, False, True), (True, True, False)])
+def test_smooth_ex_minimum_size(flags):
+    d = _cuda(G.smooth_inputs(dict(b=2, H=3, W=4, seed=95), torch.float32))
+    disp = d['disp'].requires_grad_()
+    loss, _ = SmoothReg(*flags)(disp, d['img'])
+    loss.backward()
+    rd = d['disp'].detach().double().cpu().requires_grad_()
+    want = O.smooth_reg_ex(rd, d['img'].double().cpu(), *flags)[0]
+    want.backward()
+    assert abs(loss.item() - want.item()) <= TOL_LOSS*abs(want.item())
+    assert U.rel(disp.grad.cpu().double(), rd.grad) < TOL_GRAD
+
+
+def test_regression_loss_edge_cases():
+    """All-zero mask rows, zero targets under `invert` (to_inv's guard), identical inputs (sign(0) = 0, berHu threshold 0)."""
+    from slowtv_monodepth_b200 import functional as F_
+    rs = np.random.RandomState(3)
+    pred = torch.from_numpy((0.1 + rs.random_sample((2, 1, 5, 7))).astype(np.float32)).cuda()
+    tgt = pred.clone(); tgt[0, 0, :2] = 0.0
+    mask = (tgt > 0).float()
+    for name in ('l1', 'log_l1', 'berhu'):
+        p = pred.clone().requires_grad_()
+        loss, err = F_.regr_loss(p, tgt, mask, loss_name=name, invert=True)
+        loss.backward()
+        pr = pred.double().cpu().requires_grad_()
+        want = O.regression_loss(pr, tgt.double().cpu(), mask.double().cpu(), name, True)[0]
+        want.backward()
+        assert abs(loss.item() - want.item()) <= 1e-6 + TOL_LOSS*abs(want.item())
+        assert (p.grad.cpu().double() - pr.grad).abs().max().item() <= 1e-6 + TOL_GRAD*pr.grad.abs().max().item()
