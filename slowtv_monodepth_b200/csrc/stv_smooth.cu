@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(SM_NT) smooth_fwd_kernel(SmoothParams p) {
     while (s + 1 < p.S && (int)blockIdx.x >= p.blk_off[s + 1]) ++s;
     const int blk = blockIdx.x - p.blk_off[s], i = blockIdx.y;
     const int h = p.h[s], w = p.w[s], hw = h*w;
-    const float mean = mean_from_parts(p.sum_part + ((size_t)s*p.b + i)*NCHUNK, hw);
+    __shared__ float mean_sh;   // one thread adds the 32 partial sums (in double) for the block instead of all 256
+    if (threadIdx.x == 0) mean_sh = mean_from_parts(p.sum_part + ((size_t)s*p.b + i)*NCHUNK, hw);
+    __syncthreads();
+    const float mean = mean_sh;
     const float inv_m = 1.0f/fmaxf(mean, STV_EPS32);
     const int q = blk*SM_NT + threadIdx.x;
     float v = 0.f;
@@ -160,20 +163,21 @@ __global__ void __launch_bounds__(SM_NT) smooth_bwd_kernel(SmoothParams p) {
     const float d0 = __fmul_rn(__ldg(d + q), inv_m);
     auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
     float g = 0.f;
-    float ix, iy;
-    edge_terms(p, img, s, y, x, ix, iy);
-    if (x + 1 < w) g += sgn(d0 - __fmul_rn(__ldg(d + q + 1), inv_m))*(p.use_edges ? expf(-ix) : 1.f);
-    if (y + 1 < h) g += sgn(d0 - __fmul_rn(__ldg(d + q + w), inv_m))*(p.use_edges ? expf(-iy) : 1.f);
-    if (x > 0) {
-        float jx, jy;
-        edge_terms(p, img, s, y, x - 1, jx, jy);
-        g -= sgn(__fmul_rn(__ldg(d + q - 1), inv_m) - d0)*(p.use_edges ? expf(-jx) : 1.f);
-    }
-    if (y > 0) {
-        float jx, jy;
-        edge_terms(p, img, s, y - 1, x, jx, jy);
-        g -= sgn(__fmul_rn(__ldg(d + q - w), inv_m) - d0)*(p.use_edges ? expf(-jy) : 1.f);
-    }
+    // the four edges of this pixel: weights exp(-mean_c |I(a) - I(b)|) from FIVE image samples (centre and its four neighbours; the
+    // same expression, in the same operand order, as edge_terms evaluates for the forward)
+    float c0[3] = {0.f, 0.f, 0.f}, cn[3];
+    if (p.use_edges) img_at(img, p.H, p.W, h, w, y, x, c0);
+    auto weight = [&](int yy, int xx, bool centre_first) -> float {
+        if (!p.use_edges) return 1.f;
+        img_at(img, p.H, p.W, h, w, yy, xx, cn);
+        const float a = centre_first ? (fabsf(c0[0] - cn[0]) + fabsf(c0[1] - cn[1]) + fabsf(c0[2] - cn[2]))
+                                     : (fabsf(cn[0] - c0[0]) + fabsf(cn[1] - c0[1]) + fabsf(cn[2] - c0[2]));
+        return expf(-a*(1.f/3.f));
+    };
+    if (x + 1 < w) g += sgn(d0 - __fmul_rn(__ldg(d + q + 1), inv_m))*weight(y, x + 1, true);
+    if (y + 1 < h) g += sgn(d0 - __fmul_rn(__ldg(d + q + w), inv_m))*weight(y + 1, x, true);
+    if (x > 0) g -= sgn(__fmul_rn(__ldg(d + q - 1), inv_m) - d0)*weight(y, x - 1, false);
+    if (y > 0) g -= sgn(__fmul_rn(__ldg(d + q - w), inv_m) - d0)*weight(y - 1, x, false);
     float out = gs*g*inv_m;
     if (mean >= STV_EPS32) out -= gs*Li*inv_m/(float)hw;  // d/d mean through the normalisation (clamp passes at equality)
     p.g_disp[s][(size_t)i*hw + q] = out;
