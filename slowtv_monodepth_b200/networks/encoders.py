@@ -129,6 +129,10 @@ class ResNetEncoder(nn.Module):
 
     def forward(self, x: Tensor) -> list[Tensor]:
         if x.is_cuda:
+            if self.training:   # nn.BatchNorm2d counts its training forwards: one multi-tensor launch for all layers of the encoder
+                if getattr(self, '_nbt', None) is None or (self._nbt and self._nbt[0].device != x.device):
+                    self._nbt = [m.num_batches_tracked for m in self.modules() if isinstance(m, nn.BatchNorm2d) and m.num_batches_tracked is not None]
+                if self._nbt: torch._foreach_add_(self._nbt, 1)
             # `marks`: autograd node of the first operation of each part; when it has run in backward, every gradient of that part
             # (and of everything after it in the forward order) is final — FlatAdamW starts that bucket's all-reduce from it.
             y = _stem_conv_nhwc(x, self.conv1)
