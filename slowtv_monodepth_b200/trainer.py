@@ -69,7 +69,7 @@ class MonoDepthStep(nn.Module):
         # The pose network is independent of the depth network: it runs on its own stream, forward and backward, beside it
         # (functional.branch_stream); everything it produces is joined before the loss reads it.
         br = None
-        if 'pose' in self.nets:
+        if 'pose' in self.nets and any(i != 0 for i in idxs):   # stereo-only batches have no motion to predict
             inv = lambda i: self.always_fwd_pose and i < 0
             with F_.branch_stream('pose', [x['imgs'], x['supp_imgs']]) as br:
                 pairs = torch.stack([torch.cat([s, x['imgs']] if inv(i) else [x['imgs'], s], dim=1)
@@ -102,7 +102,15 @@ class MonoDepthStep(nn.Module):
             up = {s: G.upsample_to_depth(d, size, self.min_depth, self.max_depth) for s, d in fwd['disp'].items()}
             fwd['disp_up'] = {s: v[0] for s, v in up.items()}
             fwd['depth_up'] = {s: v[1] for s, v in up.items()}
-        fwd['Ts'] = torch.stack([fwd[f'T_{i}'] for i in fwd['_idxs']])
+        # stereo support frames (index 0) take the calibrated baseline of the batch, temporal ones the predicted motion (trainer.py:347)
+        Ts = []
+        for i in fwd['_idxs']:
+            if i == 0:
+                if 'T_stereo' not in y: raise KeyError('Support index 0 (stereo pair) needs the baseline transform y["T_stereo"].')
+                Ts.append(y['T_stereo'])
+            elif f'T_{i}' not in fwd: raise KeyError(f'No pose for support index {i}: temporal support frames need a "pose" network.')
+            else: Ts.append(fwd[f'T_{i}'])
+        fwd['Ts'] = torch.stack(Ts)
         return fwd
 
     # -- trainer.py:350-472 ------------------------------------------------------------------------------------------
