@@ -251,6 +251,22 @@ int stv_regr_fwd(long long n, int loss, int invert, const float* pred, const flo
 int stv_regr_bwd(long long n, int loss, int invert, const float* pred, const float* target, const float* mask,
                  const float* grad_loss, float* g_pred, float* g_target, void* ws, size_t ws_bytes, void* stream);
 
+/* The two pointwise regularisers: OccReg (`disp_occ`, src/regularizers/occlusion.py:9-40): sign * mean(x); MaskReg (`disp_mask`,
+ * src/regularizers/mask.py:11-30): binary cross-entropy of x against 1. ws >= stv_regr_workspace_bytes(). */
+#define STV_PWREG_MEAN 0
+#define STV_PWREG_BCE_ONE 1
+int stv_pwreg_fwd(long long n, int kind, float sign, const float* x, float* loss, void* ws, size_t ws_bytes, void* stream);
+int stv_pwreg_bwd(long long n, int kind, float sign, const float* x, const float* grad_loss, float* g, void* stream);
+
+/* Feature regularisers (`feat_peaky` = FeatPeakReg, order 1; `feat_smooth` = FeatSmoothReg, order 2; src/regularizers/smooth.py:100-176):
+ * first- / second-order absolute differences of C-channel feature maps, optionally weighted by exp(-image differences) (use_edges).
+ * feat (b,C,H,W), img (b,Ci,H,W); feat_grad (b,C,H,W) nullable logging map. The backward needs the workspace the forward filled. */
+size_t stv_feat_reg_workspace_bytes(int b, int C, int Ci, int H, int W);
+int stv_feat_reg_fwd(int b, int C, int Ci, int H, int W, int order, int use_edges, const float* feat, const float* img, float* loss,
+                     float* feat_grad, void* ws, size_t ws_bytes, void* stream);
+int stv_feat_reg_bwd(int b, int C, int Ci, int H, int W, int order, int use_edges, const float* feat, const float* grad_loss,
+                     float* g_feat, void* ws, size_t ws_bytes, void* stream);
+
 /* SmoothReg.forward with every constructor flag (src/regularizers/smooth.py:12-97): use_laplacian = second-order
  * absolute gradients (compute_laplacian, :33-48), use_blur = 3x3 sigma-1 Gaussian pre-blur of every differentiated map
  * (kornia.filters.gaussian_blur2d, reflect border), use_edges = exp(-|image gradient|) weights. Single scale: disp (b,1,H,W),

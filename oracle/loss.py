@@ -432,6 +432,36 @@ def smooth_reg_ex(disp: Tensor, img: Tensor, use_edges: bool = False, use_laplac
     return ddx.mean() + ddy.mean(), disp_grad, img_grad
 
 
+def feat_peak_reg(feat: Tensor, img: Tensor, use_edges: bool = False):
+    """FeatPeakReg.forward (src/regularizers/smooth.py:111-136) -> (loss, feat_grad)."""
+    fdx, fdy = _abs_grad(feat)
+    fg = (fdx**2 + fdy**2).clamp(min=_eps(feat)).sqrt()
+    if use_edges:
+        dx, dy = _abs_grad(img, ch_mean=True)
+        fdx, fdy = fdx*(-dx).exp(), fdy*(-dy).exp()
+    return -(fdx.mean() + fdy.mean()), fg
+
+
+def feat_smooth_reg(feat: Tensor, img: Tensor, use_edges: bool = False):
+    """FeatSmoothReg.forward (src/regularizers/smooth.py:150-176) -> (loss, feat_grad)."""
+    fxx, fyy, fxy, fyx = _abs_laplacian(feat)
+    fg = (fxx**2 + fyy**2).clamp(min=_eps(feat)).sqrt()
+    if use_edges:
+        dxx, dyy, dxy, dyx = _abs_laplacian(img, ch_mean=True)
+        fxx, fyy, fxy, fyx = fxx*(-dxx).exp(), fyy*(-dyy).exp(), fxy*(-dxy).exp(), fyx*(-dyx).exp()
+    return fxx.mean() + fyy.mean() + fxy.mean() + fyx.mean(), fg
+
+
+def mask_reg(x: Tensor) -> Tensor:
+    """MaskReg.forward (src/regularizers/mask.py:20-30): F.binary_cross_entropy(x, 1)."""
+    return -(x.log().clamp(min=-100)).mean()
+
+
+def occ_reg(x: Tensor, invert: bool = False) -> Tensor:
+    """OccReg.forward (src/regularizers/occlusion.py:31-40)."""
+    return (-1 if invert else 1)*x.mean()
+
+
 def smooth_reg(disp: Tensor, img: Tensor, use_edges: bool = True):
     """-> (loss, disp_grad, image_grad)."""
     eps = _eps(disp)

@@ -46,6 +46,12 @@ REGR = {
 STEREO = {'stereo_l1': dict(loss_name='l1', b=2, S=2, H=12, W=20, seed=71)}
 HINTS = {'hints_logl1_auto': dict(loss_name='log_l1', invert=False, use_automask=True, b=2, S=2, n=2, H=16, W=24, seed=81),
          'hints_berhu_invert': dict(loss_name='berhu', invert=True, use_automask=False, b=1, S=1, n=2, H=12, W=16, seed=82)}
+FREG = {
+    'freg_peaky_edges': dict(cls='FeatPeakReg', use_edges=True, b=2, C=5, H=9, W=12, seed=91),
+    'freg_peaky_plain': dict(cls='FeatPeakReg', use_edges=False, b=1, C=3, H=6, W=7, seed=92),
+    'freg_smooth_edges': dict(cls='FeatSmoothReg', use_edges=True, b=2, C=4, H=10, W=11, seed=93),
+    'freg_smooth_plain': dict(cls='FeatSmoothReg', use_edges=False, b=1, C=6, H=7, W=9, seed=94),
+}
 FEAT = {
     'feat_l2_mean': dict(loss_name='l2', use_min=False, use_automask=False, b=2, n=2, C=6, H=16, W=24, seed=31),
     'feat_l2_min_auto': dict(loss_name='l2', use_min=True, use_automask=True, b=1, n=2, C=4, H=16, W=20, seed=32),
@@ -115,6 +121,12 @@ def hints_inputs(c: dict, dtype=torch.float64) -> dict:
     t = torch.from_numpy((0.05*rs.standard_normal((n, b, 3))).astype(np.float32)).to(dtype)
     K = torch.tensor([[.58*W, 0, .5*W, 0], [0, 1.92*H, .5*H, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=dtype).expand(b, 4, 4).clone()
     return dict(depths=depths, hints=hints, imgs=imgs, supp=supp, aa=aa, t=t, K=K)
+
+
+def freg_inputs(c: dict, dtype=torch.float64) -> dict:
+    rs = np.random.RandomState(c['seed'])
+    f = lambda *s: torch.from_numpy(rs.random_sample(s).astype(np.float32)).to(dtype)
+    return dict(feat=2*f(c['b'], c['C'], c['H'], c['W']) - 1, img=f(c['b'], 3, c['H'], c['W']), x=0.05 + 0.9*f(c['b'], 1, c['H'], c['W']))
 
 
 def main() -> None:
@@ -191,6 +203,21 @@ def main() -> None:
         for s in depths: out[f'{name}/g_depth{s}'] = depths[s].grad.numpy()
         out[f'{name}/mask'] = ld['mask_regr'].numpy().astype(np.uint8)
         print(name, float(loss), float(ld['mask_regr'].float().mean()))
+    for name, c in FREG.items():
+        d = freg_inputs(c)
+        feat = d['feat'].clone().requires_grad_()
+        loss, ld = getattr(regularizers, c['cls'])(use_edges=c['use_edges'])(feat, d['img'])
+        loss.backward()
+        out[f'{name}/loss'] = loss.detach().numpy(); out[f'{name}/g_feat'] = feat.grad.numpy()
+        out[f'{name}/feat_grad'] = ld['feat_grad'].detach().numpy()
+        print(name, float(loss))
+    d = freg_inputs(FREG['freg_peaky_edges'])
+    for name, crit in (('pw_mask', regularizers.MaskReg()), ('pw_occ', regularizers.OccReg()), ('pw_occ_inv', regularizers.OccReg(invert=True))):
+        x = d['x'].clone().requires_grad_()
+        loss, _ = crit(x)
+        loss.backward()
+        out[f'{name}/loss'] = loss.detach().numpy(); out[f'{name}/g_x'] = x.grad.numpy()
+        print(name, float(loss))
     np.savez_compressed(GOLDEN/'ext_cases.npz', **out)
     print('->', GOLDEN/'ext_cases.npz', (GOLDEN/'ext_cases.npz').stat().st_size//1024, 'KiB')
 

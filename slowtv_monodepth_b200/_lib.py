@@ -83,6 +83,11 @@ _SIGNATURES = {
     'stv_regr_workspace_bytes': (C.c_size_t, []),
     'stv_regr_fwd': (C.c_int, [C.c_longlong, C.c_int, C.c_int] + [_P]*6 + [C.c_size_t, _P]),
     'stv_regr_bwd': (C.c_int, [C.c_longlong, C.c_int, C.c_int] + [_P]*7 + [C.c_size_t, _P]),
+    'stv_pwreg_fwd': (C.c_int, [C.c_longlong, C.c_int, C.c_float] + [_P]*3 + [C.c_size_t, _P]),
+    'stv_pwreg_bwd': (C.c_int, [C.c_longlong, C.c_int, C.c_float] + [_P]*4),
+    'stv_feat_reg_workspace_bytes': (C.c_size_t, [C.c_int]*5),
+    'stv_feat_reg_fwd': (C.c_int, [C.c_int]*7 + [_P]*5 + [C.c_size_t, _P]),
+    'stv_feat_reg_bwd': (C.c_int, [C.c_int]*7 + [_P]*4 + [C.c_size_t, _P]),
     'stv_smooth_ex_workspace_bytes': (C.c_size_t, [C.c_int]*4),
     'stv_smooth_ex_fwd': (C.c_int, [C.c_int]*7 + [_P]*6 + [C.c_size_t, _P]),
     'stv_smooth_ex_bwd': (C.c_int, [C.c_int]*7 + [_P]*4 + [C.c_size_t, _P]),

@@ -170,3 +170,65 @@ extern "C" int stv_regr_bwd(long long n, int loss, int invert, const float* pred
     count_launch();
     return check_launch("regr_bwd_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The two pointwise regularisers (registry keys `disp_occ`, `disp_mask`): a mean over all elements, same partial-sum machinery.
+//   STV_PWREG_MEAN     OccReg  (src/regularizers/occlusion.py:9-40):  loss = sign * mean(x)
+//   STV_PWREG_BCE_ONE  MaskReg (src/regularizers/mask.py:11-30):      loss = F.binary_cross_entropy(x, 1) = mean(-max(log x, -100)),
+//                      gradient (x - 1) / max((1 - x) x, 1e-12) / n as ATen computes it
+// ---------------------------------------------------------------------------------------------------------------------
+namespace stv {
+
+__global__ void __launch_bounds__(RG_NT) pwreg_fwd_kernel(long long n, int kind, const float* __restrict__ x, double* __restrict__ part) {
+    __shared__ double sh[RG_NT];
+    double a = 0.0;
+    for (long long q = (long long)blockIdx.x*RG_NT + threadIdx.x; q < n; q += (long long)gridDim.x*RG_NT) {
+        const float v = __ldg(x + q);
+        a += kind == STV_PWREG_MEAN ? (double)v : (double)(-fmaxf(logf(v), -100.f));
+    }
+    a = rg_block_sum(a, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = a;
+}
+
+__global__ void __launch_bounds__(RG_NT) pwreg_reduce_kernel(int nb, const double* __restrict__ part, double scale, float* __restrict__ out) {
+    __shared__ double sh[RG_NT];
+    double a = 0.0;
+    for (int q = threadIdx.x; q < nb; q += RG_NT) a += part[q];
+    a = rg_block_sum(a, sh);
+    if (threadIdx.x == 0) *out = (float)(a*scale);
+}
+
+__global__ void __launch_bounds__(RG_NT) pwreg_bwd_kernel(long long n, int kind, float sign, const float* __restrict__ x,
+                                                          const float* __restrict__ grad_loss, float* __restrict__ g) {
+    const long long q = (long long)blockIdx.x*RG_NT + threadIdx.x;
+    if (q >= n) return;
+    const float go = __ldg(grad_loss)/(float)n;
+    if (kind == STV_PWREG_MEAN) { g[q] = sign*go; return; }
+    const float v = __ldg(x + q);
+    g[q] = go*(v - 1.f)/fmaxf((1.f - v)*v, 1e-12f);
+}
+
+}  // namespace stv
+
+extern "C" int stv_pwreg_fwd(long long n, int kind, float sign, const float* x, float* loss, void* ws, size_t ws_bytes, void* stream) {
+    STV_REQUIRE(n > 0 && x && loss, "stv_pwreg_fwd: empty input / NULL pointer");
+    STV_REQUIRE(kind == STV_PWREG_MEAN || kind == STV_PWREG_BCE_ONE, "stv_pwreg_fwd: bad kind %d", kind);
+    if (!ws || ws_bytes < stv_regr_workspace_bytes()) { set_error("stv_pwreg_fwd: workspace too small"); return STV_E_WORKSPACE; }
+    double* part = (double*)((char*)ws + sizeof(RegrScalars));
+    long long nbl = (n + RG_NT*4 - 1)/(RG_NT*4);
+    const int nb = (int)(nbl < 1 ? 1 : (nbl > RG_MAXB ? RG_MAXB : nbl));
+    pwreg_fwd_kernel<<<nb, RG_NT, 0, (cudaStream_t)stream>>>(n, kind, x, part);
+    count_launch();
+    if (int rc = check_launch("pwreg_fwd_kernel")) return rc;
+    pwreg_reduce_kernel<<<1, RG_NT, 0, (cudaStream_t)stream>>>(nb, part, (kind == STV_PWREG_MEAN ? (double)sign : 1.0)/(double)n, loss);
+    count_launch();
+    return check_launch("pwreg_reduce_kernel");
+}
+
+extern "C" int stv_pwreg_bwd(long long n, int kind, float sign, const float* x, const float* grad_loss, float* g, void* stream) {
+    STV_REQUIRE(n > 0 && x && grad_loss && g, "stv_pwreg_bwd: empty input / NULL pointer");
+    STV_REQUIRE(kind == STV_PWREG_MEAN || kind == STV_PWREG_BCE_ONE, "stv_pwreg_bwd: bad kind %d", kind);
+    pwreg_bwd_kernel<<<(unsigned)((n + RG_NT - 1)/RG_NT), RG_NT, 0, (cudaStream_t)stream>>>(n, kind, sign, x, grad_loss, g);
+    count_launch();
+    return check_launch("pwreg_bwd_kernel");
+}

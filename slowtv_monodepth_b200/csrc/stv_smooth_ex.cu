@@ -281,3 +281,163 @@ extern "C" int stv_smooth_ex_bwd(int b, int C, int H, int W, int use_edges, int 
     SX_LAUNCH(sx_normalize_bwd_kernel, gd, 256, 0, st>>>(HW, gdn, sum, dot, g_disp));
     return STV_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Feature regularisers (src/regularizers/smooth.py:100-176; registry keys `feat_peaky`, `feat_smooth`): the same building block on
+// C-channel feature maps, no mean normalisation, image-edge weights broadcast over the channels.
+//   order 1 (FeatPeakReg)    loss = -( mean(A_x f * wx) + mean(A_y f * wy) ),                 w = exp(-mean_c A(img)) | 1
+//   order 2 (FeatSmoothReg)  loss = mean(A_x A_x f * wxx) + mean(A_y A_y f * wyy) + mean(A_y A_x f * wxy) + mean(A_x A_y f * wyx),
+//                            w = exp(-mean_c of the same second differences of the image) | 1
+// feat (b, C, H, W), img (b, Ci, H, W) at the same resolution; feat_grad (b, C, H, W) = sqrt(clamp(t0^2 + t1^2, eps)) of the first two
+// terms (the logging map). The backward needs the workspace the forward filled.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace stv {
+
+// partial[plane][block] = sum over the block's pixels of term * (w ? exp(-w[image of the plane]) : 1)
+__global__ void __launch_bounds__(256) fr_wsum_kernel(int HW, int C, const float* __restrict__ term, const float* __restrict__ w,
+                                                      float* __restrict__ partial) {
+    __shared__ float red[32];
+    const int q = blockIdx.x*blockDim.x + threadIdx.x, pl = blockIdx.y;
+    float v = 0.f;
+    if (q < HW) v = term[(size_t)pl*HW + q]*(w ? __expf(-w[(size_t)(pl/C)*HW + q]) : 1.f);
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) partial[(size_t)pl*gridDim.x + blockIdx.x] = v;
+}
+
+// upstream gradient of a term: g[plane][q] = dL/dloss * coef * (w ? exp(-w) : 1)
+__global__ void __launch_bounds__(256) fr_upstream_kernel(int HW, int C, const float* __restrict__ grad_loss, float coef,
+                                                          const float* __restrict__ w, float* __restrict__ g) {
+    const int q = blockIdx.x*blockDim.x + threadIdx.x, pl = blockIdx.y;
+    if (q >= HW) return;
+    g[(size_t)pl*HW + q] = __ldg(grad_loss)*coef*(w ? __expf(-w[(size_t)(pl/C)*HW + q]) : 1.f);
+}
+
+__global__ void __launch_bounds__(256) fr_gradmap_kernel(long long n, const float* __restrict__ t0, const float* __restrict__ t1,
+                                                         float* __restrict__ out) {
+    const long long q = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (q < n) out[q] = sqrtf(fmaxf(t0[q]*t0[q] + t1[q]*t1[q], STV_EPS32));
+}
+
+}  // namespace stv
+
+namespace {
+struct FrPlan {   // floats; P = b*C feature planes, I = b*Ci image planes, B = b planes
+    size_t P, I, B, total, npart;
+    size_t a1x, a1y;          // first differences of the features (order 2 keeps them for the backward)
+    size_t t[4];              // the terms: order 1: A_x f, A_y f; order 2: xx, yy, xy, yx
+    size_t w[4];              // channel-mean image terms (b planes each)
+    size_t i0, i1;            // image-sized temporaries
+    size_t g0, g1, g2;        // feature-sized temporaries of the backward
+    size_t partial;
+};
+FrPlan fr_plan(int b, int C, int Ci, int H, int W) {
+    FrPlan p{};
+    const size_t al = 64, HW = (size_t)H*W;
+    auto take = [&](size_t& cur, size_t n) { const size_t at = cur; cur += (n + al - 1)/al*al; return at; };
+    p.P = (size_t)b*C*HW; p.I = (size_t)b*Ci*HW; p.B = (size_t)b*HW;
+    p.npart = (size_t)b*C*((HW + 255)/256);
+    size_t cur = 0;
+    p.a1x = take(cur, p.P); p.a1y = take(cur, p.P);
+    for (int k = 0; k < 4; ++k) p.t[k] = take(cur, p.P);
+    for (int k = 0; k < 4; ++k) p.w[k] = take(cur, p.B);
+    p.i0 = take(cur, p.I); p.i1 = take(cur, p.I);
+    p.g0 = take(cur, p.P); p.g1 = take(cur, p.P); p.g2 = take(cur, p.P);
+    p.partial = take(cur, 4*p.npart);
+    p.total = cur;
+    return p;
+}
+int fr_check(int b, int C, int Ci, int H, int W, int order, const char* who) {
+    STV_REQUIRE(b > 0 && C > 0 && Ci > 0 && H >= 2 && W >= 2, "%s: bad shape (b=%d C=%d Ci=%d H=%d W=%d)", who, b, C, Ci, H, W);
+    STV_REQUIRE((long long)b*C <= 65535 && (long long)b*Ci <= 65535, "%s: too many planes for one launch", who);
+    STV_REQUIRE(order == 1 || order == 2, "%s: order must be 1 (feat_peaky) or 2 (feat_smooth)", who);
+    return STV_OK;
+}
+// the four second-order terms xx, yy, xy (= A_y A_x), yx (= A_x A_y): axis of the first and of the second difference
+const int FR_AX1[4] = {0, 1, 0, 1}, FR_AX2[4] = {0, 1, 1, 0};
+}  // namespace
+
+extern "C" size_t stv_feat_reg_workspace_bytes(int b, int C, int Ci, int H, int W) {
+    if (b <= 0 || C <= 0 || Ci <= 0 || H < 2 || W < 2) return 0;
+    return fr_plan(b, C, Ci, H, W).total*sizeof(float);
+}
+
+extern "C" int stv_feat_reg_fwd(int b, int C, int Ci, int H, int W, int order, int use_edges, const float* feat, const float* img,
+                                float* loss, float* feat_grad, void* ws, size_t ws_bytes, void* stream) {
+    if (int rc = fr_check(b, C, Ci, H, W, order, "stv_feat_reg_fwd")) return rc;
+    STV_REQUIRE(feat && img && loss, "stv_feat_reg_fwd: NULL pointer");
+    if (!ws || ws_bytes < stv_feat_reg_workspace_bytes(b, C, Ci, H, W)) { set_error("stv_feat_reg_fwd: workspace too small"); return STV_E_WORKSPACE; }
+    const FrPlan p = fr_plan(b, C, Ci, H, W);
+    float* w = (float*)ws;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HW = H*W, nb = (HW + 255)/256, nterm = order == 1 ? 2 : 4;
+    const dim3 gf(nb, b*C), gi(nb, b*Ci), gb(nb, b);
+    if (order == 1) {
+        SX_LAUNCH(sx_absdiff_kernel, gf, 256, 0, st>>>(H, W, 0, 0, feat, w + p.t[0]));
+        SX_LAUNCH(sx_absdiff_kernel, gf, 256, 0, st>>>(H, W, 1, 0, feat, w + p.t[1]));
+    } else {
+        SX_LAUNCH(sx_absdiff_kernel, gf, 256, 0, st>>>(H, W, 0, 0, feat, w + p.a1x));
+        SX_LAUNCH(sx_absdiff_kernel, gf, 256, 0, st>>>(H, W, 1, 0, feat, w + p.a1y));
+        for (int k = 0; k < 4; ++k)
+            SX_LAUNCH(sx_absdiff_kernel, gf, 256, 0, st>>>(H, W, FR_AX2[k], 0, w + (FR_AX1[k] == 0 ? p.a1x : p.a1y), w + p.t[k]));
+    }
+    if (use_edges) {
+        for (int k = 0; k < nterm; ++k) {
+            SX_LAUNCH(sx_absdiff_kernel, gi, 256, 0, st>>>(H, W, order == 1 ? k : FR_AX1[k], 0, img, w + p.i0));
+            if (order == 2) {
+                SX_LAUNCH(sx_absdiff_kernel, gi, 256, 0, st>>>(H, W, FR_AX2[k], 0, w + p.i0, w + p.i1));
+                SX_LAUNCH(sx_chmean_kernel, gb, 256, 0, st>>>(HW, Ci, w + p.i1, w + p.w[k]));
+            } else SX_LAUNCH(sx_chmean_kernel, gb, 256, 0, st>>>(HW, Ci, w + p.i0, w + p.w[k]));
+        }
+    }
+    for (int k = 0; k < nterm; ++k)
+        SX_LAUNCH(fr_wsum_kernel, gf, 256, 0, st>>>(HW, C, w + p.t[k], use_edges ? w + p.w[k] : nullptr, w + p.partial + (size_t)k*p.npart));
+    const double sign = order == 1 ? -1.0 : 1.0;   // peakiness is maximised
+    SX_LAUNCH(sx_reduce_kernel, 1, 256, 0, st>>>(w + p.partial, (int)(nterm*p.npart), sign/((double)b*C*HW), loss));
+    if (feat_grad) {
+        const long long n = (long long)b*C*HW;
+        SX_LAUNCH(fr_gradmap_kernel, (unsigned)((n + 255)/256), 256, 0, st>>>(n, w + p.t[0], w + p.t[1], feat_grad));
+    }
+    return STV_OK;
+}
+
+extern "C" int stv_feat_reg_bwd(int b, int C, int Ci, int H, int W, int order, int use_edges, const float* feat, const float* grad_loss,
+                                float* g_feat, void* ws, size_t ws_bytes, void* stream) {
+    if (int rc = fr_check(b, C, Ci, H, W, order, "stv_feat_reg_bwd")) return rc;
+    STV_REQUIRE(feat && grad_loss && g_feat, "stv_feat_reg_bwd: NULL pointer");
+    if (!ws || ws_bytes < stv_feat_reg_workspace_bytes(b, C, Ci, H, W)) { set_error("stv_feat_reg_bwd: workspace too small"); return STV_E_WORKSPACE; }
+    const FrPlan p = fr_plan(b, C, Ci, H, W);
+    float* w = (float*)ws;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HW = H*W, nb = (HW + 255)/256;
+    const long long n = (long long)b*C*HW;
+    const dim3 gf(nb, b*C);
+    const unsigned nl = (unsigned)((n + 255)/256);
+    const float coef = (order == 1 ? -1.f : 1.f)/((float)b*(float)C*(float)HW);
+    float *g0 = w + p.g0, *g1 = w + p.g1, *g2 = w + p.g2;
+    auto upstream = [&](int k) -> int { SX_LAUNCH(fr_upstream_kernel, gf, 256, 0, st>>>(HW, C, grad_loss, coef, use_edges ? w + p.w[k] : nullptr, g0)); return STV_OK; };
+    // out (+)= A_axis^T (xin; gin)
+    auto adj = [&](int axis, const float* xin, const float* gin, float* out, int accumulate) -> int {
+        if (!accumulate) { SX_LAUNCH(sx_absdiff_bwd_kernel, gf, 256, 0, st>>>(H, W, axis, 0, xin, gin, out)); return STV_OK; }
+        SX_LAUNCH(sx_absdiff_bwd_kernel, gf, 256, 0, st>>>(H, W, axis, 0, xin, gin, g2));
+        SX_LAUNCH(sx_add_kernel, nl, 256, 0, st>>>(n, g2, out, 1));
+        return STV_OK;
+    };
+    if (order == 1) {
+        if (int rc = upstream(0)) return rc;
+        if (int rc = adj(0, feat, g0, g_feat, 0)) return rc;
+        if (int rc = upstream(1)) return rc;
+        return adj(1, feat, g0, g_feat, 1);
+    }
+    // order 2: gradients of the first differences (g1 = d/d a1x, then d/d a1y), each pulled back to the features
+    for (int first = 0; first < 2; ++first) {
+        const float* a1 = w + (first == 0 ? p.a1x : p.a1y);
+        int seen = 0;
+        for (int k = 0; k < 4; ++k) {
+            if (FR_AX1[k] != first) continue;
+            if (int rc = upstream(k)) return rc;
+            if (int rc = adj(FR_AX2[k], a1, g0, g1, seen++)) return rc;
+        }
+        if (int rc = adj(first, feat, g1, g_feat, first)) return rc;
+    }
+    return STV_OK;
+}

@@ -1256,6 +1256,74 @@ def smooth_loss_ex(disp: Tensor, img: Tensor, *, use_edges: bool = False, use_la
     return _SmoothLossEx.apply(_f32c(disp), _f32c(img.detach()), bool(use_edges), bool(use_laplacian), bool(use_blur))
 
 
+class _FeatReg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, img, order: int, use_edges: bool):
+        L.require_cuda(feat, img, what='feat_reg')
+        b, Cc, H, W = feat.shape
+        Ci = img.shape[1]
+        lib, dev = L.lib(), feat.device
+        with torch.cuda.device(dev):
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            fg = torch.empty_like(feat)
+            ws = _ws(lib.stv_feat_reg_workspace_bytes(b, Cc, Ci, H, W), dev)
+            L.check(lib.stv_feat_reg_fwd(b, Cc, Ci, H, W, order, int(use_edges), L.ptr(feat), L.ptr(img), L.ptr(loss), L.ptr(fg), L.ptr(ws),
+                                         ws.numel(), L.stream()), 'stv_feat_reg_fwd')
+        ctx.args = (b, Cc, Ci, H, W, order, int(use_edges))
+        ctx.save_for_backward(feat, ws)
+        ctx.mark_non_differentiable(fg)
+        return loss, fg
+
+    @staticmethod
+    def backward(ctx, g_loss, _g):
+        feat, ws = ctx.saved_tensors
+        with torch.cuda.device(feat.device):
+            g = torch.empty_like(feat)
+            L.check(L.lib().stv_feat_reg_bwd(*ctx.args, L.ptr(feat), L.ptr(g_loss.to(torch.float32).contiguous()), L.ptr(g), L.ptr(ws),
+                                             ws.numel(), L.stream()), 'stv_feat_reg_bwd')
+        return g, None, None, None
+
+
+def feat_reg(feat: Tensor, img: Tensor, *, order: int, use_edges: bool = False):
+    """FeatPeakReg (order 1) / FeatSmoothReg (order 2) forward (src/regularizers/smooth.py:100-176): feat (b,C,H,W), img (b,Ci,H,W)
+    -> (loss, feat_grad (b,C,H,W)); differentiable in `feat`."""
+    if feat.ndim != 4 or img.ndim != 4 or feat.shape[0] != img.shape[0] or feat.shape[-2:] != img.shape[-2:]:
+        raise ValueError(f'Non-matching shapes. ({tuple(feat.shape)} vs. {tuple(img.shape)})')
+    return _FeatReg.apply(_f32c(feat), _f32c(img.detach()), int(order), bool(use_edges))
+
+
+class _PointwiseReg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kind: int, sign: float):
+        L.require_cuda(x, what='pointwise_reg')
+        lib, dev = L.lib(), x.device
+        with torch.cuda.device(dev):
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            ws = _ws(lib.stv_regr_workspace_bytes(), dev)
+            L.check(lib.stv_pwreg_fwd(x.numel(), kind, float(sign), L.ptr(x), L.ptr(loss), L.ptr(ws), ws.numel(), L.stream()), 'stv_pwreg_fwd')
+        ctx.args = (x.numel(), kind, float(sign))
+        ctx.save_for_backward(x)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        x, = ctx.saved_tensors
+        with torch.cuda.device(x.device):
+            g = torch.empty_like(x)
+            L.check(L.lib().stv_pwreg_bwd(*ctx.args, L.ptr(x), L.ptr(g_loss.to(torch.float32).contiguous()), L.ptr(g), L.stream()), 'stv_pwreg_bwd')
+        return g, None, None
+
+
+def mean_reg(x: Tensor, sign: float = 1.0) -> Tensor:
+    """OccReg (src/regularizers/occlusion.py:9-40): sign * mean(x)."""
+    return _PointwiseReg.apply(_f32c(x), 0, float(sign))
+
+
+def bce_to_one(x: Tensor) -> Tensor:
+    """MaskReg (src/regularizers/mask.py:11-30): F.binary_cross_entropy(x, ones_like(x))."""
+    return _PointwiseReg.apply(_f32c(x), 1, 1.0)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Bilinear resampling (aspect-ratio augmentation)
 # ---------------------------------------------------------------------------------------------------------------------

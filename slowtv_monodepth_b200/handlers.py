@@ -7,7 +7,7 @@ from torch import Tensor
 from .losses import ReconstructionLoss, RegressionLoss
 from .regularizers import SmoothReg
 
-__all__ = ['image_recon', 'feat_recon', 'stereo_const', 'depth_regr', 'disp_smooth']
+__all__ = ['image_recon', 'feat_recon', 'stereo_const', 'depth_regr', 'disp_smooth', 'feat_smooth', 'disp_occ', 'disp_mask']
 
 
 def _disparity_sources(depths: dict[int, Tensor], size) -> tuple | None:
@@ -142,3 +142,32 @@ def depth_regr(crit: RegressionLoss, synth, photo, depths: dict[int, Tensor], ta
 def disp_smooth(crit: SmoothReg, disps: dict[int, Tensor], imgs: Tensor, *, want_maps: bool = True):
     """Reference: src/core/handlers.py:262-281. -> (loss, {'disp_grad', 'image_grad'} of the first scale)."""
     return crit.multi_scale(disps, imgs, want_maps=want_maps)
+
+
+def feat_smooth(crit, feats, imgs: Tensor, supp_feats, supp_imgs: Tensor):
+    """Reference: src/core/handlers.py:284-312 — FeatPeakReg / FeatSmoothReg over the multi-scale encoder features of the target and of
+    the support frames, the images resized to each feature map (stv_resample_bilinear), loss_s / 2**s averaged. -> (loss, {})."""
+    from . import functional as F_
+    def one(fs, im):
+        ls = [crit(f, F_.resample_bilinear(im, tuple(f.shape[-2:]), mode='interp') if f.shape[-2:] != im.shape[-2:] else im)[0]/2**s
+              for s, f in enumerate(fs)]
+        return sum(ls)/len(ls)
+    loss = one(feats, imgs)
+    loss = loss + one([f.flatten(0, 1) for f in supp_feats], supp_imgs.flatten(0, 1).contiguous())
+    return loss, {}
+
+
+def _per_scale_mean(crit, maps: dict[int, Tensor]):
+    ls = {s: crit(m) for s, m in maps.items()}
+    loss = sum(v[0] for v in ls.values())/len(ls)
+    return loss, ls[0][1] if 0 in ls else next(iter(ls.values()))[1]   # loss dict of the first scale
+
+
+def disp_occ(crit, disps: dict[int, Tensor]):
+    """Reference: src/core/handlers.py:315-329 — OccReg per scale, averaged. -> (loss, {})."""
+    return _per_scale_mean(crit, disps)
+
+
+def disp_mask(crit, masks: dict[int, Tensor]):
+    """Reference: src/core/handlers.py:332-346 — MaskReg per scale, averaged. -> (loss, {})."""
+    return _per_scale_mean(crit, masks)

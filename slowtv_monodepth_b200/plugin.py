@@ -31,7 +31,8 @@ REPLACED = {
     # the reference registers ONE class under three keys (src/losses/reconstruction.py:12)
     'loss': {'img_recon': losses.ReconstructionLoss, 'feat_recon': losses.ReconstructionLoss, 'autoenc_recon': losses.ReconstructionLoss,
              'depth_regr': losses.RegressionLoss, 'stereo_const': losses.RegressionLoss,   # src/losses/regression.py:40
-             'disp_smooth': regularizers.SmoothReg},
+             'disp_smooth': regularizers.SmoothReg, 'feat_peaky': regularizers.FeatPeakReg, 'feat_smooth': regularizers.FeatSmoothReg,
+             'disp_mask': regularizers.MaskReg, 'disp_occ': regularizers.OccReg},
 }
 _saved: dict = {}
 
@@ -83,12 +84,14 @@ def install(nets: bool = True, loss: bool = True, fast_step: bool = True) -> Non
         _saved.setdefault(('attr', 'feat_recon'), ref_handlers.feat_recon)
         _saved.setdefault(('attr', 'stereo_const'), ref_handlers.stereo_const)
         _saved.setdefault(('attr', 'depth_regr'), ref_handlers.depth_regr)
+        for name in ('feat_smooth', 'disp_occ', 'disp_mask'): _saved.setdefault(('attr', name), getattr(ref_handlers, name))
         _saved.setdefault(('attr', 'ViewSynth'), ref_trainer.ViewSynth)
         ref_handlers.image_recon = handlers.image_recon
         ref_handlers.disp_smooth = handlers.disp_smooth
         ref_handlers.feat_recon = handlers.feat_recon
         ref_handlers.stereo_const = handlers.stereo_const
         ref_handlers.depth_regr = handlers.depth_regr
+        ref_handlers.feat_smooth, ref_handlers.disp_occ, ref_handlers.disp_mask = handlers.feat_smooth, handlers.disp_occ, handlers.disp_mask
         ref_trainer.ViewSynth = geometry.ViewSynth
     # MonoDepthModule.__init__ binds `aspect_ratio_aug` by name from src.core.trainer (trainer.py:12,54-60)
     _saved.setdefault(('attr', 'aspect_ratio_aug'), ref_trainer.aspect_ratio_aug)
@@ -122,6 +125,6 @@ def uninstall() -> None:
             if val is None: reg._REG[key[1]].pop(key[2], None)
             else: reg._REG[key[1]][key[2]] = val
         elif key[0] == 'method': setattr(ref_trainer.MonoDepthModule, key[1], val)
-        elif key[1] in ('image_recon', 'disp_smooth', 'feat_recon', 'stereo_const', 'depth_regr'): setattr(ref_handlers, key[1], val)
+        elif key[1] in ('image_recon', 'disp_smooth', 'feat_recon', 'stereo_const', 'depth_regr', 'feat_smooth', 'disp_occ', 'disp_mask'): setattr(ref_handlers, key[1], val)
         else: setattr(ref_trainer, key[1], val)
     _saved.clear()

@@ -6,7 +6,7 @@ from torch import Tensor
 
 from . import functional as F_
 
-__all__ = ['SmoothReg']
+__all__ = ['SmoothReg', 'FeatPeakReg', 'FeatSmoothReg', 'MaskReg', 'OccReg']
 
 
 class SmoothReg(nn.Module):
@@ -41,3 +41,41 @@ class SmoothReg(nn.Module):
             return sum(ls)/len(ls), (maps.get(0, maps[keys[0]]) if want_maps else {})   # loss dict of the first scale (handlers.py:280)
         loss, dg, ig = F_.smooth_loss([disps[k] for k in keys], imgs, scales=keys, use_edges=self.use_edges, want_maps=want_maps)
         return loss, ({'disp_grad': dg, 'image_grad': ig} if want_maps else {})
+
+
+class FeatPeakReg(nn.Module):
+    """Reference: src/regularizers/smooth.py:100-136 (`feat_peaky`): encourage first-order feature gradients (negative mean)."""
+    def __init__(self, use_edges: bool = False):
+        super().__init__()
+        self.use_edges = use_edges
+
+    def forward(self, feat: Tensor, img: Tensor):
+        loss, fg = F_.feat_reg(feat, img, order=1, use_edges=self.use_edges)
+        return loss, {'feat_grad': fg}
+
+
+class FeatSmoothReg(nn.Module):
+    """Reference: src/regularizers/smooth.py:139-176 (`feat_smooth`): penalise second-order feature gradients (xx, yy, xy, yx)."""
+    def __init__(self, use_edges: bool = False):
+        super().__init__()
+        self.edge_aware = use_edges
+
+    def forward(self, feat: Tensor, img: Tensor):
+        loss, fg = F_.feat_reg(feat, img, order=2, use_edges=self.edge_aware)
+        return loss, {'feat_grad': fg}
+
+
+class MaskReg(nn.Module):
+    """Reference: src/regularizers/mask.py:11-30 (`disp_mask`): binary cross-entropy of the explainability mask against 1."""
+    def forward(self, x: Tensor):
+        return F_.bce_to_one(x), {}
+
+
+class OccReg(nn.Module):
+    """Reference: src/regularizers/occlusion.py:9-40 (`disp_occ`): +-mean disparity (`invert` encourages foreground instead)."""
+    def __init__(self, invert: bool = False):
+        super().__init__()
+        self.invert, self._sign = invert, (-1 if invert else 1)
+
+    def forward(self, x: Tensor):
+        return F_.mean_reg(x, self._sign), {}

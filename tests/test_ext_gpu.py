@@ -282,3 +282,54 @@ def test_regression_loss_edge_cases():
         want.backward()
         assert abs(loss.item() - want.item()) <= 1e-6 + TOL_LOSS*abs(want.item())
         assert (p.grad.cpu().double() - pr.grad).abs().max().item() <= 1e-6 + TOL_GRAD*pr.grad.abs().max().item()
+
+
+@pytest.mark.parametrize('name', list(G.FREG))
+def test_feature_regularisers_match_the_reference_classes(name):
+    from slowtv_monodepth_b200 import regularizers as R
+    c = G.FREG[name]
+    d = _cuda(G.freg_inputs(c, torch.float32))
+    feat = d['feat'].requires_grad_()
+    loss, ld = getattr(R, c['cls'])(use_edges=c['use_edges'])(feat, d['img'])
+    loss.backward()
+    want = EXT[f'{name}/loss'].item()
+    assert abs(loss.item() - want) <= TOL_LOSS*abs(want)
+    assert U.rel(feat.grad.cpu().double(), torch.from_numpy(EXT[f'{name}/g_feat'])) < TOL_GRAD
+    assert U.rel(ld['feat_grad'].cpu().double(), torch.from_numpy(EXT[f'{name}/feat_grad']).clamp(min=O.EPS32**0.5)) < 1e-5
+
+
+def test_pointwise_regularisers_and_their_handlers():
+    from slowtv_monodepth_b200 import regularizers as R
+    d = _cuda(G.freg_inputs(G.FREG['freg_peaky_edges'], torch.float32))
+    for name, crit in (('pw_mask', R.MaskReg()), ('pw_occ', R.OccReg()), ('pw_occ_inv', R.OccReg(invert=True))):
+        x = d['x'].clone().requires_grad_()
+        loss, ld = crit(x)
+        loss.backward()
+        want = EXT[f'{name}/loss'].item()
+        assert ld == {} and abs(loss.item() - want) <= TOL_LOSS*abs(want)
+        assert U.rel(x.grad.cpu().double(), torch.from_numpy(EXT[f'{name}/g_x'])) < TOL_GRAD
+    maps = {0: d['x'].clone().requires_grad_(), 1: d['x'][..., ::2, ::2].clone().requires_grad_()}
+    loss, _ = Hd.disp_occ(R.OccReg(), maps)
+    loss.backward()
+    assert abs(loss.item() - 0.5*(maps[0].mean().item() + maps[1].mean().item())) < 1e-6
+    loss, _ = Hd.disp_mask(R.MaskReg(), {0: d['x'].clone()})
+    assert abs(loss.item() - EXT['pw_mask/loss'].item()) <= TOL_LOSS*abs(EXT['pw_mask/loss'].item())
+
+
+def test_feat_smooth_handler_follows_the_reference_formulation():
+    from slowtv_monodepth_b200 import regularizers as R
+    rs = np.random.RandomState(5)
+    f = lambda *s: torch.from_numpy(rs.random_sample(s).astype(np.float32)).cuda()
+    imgs, supp = f(2, 3, 16, 24), f(2, 2, 3, 16, 24)
+    feats = [f(2, 4, 16, 24).requires_grad_(), f(2, 6, 8, 12).requires_grad_()]
+    sfeats = [f(2, 2, 4, 16, 24).requires_grad_(), f(2, 2, 6, 8, 12).requires_grad_()]
+    loss, _ = Hd.feat_smooth(R.FeatSmoothReg(use_edges=True), feats, imgs, sfeats, supp)
+    loss.backward()
+    rf = [x.detach().double().cpu().requires_grad_() for x in feats]
+    rsf = [x.detach().double().cpu().requires_grad_() for x in sfeats]
+    im, sim = imgs.double().cpu(), supp.double().cpu().flatten(0, 1)
+    one = lambda fs, img: torch.stack([O.feat_smooth_reg(x, O.resize_bilinear(img, x.shape[-2:]), True)[0]/2**s for s, x in enumerate(fs)]).mean()
+    want = one(rf, im) + one([x.flatten(0, 1) for x in rsf], sim)
+    want.backward()
+    assert abs(loss.item() - want.item()) <= TOL_LOSS*abs(want.item())
+    for a, b in zip(feats + sfeats, rf + rsf): assert U.rel(a.grad.cpu().double(), b.grad) < TOL_GRAD

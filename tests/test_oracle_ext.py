@@ -94,3 +94,24 @@ def test_depth_regr_matches_reference(name):
     assert abs(loss.item() - EXT[f'{name}/loss'].item()) <= 1e-10*abs(EXT[f'{name}/loss'].item())
     for s in range(c['S']): assert U.rel(depths[s].grad, torch.from_numpy(EXT[f'{name}/g_depth{s}'])) < 1e-8
     assert np.array_equal(masks[:c['b']].numpy().astype(np.uint8), EXT[f'{name}/mask'])
+
+
+@pytest.mark.parametrize('name', list(G.FREG))
+def test_feature_regularisers_match_reference(name):
+    c, d = G.FREG[name], G.freg_inputs(G.FREG[name])
+    feat = d['feat'].clone().requires_grad_()
+    fn = O.feat_peak_reg if c['cls'] == 'FeatPeakReg' else O.feat_smooth_reg
+    loss, fg = fn(feat, d['img'], c['use_edges'])
+    loss.backward()
+    assert abs(loss.item() - EXT[f'{name}/loss'].item()) <= 1e-12*abs(EXT[f'{name}/loss'].item())
+    assert U.rel(feat.grad, torch.from_numpy(EXT[f'{name}/g_feat'])) < 1e-10 and U.rel(fg, torch.from_numpy(EXT[f'{name}/feat_grad'])) < 1e-12
+
+
+def test_pointwise_regularisers_match_reference():
+    d = G.freg_inputs(G.FREG['freg_peaky_edges'])
+    for name, fn in (('pw_mask', O.mask_reg), ('pw_occ', O.occ_reg), ('pw_occ_inv', lambda x: O.occ_reg(x, True))):
+        x = d['x'].clone().requires_grad_()
+        loss = fn(x)
+        loss.backward()
+        assert abs(loss.item() - EXT[f'{name}/loss'].item()) <= 1e-12*abs(EXT[f'{name}/loss'].item())
+        assert U.rel(x.grad, torch.from_numpy(EXT[f'{name}/g_x'])) < 1e-12

@@ -40,6 +40,8 @@ def test_install_rebinds_the_reference_hooks_and_uninstall_restores_them():
         assert reg.LOSS_REG['feat_recon'] is losses.ReconstructionLoss and reg.LOSS_REG['autoenc_recon'] is losses.ReconstructionLoss  # one class, three keys
         assert reg.LOSS_REG['depth_regr'] is losses.RegressionLoss and reg.LOSS_REG['stereo_const'] is losses.RegressionLoss
         assert rh.feat_recon is handlers.feat_recon and rh.stereo_const is handlers.stereo_const and rh.depth_regr is handlers.depth_regr
+        assert reg.LOSS_REG['feat_peaky'] is regularizers.FeatPeakReg and reg.LOSS_REG['feat_smooth'] is regularizers.FeatSmoothReg
+        assert reg.LOSS_REG['disp_mask'] is regularizers.MaskReg and reg.LOSS_REG['disp_occ'] is regularizers.OccReg
         assert rt.ViewSynth is geometry.ViewSynth and rt.aspect_ratio_aug is aspect_ratio.aspect_ratio_aug
         assert rh.image_recon is handlers.image_recon and rh.disp_smooth is handlers.disp_smooth
 
