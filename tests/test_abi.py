@@ -70,3 +70,44 @@ def test_cpu_tensors_are_refused():
         F_.photo_loss([torch.zeros(1, 1, 8, 8)], t, t[None], torch.eye(4)[None, None], torch.eye(4)[None])
     with pytest.raises(L.StvError):
         F_.smooth_loss([torch.zeros(1, 1, 8, 8)], t)
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """Every struct of include/stv.h has the size and field offsets of its ctypes mirror (compiled with the host C compiler)."""
+    import shutil
+    import subprocess
+    from slowtv_monodepth_b200 import _lib as L
+    cc = shutil.which('gcc') or shutil.which('cc')
+    if cc is None: pytest.skip('no host C compiler')
+    pairs = {'stv_photo_cfg': L.PhotoCfg, 'stv_photo_src': L.PhotoSrc, 'stv_recon_cfg': L.ReconCfg, 'stv_smooth_cfg': L.SmoothCfg,
+             'stv_gemm_epi': L.GemmEpi, 'stv_conv_geom': L.ConvGeom}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT/"include"/"stv.h"}"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, *_ in cls._fields_: lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path/'layout.c'
+    src.write_text('\n'.join(lines))
+    subprocess.run([cc, '-std=c11', '-o', str(tmp_path/'layout'), str(src)], check=True)
+    out = subprocess.run([str(tmp_path/'layout')], capture_output=True, text=True, check=True).stdout
+    for row in out.strip().splitlines():
+        cname, size, *offs = row.split()
+        cls = pairs[cname]
+        assert int(size) == C.sizeof(cls), f'{cname}: sizeof {size} (header) vs {C.sizeof(cls)} (ctypes)'
+        assert [int(o) for o in offs] == [getattr(cls, f[0]).offset for f in cls._fields_], f'{cname}: field offsets differ'
+
+
+def test_new_entry_points_validate_their_arguments_without_a_gpu():
+    from slowtv_monodepth_b200 import _lib as L
+    lib = L.lib()
+    cfg = L.ReconCfg(b=1, n=2, C=3, H=8, W=8, loss=7, use_min=1, use_automask=0, mask_mode=0, noise_seed=0)
+    assert lib.stv_recon_ex_workspace_bytes(C.byref(cfg)) == 0 and b'bad loss' in lib.stv_last_error()
+    cfg.loss, cfg.mask_mode = 0, 5
+    assert lib.stv_recon_ex_workspace_bytes(C.byref(cfg)) == 0 and b'Invalid mask type' in lib.stv_last_error()
+    cfg.mask_mode = 1
+    assert lib.stv_recon_ex_workspace_bytes(C.byref(cfg)) > 0
+    assert lib.stv_regr_fwd(16, 9, 0, None, None, None, None, None, None, 0, None) == 1          # NULL operands / bad loss
+    assert lib.stv_smooth_ex_workspace_bytes(1, 3, 2, 8) == 0 and lib.stv_smooth_ex_workspace_bytes(1, 3, 8, 8) > 0
+    assert lib.stv_feat_reg_workspace_bytes(1, 4, 3, 1, 8) == 0 and lib.stv_feat_reg_workspace_bytes(1, 4, 3, 8, 8) > 0
+    assert lib.stv_pwreg_fwd(0, 0, 1.0, None, None, None, 0, None) == 1
