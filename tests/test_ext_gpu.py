@@ -131,27 +131,35 @@ def test_feat_recon_matches_the_reference_handler(name):
     assert U.rel(depth.grad.cpu().double(), torch.from_numpy(EXT[f'{name}/g_depth'])) < 5e-4   # through the float32 warp + sampler
 
 
-def test_image_recon_general_route_with_predicted_masks():
-    """handlers.image_recon with `masks` (explainability): stand-alone warp + general loss vs the oracle's composition."""
+@pytest.mark.parametrize('S', [1, 2])
+def test_image_recon_general_route_with_predicted_masks(S):
+    """handlers.image_recon with `masks` (explainability): stand-alone warp + general loss vs the oracle's composition; S = 2 checks
+    the (n, S, b) expansion order of handlers.py:43-66 (scale-major batches, masks stacked per scale)."""
     c = dict(b=2, n=2, C=3, H=16, W=24, seed=51)
     d = _cuda(G.feat_inputs(c, torch.float32))
     rs = np.random.RandomState(52)
-    imgs = torch.from_numpy(rs.random_sample((c['b'], 3, c['H'], c['W'])).astype(np.float32)).cuda()
-    supp = (imgs[None] + 0.2*torch.from_numpy(rs.random_sample((c['n'], c['b'], 3, c['H'], c['W'])).astype(np.float32)).cuda() - 0.1).clamp(0, 1)
-    mask = (0.2 + 0.6*torch.from_numpy(rs.random_sample((c['b'], c['n'], c['H'], c['W'])).astype(np.float32))).cuda().requires_grad_()
-    depth = d['depth'].requires_grad_()
+    f = lambda *sh: torch.from_numpy(rs.random_sample(sh).astype(np.float32)).cuda()
+    imgs = f(c['b'], 3, c['H'], c['W'])
+    supp = (imgs[None] + 0.2*f(c['n'], c['b'], 3, c['H'], c['W']) - 0.1).clamp(0, 1)
+    masks = {s: (0.2 + 0.6*f(c['b'], c['n'], c['H'], c['W'])).requires_grad_() for s in range(S)}
+    depths = {s: (d['depth']*(1 + 0.25*s)).detach().requires_grad_() for s in range(S)}
     Ts = T_from_AAt(d['aa'], d['t'])
     crit = ReconstructionLoss('ssim', True, False, 'explainability')
-    loss, ld = Hd.image_recon(crit, None, {0: depth}, {0: mask}, imgs, supp, Ts, d['K'])
+    loss, ld = Hd.image_recon(crit, None, depths, masks, imgs, supp, Ts, d['K'])
     loss.backward()
-    rdepth, rmask = depth.detach().double().cpu().requires_grad_(), mask.detach().double().cpu().requires_grad_()
-    rT, rK = Ts.double().cpu(), d['K'].double().cpu()
-    warp = torch.stack([O.view_synth(supp[k].double().cpu(), rdepth, rT[k], rK)[0] for k in range(c['n'])])
-    want = O.reconstruction_loss_ex(warp, imgs.double().cpu(), None, rmask, 'ssim', True, False, 'explainability')[0]
+    rdepth = [v.detach().double().cpu().requires_grad_() for v in depths.values()]
+    rmask = [v.detach().double().cpu().requires_grad_() for v in masks.values()]
+    rT, rK, rsupp, rimgs = Ts.double().cpu(), d['K'].double().cpu(), supp.double().cpu(), imgs.double().cpu()
+    # the reference averages over the (S*b) virtual batch: equal-sized scales -> the mean of the per-scale losses
+    want = 0
+    for s in range(S):
+        warp = torch.stack([O.view_synth(rsupp[k], rdepth[s], rT[k], rK)[0] for k in range(c['n'])])
+        want = want + O.reconstruction_loss_ex(warp, rimgs, None, rmask[s], 'ssim', True, False, 'explainability')[0]/S
     want.backward()
     assert abs(loss.item() - want.item()) <= 2e-5*abs(want.item())
-    assert U.rel(mask.grad.cpu().double(), rmask.grad) < TOL_GRAD
-    assert U.rel(depth.grad.cpu().double(), rdepth.grad) < 2e-3   # min-reprojection flips at float32 near-ties stay local
+    for s in range(S):
+        assert U.rel(masks[s].grad.cpu().double(), rmask[s].grad) < TOL_GRAD
+        assert U.rel(depths[s].grad.cpu().double(), rdepth[s].grad) < 2e-3   # min-reprojection flips at float32 near-ties stay local
     assert ld['supp_imgs_warp'].shape == supp.shape
 
 
